@@ -1,0 +1,136 @@
+"""ctypes binding of libfemb200.so (C ABI in include/femb200.h) and its in-tree build.
+
+The library is the product: if it is missing or cannot be loaded there is NO fallback --
+``load()`` raises and so does every ``Object`` constructor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libfemb200.so")
+SOURCES = ["femb_api.cu", "femb_element.cu", "femb_sparse.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+PART_L, PART_D, PART_U, PART_ALL = 1, 2, 4, 7
+
+c_int_p = C.POINTER(C.c_int)
+c_float_p = C.POINTER(C.c_float)
+
+
+class FembLevel(C.Structure):
+    _fields_ = [("n_vert", C.c_int), ("n_hex", C.c_int), ("nnz", C.c_int),
+                ("off_l", C.c_int), ("off_d", C.c_int), ("off_u", C.c_int),
+                ("color_start", C.c_int * 9),
+                ("hex", C.c_void_p), ("v2i", C.c_void_p), ("i2v", C.c_void_p),
+                ("L_ptr", C.c_void_p), ("L_col", C.c_void_p), ("U_ptr", C.c_void_p), ("U_col", C.c_void_p),
+                ("elem2nnz", C.c_void_p), ("asm_ptr", C.c_void_p), ("asm_src", C.c_void_p),
+                ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p)]
+
+
+class FembTransfer(C.Structure):
+    _fields_ = [("nrow", C.c_int), ("ncol", C.c_int), ("nnz", C.c_int),
+                ("offsets", C.c_void_p), ("columns", C.c_void_p), ("weights", C.c_void_p)]
+
+
+class FembGalerkinPlan(C.Structure):
+    _fields_ = [("n_fine", C.c_int), ("n_coarse", C.c_int), ("t_nnz", C.c_int),
+                ("t_ptr", C.c_void_p), ("t_col", C.c_void_p), ("c_ptr", C.c_void_p),
+                ("c_col", C.c_void_p), ("c_slot", C.c_void_p)]
+
+
+P = C.c_void_p
+LV = C.POINTER(FembLevel)
+TR = C.POINTER(FembTransfer)
+GP = C.POINTER(FembGalerkinPlan)
+I, F = C.c_int, C.c_float
+
+# name -> argtypes; every function returns int unless listed in _RESTYPE (mirrors include/femb200.h)
+PROTOTYPES = {
+    "femb_abi_version": [],
+    "femb_last_error": [],
+    "femb_launch_count": [],
+    "femb_check_device": [I],
+    "femb_prepare_rest": [I, P, P, P, P, P],
+    "femb_lumped_mass": [LV, P, P, P],
+    "femb_force": [LV, P, F, F, P, F, P, P, F, I, P, P, P],
+    "femb_hessian": [LV, P, F, F, P, P, P, P],
+    "femb_force_hessian": [LV, P, F, F, P, F, P, P, F, P, P, P, P, P, P],
+    "femb_energy": [LV, P, F, F, P, F, P, P, F, P, P, P],
+    "femb_coarse_pin_penalty": [LV, TR, P, F, P, P],
+    "femb_spmv": [LV, P, I, F, P, F, P, P],
+    "femb_residual": [LV, P, P, P, P, P],
+    "femb_gauss_seidel": [LV, P, P, P, I, P, P],
+    "femb_jacobi": [LV, P, P, P, P, I, P, P],
+    "femb_cg": [LV, P, P, P, P, P, P, P, I, F, I, P],
+    "femb_spd_blocks": [P, I, F, P],
+    "femb_transfer_mv": [TR, F, P, F, P, P],
+    "femb_galerkin": [LV, P, TR, TR, GP, P, I, F, P, P],
+    "femb_axpby": [I, F, P, F, P, P],
+    "femb_copy": [I, P, P, P],
+    "femb_fill": [I, F, P, P],
+    "femb_update_x": [LV, P, P, P],
+    "femb_v2i": [LV, P, P, P],
+    "femb_i2v": [LV, P, P, P],
+    "femb_inf_norm": [I, P, P, P],
+    "femb_dot": [I, P, P, P, P, P],
+}
+_RESTYPE = {"femb_last_error": C.c_char_p, "femb_launch_count": C.c_longlong}
+
+
+class FembError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libfemb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = [os.path.join(_PKG, "csrc", s) for s in SOURCES]
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + src
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise FembError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def _needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc"))]
+    deps.append(os.path.join(_ROOT, "include", "femb200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+_lib = None
+
+
+def load(rebuild: bool = False):
+    """Load (building first if sources are newer) and type the C ABI.  Raises if that is impossible."""
+    global _lib
+    if _lib is not None and not rebuild:
+        return _lib
+    if rebuild or _needs_build():
+        build()
+    lib = C.CDLL(LIB_PATH)
+    for name, args in PROTOTYPES.items():
+        fn = getattr(lib, name)            # AttributeError if the symbol is not exported
+        fn.argtypes = args
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    if lib.femb_abi_version() != 1:
+        raise FembError("libfemb200 ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = _lib.femb_last_error().decode() if _lib is not None else ""
+        raise FembError(f"{what} failed with code {rc}: {msg}")

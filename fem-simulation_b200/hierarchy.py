@@ -1,0 +1,331 @@
+"""Host-side setup of the multigrid hierarchy, vectorised (numpy), numbering identical to the reference.
+
+Mirrors ``Object.__init__`` of /root/reference/exp1/quasi_simulation/object.py:116-865, which builds
+everything with per-element Python loops and dictionaries (minutes at 1e4 hexes).  Here every
+dictionary "first seen" numbering is reproduced with stable sorts / ``np.unique`` so that the
+integer outputs (colour/index order, coarse meshes, ``fine_coarse``, interpolation triplets, the
+[L;D;U] slot maps and the element->nnz maps) are bit-identical while scaling to 1e7 hexes.
+SURVEY.md Appendix B is the specification; each function cites the reference lines it replaces.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+F32 = np.float32
+
+
+@dataclass
+class SparseW:
+    """CSR matrix with one scalar weight per entry; stands for a BSR matrix with blocks w*I3
+    (the reference stores the 36-byte blocks: object.py:422-436)."""
+    nrow: int
+    ncol: int
+    offsets: np.ndarray
+    columns: np.ndarray
+    weights: np.ndarray
+
+    @property
+    def nnz(self):
+        return int(self.columns.shape[0])
+
+    def rows(self):
+        return np.repeat(np.arange(self.nrow, dtype=np.int32), np.diff(self.offsets))
+
+    def transposed(self):
+        return coo_to_csr(self.ncol, self.nrow, self.columns, self.rows(), self.weights)
+
+    def block_values(self):
+        return self.weights[:, None, None] * np.eye(3, dtype=F32)
+
+
+def coo_to_csr(nrow, ncol, rows, cols, w) -> SparseW:
+    """sort by (row, col); entries are unique here (sparse.py:173-278 would sum duplicates)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    order = np.argsort(rows * np.int64(max(ncol, 1)) + cols, kind="stable")
+    r = rows[order]
+    offsets = np.zeros(nrow + 1, dtype=np.int64)
+    np.add.at(offsets, r + 1, 1)
+    return SparseW(int(nrow), int(ncol), np.cumsum(offsets).astype(np.int32), cols[order].astype(np.int32),
+                   np.asarray(w, dtype=F32)[order])
+
+
+@dataclass
+class LevelPattern:
+    """Fixed block pattern of one level in the reference's [L;D;U] value layout (object.py:485-697)."""
+    n: int
+    nnz: int
+    L_nnz: int
+    off_l: int
+    off_d: int
+    off_u: int
+    L_row: np.ndarray
+    L_col: np.ndarray
+    U_row: np.ndarray
+    U_col: np.ndarray
+    L_ptr: np.ndarray          # [n+1] row pointers into the L section (ours; rows are contiguous there)
+    U_ptr: np.ndarray          # [n+1] row pointers into the U section
+    GS_L_row: np.ndarray
+    GS_L_col: np.ndarray
+    GS_U_row: np.ndarray
+    GS_U_col: np.ndarray
+    GS_L_Ptr: list
+    GS_U_Ptr: list
+    block_offset: np.ndarray   # UtAUs_block_offset: [L;D;U] slot -> rank in (row,col)-sorted order
+    hex_update_offset: np.ndarray
+
+    @property
+    def D_row(self):
+        return np.arange(self.n, dtype=np.int32)
+
+    @property
+    def row(self):
+        return np.concatenate([self.L_row, self.D_row, self.U_row])
+
+    @property
+    def col(self):
+        return np.concatenate([self.L_col, self.D_row, self.U_col])
+
+
+@dataclass
+class Hierarchy:
+    dx: float
+    layer: int
+    box_min: np.ndarray
+    box_max: np.ndarray
+    dims: list
+    hexs: list
+    x: list                     # lattice positions per level (object.py:230; colouring/plots only)
+    fine_coarse: list
+    color_vertex_num: list
+    vertex2index: list
+    index2vertex: list
+    Ut: list = field(default_factory=list)
+    Ut_noOrder: list = field(default_factory=list)
+    Ut_hat: list = field(default_factory=list)
+    Ut_noOrder_hat: list = field(default_factory=list)
+    Us: list = field(default_factory=list)
+    Us_noOrder: list = field(default_factory=list)
+    Us_hat: list = field(default_factory=list)
+    Us_noOrder_hat: list = field(default_factory=list)
+    U_triplets: list = field(default_factory=list)
+    fix_idx: np.ndarray = None
+    fix_values: np.ndarray = None
+    pattern: list = field(default_factory=list)
+    shapeFuncGrad: np.ndarray = None
+
+
+def shape_func_grad() -> np.ndarray:
+    """shapeFuncGrad[a][q][c] (cpu_function.py:4-9, tables object.py:701-722), float32 products in
+    the reference's left-to-right order, Gauss abscissa literal 0.57735."""
+    h = np.array([[-1, -1, -1], [-1, -1, 1], [-1, 1, -1], [-1, 1, 1],
+                  [1, -1, -1], [1, -1, 1], [1, 1, -1], [1, 1, 1]], dtype=F32)
+    quad = h * F32(0.57735)
+    one, e8 = F32(1), F32(0.125)
+    out = np.zeros((8, 8, 3), dtype=F32)
+    for a in range(8):
+        for q in range(8):
+            out[a, q, 0] = h[a, 0] * (one + h[a, 1] * quad[q, 1]) * (one + h[a, 2] * quad[q, 2]) * e8
+            out[a, q, 1] = h[a, 1] * (one + h[a, 0] * quad[q, 0]) * (one + h[a, 2] * quad[q, 2]) * e8
+            out[a, q, 2] = h[a, 2] * (one + h[a, 1] * quad[q, 1]) * (one + h[a, 0] * quad[q, 0]) * e8
+    return out
+
+
+def _ijk(points: np.ndarray, origin: np.ndarray, spacing: float, shift: float) -> np.ndarray:
+    """cpu_function.py:12-20: ((p - origin)/spacing + shift).int() in float32."""
+    return ((points.astype(F32) - origin.astype(F32)) / F32(spacing) + F32(shift)).astype(np.int32)
+
+
+def _first_seen_ids(keys: np.ndarray):
+    """Dictionary numbering: id of each entry = rank of the first appearance of its key."""
+    uniq, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[order] = np.arange(len(uniq))
+    return rank[inv.reshape(-1)], uniq[order]
+
+
+def _color_order(color: np.ndarray):
+    """object.py:151-158."""
+    i2v = np.argsort(color, kind="stable").astype(np.int32)
+    v2i = np.empty_like(i2v)
+    v2i[i2v] = np.arange(len(i2v), dtype=np.int32)
+    cvn = [0] + np.cumsum(np.bincount(color, minlength=8)).astype(np.int64).tolist()
+    return v2i, i2v, [int(c) for c in cvn]
+
+
+# slot (i,j,k) of a coarse hex -> ordered coarse corners and weight (object.py:283-412)
+def _stencil_table():
+    cnt = np.zeros(27, dtype=np.int64)
+    corners = np.zeros((27, 8), dtype=np.int64)
+    weight = np.zeros(27, dtype=F32)
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                s = 9 * i + 3 * j + k
+                par = i % 2 + j % 2 + k % 2
+                if par == 0:
+                    c = [4 * (i // 2) + 2 * (j // 2) + (k // 2)]; w = 1.0
+                elif par == 3:
+                    c = list(range(8)); w = 0.125
+                elif par == 1:
+                    if i == 1:
+                        c = [2 * (j // 2) + (k // 2), 4 + 2 * (j // 2) + (k // 2)]
+                    elif j == 1:
+                        c = [4 * (i // 2) + (k // 2), 4 * (i // 2) + 2 + (k // 2)]
+                    else:
+                        c = [4 * (i // 2) + 2 * (j // 2), 4 * (i // 2) + 2 * (j // 2) + 1]
+                    w = 0.5
+                else:
+                    if i % 2 == 0:
+                        c = [4 * (i // 2) + 2 * ii + jj for ii in range(2) for jj in range(2)]
+                    elif j % 2 == 0:
+                        c = [4 * ii + 2 * (j // 2) + jj for ii in range(2) for jj in range(2)]
+                    else:
+                        c = [4 * ii + 2 * jj + (k // 2) for ii in range(2) for jj in range(2)]
+                    w = 0.25
+                cnt[s] = len(c); corners[s, :len(c)] = c; weight[s] = w
+    return cnt, corners, weight
+
+
+_ST_CNT, _ST_CORNERS, _ST_W = _stencil_table()
+
+
+def level_count(box_min, box_max, dx) -> int:
+    """object.py:140-143, float32 torch arithmetic."""
+    delta = torch.tensor(box_max, dtype=torch.float32) - torch.tensor(box_min, dtype=torch.float32)
+    mb = torch.min(delta)
+    mb = torch.log(mb / dx) / torch.log(torch.tensor(2.0))
+    return int(mb.int() - 1)
+
+
+def build_pattern(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int) -> LevelPattern:
+    """object.py:485-697 for one level."""
+    ih = v2i[hexagons].astype(np.int64)                                   # [Nh,8] index-order ids
+    keys = (ih[:, :, None] * np.int64(n) + ih[:, None, :]).reshape(-1)    # (r,c) for e,j,k
+    uniq, inv = np.unique(keys, return_inverse=True)
+    r = (uniq // n).astype(np.int64)
+    c = (uniq % n).astype(np.int64)
+    nnz = len(uniq)
+    L_nnz = (nnz - n) >> 1
+    off_l, off_d, off_u = 0, L_nnz, L_nnz + n
+    isL, isU = r > c, r < c
+    slot = np.empty(nnz, dtype=np.int64)
+    slot[r == c] = off_d + r[r == c]
+    slot[isU] = off_u + np.arange(int(isU.sum()))
+    slot[isL] = off_l + np.arange(int(isL.sum()))
+    assert int(isU.sum()) == L_nnz and int(isL.sum()) == L_nnz
+    block_offset = np.empty(nnz, dtype=np.int32)
+    block_offset[slot] = np.arange(nnz, dtype=np.int32)
+    L_row, L_col = r[isL].astype(np.int32), c[isL].astype(np.int32)
+    U_row, U_col = r[isU].astype(np.int32), c[isU].astype(np.int32)
+    cv = np.asarray(cvn, dtype=np.int64)
+    colU = np.searchsorted(cv, U_row, side="right") - 1
+    colL = np.searchsorted(cv, L_row, side="right") - 1
+    GS_U_row = (U_row - cv[colU]).astype(np.int32)
+    GS_U_col = (U_col - cv[colU + 1]).astype(np.int32)
+    GS_L_row = (L_row - cv[colL]).astype(np.int32)
+    GS_L_col = L_col.copy()
+    GS_U_Ptr = [int(np.searchsorted(U_row, cv[p], side="left")) for p in range(8)] + [0]
+    GS_L_Ptr = [int(np.searchsorted(L_row, cv[p + 1], side="left")) for p in range(8)] + [0]
+    L_ptr = np.searchsorted(L_row, np.arange(n + 1), side="left").astype(np.int32)
+    U_ptr = np.searchsorted(U_row, np.arange(n + 1), side="left").astype(np.int32)
+    return LevelPattern(n=n, nnz=nnz, L_nnz=L_nnz, off_l=off_l, off_d=off_d, off_u=off_u,
+                        L_row=L_row, L_col=L_col, U_row=U_row, U_col=U_col, L_ptr=L_ptr, U_ptr=U_ptr,
+                        GS_L_row=GS_L_row, GS_L_col=GS_L_col, GS_U_row=GS_U_row, GS_U_col=GS_U_col,
+                        GS_L_Ptr=GS_L_Ptr, GS_U_Ptr=GS_U_Ptr, block_offset=block_offset,
+                        hex_update_offset=slot[inv.reshape(-1)].astype(np.int32))
+
+
+def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers: int | None = None) -> Hierarchy:
+    """object.py:116-697.  ``layers`` overrides the reference's level-count formula (benchmarks only)."""
+    x0 = np.ascontiguousarray(points, dtype=F32)
+    hex0 = np.ascontiguousarray(hexagons, dtype=np.int32)
+    box_min = np.minimum(x0.min(axis=0), F32(1000.0)).astype(F32)
+    box_max = np.maximum(x0.max(axis=0), F32(-1000.0)).astype(F32)
+    layer = level_count(box_min, box_max, dx) if layers is None else int(layers)
+
+    t = _ijk(x0, box_min, dx, 0.5) % 2                                     # object.py:147-149
+    color = (t[:, 0] + 2 * t[:, 1] + 4 * t[:, 2]).astype(np.int64)
+    v2i, i2v, cvn = _color_order(color)
+    H = Hierarchy(dx=dx, layer=layer, box_min=box_min, box_max=box_max, dims=[x0.shape[0]], hexs=[hex0], x=[x0],
+                  fine_coarse=[], color_vertex_num=[cvn], vertex2index=[v2i], index2vertex=[i2v])
+
+    BIG = np.int64(1) << 20
+    for lay in range(layer - 1):                                           # object.py:171-241
+        fine_size = dx if lay == 0 else dx * 2                             # sic (object.py:175-179)
+        coarse_size = fine_size * 2
+        hx, xl = H.hexs[lay], H.x[lay]
+        key3 = _ijk(xl[hx[:, 0]], box_min, coarse_size, 0.1).astype(np.int64)        # [Nh,3]
+        hex_id, ukeys = _first_seen_ids((key3[:, 0] * BIG + key3[:, 1]) * BIG + key3[:, 2])
+        n_ch = len(ukeys)
+        ck = np.stack([ukeys // (BIG * BIG), (ukeys // BIG) % BIG, ukeys % BIG], axis=1)  # coarse hex keys, id order
+        jkl = np.array([[(a >> 2) & 1, (a >> 1) & 1, a & 1] for a in range(8)], dtype=np.int64)
+        vk3 = ck[:, None, :] + jkl[None, :, :]                                        # [n_ch,8,3]
+        vkeys = ((vk3[..., 0] * BIG + vk3[..., 1]) * BIG + vk3[..., 2]).reshape(-1)
+        vid, uvk = _first_seen_ids(vkeys)
+        coarse_hex = vid.reshape(n_ch, 8).astype(np.int32)
+        n_cv = len(uvk)
+        vk = np.stack([uvk // (BIG * BIG), (uvk // BIG) % BIG, uvk % BIG], axis=1)
+        ijk_f = _ijk(xl[hx.reshape(-1)], box_min, fine_size, 0.1).astype(np.int64).reshape(-1, 8, 3)
+        rel = ijk_f - 2 * key3[:, None, :]
+        slot = 9 * rel[..., 0] + 3 * rel[..., 1] + rel[..., 2]
+        fc = np.full((n_ch, 27), -1, dtype=np.int32)
+        fc[np.repeat(hex_id, 8), slot.reshape(-1)] = hx.reshape(-1)
+        coarse_vert = (vk.astype(F32) * F32(coarse_size) + box_min).astype(F32)
+        ccolor = 4 * (vk[:, 2] % 2) + 2 * (vk[:, 1] % 2) + (vk[:, 0] % 2)
+        cv2i, ci2v, ccvn = _color_order(ccolor)
+        H.dims.append(n_cv); H.hexs.append(coarse_hex); H.x.append(coarse_vert); H.fine_coarse.append(fc)
+        H.color_vertex_num.append(ccvn); H.vertex2index.append(cv2i); H.index2vertex.append(ci2v)
+
+    n0 = H.dims[0]
+    H.fix_idx = np.full((n0, 8), -1, dtype=np.int32)
+    H.fix_values = np.zeros((n0, 8), dtype=F32)
+    for lay in range(layer - 1):                                           # object.py:265-443
+        fc = H.fine_coarse[lay]
+        chex = H.hexs[lay + 1].astype(np.int64)
+        flat = fc.reshape(-1).astype(np.int64)
+        pos_valid = np.nonzero(flat != -1)[0]
+        _, first = np.unique(flat[pos_valid], return_index=True)
+        pos = np.sort(pos_valid[first])                                    # (HEX,slot) that handles each fine vertex
+        HEX, s = pos // 27, pos % 27
+        cnt = _ST_CNT[s]
+        ent_owner = np.repeat(np.arange(len(pos)), cnt)
+        ent_k = np.arange(len(ent_owner)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        coarse_id = chex[HEX[ent_owner], _ST_CORNERS[s[ent_owner], ent_k]]
+        fine_id = flat[pos][ent_owner]
+        w = _ST_W[s[ent_owner]]
+        norm = np.zeros(H.dims[lay + 1], dtype=F32)
+        np.add.at(norm, coarse_id, w)                                      # dyadic weights: exact in any order
+        w_norm = (w / norm[coarse_id]).astype(F32)
+        v2i_c, v2i_f = H.vertex2index[lay + 1], H.vertex2index[lay]
+        rowInd, colInd = v2i_c[coarse_id], v2i_f[fine_id]
+        H.U_triplets.append(dict(rowInd=rowInd.astype(np.int32), colInd=colInd.astype(np.int32),
+                                 rowInd_noOrder=coarse_id.astype(np.int32), colInd_noOrder=fine_id.astype(np.int32),
+                                 value=w, norm=norm))
+        nc, nf = H.dims[lay + 1], H.dims[lay]
+        H.Ut.append(coo_to_csr(nc, nf, rowInd, colInd, w_norm))
+        H.Ut_noOrder.append(coo_to_csr(nc, nf, coarse_id, fine_id, w_norm))
+        H.Ut_hat.append(coo_to_csr(nc, nf, rowInd, colInd, w))
+        H.Ut_noOrder_hat.append(coo_to_csr(nc, nf, coarse_id, fine_id, w))
+        if lay == 0:
+            H.fix_idx[fine_id, ent_k] = coarse_id
+            H.fix_values[fine_id, ent_k] = w
+    for lay in range(layer - 1):
+        H.Us.append(H.Ut[lay].transposed()); H.Us_noOrder.append(H.Ut_noOrder[lay].transposed())
+        H.Us_hat.append(H.Ut_hat[lay].transposed()); H.Us_noOrder_hat.append(H.Ut_noOrder_hat[lay].transposed())
+
+    for lay in range(layer):                                               # object.py:485-697
+        H.pattern.append(build_pattern(H.hexs[lay], H.vertex2index[lay], H.color_vertex_num[lay], H.dims[lay]))
+    H.shapeFuncGrad = shape_func_grad()
+    return H
+
+
+def default_pins(points: np.ndarray, dx: float) -> np.ndarray:
+    """object.py:762-773: every vertex with y >= y_max - dx - 1e-5 (float32 arithmetic)."""
+    y = np.asarray(points, dtype=F32)[:, 1]
+    thr = F32(F32(y.max() - F32(dx)) - F32(1e-5))
+    return np.nonzero(y >= thr)[0].astype(np.int32)

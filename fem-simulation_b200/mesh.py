@@ -1,0 +1,52 @@
+"""Voxel hexahedral meshes in the reference's numbering.
+
+The reference obtains ``(points, cells)`` from ``pv.voxelize`` and permutes the VTK node order
+to local node ``a = 4*bx + 2*by + bz`` (/root/reference/exp1/quasi_simulation/object.py:28-45).
+These helpers generate the same kind of mesh without pyvista: lattice points numbered
+x-fastest and restricted to the used ones, hexahedra numbered x-fastest.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def mesh_from_mask(mask: np.ndarray, dx: float, origin=(0.0, 0.0, 0.0)):
+    """``mask[ix,iy,iz]`` (bool) marks the kept voxels.  Returns (points f32[N,3], hexagons i32[Nh,8])."""
+    mask = np.asarray(mask, dtype=bool)
+    nx, ny, nz = mask.shape
+    iz, iy, ix = np.nonzero(np.transpose(mask, (2, 1, 0)))          # x fastest, then y, then z
+    ix = ix.astype(np.int64); iy = iy.astype(np.int64); iz = iz.astype(np.int64)
+    px, py = nx + 1, ny + 1
+    corner = np.empty((len(ix), 8), dtype=np.int64)
+    for a in range(8):
+        bx, by, bz = (a >> 2) & 1, (a >> 1) & 1, a & 1
+        corner[:, a] = (ix + bx) + px * ((iy + by) + py * (iz + bz))
+    used = np.unique(corner)
+    remap = np.full((nx + 1) * (ny + 1) * (nz + 1), -1, dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    hexagons = remap[corner].astype(np.int32)
+    gx = used % px
+    gy = (used // px) % py
+    gz = used // (px * py)
+    o = np.asarray(origin, dtype=np.float32)
+    points = np.stack([gx, gy, gz], axis=1).astype(np.float32) * np.float32(dx) + o
+    return points.astype(np.float32), hexagons
+
+
+def cube_mesh(n: int, dx: float | None = None, origin=(0.0, 0.0, 0.0)):
+    """n x n x n voxels; dx defaults to 1/n."""
+    if dx is None:
+        dx = 1.0 / n
+    return mesh_from_mask(np.ones((n, n, n), dtype=bool), dx, origin)
+
+
+def box_mesh(nx: int, ny: int, nz: int, dx: float, origin=(0.0, 0.0, 0.0)):
+    return mesh_from_mask(np.ones((nx, ny, nz), dtype=bool), dx, origin)
+
+
+def jagged_mesh(nx: int, ny: int, nz: int, dx: float, seed: int = 0, keep: float = 0.8, origin=(0.0, 0.0, 0.0)):
+    """A reproducible irregular voxel set (random carving that keeps the bounding box corners)."""
+    rng = np.random.default_rng(seed)
+    mask = rng.random((nx, ny, nz)) < keep
+    mask[0, 0, 0] = mask[-1, -1, -1] = mask[0, -1, 0] = mask[-1, 0, -1] = True
+    return mesh_from_mask(mask, dx, origin)

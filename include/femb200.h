@@ -1,0 +1,180 @@
+/*
+ * femb200.h -- C ABI of libfemb200.so: the B200 (sm_100a) implementation of the hot path of
+ * caixiao-0725/fem-simulation (implicit / quasi-static hexahedral FEM step with multigrid).
+ *
+ * The reference has no FFI of its own for this path: every operator is a `wp.launch(kernel, dim,
+ * inputs)` or a `bsr_*` call over caller-owned device arrays.  Each entry point
+ * below replaces one such operator (or a fused group of them) and cites the reference lines it
+ * stands for; paths are relative to /root/reference/exp1/quasi_simulation/ unless noted.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  All `const float*`/`float*`/`int*` arguments
+ *     are DEVICE pointers owned by the caller unless the name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Nothing allocates,
+ *     nothing synchronises, nothing reads back: every call only enqueues kernels, so a sequence of
+ *     calls can be captured in a CUDA graph.
+ *   - vectors are float[n*3] (vec3 per vertex); block values are float[nnz*9], row-major 3x3, in the
+ *     reference's [L;D;U] layout (object.py:499-505): L blocks sorted by (row,col) at [off_l, off_d),
+ *     the diagonal block of row r at off_d + r, U blocks sorted by (row,col) from off_u.
+ *   - solver vectors are in colour-sorted *index* order, geometry (x, hex, mass, pins) in *vertex*
+ *     order, exactly like the reference.
+ *   - return value: 0 on success, a negative FEMB_E_* code otherwise (femb_last_error() gives text).
+ *   - thread-compatible: no global mutable state except the last-error string.
+ */
+#ifndef FEMB200_H
+#define FEMB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEMB_OK 0
+#define FEMB_E_INVALID (-1)   /* bad argument (null pointer, negative size, bad enum) */
+#define FEMB_E_CUDA (-2)      /* a CUDA runtime call or launch failed                 */
+#define FEMB_E_NODEVICE (-3)  /* no usable sm_100 device                              */
+
+#define FEMB_ABI_VERSION 1
+
+/* matrix part selector for femb_spmv (bsr_mv on self.L / self.D / self.U / self.A) */
+#define FEMB_PART_L 1
+#define FEMB_PART_D 2
+#define FEMB_PART_U 4
+#define FEMB_PART_ALL 7
+
+/* One multigrid level: sizes + device pointers, filled once by the host after setup and read-only
+ * afterwards.  Mirrors the per-level attributes built by Object.__init__ (object.py:116-865). */
+typedef struct FembLevel {
+  int n_vert;            /* dims[l]                                                     */
+  int n_hex;             /* hexs[l].shape[0]                                            */
+  int nnz;               /* MF_nnz / UtAUs_nnz[l-1]                                     */
+  int off_l, off_d, off_u; /* object.py:503-505 / :617-619                              */
+  int color_start[9];    /* color_vertex_num[l] (object.py:151-158, :234-241)           */
+  const int* hex;        /* [n_hex*8] vertex ids, local node 4bx+2by+bz (object.py:34)  */
+  const int* v2i;        /* [n_vert] dev_vertex2index[l]                                */
+  const int* i2v;        /* [n_vert] dev_index2vertex[l]                                */
+  const int* L_ptr;      /* [n_vert+1] row pointers into the L section                  */
+  const int* L_col;      /* [L_nnz]  == MF_L_col / UtAUs_L_col                          */
+  const int* U_ptr;      /* [n_vert+1] row pointers into the U section                  */
+  const int* U_col;      /* [U_nnz]  == MF_U_col / UtAUs_U_col                          */
+  const int* elem2nnz;   /* [n_hex*64] == hex_update_offset[l] (object.py:563-569)      */
+  const int* asm_ptr;    /* [nnz+1]  CSR over value slots of the inverse of elem2nnz    */
+  const int* asm_src;    /* [n_hex*64] element-block ids (e*64+a*8+b) sorted by slot    */
+  const int* vert_elem;  /* [n_vert*8] e*8+a of the hexes incident to a vertex, -1 pad  */
+  const float* invJ;     /* [n_hex*8*9] inverse_pX_peps (quai_hexagon.py:18)            */
+  const float* detJ;     /* [n_hex*8]   det_pX_peps     (quai_hexagon.py:17)            */
+} FembLevel;
+
+/* CSR matrix with one scalar weight per entry = BSR matrix with blocks w*I3: the interpolation
+ * operators Ut/Us/Ut_hat/Us_hat/Ut_noOrder/... (object.py:247-443). */
+typedef struct FembTransfer {
+  int nrow, ncol, nnz;
+  const int* offsets;    /* [nrow+1] */
+  const int* columns;    /* [nnz]    */
+  const float* weights;  /* [nnz]    */
+} FembTransfer;
+
+/* Plan of the Galerkin product A_c = Ut_hat * (A_f * Us_hat) on fixed patterns
+ * (replaces the per-step symbolic bsr_mm, sparse.py:950-1140, object.py:1259). */
+typedef struct FembGalerkinPlan {
+  int n_fine, n_coarse;
+  int t_nnz;             /* blocks of T = A_f * Us_hat                                   */
+  const int* t_ptr;      /* [n_fine+1]                                                   */
+  const int* t_col;      /* [t_nnz] coarse index-order columns, sorted within a row      */
+  const int* c_ptr;      /* [n_coarse+1] (row,col)-sorted pattern of A_c                 */
+  const int* c_col;      /* [nnz_c]                                                      */
+  const int* c_slot;     /* [nnz_c] [L;D;U] slot of each sorted block = inverse of       */
+                         /*         UtAUs_block_offset (object.py:633-683)               */
+} FembGalerkinPlan;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int femb_abi_version(void);
+const char* femb_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long femb_launch_count(void);
+/* 0 if device `device` exists and is compute capability 10.x */
+int femb_check_device(int device);
+
+/* ---- rest state (setup) ------------------------------------------------------------------- */
+/* prepare_kernal (quai_hexagon.py:4-18): rest Jacobian per (hex,q) -> detJ[n_hex*8], invJ[n_hex*72] */
+int femb_prepare_rest(int n_hex, const int* hex, const float* x_rest, float* detJ, float* invJ, void* stream);
+/* Sum_8 + prepare_mass (cublas.py:215-218, quai_hexagon.py:20-26) as a gather: vol[n_hex], mass[n_vert] */
+int femb_lumped_mass(const FembLevel* lvl, float* vol, float* mass, void* stream);
+
+/* ---- element physics ---------------------------------------------------------------------- */
+/* compute_partial_elastic_energy_X + compute_partial_gravity_energy_X + compute_partial_fixed_energy_X
+ * (quai_hexagon.py:109-186; object.py:1234-1236): out = -dE/dx, gathered without atomics.
+ *   x [n_vert*3] vertex order; mass [n_vert] or NULL (no gravity); pin [n_vert] 0/1 flags with per-vertex
+ *   targets pin_pos [n_vert*3] (all_pin_pos) or NULL (no springs); elem_f scratch [n_hex*24];
+ *   ordered != 0: out is in index order (through v2i), else vertex order (the *_noOrder kernels). */
+int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
+               const int* pin, const float* pin_pos, float control_mag, int ordered, float* elem_f,
+               float* out, void* stream);
+/* compute_elastic_hessian (quai_hexagon.py:69-106) + the `MF_value = MF_value_fixed` copy (object.py:1233):
+ * values[slot] = sum of element blocks (+ diag_add[i]*I3 on the diagonal slot of index-order row i).
+ *   elem_k scratch [n_hex*576]; diag_add [n_vert] (index order) or NULL.
+ *   If elem_f != NULL the element forces are produced by the same element pass and `force_out` is
+ *   filled as in femb_force (same optional arguments). */
+int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add,
+                 float* elem_k, float* values, void* stream);
+int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
+                       const int* pin, const float* pin_pos, float control_mag, const float* diag_add,
+                       float* elem_f, float* elem_k, float* force_out, float* values, void* stream);
+/* compute_elastic_energy + compute_gravity_energy (quai_hexagon.py:28-64): energy[0] = total;
+ * scratch [>= 1024] floats. */
+int femb_energy(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
+                const int* pin, const float* pin_pos, float control_mag, float* scratch, float* energy,
+                void* stream);
+/* compute_fix_hessian (cublas.py:234-242): coarse pin penalty onto coarse diagonal slots.
+ * Deterministic gather over the coarse rows of `ut_no_order_hat` (vertex-order, un-normalised weights,
+ * the same (coarse, w) pairs as fix_idx/fix_values): values[off_d + v2i_c[J]] += k * sum_{pinned i} w_Ji^2 * I3 */
+int femb_coarse_pin_penalty(const FembLevel* coarse, const FembTransfer* ut_no_order_hat, const int* pin_fine,
+                            float control_mag, float* values, void* stream);
+
+/* ---- sparse algebra on the fixed [L;D;U] pattern ------------------------------------------ */
+/* bsr_mv (sparse.py:1143-1261) on self.L/self.D/self.U/self.A: y = alpha * (parts of A) x + beta * y */
+int femb_spmv(const FembLevel* lvl, const float* values, int parts, float alpha, const float* x, float beta,
+              float* y, void* stream);
+/* r = b - A x with all three parts (downSample / showError, object.py:1022-1026,1057-1059) */
+int femb_residual(const FembLevel* lvl, const float* values, const float* b, const float* x, float* r, void* stream);
+/* PerformGaussSeidel (object.py:886-929): `iterations` x (backward + forward 8-colour block sweep),
+ * dx starts at 0, diagonal blocks "inverted" by solve3x3 (cublas.py:59-91).  not_spd (int[1], may be
+ * NULL) counts the `print('not spd')` events (cublas.py:79-80). */
+int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b, float* dx, int iterations,
+                      int* not_spd, void* stream);
+/* PerformJacobi (object.py:869-884); scratch [n_vert*3] */
+int femb_jacobi(const FembLevel* lvl, const float* values, const float* b, float* dx, float* scratch,
+                int iterations, int* not_spd, void* stream);
+/* PerformConjugateGradient / _WithInitX (object.py:931-1019) without host read-backs: the scalar
+ * recurrences and the three exit tests (r1 < EPSILON, r1 <= tol*r, dot < 1e-10, k > iterations) are
+ * evaluated on the device; work = r[n*3], p[n*3], ap[n*3] ; state = float[64] scratch.
+ * with_init_x != 0 keeps dx as the initial guess. */
+int femb_cg(const FembLevel* lvl, const float* values, const float* b, float* dx, float* r, float* p, float* ap,
+            float* state, int iterations, float tol, int with_init_x, void* stream);
+/* spd_matrix33f (cublas.py:115-125) on n blocks in place */
+int femb_spd_blocks(float* values, int n_blocks, float spd_value, void* stream);
+/* scalar-weight CSR product y = alpha * T x + beta * y (bsr_mv on Ut/Us/..., e.g. object.py:1027,1032) */
+int femb_transfer_mv(const FembTransfer* t, float alpha, const float* x, float beta, float* y, void* stream);
+/* A_c = Ut_hat (A_f Us_hat), spd_matrix33f on every block (if spd != 0), written in [L;D;U] layout
+ * (object.py:1259-1261).  t_values scratch [t_nnz*9]. */
+int femb_galerkin(const FembLevel* fine, const float* fine_values, const FembTransfer* ut_hat,
+                  const FembTransfer* us_hat, const FembGalerkinPlan* plan, float* t_values, int spd,
+                  float spd_value, float* coarse_values, void* stream);
+
+/* ---- vectors ------------------------------------------------------------------------------- */
+int femb_axpby(int n, float a, const float* x, float b, float* y, void* stream);          /* y = a x + b y (cublas.py:160-163) */
+int femb_copy(int n, const float* x, float* y, void* stream);
+int femb_fill(int n, float v, float* y, void* stream);
+/* update_deltaX_kernel (cublas.py:20-24): x[i2v[i]] += dx[i] */
+int femb_update_x(const FembLevel* lvl, const float* dx, float* x, void* stream);
+/* V2I / I2V (cublas.py:203-213): ordered[v2i[v]] = vert[v]  /  vert[i2v[i]] = ordered[i] */
+int femb_v2i(const FembLevel* lvl, const float* vert, float* ordered, void* stream);
+int femb_i2v(const FembLevel* lvl, const float* ordered, float* vert, void* stream);
+/* Inf_norm (cublas.py:38-48): out[0] = max |x_k| (out is zeroed by the call) */
+int femb_inf_norm(int n, const float* x, float* out, void* stream);
+/* cublasSdot / square_sum (cublas.py:32-36,198-201), deterministic two-level reduction; scratch >= 1024 */
+int femb_dot(int n, const float* x, const float* y, float* scratch, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMB200_H */

@@ -1,0 +1,241 @@
+"""GPU parity: every operator of the C ABI and every solver entry point of ``Object`` against the CPU
+oracle (oracle/ref_*.py, the line-by-line restatement of the reference) on identical seeded inputs.
+
+Tolerances (fp32 path, BASELINE.json north_star): integer maps bit-exact (tests/test_hierarchy.py);
+floating-point arrays within REL = 1e-5 of the oracle, measured as max|a-b| / max|b| (the oracle's own
+fp32-vs-fp64 gap is of the same order, see test_oracle.py).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from fem_simulation_b200 import Object, _lib, mesh  # noqa: E402
+from oracle import ref_kernels as K  # noqa: E402
+from oracle import ref_solvers  # noqa: E402
+
+REL = 1e-5
+
+
+def close(a, b, rel=REL, what=""):
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+    assert err <= rel * scale, f"{what}: max err {err:.3e} > {rel:g} * {scale:.3e}"
+
+
+MESHES = {
+    "cube9": lambda: mesh.cube_mesh(9, 0.05),
+    "jag2": lambda: mesh.jagged_mesh(10, 9, 11, 0.05, seed=1),
+    "jag3": lambda: mesh.jagged_mesh(18, 17, 19, 0.05, seed=2, keep=0.7, origin=(-0.3, 0.1, 0.2)),
+}
+
+
+@pytest.fixture(scope="module", params=list(MESHES))
+def pair(request):
+    pts, hx = MESHES[request.param]()
+    obj = Object((pts, hx), 0.05, [], use_graphs=False)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [])
+    rng = np.random.default_rng(7)
+    xp = (ref.x_gpu_layer[0] + rng.normal(size=ref.x_gpu_layer[0].shape).astype(np.float32) * 0.002).astype(np.float32)
+    return obj, ref, xp
+
+
+def test_rest_data(pair):
+    obj, ref, _ = pair
+    for l in range(obj.layer):
+        close(obj.x_gpu_layer[l] if l else obj.x_cpu, ref.x_gpu_layer[l] if l else ref.x_cpu, what=f"x_gpu_layer[{l}]")
+        close(obj.det_pX_peps_gpu[l], ref.det[l], what=f"det[{l}]")
+        close(obj.inverse_pX_peps_gpu[l], ref.inv[l], what=f"inv[{l}]")
+        close(obj.m_gpu[l], ref.m[l], what=f"mass[{l}]")
+    assert obj.N_pin == ref.N_pin and np.array_equal(obj.pin_gpu.cpu().numpy(), ref.pin)
+
+
+def test_force_energy_hessian(pair):
+    obj, ref, xp = pair
+    x = torch.from_numpy(xp).to(obj.device)
+    out = torch.zeros_like(x)
+    obj._force(x, out)
+    g = np.zeros_like(xp); ref.force(xp, g)
+    close(out, g, what="force (index order)")
+    obj._force(x, out, ordered=False, gravity=False, pins=False)
+    g = np.zeros_like(xp)
+    K.elastic_force(xp, ref.hexs[0], None, ref.sfg, ref.det[0], ref.inv[0], ref.mu, ref.la, g)
+    close(out, g, what="elastic force (vertex order)")
+    e = obj.total_energy(x)
+    e_ref = float(ref.total_energy(xp))
+    assert abs(e - e_ref) <= 2e-5 * abs(e_ref)
+    vals = torch.zeros_like(obj.MF_value_gpu)
+    obj._hessian(0, x, vals, obj.diag_fixed)
+    v = ref.MF_value_fixed.copy(); ref.hessian(0, xp, v)
+    close(vals, v, what="hessian [L;D;U] values")
+    f2 = torch.zeros_like(x); vals2 = torch.zeros_like(vals)
+    obj._force_hessian(x, f2, vals2, obj.diag_fixed)
+    g = np.zeros_like(xp); ref.force(xp, g)
+    close(f2, g, what="fused force"); close(vals2, v, what="fused hessian")
+    # symmetry H_ab = H_ba^T through the pattern
+    if obj.layer > 1:
+        x1 = torch.from_numpy(ref.x_gpu_layer[1] * np.float32(1.01)).to(obj.device)
+        v1 = torch.zeros_like(obj.UtAUs_values[0])
+        obj._hessian(1, x1, v1)
+        r1 = np.zeros_like(ref.UtAUs_values[0]); ref.hessian(1, ref.x_gpu_layer[1] * np.float32(1.01), r1)
+        close(v1, r1, what="coarse re-discretised hessian")
+
+
+def _load_state(obj, ref, xp):
+    """Same matrix + rhs on both sides (built by the oracle, uploaded to the device)."""
+    ref.MF_value[...] = ref.MF_value_fixed; ref.hessian(0, xp, ref.MF_value)
+    ref.grad[...] = 0; ref.force(xp, ref.grad)
+    ref.set_LUD(0)
+    obj.MF_value_gpu.copy_(torch.from_numpy(ref.MF_value))
+    ref.dev_B_fixed[0][...] = ref.grad
+    obj.dev_B_fixed[0].copy_(torch.from_numpy(ref.grad))
+
+
+def test_spmv_parts(pair):
+    obj, ref, xp = pair
+    _load_state(obj, ref, xp)
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=xp.shape).astype(np.float32)
+    y0 = rng.normal(size=xp.shape).astype(np.float32)
+    xv = torch.from_numpy(v).to(obj.device)
+    for parts, mats in ((_lib.PART_L, [ref.Lm]), (_lib.PART_D, [ref.Dm]), (_lib.PART_U, [ref.Um]),
+                        (_lib.PART_ALL, [ref.Lm, ref.Um, ref.Dm])):
+        y = torch.from_numpy(y0.copy()).to(obj.device)
+        obj._spmv(0, parts, -0.5, xv, 2.0, y)
+        acc = np.zeros_like(v)
+        for m in mats:
+            ref_solvers.bsr_mv(m[0], v, acc, alpha=1.0, beta=1.0)
+        close(y, -0.5 * acc + 2.0 * y0, what=f"spmv parts={parts}")
+    r = torch.zeros_like(xv)
+    obj._residual(0, obj.dev_B_fixed[0], xv, r)
+    acc = np.zeros_like(v)
+    for m in (ref.Lm, ref.Um, ref.Dm):
+        ref_solvers.bsr_mv(m[0], v, acc, alpha=1.0, beta=1.0)
+    close(r, ref.grad - acc, what="residual")
+
+
+@pytest.mark.parametrize("iters", [1, 3])
+def test_gauss_seidel(pair, iters):
+    obj, ref, xp = pair
+    _load_state(obj, ref, xp)
+    obj.PerformGaussSeidel(0, iters)
+    ref.PerformGaussSeidel(0, iters)
+    close(obj.dev_delta_x[0], ref.dev_delta_x[0], what=f"GS x{iters}")
+
+
+def test_jacobi_and_cg(pair):
+    obj, ref, xp = pair
+    _load_state(obj, ref, xp)
+    obj.PerformJacobi(0, 1); ref.PerformJacobi(0, 1)
+    close(obj.dev_delta_x[0], ref.dev_delta_x[0], what="Jacobi x1")
+    obj.PerformJacobi(0, 3); ref.PerformJacobi(0, 3)
+    close(obj.dev_delta_x[0], ref.dev_delta_x[0], what="Jacobi x3")
+    obj.PerformConjugateGradient(0, 5); ref.PerformConjugateGradient(0, 5)
+    close(obj.dev_delta_x[0], ref.dev_delta_x[0], rel=5e-5, what="CG(5)")
+    obj.PerformConjugateGradient_WithInitX(0, 4); ref.PerformConjugateGradient_WithInitX(0, 4)
+    close(obj.dev_delta_x[0], ref.dev_delta_x[0], rel=5e-5, what="CG with init x")
+    # zero right-hand side: r1 < EPSILON exit leaves dx = 0 (object.py:944-945)
+    obj.dev_B_fixed[0].zero_()
+    obj.PerformConjugateGradient(0, 5)
+    assert float(obj.dev_delta_x[0].abs().max()) == 0.0
+
+
+def test_transfers(pair):
+    obj, ref, xp = pair
+    if obj.layer < 2:
+        pytest.skip("single level")
+    rng = np.random.default_rng(5)
+    for name in ("Ut", "Ut_hat", "Ut_noOrder", "Ut_noOrder_hat", "Us", "Us_hat", "Us_noOrder", "Us_noOrder_hat"):
+        T = getattr(obj, name)[0]
+        R = getattr(ref, name)[0]
+        v = rng.normal(size=(T.ncol, 3)).astype(np.float32)
+        y0 = rng.normal(size=(T.nrow, 3)).astype(np.float32)
+        y = torch.from_numpy(y0.copy()).to(obj.device)
+        obj._transfer(T, 1.0, torch.from_numpy(v).to(obj.device), 1.0, y)
+        yr = y0.copy(); ref_solvers.bsr_mv(R, v, yr, alpha=1.0, beta=1.0)
+        close(y, yr, what=name)
+        assert T.nnz == R["nnz"] and np.array_equal(T.columns.cpu().numpy(), R["columns"])
+        close(T.values, R["values"][:, None, None] * np.eye(3, dtype=np.float32), rel=0, what=name + ".values")
+
+
+def test_galerkin_and_spd(pair):
+    obj, ref, xp = pair
+    if obj.layer < 2:
+        pytest.skip("single level")
+    _load_state(obj, ref, xp)
+    ref.galerkin()
+    obj.galerkin()
+    for l in range(1, obj.layer):
+        close(obj.UtAUs_values[l - 1], ref.UtAUs_values[l - 1], rel=2e-5, what=f"Galerkin level {l}")
+    blocks = ref.MF_value[:4096].copy()
+    b = torch.from_numpy(blocks.copy()).to(obj.device)
+    obj._spd(b)
+    close(b, K.spd_matrix33f(blocks, 1e-3), rel=2e-5, what="spd_matrix33f")
+
+
+def test_vcycle(pair):
+    obj, ref, xp = pair
+    _load_state(obj, ref, xp)
+    ref.galerkin(); obj.galerkin()
+    for l in range(1, obj.layer):          # identical coarse operators on both sides
+        obj.UtAUs_values[l - 1].copy_(torch.from_numpy(ref.UtAUs_values[l - 1]))
+    ref.VCycle(0); ref.finish()
+    obj.VCycle(0); obj.finish()
+    close(obj.dev_x_solved[0], ref.dev_x_solved[0], rel=5e-5, what="V-cycle correction")
+
+
+@pytest.mark.parametrize("method,steps", [("NewtonMultigrid", 3), ("Newton", 3), ("FASv3", 4), ("FASv2", 3), ("FASv1", 2), ("FASv0", 2)])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_nonlinear_steps(method, steps, graphs):
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    obj = Object((pts, hx), 0.05, [], use_graphs=graphs)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [])
+    getattr(obj, method)(steps)
+    getattr(ref, method)(steps)
+    xa = obj.dev_x_solved[0] if method in ("FASv0", "FASv1") else obj.x_gpu_layer[0]
+    xb = ref.dev_x_solved[0] if method in ("FASv0", "FASv1") else ref.x_gpu_layer[0]
+    close(xa, xb, what=f"{method} positions after {steps} steps")
+    # displacement (what the solver actually produced) to 1e-3 of its own scale
+    da = xa.cpu().numpy() - ref.S["x0"]; db = xb - ref.S["x0"]
+    close(da, db, rel=2e-3, what=f"{method} displacement")
+
+
+def test_pinlist_and_three_levels():
+    pts, hx = mesh.jagged_mesh(18, 17, 19, 0.05, seed=2, keep=0.7, origin=(-0.3, 0.1, 0.2))
+    obj = Object((pts, hx), 0.05, [100], use_graphs=True)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [100])
+    assert obj.layer == 3 and obj.N_pin == 1
+    obj.NewtonMultigrid(3); ref.NewtonMultigrid(3)
+    close(obj.x_gpu_layer[0], ref.x_gpu_layer[0], what="3-level Newton-MG, displaced pin")
+    close(obj.x_gpu_layer[0].cpu().numpy() - ref.S["x0"], ref.x_gpu_layer[0] - ref.S["x0"], rel=2e-3, what="displacement")
+
+
+def test_convergence_curve():
+    """compare(): the sampled energy / log10 force-norm curves of both loops (object.py:1514-1598)."""
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    obj = Object((pts, hx), 0.05, [], use_graphs=True)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [])
+    obj.compare(100); ref.compare(100)
+    assert obj.plot_x == ref.plot_x and len(obj.plot_x) == 100
+    for a, b, nm in ((obj.plot_energy_newton, ref.plot_energy_newton, "E newton"), (obj.plot_energy_newtonMultigrid, ref.plot_energy_newtonMultigrid, "E fas")):
+        close(np.array(a), np.array(b, dtype=np.float64), rel=1e-5, what=nm)
+    for a, b, nm in ((obj.plot_InfNorm_newton, ref.plot_InfNorm_newton, "|f| newton"), (obj.plot_InfNorm_newtonMultigrid, ref.plot_InfNorm_newtonMultigrid, "|f| fas")):
+        fa, fb = 10.0 ** np.array(a), 10.0 ** np.array(b, dtype=np.float64)
+        assert np.all(np.abs(fa - fb) <= 1e-3 * fb + 1e-5 * fb.max()), nm
+
+
+def test_empty_and_errors():
+    lib = _lib.load()
+    lv = _lib.FembLevel()
+    assert lib.femb_spmv(C.byref(lv), None, 7, 1.0, None, 0.0, None, None) == -1
+    assert b"invalid argument" in lib.femb_last_error()
+    z = torch.zeros(3, device="cuda")
+    assert lib.femb_axpby(0, 1.0, z.data_ptr(), 1.0, z.data_ptr(), None) == 0
+    assert lib.femb_inf_norm(0, z.data_ptr(), z.data_ptr(), None) == 0
+    assert lib.femb_launch_count() > 0

@@ -1,0 +1,106 @@
+"""CPU: the product's vectorised setup against the literal restatement of the reference loops
+(oracle/ref_setup.py <- /root/reference/exp1/quasi_simulation/object.py:116-865): every integer map
+bit-exact, every weight bit-exact."""
+import numpy as np
+import pytest
+
+from fem_simulation_b200 import hierarchy, mesh
+from oracle import ref_setup
+
+CASES = {
+    "cube5": lambda: (mesh.cube_mesh(5, 0.05), 0.05),                                  # 1 level
+    "cube9": lambda: (mesh.cube_mesh(9, 0.05), 0.05),                                  # 2 levels
+    "jag2": lambda: (mesh.jagged_mesh(10, 9, 11, 0.05, seed=1), 0.05),                 # 2 levels, ragged
+    "jag3": lambda: (mesh.jagged_mesh(18, 17, 19, 0.05, seed=2, keep=0.7, origin=(-0.3, 0.1, 0.2)), 0.05),  # 3 levels
+    "box_dx01": lambda: (mesh.box_mesh(9, 12, 10, 0.1, origin=(0.5, -1.0, 2.0)), 0.1),
+}
+
+
+def _eq(a, b, name):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{name}: shape {a.shape} != {b.shape}"
+    assert np.array_equal(a, b), f"{name}: values differ"
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_setup_bit_exact(case):
+    (points, hexs), dx = CASES[case]()
+    S = ref_setup.build_setup(points, hexs, dx, [])
+    H = hierarchy.build_hierarchy(points, hexs, dx)
+    assert S["layer"] == H.layer and S["dims"] == H.dims
+    for l in range(H.layer):
+        for nm in ["hexs", "x", "vertex2index", "index2vertex", "color_vertex_num"]:
+            _eq(S[nm][l], getattr(H, nm)[l], f"{nm}[{l}]")
+        p, q = S["pattern"][l], H.pattern[l]
+        for nm in ["nnz", "L_nnz", "off_l", "off_d", "off_u", "L_row", "L_col", "U_row", "U_col", "GS_L_row", "GS_L_col",
+                   "GS_U_row", "GS_U_col", "GS_L_Ptr", "GS_U_Ptr", "block_offset", "hex_update_offset", "row", "col"]:
+            _eq(p[nm], getattr(q, nm), f"pattern[{l}].{nm}")
+    for l in range(H.layer - 1):
+        _eq(S["fine_coarse"][l], H.fine_coarse[l], f"fine_coarse[{l}]")
+        for nm in ["rowInd", "colInd", "rowInd_noOrder", "colInd_noOrder", "value", "norm"]:
+            _eq(S["U_triplets"][l][nm], H.U_triplets[l][nm], f"U_triplets[{l}].{nm}")
+        for nm in ["Ut", "Ut_noOrder", "Ut_hat", "Ut_noOrder_hat", "Us", "Us_noOrder", "Us_hat", "Us_noOrder_hat"]:
+            a, b = S[nm][l], getattr(H, nm)[l]
+            _eq(a["offsets"], b.offsets, nm + ".offsets"); _eq(a["columns"], b.columns, nm + ".columns")
+            _eq(a["values"], b.weights, nm + ".values")
+    _eq(S["fix_idx"], H.fix_idx, "fix_idx"); _eq(S["fix_values"], H.fix_values, "fix_values")
+    _eq(S["shapeFuncGrad"], H.shapeFuncGrad, "shapeFuncGrad")
+    _eq(S["pin_list"], hierarchy.default_pins(points, dx), "default pins")
+
+
+def test_hierarchy_properties_large():
+    """Size-independent properties on a mesh the literal oracle cannot finish quickly (n=40: 64 k hexes)."""
+    points, hexs = mesh.cube_mesh(40)
+    H = hierarchy.build_hierarchy(points, hexs, 1.0 / 40)
+    assert H.layer == 4 and H.dims[0] == 41 ** 3
+    for l in range(H.layer):
+        p = H.pattern[l]
+        n = H.dims[l]
+        assert np.array_equal(np.sort(H.vertex2index[l]), np.arange(n))
+        assert np.array_equal(H.index2vertex[l][H.vertex2index[l]], np.arange(n))
+        assert p.nnz == 2 * p.L_nnz + n
+        # pattern symmetric: (r,c) in U  <->  (c,r) in L
+        assert np.array_equal(np.sort(p.U_row.astype(np.int64) * n + p.U_col), np.sort(p.L_col.astype(np.int64) * n + p.L_row))
+        assert p.hex_update_offset.min() == 0 and p.hex_update_offset.max() == p.nnz - 1
+        # no two vertices of one colour share a hexahedron (the GS sweeps rely on it)
+        cv = np.asarray(H.color_vertex_num[l])
+        assert np.all(np.searchsorted(cv, p.U_row, side="right") != np.searchsorted(cv, p.U_col, side="right"))
+    for l in range(H.layer - 1):
+        ut, us_hat = H.Ut[l], H.Us_hat[l]
+        rs = np.zeros(ut.nrow, np.float64); np.add.at(rs, ut.rows(), ut.weights)
+        assert np.allclose(rs, 1.0, atol=1e-6)                      # Ut rows are normalised
+        ps = np.zeros(us_hat.nrow, np.float64); np.add.at(ps, us_hat.rows(), us_hat.weights)
+        assert np.allclose(ps, 1.0)                                 # prolongation is a partition of unity
+    # levels >= 3 do not coarsen (reference bug object.py:175-179, reproduced on purpose)
+    assert H.dims[3] == H.dims[2]
+
+
+def test_reference_cpu_functions_match():
+    """cpu_function.py is importable here: pin our formulas against the reference's own functions."""
+    import os, sys
+    ref = "/root/reference/exp1/quasi_simulation"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    import torch
+    sys.path.insert(0, ref)
+    try:
+        import cpu_function as cf
+    finally:
+        sys.path.remove(ref)
+    sfg = torch.zeros((8, 8, 3), dtype=torch.float32)
+    help_ = torch.tensor([[-1, -1, -1], [-1, -1, 1], [-1, 1, -1], [-1, 1, 1], [1, -1, -1], [1, -1, 1], [1, 1, -1], [1, 1, 1]], dtype=torch.float32)
+    quad = help_ * 0.57735
+    cf.calShapeFuncGrad(sfg, help_, quad)
+    assert np.array_equal(sfg.numpy(), hierarchy.shape_func_grad())
+    assert np.array_equal(sfg.numpy(), ref_setup.cal_shape_func_grad())
+    rng = np.random.default_rng(0)
+    pts = (rng.integers(0, 40, size=(200, 3)) * 0.05).astype(np.float32) + np.float32(0.3)
+    org = np.array([0.3, 0.3, 0.3], np.float32)
+    for sp, sh in ((0.05, 0.5), (0.1, 0.1), (0.2, 0.1)):
+        mine = hierarchy._ijk(pts, org, sp, sh)
+        for k in range(len(pts)):
+            if sh == 0.1:
+                assert cf.ijk_index(torch.tensor(pts[k]), torch.tensor(org), sp) == mine[k].tolist()
+            else:
+                c = mine[k] % 2
+                assert int(cf.color_ind(torch.tensor(pts[k]), torch.tensor(org), sp)) == int(c[0] + 2 * c[1] + 4 * c[2])
