@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- Newton-multigrid quasi-static steps/s on the synthetic voxel cube (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--n 100] [--method nmg|fasv3]
+
+One "step" = one loop body of ``Object.NewtonMultigrid`` (object.py:1231-1296 of the reference): force +
+element Hessians + assembly, Galerkin coarse operators, one V-cycle (3+3 symmetric 8-colour GS per
+level), full Newton update.  Workload at N=1: cube n=100 (1 000 000 hexahedra, 1 030 301 vertices,
+3.09 M dof), the reference's level-count formula (5 levels).  ``value`` = steps/s with all inputs
+resident in HBM (CUDA-graph replay, CUDA events); ``e2e`` = the same step through the public API with the
+state vector coming from pinned host memory and going back every step.  N>1: one process per GPU, each
+rank owns one mesh block (weak scaling; see DESIGN.md "multi-GPU").
+
+``--impl reference`` times the CPU restatement of the reference algorithm (the reference has no CPU
+path and cannot run here: SURVEY.md 8c) on the box's host cores on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=100, help="voxels per cube edge (100 -> 1 M hexahedra)")
+    ap.add_argument("--method", default="nmg", choices=["nmg", "fasv3"])
+    ap.add_argument("--layers", type=int, default=0, help="0 = the reference's level-count formula")
+    ap.add_argument("--cpu-n", type=int, default=0, help="cube edge of the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pass_bytes(V, Z):
+    """Algorithmic bytes of one full-matrix pass: values+col of every block, row pointer, b, x, out."""
+    return Z * (36 + 4) + V * (4 + 12 + 12 + 12)
+
+
+def step_bytes(obj, method):
+    """Algorithmic bytes of one step from the actual V, Z, N_h of every level (SURVEY.md 8d formulas)."""
+    H = obj.hierarchy
+    V = H.dims
+    Z = [p.nnz for p in H.pattern]
+    Nh = [h.shape[0] for h in H.hexs]
+    L = H.layer
+    force = 352 * Nh[0] + 24 * V[0]
+    assembly = 352 * Nh[0] + Z[0] * 36 + 256 * Nh[0]
+    if method == "nmg":
+        total = force + assembly
+        for l in range(L):
+            gs_it = 3 if l == L - 1 else 6
+            total += (2 * gs_it - 0.5 * (1 if l == L - 1 else 2)) * pass_bytes(V[l], Z[l])     # first half-sweep skips L
+            if l < L - 1:
+                nnzP = H.Ut_hat[l].nnz
+                total += pass_bytes(V[l], Z[l])                                                  # residual
+                total += 2 * (nnzP * 8 + (V[l] + V[l + 1]) * 12 + V[l + 1] * 4)                   # restrict + prolong
+                total += pass_bytes(V[l], Z[l])                                                  # rhs update
+                total += Z[l] * 40 + Z[l + 1] * 36                                               # Galerkin RAP
+        return total
+    nnzP = H.Ut_hat[0].nnz
+    total = 2 * force + assembly + 1.5 * pass_bytes(V[0], Z[0])
+    total += 3 * (nnzP * 8 + (V[0] + V[1]) * 12 + V[1] * 4)
+    total += 352 * Nh[1] + Z[1] * 36 + 256 * Nh[1] + V[1] * (36 + 24)
+    return total
+
+
+def gs_launch_bytes(obj, iterations=3):
+    """Average algorithmic bytes of one colour launch of the row-pass kernel in femb_gauss_seidel(level 0)."""
+    H = obj.hierarchy
+    total = (2 * iterations - 0.5) * pass_bytes(H.dims[0], H.pattern[0].nnz)
+    return total / (16 * iterations)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    from fem_simulation_b200 import Object, _lib
+    lib = _lib.load()
+    n = args.n
+    t0 = time.time()
+    obj = Object(f"cube:{n}", 1.0 / n, [], device=str(dev), layers=(args.layers or None), use_graphs=True)
+    setup_s = time.time() - t0
+    body = obj._newton_mg_body if args.method == "nmg" else (lambda: obj._fas_v123_body(obj.x_gpu_layer[0], False, True, True, True))
+    key = "nmg" if args.method == "nmg" else "fasv3"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up (first call also captures the CUDA graph) ------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        obj._run_step(key, body)
+    barrier()
+    # ---- device-resident timing -------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.femb_launch_count()
+    obj.use_graphs = False
+    obj._run_step(key, body)                       # one eager step only to count this step's launches
+    launches_per_step = lib.femb_launch_count() - l0
+    obj.use_graphs = True
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        obj._run_step(key, body)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # ---- end-to-end: state from pinned host memory in, new state back out, every step ------------
+    x_host = obj.x_gpu_layer[0].cpu().pin_memory()
+    out_host = torch.empty_like(x_host).pin_memory()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        obj.x_gpu_layer[0].copy_(x_host, non_blocking=True)
+        obj._run_step(key, body)
+        out_host.copy_(obj.x_gpu_layer[0], non_blocking=True)
+        x_host, out_host = out_host, x_host
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    # ---- dominant kernel: the row pass inside femb_gauss_seidel on the fine level -----------------
+    reps = 5
+    obj.PerformGaussSeidel(0, 3)
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    for _ in range(reps):
+        obj.PerformGaussSeidel(0, 3)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    gs_ms_per_launch = ev0.elapsed_time(ev1) / (reps * 48)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = gs_launch_bytes(obj) / (gs_ms_per_launch * 1e-3) / 1e9
+    sb = step_bytes(obj, args.method)
+    H = obj.hierarchy
+    line = {
+        "metric": "newton_mg_steps_per_sec" if args.method == "nmg" else "fasv3_steps_per_sec",
+        "value": world * args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"voxel cube n={n}: {H.hexs[0].shape[0]} hexahedra, {H.dims[0]} vertices, {H.layer} levels "
+                               f"({'reference level formula' if not args.layers else 'forced'}), "
+                               f"{'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin)' if args.method == 'nmg' else 'FASv3 two-level step'}, "
+                               "mu=250 la=0 g=-4.9 k=100, default top-layer pins",
+                   "levels": H.layer, "dims": H.dims, "nnz_blocks": [p.nnz for p in H.pattern],
+                   "parallelism": f"{world} rank(s), one mesh block per rank, no exchange" if world > 1 else "single GPU",
+                   "l2": "working set (matrix values %.2f GB) >> 126 MB L2, no flush needed" % (H.pattern[0].nnz * 36 / 1e9),
+                   "setup_s": round(setup_s, 1), "timing": "CUDA events around CUDA-graph replays, max over ranks"},
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": H.dims[0] * 12,
+                "d2h_bytes_per_step": H.dims[0] * 12},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "step_hbm": {"algorithmic_bytes_per_step": sb, "achieved_GBps": sb / (ms / args.steps * 1e-3) / 1e9,
+                     "frac_of_peak": sb / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "roofline": {"bound": "hbm", "kernel": "row_pass_kernel<GS> (femb_gauss_seidel, fine level, per colour launch)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                     "us_per_launch": gs_ms_per_launch * 1e3},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, sample_only=True)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, sample_only=False, steps=1, warmup=0):
+    """The CPU restatement of the reference algorithm (oracle/) timed on a bounded sample: a smaller cube,
+    throughput scaled to the benchmark's hexahedron count."""
+    import numpy as np
+    from fem_simulation_b200 import mesh
+    from oracle import ref_solvers
+    n_s = args.cpu_n or 24
+    pts, hx = mesh.cube_mesh(n_s)
+    ref = ref_solvers.RefObject(pts, hx, 1.0 / n_s, [])
+    fn = ref.NewtonMultigrid if args.method == "nmg" else ref.FASv3
+    for _ in range(warmup):
+        fn(1)
+    t0 = time.time()
+    for _ in range(steps):
+        fn(1)
+    dt = (time.time() - t0) / steps
+    scale = hx.shape[0] / float(args.n ** 3)
+    return {"value": scale / dt, "unit": "steps/s", "cores": 1, "kind": "port",
+            "sample": f"numpy oracle, {steps} step(s) on cube n={n_s} ({hx.shape[0]} hexahedra, {ref.layer} levels), "
+                      f"{dt:.2f} s/step, throughput scaled by hexahedron count to n={args.n}", "s_per_sample_step": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    n = args.n
+    line = {"impl": "reference", "metric": "newton_mg_steps_per_sec" if args.method == "nmg" else "fasv3_steps_per_sec",
+            "value": cb["value"], "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"voxel cube n={n}: {n ** 3} hexahedra; CPU restatement of the reference algorithm "
+                                   "(the reference is GPU-only Warp code and cannot run here)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
