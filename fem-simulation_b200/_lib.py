@@ -28,7 +28,7 @@ class FembLevel(C.Structure):
                 ("color_start", C.c_int * 9),
                 ("hex", C.c_void_p), ("v2i", C.c_void_p), ("i2v", C.c_void_p),
                 ("L_ptr", C.c_void_p), ("L_col", C.c_void_p), ("U_ptr", C.c_void_p), ("U_col", C.c_void_p),
-                ("elem2nnz", C.c_void_p), ("asm_ptr", C.c_void_p), ("asm_src", C.c_void_p),
+                ("elem2nnz", C.c_void_p), ("asm_ptr", C.c_void_p), ("asm_pos", C.c_void_p),
                 ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p)]
 
 
@@ -40,7 +40,8 @@ class FembTransfer(C.Structure):
 class FembGalerkinPlan(C.Structure):
     _fields_ = [("n_fine", C.c_int), ("n_coarse", C.c_int), ("t_nnz", C.c_int),
                 ("t_ptr", C.c_void_p), ("t_col", C.c_void_p), ("c_ptr", C.c_void_p),
-                ("c_col", C.c_void_p), ("c_slot", C.c_void_p)]
+                ("c_col", C.c_void_p), ("c_slot", C.c_void_p), ("t_slot", C.c_void_p), ("c_slot8", C.c_void_p),
+                ("ut_q", C.c_void_p)]
 
 
 P = C.c_void_p
@@ -69,7 +70,7 @@ PROTOTYPES = {
     "femb_cg": [LV, P, P, P, P, P, P, P, I, F, I, P],
     "femb_spd_blocks": [P, I, F, P],
     "femb_transfer_mv": [TR, F, P, F, P, P],
-    "femb_galerkin": [LV, P, TR, TR, GP, P, I, F, P, P],
+    "femb_galerkin": [LV, LV, P, TR, TR, GP, P, I, F, P, P],
     "femb_axpby": [I, F, P, F, P, P],
     "femb_copy": [I, P, P, P],
     "femb_fill": [I, F, P, P],

@@ -139,7 +139,8 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
 
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both
 template <int kMode>
-__global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
+__global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, const int* __restrict__ asm_pos, float* __restrict__ elem_f,
+                                                           float* __restrict__ elem_k) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
   extern __shared__ __align__(16) float smem[];
@@ -228,12 +229,13 @@ __global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, float* __r
     }
   }
   if (live) {
-    float4* dst = reinterpret_cast<float4*>(elem_k + ((size_t)e * 8 + sub) * 72);
+    // block (a,b) goes to its rank in value-slot order, so that the assembly gather streams contiguously
+    const int* pos = asm_pos + (size_t)e * 64 + sub * 8;
 #pragma unroll
-    for (int v = 0; v < 18; ++v) {
-      const int i0 = 4 * v;
-      dst[v] = make_float4(K[i0 / 9][i0 % 9], K[(i0 + 1) / 9][(i0 + 1) % 9], K[(i0 + 2) / 9][(i0 + 2) % 9],
-                           K[(i0 + 3) / 9][(i0 + 3) % 9]);
+    for (int b = 0; b < 8; ++b) {
+      float* dst = elem_k + (size_t)__ldg(pos + b) * 9;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dst[k] = K[b][k];
     }
   }
 }
@@ -246,9 +248,8 @@ static size_t element_smem() {
   return f * sizeof(float);
 }
 
-// values[slot*9+k] = sum over the element blocks mapped to `slot` (+ diag_add on diagonal slots)
+// values[slot*9+k] = sum over the element blocks mapped to `slot` (contiguous in elem_k) (+ diag_add)
 __global__ void __launch_bounds__(256) assemble_gather_kernel(long long total, const int* __restrict__ asm_ptr,
-                                                             const int* __restrict__ asm_src,
                                                              const float* __restrict__ elem_k,
                                                              const float* __restrict__ diag_add, int off_d, int n_vert,
                                                              float* __restrict__ values) {
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256) assemble_gather_kernel(long long total, c
     const int r = slot - off_d;
     if (r >= 0 && r < n_vert) v = __ldg(diag_add + r);
   }
-  for (int p = p0; p < p1; ++p) v += __ldg(elem_k + (size_t)__ldg(asm_src + p) * 9 + k);
+  for (int p = p0; p < p1; ++p) v += __ldg(elem_k + (size_t)p * 9 + k);
   values[t] = v;
 }
 
@@ -436,7 +437,7 @@ static int launch_element(const FembLevel* l, const float* x, float mu, float la
     cudaFuncSetAttribute(element_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  element_kernel<kMode><<<cdiv(l->n_hex, EPB), ETHREADS, smem, st>>>(make_in(l, x, mu, la), elem_f, elem_k);
+  element_kernel<kMode><<<cdiv(l->n_hex, EPB), ETHREADS, smem, st>>>(make_in(l, x, mu, la), l->asm_pos, elem_f, elem_k);
   count_launch();
   return check_launch("element_kernel");
 }
@@ -453,7 +454,7 @@ static int launch_force_gather(const FembLevel* l, const float* x, const float* 
 
 static int launch_assemble(const FembLevel* l, const float* diag_add, const float* elem_k, float* values, cudaStream_t st) {
   const long long total = (long long)l->nnz * 9;
-  assemble_gather_kernel<<<cdiv(total, 256), 256, 0, st>>>(total, l->asm_ptr, l->asm_src, elem_k, diag_add, l->off_d,
+  assemble_gather_kernel<<<cdiv(total, 256), 256, 0, st>>>(total, l->asm_ptr, elem_k, diag_add, l->off_d,
                                                            l->n_vert, values);
   count_launch();
   return check_launch("assemble_gather_kernel");
@@ -501,7 +502,7 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add, float* elem_k,
                  float* values, void* stream) {
   FEMB_REQUIRE(lvl && x && elem_k && values, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->asm_ptr && lvl->asm_src, "level not initialised");
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->asm_ptr && lvl->asm_pos, "level not initialised");
   if (lvl->n_hex > 0) {
     int rc = launch_element<1>(lvl, x, mu, lambda, nullptr, elem_k, as_stream(stream));
     if (rc) return rc;
@@ -514,7 +515,7 @@ int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lam
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add, float* elem_f,
                        float* elem_k, float* force_out, float* values, void* stream) {
   FEMB_REQUIRE(lvl && x && elem_f && elem_k && force_out && values, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->asm_ptr && lvl->asm_src && lvl->vert_elem && lvl->v2i,
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->asm_ptr && lvl->asm_pos && lvl->vert_elem && lvl->v2i,
                "level not initialised");
   if (lvl->n_hex > 0) {
     int rc = launch_element<2>(lvl, x, mu, lambda, elem_f, elem_k, as_stream(stream));

@@ -43,104 +43,217 @@ struct RowArgs {
   const float* active;         // optional device flag: 0 -> kernel is a no-op (CG early exit)
 };
 
-template <int kMode>
-__global__ void __launch_bounds__(RP_THREADS) row_pass_kernel(RowArgs a) {
-  if (a.active != nullptr && *a.active == 0.f) return;
-  __shared__ float s_val[RP_CAP * 9];
-  __shared__ int s_col[RP_CAP];
-  __shared__ float s_diag[RP_ROWS * 9];
-  __shared__ int s_ptr[2][RP_ROWS + 1];
-  __shared__ float s_red[RP_SUBS][RP_ROWS][3];
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct RowSmem {
+  alignas(128) float val[RP_CAP * 9 + 16];   // [L chunk | U chunk], each starting on a 16-byte boundary
+  alignas(16) int col[RP_CAP + 16];
+  alignas(16) float diag[RP_ROWS * 9 + 8];
+  int ptr[2][RP_ROWS + 1];
+  float red[RP_SUBS][RP_ROWS][3];
+  alignas(8) uint64_t bar;
+};
+
+// One block of <= RP_ROWS consecutive rows.  kCoherent: x is being updated by other CTAs of the same
+// (cooperative) launch, so it is read through L2 (ld.global.cg) instead of the per-SM L1.
+// The values / L_col / U_col arrays must be 16-byte aligned and readable 16 bytes past their end
+// (the bulk copies are rounded out to 16-byte granules).
+template <int kMode, bool kCoherent>
+__device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, RowSmem& sm, uint32_t& phase) {
   const int tid = threadIdx.x;
-  const int r0 = a.row_begin + blockIdx.x * RP_ROWS;
-  const int nrow = min(RP_ROWS, a.row_end - r0);
   const bool useL = (a.parts & FEMB_PART_L) != 0, useU = (a.parts & FEMB_PART_U) != 0;
   const bool needD = (kMode == RM_GS || kMode == RM_JACOBI) || (a.parts & FEMB_PART_D) != 0;
   if (tid <= nrow) {
-    s_ptr[0][tid] = useL ? __ldg(a.L_ptr + r0 + tid) : 0;
-    s_ptr[1][tid] = useU ? __ldg(a.U_ptr + r0 + tid) : 0;
+    sm.ptr[0][tid] = useL ? __ldg(a.L_ptr + r0 + tid) : 0;
+    sm.ptr[1][tid] = useU ? __ldg(a.U_ptr + r0 + tid) : 0;
   }
   __syncthreads();
-  const int L0 = s_ptr[0][0], U0 = s_ptr[1][0];
-  const int nL = s_ptr[0][nrow] - L0, nU = s_ptr[1][nrow] - U0;
+  const int L0 = sm.ptr[0][0], U0 = sm.ptr[1][0];
+  const int nL = sm.ptr[0][nrow] - L0, nU = sm.ptr[1][nrow] - U0;
   const bool staged = (nL + nU) <= RP_CAP;
-  if (staged) {
-    const float* srcL = a.values + ((size_t)a.off_l + L0) * 9;
-    for (int i = tid; i < nL * 9; i += RP_THREADS) s_val[i] = __ldg(srcL + i);
-    const float* srcU = a.values + ((size_t)a.off_u + U0) * 9;
-    float* dstU = s_val + nL * 9;
-    for (int i = tid; i < nU * 9; i += RP_THREADS) dstU[i] = __ldg(srcU + i);
-    for (int i = tid; i < nL; i += RP_THREADS) s_col[i] = __ldg(a.L_col + L0 + i);
-    for (int i = tid; i < nU; i += RP_THREADS) s_col[nL + i] = __ldg(a.U_col + U0 + i);
+  // float / int offsets of the wanted data inside the staged (16-byte rounded) chunks
+  const size_t gL = ((size_t)a.off_l + L0) * 9, gU = ((size_t)a.off_u + U0) * 9, gD = ((size_t)a.off_d + r0) * 9;
+  const int preL = (int)(gL & 3), preU = (int)(gU & 3), preD = (int)(gD & 3);
+  const int baseU = (preL + nL * 9 + 3) & ~3;
+  const int cpreL = L0 & 3, cpreU = U0 & 3;
+  const int cbaseU = (cpreL + nL + 3) & ~3;
+  if (tid == 0) {
+    uint32_t bytes = 0;
+    const uint32_t bL = (uint32_t)((preL + nL * 9) * 4 + 15) & ~15u, bU = (uint32_t)((preU + nU * 9) * 4 + 15) & ~15u;
+    const uint32_t bD = (uint32_t)((preD + nrow * 9) * 4 + 15) & ~15u;
+    const uint32_t cL = (uint32_t)((cpreL + nL) * 4 + 15) & ~15u, cU = (uint32_t)((cpreU + nU) * 4 + 15) & ~15u;
+    if (staged && nL > 0) bytes += bL + cL;
+    if (staged && nU > 0) bytes += bU + cU;
+    if (needD) bytes += bD;
+    mbar_expect_tx(&sm.bar, bytes);
+    if (staged && nL > 0) {
+      bulk_g2s(sm.val, a.values + (gL - preL), bL, &sm.bar);
+      bulk_g2s(sm.col, a.L_col + (L0 - cpreL), cL, &sm.bar);
+    }
+    if (staged && nU > 0) {
+      bulk_g2s(sm.val + baseU, a.values + (gU - preU), bU, &sm.bar);
+      bulk_g2s(sm.col + cbaseU, a.U_col + (U0 - cpreU), cU, &sm.bar);
+    }
+    if (needD) bulk_g2s(sm.diag, a.values + (gD - preD), bD, &sm.bar);
   }
-  if (needD) {
-    const float* srcD = a.values + ((size_t)a.off_d + r0) * 9;
-    for (int i = tid; i < nrow * 9; i += RP_THREADS) s_diag[i] = __ldg(srcD + i);
-  }
-  __syncthreads();
+  mbar_wait(&sm.bar, phase);
+  phase ^= 1u;
 
+  const float* vL = sm.val + preL;
+  const float* vU = sm.val + baseU + preU;
+  const int* cLs = sm.col + cpreL;
+  const int* cUs = sm.col + cbaseU + cpreU;
   const int rl = tid % RP_ROWS, sub = tid / RP_ROWS;
   float acc[3] = {0.f, 0.f, 0.f};
   if (rl < nrow) {
-    const int lb = s_ptr[0][rl] - L0, cntL = s_ptr[0][rl + 1] - s_ptr[0][rl];
-    const int ub = s_ptr[1][rl] - U0, cntU = s_ptr[1][rl + 1] - s_ptr[1][rl];
+    const int lb = sm.ptr[0][rl] - L0, cntL = sm.ptr[0][rl + 1] - sm.ptr[0][rl];
+    const int ub = sm.ptr[1][rl] - U0, cntU = sm.ptr[1][rl + 1] - sm.ptr[1][rl];
     const int n = cntL + cntU;
-    for (int j = sub; j < n; j += RP_SUBS) {
-      const bool isL = j < cntL;
-      const int loc = isL ? (lb + j) : (nL + ub + (j - cntL));
-      int col;
-      float m[9];
-      if (staged) {
-        col = s_col[loc];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) m[k] = s_val[loc * 9 + k];
-      } else {
+    if (staged) {
+      for (int j = sub; j < n; j += 2 * RP_SUBS) {      // two blocks per trip: both x gathers in flight together
+        const int j1 = j + RP_SUBS;
+        const bool two = j1 < n;
+        const float* m0 = (j < cntL) ? vL + (lb + j) * 9 : vU + (ub + j - cntL) * 9;
+        const int c0 = (j < cntL) ? cLs[lb + j] : cUs[ub + j - cntL];
+        const float* m1 = m0;
+        int c1 = c0;
+        if (two) {
+          m1 = (j1 < cntL) ? vL + (lb + j1) * 9 : vU + (ub + j1 - cntL) * 9;
+          c1 = (j1 < cntL) ? cLs[lb + j1] : cUs[ub + j1 - cntL];
+        }
+        float p0, p1, p2, q0, q1, q2;
+        if (kCoherent) {
+          p0 = __ldcg(a.x + 3 * (size_t)c0); p1 = __ldcg(a.x + 3 * (size_t)c0 + 1); p2 = __ldcg(a.x + 3 * (size_t)c0 + 2);
+          q0 = __ldcg(a.x + 3 * (size_t)c1); q1 = __ldcg(a.x + 3 * (size_t)c1 + 1); q2 = __ldcg(a.x + 3 * (size_t)c1 + 2);
+        } else {
+          p0 = a.x[3 * (size_t)c0]; p1 = a.x[3 * (size_t)c0 + 1]; p2 = a.x[3 * (size_t)c0 + 2];
+          q0 = a.x[3 * (size_t)c1]; q1 = a.x[3 * (size_t)c1 + 1]; q2 = a.x[3 * (size_t)c1 + 2];
+        }
+        acc[0] += m0[0] * p0 + m0[1] * p1 + m0[2] * p2;
+        acc[1] += m0[3] * p0 + m0[4] * p1 + m0[5] * p2;
+        acc[2] += m0[6] * p0 + m0[7] * p1 + m0[8] * p2;
+        if (two) {
+          acc[0] += m1[0] * q0 + m1[1] * q1 + m1[2] * q2;
+          acc[1] += m1[3] * q0 + m1[4] * q1 + m1[5] * q2;
+          acc[2] += m1[6] * q0 + m1[7] * q1 + m1[8] * q2;
+        }
+      }
+    } else {
+      for (int j = sub; j < n; j += RP_SUBS) {           // oversized rows: straight from global memory
+        const bool isL = j < cntL;
         const size_t g = isL ? ((size_t)a.off_l + L0 + lb + j) : ((size_t)a.off_u + U0 + ub + (j - cntL));
-        col = isL ? __ldg(a.L_col + L0 + lb + j) : __ldg(a.U_col + U0 + ub + (j - cntL));
+        const int col = isL ? __ldg(a.L_col + L0 + lb + j) : __ldg(a.U_col + U0 + ub + (j - cntL));
+        float m[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) m[k] = __ldg(a.values + g * 9 + k);
+        const float x0 = __ldcg(a.x + 3 * (size_t)col), x1 = __ldcg(a.x + 3 * (size_t)col + 1), x2 = __ldcg(a.x + 3 * (size_t)col + 2);
+        acc[0] += m[0] * x0 + m[1] * x1 + m[2] * x2;
+        acc[1] += m[3] * x0 + m[4] * x1 + m[5] * x2;
+        acc[2] += m[6] * x0 + m[7] * x1 + m[8] * x2;
       }
-      const float x0 = a.x[3 * (size_t)col], x1 = a.x[3 * (size_t)col + 1], x2 = a.x[3 * (size_t)col + 2];
-      acc[0] += m[0] * x0 + m[1] * x1 + m[2] * x2;
-      acc[1] += m[3] * x0 + m[4] * x1 + m[5] * x2;
-      acc[2] += m[6] * x0 + m[7] * x1 + m[8] * x2;
     }
   }
-  s_red[sub][rl][0] = acc[0]; s_red[sub][rl][1] = acc[1]; s_red[sub][rl][2] = acc[2];
+  sm.red[sub][rl][0] = acc[0]; sm.red[sub][rl][1] = acc[1]; sm.red[sub][rl][2] = acc[2];
   __syncthreads();
-  if (tid >= nrow) return;
-  const int r = r0 + tid;
-  float s[3];
+  if (tid < nrow) {
+    const int r = r0 + tid;
+    float s[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) s[c] = (s_red[0][tid][c] + s_red[1][tid][c]) + (s_red[2][tid][c] + s_red[3][tid][c]);
-  const float* D = s_diag + tid * 9;
-  if (kMode == RM_SPMV || kMode == RM_RESIDUAL) {
-    if (a.parts & FEMB_PART_D) {
-      const float x0 = a.x[3 * (size_t)r], x1 = a.x[3 * (size_t)r + 1], x2 = a.x[3 * (size_t)r + 2];
-      s[0] += D[0] * x0 + D[1] * x1 + D[2] * x2;
-      s[1] += D[3] * x0 + D[4] * x1 + D[5] * x2;
-      s[2] += D[6] * x0 + D[7] * x1 + D[8] * x2;
+    for (int c = 0; c < 3; ++c) s[c] = (sm.red[0][tid][c] + sm.red[1][tid][c]) + (sm.red[2][tid][c] + sm.red[3][tid][c]);
+    const float* D = sm.diag + preD + tid * 9;
+    if (kMode == RM_SPMV || kMode == RM_RESIDUAL) {
+      if (a.parts & FEMB_PART_D) {
+        const float x0 = a.x[3 * (size_t)r], x1 = a.x[3 * (size_t)r + 1], x2 = a.x[3 * (size_t)r + 2];
+        s[0] += D[0] * x0 + D[1] * x1 + D[2] * x2;
+        s[1] += D[3] * x0 + D[4] * x1 + D[5] * x2;
+        s[2] += D[6] * x0 + D[7] * x1 + D[8] * x2;
+      }
+    }
+    if (kMode == RM_SPMV) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = a.alpha * s[c];
+        if (a.beta != 0.f) v += a.beta * a.y[3 * (size_t)r + c];
+        a.y[3 * (size_t)r + c] = v;
+      }
+    } else if (kMode == RM_RESIDUAL) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a.y[3 * (size_t)r + c] = a.b[3 * (size_t)r + c] - s[c];
+    } else {
+      // x_r = solve3x3(D_r, b_r - sum, 0)                       (Colored_GS_MF_Kernel, cublas.py:129-135)
+      float rhs[3], xs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rhs[c] = a.b[3 * (size_t)r + c] - s[c];
+      const int bad = solve3x3(D, rhs, xs);
+      if (bad && a.not_spd != nullptr) atomicAdd(a.not_spd, 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a.y[3 * (size_t)r + c] = xs[c];
     }
   }
-  if (kMode == RM_SPMV) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v = a.alpha * s[c];
-      if (a.beta != 0.f) v += a.beta * a.y[3 * (size_t)r + c];
-      a.y[3 * (size_t)r + c] = v;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(RP_THREADS) row_pass_kernel(RowArgs a) {
+  if (a.active != nullptr && *a.active == 0.f) return;
+  __shared__ RowSmem sm;
+  if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
+  uint32_t phase = 0;
+  const int r0 = a.row_begin + blockIdx.x * RP_ROWS;
+  row_block<kMode, false>(a, r0, min(RP_ROWS, a.row_end - r0), sm, phase);
+}
+
+// Whole femb_gauss_seidel call in ONE cooperative launch (levels whose colour fits the resident grid):
+// iterations x 16 colour phases separated by grid-wide barriers instead of 16 launches per iteration.
+struct GsCoopArgs {
+  RowArgs base;
+  int color_start[9];
+  int iterations;
+};
+}  // namespace femb
+#include <cooperative_groups.h>
+namespace femb {
+__global__ void __launch_bounds__(RP_THREADS) gs_coop_kernel(GsCoopArgs g) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ RowSmem sm;
+  if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
+  uint32_t phase = 0;
+  RowArgs a = g.base;
+  for (int it = 0; it < g.iterations; ++it) {
+    for (int half = 0; half < 2; ++half) {
+      for (int ci = 0; ci < 8; ++ci) {
+        const int c = half == 0 ? 7 - ci : ci;                   // backward then forward sweep (object.py:893-908)
+        a.parts = (it == 0 && half == 0) ? FEMB_PART_U : (FEMB_PART_L | FEMB_PART_U);
+        const int rb = g.color_start[c], re = g.color_start[c + 1];
+        for (int r0 = rb + blockIdx.x * RP_ROWS; r0 < re; r0 += gridDim.x * RP_ROWS) {
+          row_block<RM_GS, true>(a, r0, min(RP_ROWS, re - r0), sm, phase);
+          __syncthreads();                                       // smem is reused by the next block
+        }
+        grid.sync();
+      }
     }
-  } else if (kMode == RM_RESIDUAL) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) a.y[3 * (size_t)r + c] = a.b[3 * (size_t)r + c] - s[c];
-  } else {
-    // x_r = solve3x3(D_r, b_r - sum, 0)                         (Colored_GS_MF_Kernel, cublas.py:129-135)
-    float rhs[3], xs[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) rhs[c] = a.b[3 * (size_t)r + c] - s[c];
-    const int bad = solve3x3(D, rhs, xs);
-    if (bad && a.not_spd != nullptr) atomicAdd(a.not_spd, 1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) a.y[3 * (size_t)r + c] = xs[c];
   }
 }
 
@@ -160,6 +273,19 @@ static int launch_rows(const RowArgs& a, cudaStream_t st) {
   row_pass_kernel<kMode><<<cdiv(n, RP_ROWS), RP_THREADS, 0, st>>>(a);
   count_launch();
   return check_launch("row_pass_kernel");
+}
+
+// resident CTAs of gs_coop_kernel on the current device (0 if cooperative launch is unsupported)
+static int coop_capacity() {
+  static int cap = -1;
+  if (cap >= 0) return cap;
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_coop_kernel, RP_THREADS, 0);
+  cap = coop ? sms * per_sm : 0;
+  return cap;
 }
 
 // ---- vector kernels -----------------------------------------------------------------------------
@@ -285,83 +411,148 @@ __global__ void __launch_bounds__(256) transfer_kernel(int nrow, const int* __re
 }
 
 // ---- Galerkin product on fixed patterns -----------------------------------------------------------
-constexpr int GK_THREADS = 64;
-constexpr int GK_SLOTS = 27;
+// A_c = Ut_hat (A_f Us_hat) in two streaming stages with precomputed slot plans (no searches, no atomics,
+// fixed summation order = the row-major order of _bsr_mm_compute_values, sparse.py:873-901):
+//   stage 1  T = A_f Us_hat : 32 fine rows per CTA, the rows' blocks staged by bulk copies like the row
+//            pass, 9 threads per row (one per block entry) accumulate the <= 27 T blocks of the row
+//   stage 2  A_c = Ut_hat T : 32 coarse vertices per CTA (vertex order, so the <= 8 parents of a fine row
+//            are processed close in time and T is read from HBM once), 9 threads per coarse row,
+//            spd_matrix33f in the epilogue, output written to the [L;D;U] slot of every block.
+constexpr int GA_ROWS = 32;
+constexpr int GA_THREADS = GA_ROWS * 9;
+constexpr int GA_SLOTS = 27;
 
-__device__ __forceinline__ int find_col(const int* cols, int n, int key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(cols + mid) < key) lo = mid + 1; else hi = mid;
+struct GaSmem {
+  alignas(128) float val[RP_CAP * 9 + 16];
+  alignas(16) int col[RP_CAP + 16];
+  alignas(16) float diag[GA_ROWS * 9 + 8];
+  alignas(16) unsigned char tsl[(RP_CAP + GA_ROWS) * 8 + 64];   // t_slot of the L chunk | U chunk | D chunk
+  int ptr[2][GA_ROWS + 1];
+  float acc[GA_ROWS * GA_SLOTS * 9];
+  alignas(8) uint64_t bar;
+};
+
+__global__ void __launch_bounds__(GA_THREADS) galerkin_ap_kernel(RowArgs a, int n_fine, const int* __restrict__ p_off,
+                                                                const float* __restrict__ p_w,
+                                                                const unsigned char* __restrict__ t_slot,
+                                                                const int* __restrict__ t_ptr, float* __restrict__ t_val) {
+  extern __shared__ __align__(128) unsigned char ga_raw[];
+  GaSmem& sm = *reinterpret_cast<GaSmem*>(ga_raw);
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * GA_ROWS;
+  const int nrow = min(GA_ROWS, n_fine - r0);
+  if (tid == 0) mbar_init(&sm.bar, 1);
+  if (tid <= nrow) {
+    sm.ptr[0][tid] = __ldg(a.L_ptr + r0 + tid);
+    sm.ptr[1][tid] = __ldg(a.U_ptr + r0 + tid);
   }
-  return lo;
-}
-
-// T = A_f * Us_hat : thread per fine row, private accumulators acc[slot*9+k][thread] in shared memory
-__global__ void __launch_bounds__(GK_THREADS) galerkin_ap_kernel(int n_fine, const int* __restrict__ L_ptr,
-                                                                const int* __restrict__ L_col, const int* __restrict__ U_ptr,
-                                                                const int* __restrict__ U_col, const float* __restrict__ values,
-                                                                int off_l, int off_d, int off_u, const int* __restrict__ p_off,
-                                                                const int* __restrict__ p_col, const float* __restrict__ p_w,
-                                                                const int* __restrict__ t_ptr, const int* __restrict__ t_col,
-                                                                float* __restrict__ t_val) {
-  extern __shared__ float s_acc[];
-  const int i = blockIdx.x * GK_THREADS + threadIdx.x;
-  if (i >= n_fine) return;
-  float* acc = s_acc + threadIdx.x;
+  for (int i = tid; i < GA_ROWS * GA_SLOTS * 9; i += GA_THREADS) sm.acc[i] = 0.f;
+  __syncthreads();
+  const int L0 = sm.ptr[0][0], U0 = sm.ptr[1][0];
+  const int nL = sm.ptr[0][nrow] - L0, nU = sm.ptr[1][nrow] - U0;
+  const bool staged = (nL + nU) <= RP_CAP;
+  const size_t sL = (size_t)a.off_l + L0, sU = (size_t)a.off_u + U0, sD = (size_t)a.off_d + r0;   // first [L;D;U] slots
+  const size_t gL = sL * 9, gU = sU * 9, gD = sD * 9;
+  const int preL = (int)(gL & 3), preU = (int)(gU & 3), preD = (int)(gD & 3);
+  const int baseU = (preL + nL * 9 + 3) & ~3;
+  const int cpreL = L0 & 3, cpreU = U0 & 3;
+  const int cbaseU = (cpreL + nL + 3) & ~3;
+  // t_slot chunks (8 bytes per block): byte offsets inside sm.tsl
+  const int tpreL = (int)((sL * 8) & 15), tpreU = (int)((sU * 8) & 15), tpreD = (int)((sD * 8) & 15);
+  const int tbaseU = (tpreL + nL * 8 + 15) & ~15;
+  const int tbaseD = tbaseU + ((tpreU + nU * 8 + 15) & ~15);
+  if (tid == 0) {
+    const uint32_t bL = (uint32_t)((preL + nL * 9) * 4 + 15) & ~15u, bU = (uint32_t)((preU + nU * 9) * 4 + 15) & ~15u;
+    const uint32_t bD = (uint32_t)((preD + nrow * 9) * 4 + 15) & ~15u;
+    const uint32_t cL = (uint32_t)((cpreL + nL) * 4 + 15) & ~15u, cU = (uint32_t)((cpreU + nU) * 4 + 15) & ~15u;
+    const uint32_t tL = (uint32_t)(tpreL + nL * 8 + 15) & ~15u, tU = (uint32_t)(tpreU + nU * 8 + 15) & ~15u;
+    const uint32_t tD = (uint32_t)(tpreD + nrow * 8 + 15) & ~15u;
+    uint32_t bytes = bD + tD;
+    if (staged && nL > 0) bytes += bL + cL + tL;
+    if (staged && nU > 0) bytes += bU + cU + tU;
+    mbar_expect_tx(&sm.bar, bytes);
+    if (staged && nL > 0) {
+      bulk_g2s(sm.val, a.values + (gL - preL), bL, &sm.bar);
+      bulk_g2s(sm.col, a.L_col + (L0 - cpreL), cL, &sm.bar);
+      bulk_g2s(sm.tsl, t_slot + (sL * 8 - tpreL), tL, &sm.bar);
+    }
+    if (staged && nU > 0) {
+      bulk_g2s(sm.val + baseU, a.values + (gU - preU), bU, &sm.bar);
+      bulk_g2s(sm.col + cbaseU, a.U_col + (U0 - cpreU), cU, &sm.bar);
+      bulk_g2s(sm.tsl + tbaseU, t_slot + (sU * 8 - tpreU), tU, &sm.bar);
+    }
+    bulk_g2s(sm.diag, a.values + (gD - preD), bD, &sm.bar);
+    bulk_g2s(sm.tsl + tbaseD, t_slot + (sD * 8 - tpreD), tD, &sm.bar);
+  }
+  mbar_wait(&sm.bar, 0);
+  const int rl = tid / 9, k = tid - rl * 9;
+  if (rl >= nrow) return;
+  const int i = r0 + rl;
+  const int lb = sm.ptr[0][rl] - L0, cntL = sm.ptr[0][rl + 1] - sm.ptr[0][rl];
+  const int ub = sm.ptr[1][rl] - U0, cntU = sm.ptr[1][rl + 1] - sm.ptr[1][rl];
+  float* acc = sm.acc + rl * GA_SLOTS * 9 + k;
+  const int total = cntL + 1 + cntU;
+  for (int jj = 0; jj < total; ++jj) {                       // column order: L blocks, D, U blocks
+    float v;
+    int j;
+    const unsigned char* ts;
+    if (jj < cntL) {
+      const int loc = lb + jj;
+      if (staged) { v = sm.val[preL + loc * 9 + k]; j = sm.col[cpreL + loc]; ts = sm.tsl + tpreL + loc * 8; }
+      else { v = __ldg(a.values + (sL + loc) * 9 + k); j = __ldg(a.L_col + L0 + loc); ts = t_slot + (sL + loc) * 8; }
+    } else if (jj == cntL) {
+      v = sm.diag[preD + rl * 9 + k]; j = i; ts = sm.tsl + tbaseD + tpreD + rl * 8;
+    } else {
+      const int loc = ub + (jj - cntL - 1);
+      if (staged) { v = sm.val[baseU + preU + loc * 9 + k]; j = sm.col[cbaseU + cpreU + loc]; ts = sm.tsl + tbaseU + tpreU + loc * 8; }
+      else { v = __ldg(a.values + (sU + loc) * 9 + k); j = __ldg(a.U_col + U0 + loc); ts = t_slot + (sU + loc) * 8; }
+    }
+    const int p0 = __ldg(p_off + j), np = __ldg(p_off + j + 1) - p0;
+    for (int p = 0; p < np; ++p) acc[(int)ts[p] * 9] += v * __ldg(p_w + p0 + p);
+  }
   const int t0 = __ldg(t_ptr + i), tn = __ldg(t_ptr + i + 1) - t0;
-  for (int s = 0; s < tn * 9; ++s) acc[s * GK_THREADS] = 0.f;
-  const int l0 = __ldg(L_ptr + i), l1 = __ldg(L_ptr + i + 1), u0 = __ldg(U_ptr + i), u1 = __ldg(U_ptr + i + 1);
-  const int total = (l1 - l0) + 1 + (u1 - u0);
-  for (int jj = 0; jj < total; ++jj) {          // blocks of row i in column order: L, D, U
-    int j; size_t g;
-    if (jj < l1 - l0) { j = __ldg(L_col + l0 + jj); g = (size_t)off_l + l0 + jj; }
-    else if (jj == l1 - l0) { j = i; g = (size_t)off_d + i; }
-    else { const int u = u0 + (jj - (l1 - l0) - 1); j = __ldg(U_col + u); g = (size_t)off_u + u; }
-    float m[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) m[k] = __ldg(values + g * 9 + k);
-    for (int p = __ldg(p_off + j); p < __ldg(p_off + j + 1); ++p) {
-      const int J = __ldg(p_col + p);
-      const float w = __ldg(p_w + p);
-      const int slot = find_col(t_col + t0, tn, J);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc[(slot * 9 + k) * GK_THREADS] += m[k] * w;
-    }
-  }
-  for (int s = 0; s < tn * 9; ++s) t_val[(size_t)t0 * 9 + s] = acc[s * GK_THREADS];
+  for (int sl = 0; sl < tn; ++sl) t_val[((size_t)t0 + sl) * 9 + k] = acc[sl * 9];
 }
 
-// A_c = Ut_hat * T (+ spd_matrix33f), written to the [L;D;U] slot of each (row,col)-sorted block
-__global__ void __launch_bounds__(GK_THREADS) galerkin_rt_kernel(int n_coarse, const int* __restrict__ r_off,
-                                                                const int* __restrict__ r_col, const float* __restrict__ r_w,
-                                                                const int* __restrict__ t_ptr, const int* __restrict__ t_col,
-                                                                const float* __restrict__ t_val, const int* __restrict__ c_ptr,
-                                                                const int* __restrict__ c_col, const int* __restrict__ c_slot,
+__global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, const int* __restrict__ v2i_c,
+                                                                const int* __restrict__ r_off, const int* __restrict__ r_col,
+                                                                const float* __restrict__ r_w,
+                                                                const unsigned char* __restrict__ ut_q,
+                                                                const int* __restrict__ t_ptr, const float* __restrict__ t_val,
+                                                                const unsigned char* __restrict__ c_slot8,
+                                                                const int* __restrict__ c_ptr, const int* __restrict__ c_slot,
                                                                 int spd, float spd_value, float* __restrict__ out) {
-  extern __shared__ float s_acc[];
-  const int I = blockIdx.x * GK_THREADS + threadIdx.x;
-  if (I >= n_coarse) return;
-  float* acc = s_acc + threadIdx.x;
-  const int c0 = __ldg(c_ptr + I), cn = __ldg(c_ptr + I + 1) - c0;
-  for (int s = 0; s < cn * 9; ++s) acc[s * GK_THREADS] = 0.f;
-  for (int p = __ldg(r_off + I); p < __ldg(r_off + I + 1); ++p) {
-    const int i = __ldg(r_col + p);
-    const float w = __ldg(r_w + p);
-    for (int t = __ldg(t_ptr + i); t < __ldg(t_ptr + i + 1); ++t) {
-      const int slot = find_col(c_col + c0, cn, __ldg(t_col + t));
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc[(slot * 9 + k) * GK_THREADS] += w * __ldg(t_val + (size_t)t * 9 + k);
+  __shared__ float s_acc[GA_ROWS * GA_SLOTS * 9];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < GA_ROWS * GA_SLOTS * 9; i += GA_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const int rl = tid / 9, k = tid - rl * 9;
+  const int v = blockIdx.x * GA_ROWS + rl;
+  const bool live = v < n_coarse;
+  int I = 0;
+  float* acc = s_acc + rl * GA_SLOTS * 9;
+  if (live) {
+    I = __ldg(v2i_c + v);
+    for (int e = __ldg(r_off + I); e < __ldg(r_off + I + 1); ++e) {     // children of I in column order
+      const int i = __ldg(r_col + e);
+      const float w = __ldg(r_w + e);
+      const int q = ut_q[e];
+      const int t1 = __ldg(t_ptr + i + 1);
+      for (int t = __ldg(t_ptr + i); t < t1; ++t)
+        acc[(int)c_slot8[(size_t)t * 8 + q] * 9 + k] += w * __ldg(t_val + (size_t)t * 9 + k);
     }
   }
-  for (int s = 0; s < cn; ++s) {
+  __syncthreads();
+  if (!live) return;
+  const int c0 = __ldg(c_ptr + I), cn = __ldg(c_ptr + I + 1) - c0;
+  for (int sl = k; sl < cn; sl += 9) {
     float m[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) m[k] = acc[(s * 9 + k) * GK_THREADS];
+    for (int e = 0; e < 9; ++e) m[e] = acc[sl * 9 + e];
     if (spd) spd_block(m, spd_value);
-    float* d = out + (size_t)__ldg(c_slot + c0 + s) * 9;
+    float* d = out + (size_t)__ldg(c_slot + c0 + sl) * 9;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) d[k] = m[k];
+    for (int e = 0; e < 9; ++e) d[e] = m[e];
   }
 }
 
@@ -407,8 +598,27 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
   cudaStream_t st = as_stream(stream);
   if (lvl->n_vert == 0) return FEMB_OK;
   cudaMemsetAsync(dx, 0, sizeof(float) * 3 * (size_t)lvl->n_vert, st);           // object.py:887
+  if (iterations == 0) return FEMB_OK;
   RowArgs a = base_args(lvl, values);
   a.parts = FEMB_PART_L | FEMB_PART_U; a.x = dx; a.y = dx; a.b = b; a.not_spd = not_spd;
+  int max_blocks = 1;
+  for (int c = 0; c < 8; ++c) max_blocks = max(max_blocks, (int)cdiv(lvl->color_start[c + 1] - lvl->color_start[c], RP_ROWS));
+  const int cap = coop_capacity();
+  if (cap > 0 && max_blocks <= 2 * cap) {
+    // small level: one cooperative launch, grid-wide barrier between the 16 colour phases
+    GsCoopArgs g;
+    g.base = a; g.iterations = iterations;
+    for (int c = 0; c < 9; ++c) g.color_start[c] = lvl->color_start[c];
+    void* params[] = {&g};
+    const int grid = min(max_blocks, cap);
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)gs_coop_kernel, dim3(grid), dim3(RP_THREADS), params, 0, st);
+    count_launch();
+    if (e != cudaSuccess) {
+      set_error("gs_coop_kernel: %s", cudaGetErrorString(e));
+      return FEMB_E_CUDA;
+    }
+    return FEMB_OK;
+  }
   for (int it = 0; it < iterations; ++it) {
     for (int c = 7; c >= 0; --c) {                                                // backward sweep, object.py:893-898
       a.row_begin = lvl->color_start[c]; a.row_end = lvl->color_start[c + 1];
@@ -503,30 +713,30 @@ int femb_transfer_mv(const FembTransfer* t, float alpha, const float* x, float b
   return check_launch("transfer_kernel");
 }
 
-int femb_galerkin(const FembLevel* fine, const float* fine_values, const FembTransfer* ut_hat, const FembTransfer* us_hat,
-                  const FembGalerkinPlan* plan, float* t_values, int spd, float spd_value, float* coarse_values,
-                  void* stream) {
-  FEMB_REQUIRE(fine && fine_values && ut_hat && us_hat && plan && t_values && coarse_values, "null pointer");
-  FEMB_REQUIRE(plan->n_fine == fine->n_vert && us_hat->nrow == fine->n_vert && ut_hat->nrow == plan->n_coarse,
-               "inconsistent sizes");
+int femb_galerkin(const FembLevel* fine, const FembLevel* coarse, const float* fine_values, const FembTransfer* ut_hat,
+                  const FembTransfer* us_hat, const FembGalerkinPlan* plan, float* t_values, int spd, float spd_value,
+                  float* coarse_values, void* stream) {
+  FEMB_REQUIRE(fine && coarse && fine_values && ut_hat && us_hat && plan && t_values && coarse_values, "null pointer");
+  FEMB_REQUIRE(plan->n_fine == fine->n_vert && us_hat->nrow == fine->n_vert && ut_hat->nrow == plan->n_coarse &&
+                   coarse->n_vert == plan->n_coarse, "inconsistent sizes");
+  FEMB_REQUIRE(plan->t_slot && plan->c_slot8 && plan->ut_q && plan->t_ptr && plan->c_ptr && plan->c_slot, "plan not initialised");
   static bool configured = false;
-  const size_t smem = sizeof(float) * GK_THREADS * GK_SLOTS * 9;
   if (!configured) {
-    cudaFuncSetAttribute(galerkin_ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(galerkin_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(galerkin_ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaSmem));
     configured = true;
   }
   cudaStream_t st = as_stream(stream);
   if (plan->n_fine > 0) {
-    galerkin_ap_kernel<<<cdiv(plan->n_fine, GK_THREADS), GK_THREADS, smem, st>>>(
-        plan->n_fine, fine->L_ptr, fine->L_col, fine->U_ptr, fine->U_col, fine_values, fine->off_l, fine->off_d, fine->off_u,
-        us_hat->offsets, us_hat->columns, us_hat->weights, plan->t_ptr, plan->t_col, t_values);
+    RowArgs a = base_args(fine, fine_values);
+    galerkin_ap_kernel<<<cdiv(plan->n_fine, GA_ROWS), GA_THREADS, sizeof(GaSmem), st>>>(a, plan->n_fine, us_hat->offsets,
+                                                                                      us_hat->weights, plan->t_slot, plan->t_ptr,
+                                                                                      t_values);
     count_launch();
   }
   if (plan->n_coarse > 0) {
-    galerkin_rt_kernel<<<cdiv(plan->n_coarse, GK_THREADS), GK_THREADS, smem, st>>>(
-        plan->n_coarse, ut_hat->offsets, ut_hat->columns, ut_hat->weights, plan->t_ptr, plan->t_col, t_values, plan->c_ptr,
-        plan->c_col, plan->c_slot, spd, spd_value, coarse_values);
+    galerkin_rt_kernel<<<cdiv(plan->n_coarse, GA_ROWS), GA_THREADS, 0, st>>>(
+        plan->n_coarse, coarse->v2i, ut_hat->offsets, ut_hat->columns, ut_hat->weights, plan->ut_q, plan->t_ptr, t_values,
+        plan->c_slot8, plan->c_ptr, plan->c_slot, spd, spd_value, coarse_values);
     count_launch();
   }
   return check_launch("galerkin");

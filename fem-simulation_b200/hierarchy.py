@@ -329,3 +329,75 @@ def default_pins(points: np.ndarray, dx: float) -> np.ndarray:
     y = np.asarray(points, dtype=F32)[:, 1]
     thr = F32(F32(y.max() - F32(dx)) - F32(1e-5))
     return np.nonzero(y >= thr)[0].astype(np.int32)
+
+
+def build_galerkin_plan(H: Hierarchy, l: int) -> dict:
+    """Fixed patterns and slot plans of the Galerkin product A_{l+1} = Ut_hat[l] (A_l Us_hat[l]).
+
+    Replaces the symbolic half of ``bsr_mm`` (sparse.py:1018-1091), which the reference repeats every step
+    (object.py:1259).  Returns numpy arrays:
+      t_ptr/t_col   CSR pattern of T = A_l Us_hat (columns sorted)
+      c_ptr/c_col   (row,col)-sorted pattern of A_{l+1}; c_slot = its [L;D;U] slot (inverse of UtAUs_block_offset)
+      t_slot[s,p]   fine block s (in [L;D;U] slot order, column j), p-th parent J of j -> position of J in T row
+      c_slot8[t,q]  T block t = (i,J), q-th parent I of i -> position of J in the sorted row I of A_{l+1}
+      ut_q[e]       Ut_hat entry e = (I,i) -> q with parent_q(i) == I
+    """
+    import scipy.sparse as sp
+    p, pc = H.pattern[l], H.pattern[l + 1]
+    nf, nc = H.dims[l], H.dims[l + 1]
+    us, ut = H.Us_hat[l], H.Ut_hat[l]
+    A = sp.csr_matrix((np.ones(p.nnz, np.int32), (p.row, p.col)), shape=(nf, nf))
+    Pm = sp.csr_matrix((np.ones(us.nnz, np.int32), us.columns, us.offsets), shape=(nf, nc))
+    T = (A @ Pm).tocsr()
+    T.sort_indices()
+    R = sp.csr_matrix((np.ones(ut.nnz, np.int32), ut.columns, ut.offsets), shape=(nc, nf))
+    Cc = (R @ T).tocsr()
+    Cc.sort_indices()
+    # the product pattern must equal the coarse hex adjacency (block_values_reorder relies on it, object.py:1261)
+    inv = np.empty(pc.nnz, dtype=np.int64)
+    inv[pc.block_offset] = np.arange(pc.nnz)                       # sorted rank -> [L;D;U] slot
+    if Cc.nnz != pc.nnz or not np.array_equal(Cc.indices, pc.col[inv]) or not np.array_equal(
+            np.repeat(np.arange(nc), np.diff(Cc.indptr)), pc.row[inv]):
+        raise ValueError(f"Galerkin pattern of level {l + 1} differs from its hex adjacency pattern")
+    t_ptr = T.indptr.astype(np.int64)
+    t_col = T.indices.astype(np.int64)
+    c_ptr = Cc.indptr.astype(np.int64)
+    us_off = us.offsets.astype(np.int64)
+    us_col = us.columns.astype(np.int64)
+    cntp = np.diff(us_off)
+    if cntp.max(initial=0) > 8 or np.diff(t_ptr).max(initial=0) > 27 or np.diff(c_ptr).max(initial=0) > 27:
+        raise ValueError("Galerkin plan: more than 8 parents or more than 27 blocks in a row")
+    Tkeys = np.repeat(np.arange(nf, dtype=np.int64), np.diff(t_ptr)) * nc + t_col
+    Ckeys = np.repeat(np.arange(nc, dtype=np.int64), np.diff(c_ptr)) * nc + Cc.indices.astype(np.int64)
+
+    def expand(rows_of, cols_for_parents, keys_sorted, row_ptr, key_row_is_parent):
+        n = len(cols_for_parents)
+        out = np.full((n, 8), 255, dtype=np.uint8)
+        CH = 1 << 22
+        for s0 in range(0, n, CH):
+            src = cols_for_parents[s0:s0 + CH]
+            np_s = cntp[src]
+            owner = np.repeat(np.arange(len(src), dtype=np.int64), np_s)
+            pidx = np.arange(len(owner), dtype=np.int64) - np.repeat(np.cumsum(np_s) - np_s, np_s)
+            par = us_col[us_off[src[owner]] + pidx]
+            other = rows_of[s0:s0 + CH][owner]
+            if key_row_is_parent:
+                key, row = par * nc + other, par
+            else:
+                key, row = other * nc + par, other
+            pos = np.searchsorted(keys_sorted, key)
+            if not np.array_equal(keys_sorted[np.minimum(pos, len(keys_sorted) - 1)], key):
+                raise ValueError("Galerkin plan: product pattern is missing an entry")
+            out[s0 + owner, pidx] = (pos - row_ptr[row]).astype(np.uint8)
+        return out
+
+    t_slot = expand(p.row.astype(np.int64), p.col.astype(np.int64), Tkeys, t_ptr, False)
+    t_rows = np.repeat(np.arange(nf, dtype=np.int64), np.diff(t_ptr))
+    c_slot8 = expand(t_col, t_rows, Ckeys, c_ptr, True)
+    ut_rows = np.repeat(np.arange(nc, dtype=np.int64), np.diff(ut.offsets))
+    ukeys = np.repeat(np.arange(nf, dtype=np.int64), cntp) * nc + us_col
+    ut_cols = ut.columns.astype(np.int64)
+    ut_q = (np.searchsorted(ukeys, ut_cols * nc + ut_rows) - us_off[ut_cols]).astype(np.uint8)
+    return dict(n_fine=nf, n_coarse=nc, t_ptr=T.indptr.astype(np.int32), t_col=T.indices.astype(np.int32),
+                c_ptr=Cc.indptr.astype(np.int32), c_col=Cc.indices.astype(np.int32), c_slot=inv.astype(np.int32),
+                t_slot=t_slot, c_slot8=c_slot8, ut_q=ut_q)

@@ -101,7 +101,9 @@ class Object:
         for l in range(L):
             p = H.pattern[l]
             n, nh = H.dims[l], H.hexs[l].shape[0]
-            order = np.argsort(p.hex_update_offset, kind="stable").astype(np.int32)
+            order = np.argsort(p.hex_update_offset, kind="stable")
+            asm_pos = np.empty(len(order), dtype=np.int32)
+            asm_pos[order] = np.arange(len(order), dtype=np.int32)      # rank of block e*64+a*8+b in slot order
             asm_ptr = np.zeros(p.nnz + 1, dtype=np.int64)
             np.add.at(asm_ptr, p.hex_update_offset.astype(np.int64) + 1, 1)
             asm_ptr = np.cumsum(asm_ptr).astype(np.int32)
@@ -112,8 +114,10 @@ class Object:
             assert cnt.max(initial=0) <= 8, "a vertex belongs to more than 8 hexahedra"
             start = np.cumsum(cnt) - cnt
             ve[flat[o2], np.arange(len(o2)) - start[flat[o2]]] = o2.astype(np.int32)      # e*8+a
-            d = dict(L_ptr=_dev(p.L_ptr, dev), L_col=_dev(p.L_col, dev), U_ptr=_dev(p.U_ptr, dev), U_col=_dev(p.U_col, dev),
-                     asm_ptr=_dev(asm_ptr, dev), asm_src=_dev(order, dev), vert_elem=_dev(ve, dev),
+            pad = np.zeros(4, np.int32)                                  # bulk copies are rounded out to 16 bytes
+            d = dict(L_ptr=_dev(p.L_ptr, dev), L_col=_dev(np.concatenate([p.L_col, pad]), dev)[:p.L_nnz],
+                     U_ptr=_dev(p.U_ptr, dev), U_col=_dev(np.concatenate([p.U_col, pad]), dev)[:p.L_nnz],
+                     asm_ptr=_dev(asm_ptr, dev), asm_pos=_dev(asm_pos, dev), vert_elem=_dev(ve, dev),
                      invJ=torch.zeros((nh, 8, 3, 3), device=dev), detJ=torch.zeros((nh, 8), device=dev))
             self._pat.append(d)
             lv = _lib.FembLevel()
@@ -125,7 +129,7 @@ class Object:
             lv.v2i = self.dev_vertex2index[l].data_ptr()
             lv.i2v = self.dev_index2vertex[l].data_ptr()
             lv.elem2nnz = self.hex_update_offset_gpu[l].data_ptr()
-            for k in ("L_ptr", "L_col", "U_ptr", "U_col", "asm_ptr", "asm_src", "vert_elem", "invJ", "detJ"):
+            for k in ("L_ptr", "L_col", "U_ptr", "U_col", "asm_ptr", "asm_pos", "vert_elem", "invJ", "detJ"):
                 setattr(lv, k, d[k].data_ptr())
             self.levels.append(lv)
             self.inverse_pX_peps_gpu.append(d["invJ"])
@@ -179,8 +183,8 @@ class Object:
         self.diag_fixed[self.dev_vertex2index[0][self.pin_list_gpu.long()].long()] = self.control_mag
 
         # ---- matrices and work vectors (object.py:797-855) ---------------------------------------
-        self.MF_value_gpu = torch.zeros((p0.nnz, 3, 3), device=dev)
-        self.UtAUs_values = [torch.zeros((H.pattern[l].nnz, 3, 3), device=dev) for l in range(1, L)]
+        self.MF_value_gpu = self.new_values(0)
+        self.UtAUs_values = [self.new_values(l) for l in range(1, L)]
         vec = lambda i: torch.zeros((H.dims[i], 3), device=dev)
         self.dev_E = [vec(i) for i in range(L)]; self.dev_R = [vec(i) for i in range(L)]
         self.dev_P = [vec(i) for i in range(L)]; self.dev_AP = [vec(i) for i in range(L)]
@@ -227,6 +231,12 @@ class Object:
         from . import voxelize
         return voxelize.voxelize_obj(mesh_path, dx)
 
+    def new_values(self, layer):
+        """Zeroed block-value array [nnz,3,3] of a level, padded as the bulk-copy kernels require (femb200.h)."""
+        nnz = self.hierarchy.pattern[layer].nnz
+        buf = torch.zeros(nnz * 9 + 8, device=self.device)
+        return buf[:nnz * 9].view(nnz, 3, 3)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -263,33 +273,19 @@ class Object:
         return BsrView(n, n, offsets, columns, lambda: self._values(l)[inv_t.to(self.device)])
 
     def _build_galerkin_plan(self, l):
-        """Fixed patterns of T = A_l * Us_hat[l] and of A_{l+1} (replaces the symbolic half of bsr_mm,
-        sparse.py:1018-1091, which the reference repeats every step)."""
-        import scipy.sparse as sp
-        H = self.hierarchy
-        p, pc = H.pattern[l], H.pattern[l + 1]
-        nf, nc = H.dims[l], H.dims[l + 1]
-        A = sp.csr_matrix((np.ones(p.nnz, np.int32), (p.row, p.col)), shape=(nf, nf))
-        us = H.Us_hat[l]
-        Pm = sp.csr_matrix((np.ones(us.nnz, np.int32), us.columns, us.offsets), shape=(nf, nc))
-        T = (A @ Pm).tocsr()
-        T.sort_indices()
-        ut = H.Ut_hat[l]
-        R = sp.csr_matrix((np.ones(ut.nnz, np.int32), ut.columns, ut.offsets), shape=(nc, nf))
-        Cc = (R @ T).tocsr()
-        Cc.sort_indices()
-        # the product pattern must equal the coarse hex adjacency (block_values_reorder relies on it, object.py:1261)
-        inv = np.empty(pc.nnz, dtype=np.int64)
-        inv[pc.block_offset] = np.arange(pc.nnz)                       # sorted rank -> [L;D;U] slot
-        if Cc.nnz != pc.nnz or not np.array_equal(Cc.indices, pc.col[inv]):
-            raise _lib.FembError(f"Galerkin pattern of level {l + 1} differs from its hex adjacency pattern")
+        """Upload the fixed-pattern plan of A_{l+1} = Ut_hat (A_l Us_hat) (hierarchy.build_galerkin_plan)."""
+        g = hierarchy.build_galerkin_plan(self.hierarchy, l)
         dev = self.device
-        t = dict(t_ptr=_dev(T.indptr.astype(np.int32), dev), t_col=_dev(T.indices.astype(np.int32), dev),
-                 c_ptr=_dev(Cc.indptr.astype(np.int32), dev), c_col=_dev(Cc.indices.astype(np.int32), dev),
-                 c_slot=_dev(inv.astype(np.int32), dev), t_values=torch.empty(T.nnz * 9, device=dev))
-        plan = _lib.FembGalerkinPlan(nf, nc, T.nnz, t["t_ptr"].data_ptr(), t["t_col"].data_ptr(), t["c_ptr"].data_ptr(),
-                                     t["c_col"].data_ptr(), t["c_slot"].data_ptr())
-        t["plan"] = plan
+        padb = np.zeros(16, np.uint8)
+        t = dict(t_ptr=_dev(g["t_ptr"], dev), t_col=_dev(g["t_col"], dev), c_ptr=_dev(g["c_ptr"], dev),
+                 c_col=_dev(g["c_col"], dev), c_slot=_dev(g["c_slot"], dev),
+                 t_values=torch.empty(len(g["t_col"]) * 9, device=dev),
+                 t_slot=_dev(np.concatenate([g["t_slot"].reshape(-1), padb]), dev),
+                 c_slot8=_dev(g["c_slot8"].reshape(-1), dev), ut_q=_dev(g["ut_q"], dev))
+        t["plan"] = _lib.FembGalerkinPlan(g["n_fine"], g["n_coarse"], len(g["t_col"]), t["t_ptr"].data_ptr(),
+                                          t["t_col"].data_ptr(), t["c_ptr"].data_ptr(), t["c_col"].data_ptr(),
+                                          t["c_slot"].data_ptr(), t["t_slot"].data_ptr(), t["c_slot8"].data_ptr(),
+                                          t["ut_q"].data_ptr())
         return t
 
     # ------------------------------------------------------------------------------------------
@@ -458,7 +454,7 @@ class Object:
         """object.py:1252-1264 minus the rebuilds: A_i = Ut_hat (A_{i-1} Us_hat), spd_matrix33f, [L;D;U] layout."""
         for i in range(1, self.layer):
             t = self._plans[i - 1]
-            _lib.check(self.lib.femb_galerkin(C.byref(self.levels[i - 1]), self._values(i - 1).data_ptr(),
+            _lib.check(self.lib.femb_galerkin(C.byref(self.levels[i - 1]), C.byref(self.levels[i]), self._values(i - 1).data_ptr(),
                                               C.byref(self.Ut_hat[i - 1].c), C.byref(self.Us_hat[i - 1].c), C.byref(t["plan"]),
                                               t["t_values"].data_ptr(), 1, self.spd_value, self.UtAUs_values[i - 1].data_ptr(),
                                               self._stream()), "femb_galerkin")

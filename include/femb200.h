@@ -57,8 +57,8 @@ typedef struct FembLevel {
   const int* U_ptr;      /* [n_vert+1] row pointers into the U section                  */
   const int* U_col;      /* [U_nnz]  == MF_U_col / UtAUs_U_col                          */
   const int* elem2nnz;   /* [n_hex*64] == hex_update_offset[l] (object.py:563-569)      */
-  const int* asm_ptr;    /* [nnz+1]  CSR over value slots of the inverse of elem2nnz    */
-  const int* asm_src;    /* [n_hex*64] element-block ids (e*64+a*8+b) sorted by slot    */
+  const int* asm_ptr;    /* [nnz+1]  CSR over value slots of the slot-sorted blocks     */
+  const int* asm_pos;    /* [n_hex*64] rank of element block e*64+a*8+b in slot order   */
   const int* vert_elem;  /* [n_vert*8] e*8+a of the hexes incident to a vertex, -1 pad  */
   const float* invJ;     /* [n_hex*8*9] inverse_pX_peps (quai_hexagon.py:18)            */
   const float* detJ;     /* [n_hex*8]   det_pX_peps     (quai_hexagon.py:17)            */
@@ -84,7 +84,16 @@ typedef struct FembGalerkinPlan {
   const int* c_col;      /* [nnz_c]                                                      */
   const int* c_slot;     /* [nnz_c] [L;D;U] slot of each sorted block = inverse of       */
                          /*         UtAUs_block_offset (object.py:633-683)               */
+  const unsigned char* t_slot;  /* [nnz_f*8] fine block s (in [L;D;U] slot order, column j), p-th parent */
+                                /*           of j -> position of that parent in T row(s); 255 = none     */
+  const unsigned char* c_slot8; /* [t_nnz*8] T block t=(i,J), q-th parent I of i -> position of J in     */
+                                /*           the sorted row I of A_c; 255 = none                         */
+  const unsigned char* ut_q;    /* [nnz(Ut_hat)] entry (I,i) -> q with parent_q(i) == I                   */
 } FembGalerkinPlan;
+
+/* Alignment contract of the streaming kernels: block-value arrays and the L_col / U_col arrays are
+ * staged with 16-byte-granular bulk copies (cp.async.bulk), so their base must be 16-byte aligned and
+ * they must be readable up to 16 bytes past their logical end (allocate 4 extra elements). */
 
 /* ---- library ------------------------------------------------------------------------------ */
 int femb_abi_version(void);
@@ -156,9 +165,9 @@ int femb_spd_blocks(float* values, int n_blocks, float spd_value, void* stream);
 int femb_transfer_mv(const FembTransfer* t, float alpha, const float* x, float beta, float* y, void* stream);
 /* A_c = Ut_hat (A_f Us_hat), spd_matrix33f on every block (if spd != 0), written in [L;D;U] layout
  * (object.py:1259-1261).  t_values scratch [t_nnz*9]. */
-int femb_galerkin(const FembLevel* fine, const float* fine_values, const FembTransfer* ut_hat,
-                  const FembTransfer* us_hat, const FembGalerkinPlan* plan, float* t_values, int spd,
-                  float spd_value, float* coarse_values, void* stream);
+int femb_galerkin(const FembLevel* fine, const FembLevel* coarse, const float* fine_values,
+                  const FembTransfer* ut_hat, const FembTransfer* us_hat, const FembGalerkinPlan* plan,
+                  float* t_values, int spd, float spd_value, float* coarse_values, void* stream);
 
 /* ---- vectors ------------------------------------------------------------------------------- */
 int femb_axpby(int n, float a, const float* x, float b, float* y, void* stream);          /* y = a x + b y (cublas.py:160-163) */

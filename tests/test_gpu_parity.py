@@ -87,12 +87,12 @@ def test_force_energy_hessian(pair):
     e = obj.total_energy(x)
     e_ref = float(ref.total_energy(xp))
     assert abs(e - e_ref) <= 2e-5 * abs(e_ref)
-    vals = torch.zeros_like(obj.MF_value_gpu)
+    vals = obj.new_values(0)
     obj._hessian(0, x, vals, obj.diag_fixed)
     v = ref.MF_value_fixed.copy(); ref.hessian(0, xp, v)
     v64 = r64.MF_value_fixed.copy(); r64.hessian(0, x64, v64)
     close64(vals, v, v64, what="hessian [L;D;U] values")
-    f2 = torch.zeros_like(x); vals2 = torch.zeros_like(vals)
+    f2 = torch.zeros_like(x); vals2 = obj.new_values(0)
     obj._force_hessian(x, f2, vals2, obj.diag_fixed)
     g = np.zeros_like(xp); ref.force(xp, g)
     g64 = np.zeros_like(x64); r64.force(x64, g64)
@@ -100,7 +100,7 @@ def test_force_energy_hessian(pair):
     # symmetry H_ab = H_ba^T through the pattern
     if obj.layer > 1:
         x1 = torch.from_numpy(ref.x_gpu_layer[1] * np.float32(1.01)).to(obj.device)
-        v1 = torch.zeros_like(obj.UtAUs_values[0])
+        v1 = obj.new_values(1)
         obj._hessian(1, x1, v1)
         r1 = np.zeros_like(ref.UtAUs_values[0]); ref.hessian(1, ref.x_gpu_layer[1] * np.float32(1.01), r1)
         close(v1, r1, what="coarse re-discretised hessian")
@@ -236,17 +236,25 @@ def test_pinlist_and_three_levels():
 
 
 def test_convergence_curve():
-    """compare(): the sampled energy / log10 force-norm curves of both loops (object.py:1514-1598)."""
+    """compare(100): the sampled energy / |f|inf curves of both loops (object.py:1514-1598) against the golden
+    oracle curves (tests/golden/compare_cube9.npz, float32 and float64 twins of the oracle).
+    Energies and final positions: 1e-5 relative.  Force norms: the iteration is chaotic at round-off level (the
+    1e-10 cut-offs of solve3x3 switch rows on and off), so the float32 oracle itself drifts from the float64 one
+    (up to O(1) late in the FAS loop); the band is max(1e-3, 3 x running max of that oracle gap)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "compare_cube9.npz"))
     pts, hx = mesh.cube_mesh(9, 0.05)
     obj = Object((pts, hx), 0.05, [], use_graphs=True)
-    ref = ref_solvers.RefObject(pts, hx, 0.05, [])
-    obj.compare(100); ref.compare(100)
-    assert obj.plot_x == ref.plot_x and len(obj.plot_x) == 100
-    for a, b, nm in ((obj.plot_energy_newton, ref.plot_energy_newton, "E newton"), (obj.plot_energy_newtonMultigrid, ref.plot_energy_newtonMultigrid, "E fas")):
-        close(np.array(a), np.array(b, dtype=np.float64), rel=1e-5, what=nm)
-    for a, b, nm in ((obj.plot_InfNorm_newton, ref.plot_InfNorm_newton, "|f| newton"), (obj.plot_InfNorm_newtonMultigrid, ref.plot_InfNorm_newtonMultigrid, "|f| fas")):
-        fa, fb = 10.0 ** np.array(a), 10.0 ** np.array(b, dtype=np.float64)
-        assert np.all(np.abs(fa - fb) <= 1e-3 * fb + 1e-5 * fb.max()), nm
+    obj.compare(100)
+    assert obj.plot_x == gold["plot_x_f64"].tolist() and len(obj.plot_x) == 100
+    for mine, key in ((obj.plot_energy_newton, "energy_newton"), (obj.plot_energy_newtonMultigrid, "energy_fas")):
+        close(np.array(mine), gold[key + "_f64"], rel=1e-5, what=key)
+    for mine, key in ((obj.plot_InfNorm_newton, "lognorm_newton"), (obj.plot_InfNorm_newtonMultigrid, "lognorm_fas")):
+        f, f32, f64 = 10.0 ** np.array(mine), 10.0 ** gold[key + "_f32"], 10.0 ** gold[key + "_f64"]
+        band = np.maximum(1e-3, 3.0 * np.maximum.accumulate(np.abs(f32 - f64) / f64))
+        assert np.all(np.abs(f - f64) / f64 <= band), key
+        assert np.all(np.abs(f[:10] - f64[:10]) <= 1e-3 * f64[:10]), key + " (first 10 samples)"
+    close(obj.x_gpu_layer[0], gold["x_final_f64"], rel=1e-5, what="final positions")
 
 
 def test_empty_and_errors():

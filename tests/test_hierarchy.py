@@ -104,3 +104,35 @@ def test_reference_cpu_functions_match():
             else:
                 c = mine[k] % 2
                 assert int(cf.color_ind(torch.tensor(pts[k]), torch.tensor(org), sp)) == int(c[0] + 2 * c[1] + 4 * c[2])
+
+
+def test_galerkin_plan_emulation():
+    """The slot plans of hierarchy.build_galerkin_plan drive the two CUDA stages; emulate both stages in numpy
+    and compare with the oracle's bsr_mm(Ut_hat, bsr_mm(A, Us_hat)) (sparse.py:822-1140)."""
+    from oracle import ref_solvers
+    from oracle.ref_setup import bsr_from_triplets
+    points, hexs = mesh.jagged_mesh(10, 9, 11, 0.05, seed=1)
+    H = hierarchy.build_hierarchy(points, hexs, 0.05)
+    rng = np.random.default_rng(0)
+    for l in range(H.layer - 1):
+        g = hierarchy.build_galerkin_plan(H, l)
+        p, pc, us, ut = H.pattern[l], H.pattern[l + 1], H.Us_hat[l], H.Ut_hat[l]
+        vals = rng.normal(size=(p.nnz, 3, 3))
+        T = np.zeros((len(g["t_col"]), 3, 3))
+        for s in range(p.nnz):
+            i, j = p.row[s], p.col[s]
+            for pp in range(us.offsets[j + 1] - us.offsets[j]):
+                T[g["t_ptr"][i] + g["t_slot"][s, pp]] += us.weights[us.offsets[j] + pp] * vals[s]
+        out = np.zeros((pc.nnz, 3, 3))
+        for I in range(H.dims[l + 1]):
+            for e in range(ut.offsets[I], ut.offsets[I + 1]):
+                i, w, q = ut.columns[e], ut.weights[e], g["ut_q"][e]
+                for t in range(g["t_ptr"][i], g["t_ptr"][i + 1]):
+                    out[g["c_slot"][g["c_ptr"][I] + g["c_slot8"][t, q]]] += w * T[t]
+        A = bsr_from_triplets(H.dims[l], H.dims[l], p.row, p.col, vals.astype(np.float32))
+        A["values"] = A["values"].astype(np.float64)
+        Us = dict(nrow=us.nrow, ncol=us.ncol, nnz=us.nnz, offsets=us.offsets, columns=us.columns, values=us.weights.astype(np.float64))
+        Ut = dict(nrow=ut.nrow, ncol=ut.ncol, nnz=ut.nnz, offsets=ut.offsets, columns=ut.columns, values=ut.weights.astype(np.float64))
+        Cm = ref_solvers.bsr_mm(Ut, ref_solvers.bsr_mm(A, Us))
+        ref = Cm["values"][pc.block_offset]
+        assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
