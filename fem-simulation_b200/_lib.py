@@ -28,7 +28,7 @@ class FembLevel(C.Structure):
                 ("color_start", C.c_int * 9),
                 ("hex", C.c_void_p), ("v2i", C.c_void_p), ("i2v", C.c_void_p),
                 ("L_ptr", C.c_void_p), ("L_col", C.c_void_p), ("U_ptr", C.c_void_p), ("U_col", C.c_void_p),
-                ("elem2nnz", C.c_void_p), ("asm_ptr", C.c_void_p), ("asm_pos", C.c_void_p),
+                ("elem2nnz", C.c_void_p),
                 ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p)]
 
 
@@ -41,7 +41,7 @@ class FembGalerkinPlan(C.Structure):
     _fields_ = [("n_fine", C.c_int), ("n_coarse", C.c_int), ("t_nnz", C.c_int),
                 ("t_ptr", C.c_void_p), ("t_col", C.c_void_p), ("c_ptr", C.c_void_p),
                 ("c_col", C.c_void_p), ("c_slot", C.c_void_p), ("t_slot", C.c_void_p), ("c_slot8", C.c_void_p),
-                ("ut_q", C.c_void_p)]
+                ("ut_q", C.c_void_p), ("dyadic", C.c_int)]
 
 
 P = C.c_void_p

@@ -139,8 +139,7 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
 
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both
 template <int kMode>
-__global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, const int* __restrict__ asm_pos, float* __restrict__ elem_f,
-                                                           float* __restrict__ elem_k) {
+__global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
   extern __shared__ __align__(16) float smem[];
@@ -229,13 +228,12 @@ __global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, const int*
     }
   }
   if (live) {
-    // block (a,b) goes to its rank in value-slot order, so that the assembly gather streams contiguously
-    const int* pos = asm_pos + (size_t)e * 64 + sub * 8;
+    float4* dst = reinterpret_cast<float4*>(elem_k + ((size_t)e * 8 + sub) * 72);    // K[e][a][b][3][3], a = sub
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      float* dst = elem_k + (size_t)__ldg(pos + b) * 9;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) dst[k] = K[b][k];
+    for (int v = 0; v < 18; ++v) {
+      const int i0 = 4 * v;
+      dst[v] = make_float4(K[i0 / 9][i0 % 9], K[(i0 + 1) / 9][(i0 + 1) % 9], K[(i0 + 2) / 9][(i0 + 2) % 9],
+                           K[(i0 + 3) / 9][(i0 + 3) % 9]);
     }
   }
 }
@@ -248,23 +246,74 @@ static size_t element_smem() {
   return f * sizeof(float);
 }
 
-// values[slot*9+k] = sum over the element blocks mapped to `slot` (contiguous in elem_k) (+ diag_add)
-__global__ void __launch_bounds__(256) assemble_gather_kernel(long long total, const int* __restrict__ asm_ptr,
-                                                             const float* __restrict__ elem_k,
-                                                             const float* __restrict__ diag_add, int off_d, int n_vert,
-                                                             float* __restrict__ values) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int slot = (int)(t / 9);
-  const int k = (int)(t - (long long)slot * 9);
-  const int p0 = __ldg(asm_ptr + slot), p1 = __ldg(asm_ptr + slot + 1);
-  float v = 0.f;
-  if (diag_add != nullptr && (k == 0 || k == 4 || k == 8)) {
-    const int r = slot - off_d;
-    if (r >= 0 && r < n_vert) v = __ldg(diag_add + r);
+// Row-centric assembly: 32 index-order rows per CTA, 9 threads per row (one per block entry).  A row reads
+// row `a` of the element matrices of its <= 8 incident hexahedra (8 blocks = 288 contiguous, 32-byte aligned
+// bytes each), folds them into the row's <= 27 value slots through the element->nnz map and writes the row's
+// L, D and U segments.  Fixed summation order (incidence order, then b), no atomics.
+constexpr int AS_ROWS = 32;
+constexpr int AS_THREADS = AS_ROWS * 9;
+constexpr int AS_SLOTS = 28;
+__global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(int n_vert, const int* __restrict__ i2v,
+                                                                  const int* __restrict__ vert_elem,
+                                                                  const int* __restrict__ elem2nnz,
+                                                                  const int* __restrict__ L_ptr, const int* __restrict__ U_ptr,
+                                                                  int off_l, int off_d, int off_u,
+                                                                  const float* __restrict__ elem_k,
+                                                                  const float* __restrict__ diag_add, float* __restrict__ values) {
+  __shared__ float s_acc[AS_ROWS * AS_SLOTS * 9];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < AS_ROWS * AS_SLOTS * 9; i += AS_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const int rl = tid / 9, k = tid - rl * 9;
+  const int r = blockIdx.x * AS_ROWS + rl;
+  if (r >= n_vert) return;
+  const int v = __ldg(i2v + r);
+  const int lp = __ldg(L_ptr + r), nl = __ldg(L_ptr + r + 1) - lp;
+  const int up = __ldg(U_ptr + r), nu = __ldg(U_ptr + r + 1) - up;
+  float* acc = s_acc + rl * AS_SLOTS * 9 + k;
+  const bool fits = nl + 1 + nu <= AS_SLOTS;
+  if (fits) {
+    int ea[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ea[j] = __ldg(vert_elem + (size_t)v * 8 + j);
+#pragma unroll 2
+    for (int j = 0; j < 8; ++j) {
+      if (ea[j] < 0) continue;
+      const float* src = elem_k + (size_t)ea[j] * 72 + k;
+      const int* map = elem2nnz + (size_t)ea[j] * 8;
+      float kv[8];
+      int sl[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { kv[b] = __ldg(src + 9 * b); sl[b] = __ldg(map + b); }
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int s = sl[b];
+        const int loc = s < off_d ? (s - off_l - lp) : (s < off_u ? nl : nl + 1 + (s - off_u - up));
+        acc[loc * 9] += kv[b];
+      }
+    }
+    for (int loc = 0; loc < nl; ++loc) values[((size_t)off_l + lp + loc) * 9 + k] = acc[loc * 9];
+    float d = acc[nl * 9];
+    if (diag_add != nullptr && (k == 0 || k == 4 || k == 8)) d += __ldg(diag_add + r);
+    values[((size_t)off_d + r) * 9 + k] = d;
+    for (int loc = 0; loc < nu; ++loc) values[((size_t)off_u + up + loc) * 9 + k] = acc[(nl + 1 + loc) * 9];
+  } else {
+    // rows with more than 27 blocks (not produced by hexahedral lattices): one slot at a time
+    for (int part = 0; part < 3; ++part) {
+      const int cnt = part == 0 ? nl : (part == 1 ? 1 : nu);
+      for (int loc = 0; loc < cnt; ++loc) {
+        const int slot = part == 0 ? off_l + lp + loc : (part == 1 ? off_d + r : off_u + up + loc);
+        float sum = (part == 1 && diag_add != nullptr && (k == 0 || k == 4 || k == 8)) ? __ldg(diag_add + r) : 0.f;
+        for (int j = 0; j < 8; ++j) {
+          const int e8 = __ldg(vert_elem + (size_t)v * 8 + j);
+          if (e8 < 0) continue;
+          for (int b = 0; b < 8; ++b)
+            if (__ldg(elem2nnz + (size_t)e8 * 8 + b) == slot) sum += __ldg(elem_k + (size_t)e8 * 72 + 9 * b + k);
+        }
+        values[(size_t)slot * 9 + k] = sum;
+      }
+    }
   }
-  for (int p = p0; p < p1; ++p) v += __ldg(elem_k + (size_t)p * 9 + k);
-  values[t] = v;
 }
 
 // out[row] = sum of the element forces of the incident hexahedra + gravity + pin spring
@@ -437,7 +486,7 @@ static int launch_element(const FembLevel* l, const float* x, float mu, float la
     cudaFuncSetAttribute(element_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  element_kernel<kMode><<<cdiv(l->n_hex, EPB), ETHREADS, smem, st>>>(make_in(l, x, mu, la), l->asm_pos, elem_f, elem_k);
+  element_kernel<kMode><<<cdiv(l->n_hex, EPB), ETHREADS, smem, st>>>(make_in(l, x, mu, la), elem_f, elem_k);
   count_launch();
   return check_launch("element_kernel");
 }
@@ -453,11 +502,11 @@ static int launch_force_gather(const FembLevel* l, const float* x, const float* 
 }
 
 static int launch_assemble(const FembLevel* l, const float* diag_add, const float* elem_k, float* values, cudaStream_t st) {
-  const long long total = (long long)l->nnz * 9;
-  assemble_gather_kernel<<<cdiv(total, 256), 256, 0, st>>>(total, l->asm_ptr, elem_k, diag_add, l->off_d,
-                                                           l->n_vert, values);
+  assemble_rows_kernel<<<cdiv(l->n_vert, AS_ROWS), AS_THREADS, 0, st>>>(l->n_vert, l->i2v, l->vert_elem, l->elem2nnz, l->L_ptr,
+                                                                        l->U_ptr, l->off_l, l->off_d, l->off_u, elem_k, diag_add,
+                                                                        values);
   count_launch();
-  return check_launch("assemble_gather_kernel");
+  return check_launch("assemble_rows_kernel");
 }
 
 }  // namespace femb
@@ -502,7 +551,7 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add, float* elem_k,
                  float* values, void* stream) {
   FEMB_REQUIRE(lvl && x && elem_k && values, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->asm_ptr && lvl->asm_pos, "level not initialised");
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v, "level not initialised");
   if (lvl->n_hex > 0) {
     int rc = launch_element<1>(lvl, x, mu, lambda, nullptr, elem_k, as_stream(stream));
     if (rc) return rc;
@@ -515,7 +564,7 @@ int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lam
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add, float* elem_f,
                        float* elem_k, float* force_out, float* values, void* stream) {
   FEMB_REQUIRE(lvl && x && elem_f && elem_k && force_out && values, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->asm_ptr && lvl->asm_pos && lvl->vert_elem && lvl->v2i,
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->vert_elem && lvl->v2i,
                "level not initialised");
   if (lvl->n_hex > 0) {
     int rc = launch_element<2>(lvl, x, mu, lambda, elem_f, elem_k, as_stream(stream));

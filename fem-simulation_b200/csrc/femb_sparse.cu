@@ -432,6 +432,7 @@ struct GaSmem {
   alignas(8) uint64_t bar;
 };
 
+template <bool kDyadic>
 __global__ void __launch_bounds__(GA_THREADS) galerkin_ap_kernel(RowArgs a, int n_fine, const int* __restrict__ p_off,
                                                                 const float* __restrict__ p_w,
                                                                 const unsigned char* __restrict__ t_slot,
@@ -507,8 +508,18 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_ap_kernel(RowArgs a, int 
       if (staged) { v = sm.val[baseU + preU + loc * 9 + k]; j = sm.col[cbaseU + cpreU + loc]; ts = sm.tsl + tbaseU + tpreU + loc * 8; }
       else { v = __ldg(a.values + (sU + loc) * 9 + k); j = __ldg(a.U_col + U0 + loc); ts = t_slot + (sU + loc) * 8; }
     }
-    const int p0 = __ldg(p_off + j), np = __ldg(p_off + j + 1) - p0;
-    for (int p = 0; p < np; ++p) acc[(int)ts[p] * 9] += v * __ldg(p_w + p0 + p);
+    if (kDyadic) {
+      // weights 2^-e (e = 0..3) travel in bits 5-6 of the plan byte: no global load in the inner loop
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const unsigned b8 = ts[p];
+        if (b8 == 255u) break;
+        acc[(int)(b8 & 31u) * 9] += v * __int_as_float((127 - (int)(b8 >> 5)) << 23);
+      }
+    } else {
+      const int p0 = __ldg(p_off + j), np = __ldg(p_off + j + 1) - p0;
+      for (int p = 0; p < np; ++p) acc[(int)(ts[p] & 31u) * 9] += v * __ldg(p_w + p0 + p);
+    }
   }
   const int t0 = __ldg(t_ptr + i), tn = __ldg(t_ptr + i + 1) - t0;
   for (int sl = 0; sl < tn; ++sl) t_val[((size_t)t0 + sl) * 9 + k] = acc[sl * 9];
@@ -722,15 +733,19 @@ int femb_galerkin(const FembLevel* fine, const FembLevel* coarse, const float* f
   FEMB_REQUIRE(plan->t_slot && plan->c_slot8 && plan->ut_q && plan->t_ptr && plan->c_ptr && plan->c_slot, "plan not initialised");
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(galerkin_ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaSmem));
+    cudaFuncSetAttribute(galerkin_ap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaSmem));
+    cudaFuncSetAttribute(galerkin_ap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaSmem));
     configured = true;
   }
   cudaStream_t st = as_stream(stream);
   if (plan->n_fine > 0) {
     RowArgs a = base_args(fine, fine_values);
-    galerkin_ap_kernel<<<cdiv(plan->n_fine, GA_ROWS), GA_THREADS, sizeof(GaSmem), st>>>(a, plan->n_fine, us_hat->offsets,
-                                                                                      us_hat->weights, plan->t_slot, plan->t_ptr,
-                                                                                      t_values);
+    if (plan->dyadic)
+      galerkin_ap_kernel<true><<<cdiv(plan->n_fine, GA_ROWS), GA_THREADS, sizeof(GaSmem), st>>>(
+          a, plan->n_fine, us_hat->offsets, us_hat->weights, plan->t_slot, plan->t_ptr, t_values);
+    else
+      galerkin_ap_kernel<false><<<cdiv(plan->n_fine, GA_ROWS), GA_THREADS, sizeof(GaSmem), st>>>(
+          a, plan->n_fine, us_hat->offsets, us_hat->weights, plan->t_slot, plan->t_ptr, t_values);
     count_launch();
   }
   if (plan->n_coarse > 0) {

@@ -392,6 +392,15 @@ def build_galerkin_plan(H: Hierarchy, l: int) -> dict:
         return out
 
     t_slot = expand(p.row.astype(np.int64), p.col.astype(np.int64), Tkeys, t_ptr, False)
+    # dyadic interpolation weights (always the case for the reference's Us_hat) ride in bits 5-6 of the plan byte
+    expo = -np.log2(us.weights.astype(np.float64))
+    dyadic = bool(us.nnz == 0 or (np.all(expo == np.round(expo)) and expo.min() >= 0 and expo.max() <= 3))
+    if dyadic:
+        ebits = np.zeros((nf, 8), dtype=np.uint8)
+        rows_u = np.repeat(np.arange(nf, dtype=np.int64), cntp)
+        ebits[rows_u, np.arange(us.nnz, dtype=np.int64) - us_off[rows_u]] = expo.astype(np.uint8) << 5
+        valid = t_slot != 255
+        t_slot = np.where(valid, t_slot | ebits[p.col.astype(np.int64)], 255).astype(np.uint8)
     t_rows = np.repeat(np.arange(nf, dtype=np.int64), np.diff(t_ptr))
     c_slot8 = expand(t_col, t_rows, Ckeys, c_ptr, True)
     ut_rows = np.repeat(np.arange(nc, dtype=np.int64), np.diff(ut.offsets))
@@ -400,4 +409,4 @@ def build_galerkin_plan(H: Hierarchy, l: int) -> dict:
     ut_q = (np.searchsorted(ukeys, ut_cols * nc + ut_rows) - us_off[ut_cols]).astype(np.uint8)
     return dict(n_fine=nf, n_coarse=nc, t_ptr=T.indptr.astype(np.int32), t_col=T.indices.astype(np.int32),
                 c_ptr=Cc.indptr.astype(np.int32), c_col=Cc.indices.astype(np.int32), c_slot=inv.astype(np.int32),
-                t_slot=t_slot, c_slot8=c_slot8, ut_q=ut_q)
+                t_slot=t_slot, c_slot8=c_slot8, ut_q=ut_q, dyadic=dyadic)

@@ -101,12 +101,6 @@ class Object:
         for l in range(L):
             p = H.pattern[l]
             n, nh = H.dims[l], H.hexs[l].shape[0]
-            order = np.argsort(p.hex_update_offset, kind="stable")
-            asm_pos = np.empty(len(order), dtype=np.int32)
-            asm_pos[order] = np.arange(len(order), dtype=np.int32)      # rank of block e*64+a*8+b in slot order
-            asm_ptr = np.zeros(p.nnz + 1, dtype=np.int64)
-            np.add.at(asm_ptr, p.hex_update_offset.astype(np.int64) + 1, 1)
-            asm_ptr = np.cumsum(asm_ptr).astype(np.int32)
             ve = np.full((n, 8), -1, dtype=np.int32)
             flat = H.hexs[l].reshape(-1).astype(np.int64)
             o2 = np.argsort(flat, kind="stable")
@@ -117,7 +111,7 @@ class Object:
             pad = np.zeros(4, np.int32)                                  # bulk copies are rounded out to 16 bytes
             d = dict(L_ptr=_dev(p.L_ptr, dev), L_col=_dev(np.concatenate([p.L_col, pad]), dev)[:p.L_nnz],
                      U_ptr=_dev(p.U_ptr, dev), U_col=_dev(np.concatenate([p.U_col, pad]), dev)[:p.L_nnz],
-                     asm_ptr=_dev(asm_ptr, dev), asm_pos=_dev(asm_pos, dev), vert_elem=_dev(ve, dev),
+                     vert_elem=_dev(ve, dev),
                      invJ=torch.zeros((nh, 8, 3, 3), device=dev), detJ=torch.zeros((nh, 8), device=dev))
             self._pat.append(d)
             lv = _lib.FembLevel()
@@ -129,7 +123,7 @@ class Object:
             lv.v2i = self.dev_vertex2index[l].data_ptr()
             lv.i2v = self.dev_index2vertex[l].data_ptr()
             lv.elem2nnz = self.hex_update_offset_gpu[l].data_ptr()
-            for k in ("L_ptr", "L_col", "U_ptr", "U_col", "asm_ptr", "asm_pos", "vert_elem", "invJ", "detJ"):
+            for k in ("L_ptr", "L_col", "U_ptr", "U_col", "vert_elem", "invJ", "detJ"):
                 setattr(lv, k, d[k].data_ptr())
             self.levels.append(lv)
             self.inverse_pX_peps_gpu.append(d["invJ"])
@@ -285,7 +279,7 @@ class Object:
         t["plan"] = _lib.FembGalerkinPlan(g["n_fine"], g["n_coarse"], len(g["t_col"]), t["t_ptr"].data_ptr(),
                                           t["t_col"].data_ptr(), t["c_ptr"].data_ptr(), t["c_col"].data_ptr(),
                                           t["c_slot"].data_ptr(), t["t_slot"].data_ptr(), t["c_slot8"].data_ptr(),
-                                          t["ut_q"].data_ptr())
+                                          t["ut_q"].data_ptr(), int(g["dyadic"]))
         return t
 
     # ------------------------------------------------------------------------------------------

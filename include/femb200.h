@@ -57,8 +57,6 @@ typedef struct FembLevel {
   const int* U_ptr;      /* [n_vert+1] row pointers into the U section                  */
   const int* U_col;      /* [U_nnz]  == MF_U_col / UtAUs_U_col                          */
   const int* elem2nnz;   /* [n_hex*64] == hex_update_offset[l] (object.py:563-569)      */
-  const int* asm_ptr;    /* [nnz+1]  CSR over value slots of the slot-sorted blocks     */
-  const int* asm_pos;    /* [n_hex*64] rank of element block e*64+a*8+b in slot order   */
   const int* vert_elem;  /* [n_vert*8] e*8+a of the hexes incident to a vertex, -1 pad  */
   const float* invJ;     /* [n_hex*8*9] inverse_pX_peps (quai_hexagon.py:18)            */
   const float* detJ;     /* [n_hex*8]   det_pX_peps     (quai_hexagon.py:17)            */
@@ -85,10 +83,12 @@ typedef struct FembGalerkinPlan {
   const int* c_slot;     /* [nnz_c] [L;D;U] slot of each sorted block = inverse of       */
                          /*         UtAUs_block_offset (object.py:633-683)               */
   const unsigned char* t_slot;  /* [nnz_f*8] fine block s (in [L;D;U] slot order, column j), p-th parent */
-                                /*           of j -> position of that parent in T row(s); 255 = none     */
+                                /*           of j -> bits 0-4: position of that parent in T row(s),      */
+                                /*           bits 5-6: e with weight 2^-e (used if dyadic); 255 = none   */
   const unsigned char* c_slot8; /* [t_nnz*8] T block t=(i,J), q-th parent I of i -> position of J in     */
                                 /*           the sorted row I of A_c; 255 = none                         */
   const unsigned char* ut_q;    /* [nnz(Ut_hat)] entry (I,i) -> q with parent_q(i) == I                   */
+  int dyadic;                   /* 1: every Us_hat weight is 1, 1/2, 1/4 or 1/8 and is encoded in t_slot  */
 } FembGalerkinPlan;
 
 /* Alignment contract of the streaming kernels: block-value arrays and the L_col / U_col arrays are
@@ -120,7 +120,7 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
                float* out, void* stream);
 /* compute_elastic_hessian (quai_hexagon.py:69-106) + the `MF_value = MF_value_fixed` copy (object.py:1233):
  * values[slot] = sum of element blocks (+ diag_add[i]*I3 on the diagonal slot of index-order row i).
- *   elem_k scratch [n_hex*576]; diag_add [n_vert] (index order) or NULL.
+ *   elem_k scratch [n_hex*576] (element matrices K[e][a][b][3][3]); diag_add [n_vert] (index order) or NULL.
  *   If elem_f != NULL the element forces are produced by the same element pass and `force_out` is
  *   filled as in femb_force (same optional arguments). */
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add,

@@ -122,7 +122,9 @@ def test_galerkin_plan_emulation():
         for s in range(p.nnz):
             i, j = p.row[s], p.col[s]
             for pp in range(us.offsets[j + 1] - us.offsets[j]):
-                T[g["t_ptr"][i] + g["t_slot"][s, pp]] += us.weights[us.offsets[j] + pp] * vals[s]
+                b8 = int(g["t_slot"][s, pp])
+                assert g["dyadic"] and 2.0 ** -(b8 >> 5) == us.weights[us.offsets[j] + pp]
+                T[g["t_ptr"][i] + (b8 & 31)] += 2.0 ** -(b8 >> 5) * vals[s]
         out = np.zeros((pc.nnz, 3, 3))
         for I in range(H.dims[l + 1]):
             for e in range(ut.offsets[I], ut.offsets[I + 1]):
