@@ -270,13 +270,13 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(int n_vert, c
   const int v = __ldg(i2v + r);
   const int lp = __ldg(L_ptr + r), nl = __ldg(L_ptr + r + 1) - lp;
   const int up = __ldg(U_ptr + r), nu = __ldg(U_ptr + r + 1) - up;
-  float* acc = s_acc + rl * AS_SLOTS * 9 + k;
+  float* acc = s_acc + tid;                       // acc[slot][tid]: bank == lane, conflict-free for any slot pattern
   const bool fits = nl + 1 + nu <= AS_SLOTS;
   if (fits) {
     int ea[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) ea[j] = __ldg(vert_elem + (size_t)v * 8 + j);
-#pragma unroll 2
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (ea[j] < 0) continue;
       const float* src = elem_k + (size_t)ea[j] * 72 + k;
@@ -289,14 +289,14 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(int n_vert, c
       for (int b = 0; b < 8; ++b) {
         const int s = sl[b];
         const int loc = s < off_d ? (s - off_l - lp) : (s < off_u ? nl : nl + 1 + (s - off_u - up));
-        acc[loc * 9] += kv[b];
+        acc[loc * AS_THREADS] += kv[b];
       }
     }
-    for (int loc = 0; loc < nl; ++loc) values[((size_t)off_l + lp + loc) * 9 + k] = acc[loc * 9];
-    float d = acc[nl * 9];
+    for (int loc = 0; loc < nl; ++loc) values[((size_t)off_l + lp + loc) * 9 + k] = acc[loc * AS_THREADS];
+    float d = acc[nl * AS_THREADS];
     if (diag_add != nullptr && (k == 0 || k == 4 || k == 8)) d += __ldg(diag_add + r);
     values[((size_t)off_d + r) * 9 + k] = d;
-    for (int loc = 0; loc < nu; ++loc) values[((size_t)off_u + up + loc) * 9 + k] = acc[(nl + 1 + loc) * 9];
+    for (int loc = 0; loc < nu; ++loc) values[((size_t)off_u + up + loc) * 9 + k] = acc[(nl + 1 + loc) * AS_THREADS];
   } else {
     // rows with more than 27 blocks (not produced by hexahedral lattices): one slot at a time
     for (int part = 0; part < 3; ++part) {

@@ -132,32 +132,27 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
     const int ub = sm.ptr[1][rl] - U0, cntU = sm.ptr[1][rl + 1] - sm.ptr[1][rl];
     const int n = cntL + cntU;
     if (staged) {
-      for (int j = sub; j < n; j += 2 * RP_SUBS) {      // two blocks per trip: both x gathers in flight together
-        const int j1 = j + RP_SUBS;
-        const bool two = j1 < n;
-        const float* m0 = (j < cntL) ? vL + (lb + j) * 9 : vU + (ub + j - cntL) * 9;
-        const int c0 = (j < cntL) ? cLs[lb + j] : cUs[ub + j - cntL];
-        const float* m1 = m0;
-        int c1 = c0;
-        if (two) {
-          m1 = (j1 < cntL) ? vL + (lb + j1) * 9 : vU + (ub + j1 - cntL) * 9;
-          c1 = (j1 < cntL) ? cLs[lb + j1] : cUs[ub + j1 - cntL];
+      constexpr int MAXB = 7;                            // ceil(27 / RP_SUBS) blocks per thread: one trip
+      for (int j0 = sub; j0 < n; j0 += MAXB * RP_SUBS) {
+        const float* m[MAXB];
+        float xv[MAXB][3];
+#pragma unroll
+        for (int u = 0; u < MAXB; ++u) {                 // issue every x gather of this thread first
+          const int j = j0 + u * RP_SUBS;
+          const bool ok = j < n;
+          const int jj = ok ? j : j0;
+          m[u] = (jj < cntL) ? vL + (lb + jj) * 9 : vU + (ub + jj - cntL) * 9;
+          const int c = (jj < cntL) ? cLs[lb + jj] : cUs[ub + jj - cntL];
+          const float* xp = a.x + 3 * (size_t)c;
+          if (kCoherent) { xv[u][0] = __ldcg(xp); xv[u][1] = __ldcg(xp + 1); xv[u][2] = __ldcg(xp + 2); }
+          else { xv[u][0] = xp[0]; xv[u][1] = xp[1]; xv[u][2] = xp[2]; }
+          if (!ok) { xv[u][0] = 0.f; xv[u][1] = 0.f; xv[u][2] = 0.f; }
         }
-        float p0, p1, p2, q0, q1, q2;
-        if (kCoherent) {
-          p0 = __ldcg(a.x + 3 * (size_t)c0); p1 = __ldcg(a.x + 3 * (size_t)c0 + 1); p2 = __ldcg(a.x + 3 * (size_t)c0 + 2);
-          q0 = __ldcg(a.x + 3 * (size_t)c1); q1 = __ldcg(a.x + 3 * (size_t)c1 + 1); q2 = __ldcg(a.x + 3 * (size_t)c1 + 2);
-        } else {
-          p0 = a.x[3 * (size_t)c0]; p1 = a.x[3 * (size_t)c0 + 1]; p2 = a.x[3 * (size_t)c0 + 2];
-          q0 = a.x[3 * (size_t)c1]; q1 = a.x[3 * (size_t)c1 + 1]; q2 = a.x[3 * (size_t)c1 + 2];
-        }
-        acc[0] += m0[0] * p0 + m0[1] * p1 + m0[2] * p2;
-        acc[1] += m0[3] * p0 + m0[4] * p1 + m0[5] * p2;
-        acc[2] += m0[6] * p0 + m0[7] * p1 + m0[8] * p2;
-        if (two) {
-          acc[0] += m1[0] * q0 + m1[1] * q1 + m1[2] * q2;
-          acc[1] += m1[3] * q0 + m1[4] * q1 + m1[5] * q2;
-          acc[2] += m1[6] * q0 + m1[7] * q1 + m1[8] * q2;
+#pragma unroll
+        for (int u = 0; u < MAXB; ++u) {
+          acc[0] += m[u][0] * xv[u][0] + m[u][1] * xv[u][1] + m[u][2] * xv[u][2];
+          acc[1] += m[u][3] * xv[u][0] + m[u][4] * xv[u][1] + m[u][5] * xv[u][2];
+          acc[2] += m[u][6] * xv[u][0] + m[u][7] * xv[u][1] + m[u][8] * xv[u][2];
         }
       }
     } else {
@@ -491,7 +486,7 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_ap_kernel(RowArgs a, int 
   const int i = r0 + rl;
   const int lb = sm.ptr[0][rl] - L0, cntL = sm.ptr[0][rl + 1] - sm.ptr[0][rl];
   const int ub = sm.ptr[1][rl] - U0, cntU = sm.ptr[1][rl + 1] - sm.ptr[1][rl];
-  float* acc = sm.acc + rl * GA_SLOTS * 9 + k;
+  float* acc = sm.acc + tid;                      // acc[slot][tid]: bank == lane, conflict-free
   const int total = cntL + 1 + cntU;
   for (int jj = 0; jj < total; ++jj) {                       // column order: L blocks, D, U blocks
     float v;
@@ -514,15 +509,15 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_ap_kernel(RowArgs a, int 
       for (int p = 0; p < 8; ++p) {
         const unsigned b8 = ts[p];
         if (b8 == 255u) break;
-        acc[(int)(b8 & 31u) * 9] += v * __int_as_float((127 - (int)(b8 >> 5)) << 23);
+        acc[(int)(b8 & 31u) * GA_THREADS] += v * __int_as_float((127 - (int)(b8 >> 5)) << 23);
       }
     } else {
       const int p0 = __ldg(p_off + j), np = __ldg(p_off + j + 1) - p0;
-      for (int p = 0; p < np; ++p) acc[(int)(ts[p] & 31u) * 9] += v * __ldg(p_w + p0 + p);
+      for (int p = 0; p < np; ++p) acc[(int)(ts[p] & 31u) * GA_THREADS] += v * __ldg(p_w + p0 + p);
     }
   }
   const int t0 = __ldg(t_ptr + i), tn = __ldg(t_ptr + i + 1) - t0;
-  for (int sl = 0; sl < tn; ++sl) t_val[((size_t)t0 + sl) * 9 + k] = acc[sl * 9];
+  for (int sl = 0; sl < tn; ++sl) t_val[((size_t)t0 + sl) * 9 + k] = acc[sl * GA_THREADS];
 }
 
 __global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, const int* __restrict__ v2i_c,
@@ -541,7 +536,7 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, c
   const int v = blockIdx.x * GA_ROWS + rl;
   const bool live = v < n_coarse;
   int I = 0;
-  float* acc = s_acc + rl * GA_SLOTS * 9;
+  float* acc = s_acc + tid;                       // acc[slot][tid]
   if (live) {
     I = __ldg(v2i_c + v);
     for (int e = __ldg(r_off + I); e < __ldg(r_off + I + 1); ++e) {     // children of I in column order
@@ -550,7 +545,7 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, c
       const int q = ut_q[e];
       const int t1 = __ldg(t_ptr + i + 1);
       for (int t = __ldg(t_ptr + i); t < t1; ++t)
-        acc[(int)c_slot8[(size_t)t * 8 + q] * 9 + k] += w * __ldg(t_val + (size_t)t * 9 + k);
+        acc[(int)c_slot8[(size_t)t * 8 + q] * GA_THREADS] += w * __ldg(t_val + (size_t)t * 9 + k);
     }
   }
   __syncthreads();
@@ -559,7 +554,7 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, c
   for (int sl = k; sl < cn; sl += 9) {
     float m[9];
 #pragma unroll
-    for (int e = 0; e < 9; ++e) m[e] = acc[sl * 9 + e];
+    for (int e = 0; e < 9; ++e) m[e] = s_acc[sl * GA_THREADS + rl * 9 + e];
     if (spd) spd_block(m, spd_value);
     float* d = out + (size_t)__ldg(c_slot + c0 + sl) * 9;
 #pragma unroll
