@@ -25,12 +25,13 @@ namespace femb {
 constexpr int EPB = 16;            // hexahedra per CTA
 constexpr int ETHREADS = EPB * 8;  // 128 threads
 
-// per (hexahedron, Gauss point) record in shared memory, in floats
-constexpr int QP_F = 0;       // F[9]
-constexpr int QP_FFT = 9;     // det*mu * F F^T, symmetric: 00 01 02 11 12 22
-constexpr int QP_C = 15;      // cmu = det*mu, cla = det*la
-constexpr int QP_GUT = 20;    // per node b: g_b[3], u_b[3], det*S g_b[3]  -> 72 floats
-constexpr int QP_SIZE = 93;   // odd: lanes (stride 93) and hexahedra (stride 744) hit distinct banks
+// per (hexahedron, Gauss point) record in shared memory, in floats; written and read as float4:
+//   [0..5] det*mu * F F^T (symmetric: 00 01 02 11 12 22)   [6] det*mu   [7] det*la
+//   [8 + 9 b ..] per node b: g_b[3], u_b[3], det * S g_b[3]                      (72 floats)
+constexpr int QP_FFT = 0;
+constexpr int QP_C = 6;
+constexpr int QP_GUT = 8;
+constexpr int QP_SIZE = 84;   // 21 float4: 16-byte accesses of 8 consecutive lanes hit distinct banks (21 is odd)
 constexpr int FQ_SIZE = 25;   // per (hexahedron, Gauss point) nodal forces 8x3, padded
 
 struct ElemIn {
@@ -103,18 +104,17 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
     P[3 * r + 1] = F[3 * r] * S[1] + F[3 * r + 1] * S[3] + F[3 * r + 2] * S[4];
     P[3 * r + 2] = F[3 * r] * S[2] + F[3 * r + 1] * S[4] + F[3 * r + 2] * S[5];
   }
+  float R[QP_SIZE];
   if (want_rec) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) rec[QP_F + k] = F[k];
     const float cmu = det * in.mu;
-    rec[QP_FFT + 0] = cmu * (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
-    rec[QP_FFT + 1] = cmu * (F[0] * F[3] + F[1] * F[4] + F[2] * F[5]);
-    rec[QP_FFT + 2] = cmu * (F[0] * F[6] + F[1] * F[7] + F[2] * F[8]);
-    rec[QP_FFT + 3] = cmu * (F[3] * F[3] + F[4] * F[4] + F[5] * F[5]);
-    rec[QP_FFT + 4] = cmu * (F[3] * F[6] + F[4] * F[7] + F[5] * F[8]);
-    rec[QP_FFT + 5] = cmu * (F[6] * F[6] + F[7] * F[7] + F[8] * F[8]);
-    rec[QP_C + 0] = cmu;
-    rec[QP_C + 1] = det * in.la;
+    R[QP_FFT + 0] = cmu * (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
+    R[QP_FFT + 1] = cmu * (F[0] * F[3] + F[1] * F[4] + F[2] * F[5]);
+    R[QP_FFT + 2] = cmu * (F[0] * F[6] + F[1] * F[7] + F[2] * F[8]);
+    R[QP_FFT + 3] = cmu * (F[3] * F[3] + F[4] * F[4] + F[5] * F[5]);
+    R[QP_FFT + 4] = cmu * (F[3] * F[6] + F[4] * F[7] + F[5] * F[8]);
+    R[QP_FFT + 5] = cmu * (F[6] * F[6] + F[7] * F[7] + F[8] * F[8]);
+    R[QP_C + 0] = cmu;
+    R[QP_C + 1] = det * in.la;
   }
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
 #pragma unroll
     for (int r = 0; r < 3; ++r) fq[b][r] = -det * (P[3 * r] * g[0] + P[3 * r + 1] * g[1] + P[3 * r + 2] * g[2]);
     if (want_rec) {
-      float* o = rec + QP_GUT + 9 * b;
+      float* o = R + QP_GUT + 9 * b;
       o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
 #pragma unroll
       for (int r = 0; r < 3; ++r) o[3 + r] = F[3 * r] * g[0] + F[3 * r + 1] * g[1] + F[3 * r + 2] * g[2];
@@ -134,6 +134,11 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
       o[7] = det * (S[1] * g[0] + S[3] * g[1] + S[4] * g[2]);
       o[8] = det * (S[2] * g[0] + S[4] * g[1] + S[5] * g[2]);
     }
+  }
+  if (want_rec) {
+    float4* r4 = reinterpret_cast<float4*>(rec);
+#pragma unroll
+    for (int v = 0; v < 20; ++v) r4[v] = make_float4(R[4 * v], R[4 * v + 1], R[4 * v + 2], R[4 * v + 3]);
   }
 }
 
@@ -194,17 +199,22 @@ __global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, float* __r
 #pragma unroll 1
   for (int q = 0; q < 8; ++q) {
     const float* r = s_rec + ((size_t)le * 8 + q) * QP_SIZE;
-    float FFT[6];
+    float G[80];                                           // the whole Gauss-point record, 20 broadcast LDS.128
+    const float4* r4 = reinterpret_cast<const float4*>(r);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) FFT[k] = r[QP_FFT + k];
-    const float cmu = r[QP_C], cla = r[QP_C + 1];
-    const float* ga = r + QP_GUT + 9 * sub;
+    for (int v = 0; v < 20; ++v) {
+      const float4 t4 = r4[v];
+      G[4 * v] = t4.x; G[4 * v + 1] = t4.y; G[4 * v + 2] = t4.z; G[4 * v + 3] = t4.w;
+    }
+    const float* FFT = G + QP_FFT;
+    const float cmu = G[QP_C], cla = G[QP_C + 1];
+    const float* ga = r + QP_GUT + 9 * sub;                // own node: runtime index, scalar loads
     const float g_a[3] = {ga[0], ga[1], ga[2]};
     const float ua_mu[3] = {cmu * ga[3], cmu * ga[4], cmu * ga[5]};
     const float ua_la[3] = {cla * ga[3], cla * ga[4], cla * ga[5]};
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      const float* gb = r + QP_GUT + 9 * b;
+      const float* gb = G + QP_GUT + 9 * b;
       const float g_b[3] = {gb[0], gb[1], gb[2]};
       const float u_b[3] = {gb[3], gb[4], gb[5]};
       const float s1 = g_a[0] * gb[6] + g_a[1] * gb[7] + g_a[2] * gb[8];       // det * g_a . S g_b
@@ -246,12 +256,13 @@ static size_t element_smem() {
   return f * sizeof(float);
 }
 
-// Row-centric assembly: 32 index-order rows per CTA, 9 threads per row (one per block entry).  A row reads
-// row `a` of the element matrices of its <= 8 incident hexahedra (8 blocks = 288 contiguous, 32-byte aligned
-// bytes each), folds them into the row's <= 27 value slots through the element->nnz map and writes the row's
-// L, D and U segments.  Fixed summation order (incidence order, then b), no atomics.
-constexpr int AS_ROWS = 32;
-constexpr int AS_THREADS = AS_ROWS * 9;
+// Row-centric assembly, one warp per index-order row.  A row needs row `a` of the element matrices of its
+// <= 8 incident hexahedra: 8 blocks = 288 contiguous, 16-byte aligned bytes each, fetched as 18 float4 by 18
+// lanes (all 8 fetches in flight before the first is consumed).  The blocks are folded into the row's <= 27
+// value slots through the element->nnz map in shared memory (fixed order: incidence order, then b; no
+// atomics) and the row's L, D and U segments are written with coalesced stores.
+constexpr int AS_WARPS = 8;
+constexpr int AS_THREADS = AS_WARPS * 32;
 constexpr int AS_SLOTS = 28;
 __global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(int n_vert, const int* __restrict__ i2v,
                                                                   const int* __restrict__ vert_elem,
@@ -260,57 +271,77 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(int n_vert, c
                                                                   int off_l, int off_d, int off_u,
                                                                   const float* __restrict__ elem_k,
                                                                   const float* __restrict__ diag_add, float* __restrict__ values) {
-  __shared__ float s_acc[AS_ROWS * AS_SLOTS * 9];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < AS_ROWS * AS_SLOTS * 9; i += AS_THREADS) s_acc[i] = 0.f;
-  __syncthreads();
-  const int rl = tid / 9, k = tid - rl * 9;
-  const int r = blockIdx.x * AS_ROWS + rl;
-  if (r >= n_vert) return;
+  __shared__ float s_acc[AS_WARPS][AS_SLOTS * 9 + 4];
+  __shared__ __align__(16) float s_stage[AS_WARPS][8][72];
+  __shared__ int s_loc[AS_WARPS][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.x * AS_WARPS + w;
+  if (r >= n_vert) return;                                   // warp-uniform
   const int v = __ldg(i2v + r);
   const int lp = __ldg(L_ptr + r), nl = __ldg(L_ptr + r + 1) - lp;
   const int up = __ldg(U_ptr + r), nu = __ldg(U_ptr + r + 1) - up;
-  float* acc = s_acc + tid;                       // acc[slot][tid]: bank == lane, conflict-free for any slot pattern
+  // incident hexahedra (e*8+a): lane j < 8 holds entry j
+  const int my_ea = lane < 8 ? __ldg(vert_elem + (size_t)v * 8 + lane) : -1;
+  float4 seg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ea = __shfl_sync(0xffffffffu, my_ea, j);
+    seg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ea >= 0 && lane < 18) seg[j] = __ldg(reinterpret_cast<const float4*>(elem_k + (size_t)ea * 72) + lane);
+  }
+  // local slot of every (j,b): lanes handle 2 map entries each
   const bool fits = nl + 1 + nu <= AS_SLOTS;
-  if (fits) {
-    int ea[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ea[j] = __ldg(vert_elem + (size_t)v * 8 + j);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (ea[j] < 0) continue;
-      const float* src = elem_k + (size_t)ea[j] * 72 + k;
-      const int* map = elem2nnz + (size_t)ea[j] * 8;
-      float kv[8];
-      int sl[8];
-#pragma unroll
-      for (int b = 0; b < 8; ++b) { kv[b] = __ldg(src + 9 * b); sl[b] = __ldg(map + b); }
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const int s = sl[b];
-        const int loc = s < off_d ? (s - off_l - lp) : (s < off_u ? nl : nl + 1 + (s - off_u - up));
-        acc[loc * AS_THREADS] += kv[b];
-      }
+  for (int h = 0; h < 2; ++h) {
+    const int t = lane + 32 * h, j = t >> 3, b = t & 7;
+    const int ea = __shfl_sync(0xffffffffu, my_ea, j);
+    int loc = -1;
+    if (ea >= 0) {
+      const int s = __ldg(elem2nnz + (size_t)ea * 8 + b);
+      loc = s < off_d ? (s - off_l - lp) : (s < off_u ? nl : nl + 1 + (s - off_u - up));
+      if (!fits) loc = s;                                    // oversized rows keep the global slot (slow path below)
     }
-    for (int loc = 0; loc < nl; ++loc) values[((size_t)off_l + lp + loc) * 9 + k] = acc[loc * AS_THREADS];
-    float d = acc[nl * AS_THREADS];
-    if (diag_add != nullptr && (k == 0 || k == 4 || k == 8)) d += __ldg(diag_add + r);
-    values[((size_t)off_d + r) * 9 + k] = d;
-    for (int loc = 0; loc < nu; ++loc) values[((size_t)off_u + up + loc) * 9 + k] = acc[(nl + 1 + loc) * AS_THREADS];
+    s_loc[w][t] = loc;
+  }
+  for (int i = lane; i < AS_SLOTS * 9; i += 32) s_acc[w][i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (lane < 18) *reinterpret_cast<float4*>(&s_stage[w][j][4 * lane]) = seg[j];
+  __syncwarp();
+  if (fits) {
+    for (int j = 0; j < 8; ++j) {
+      if (s_loc[w][8 * j] < 0) continue;                     // hexahedron slot unused (boundary vertex); warp-uniform
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        const int t = lane + 32 * h;
+        if (t < 72) {
+          const int b = t / 9, k = t - 9 * b;
+          s_acc[w][s_loc[w][8 * j + b] * 9 + k] += s_stage[w][j][t];
+        }
+      }
+      __syncwarp();
+    }
+    float* outL = values + ((size_t)off_l + lp) * 9;
+    for (int i = lane; i < nl * 9; i += 32) outL[i] = s_acc[w][i];
+    if (lane < 9) {
+      float d = s_acc[w][nl * 9 + lane];
+      if (diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) d += __ldg(diag_add + r);
+      values[((size_t)off_d + r) * 9 + lane] = d;
+    }
+    float* outU = values + ((size_t)off_u + up) * 9;
+    for (int i = lane; i < nu * 9; i += 32) outU[i] = s_acc[w][(nl + 1) * 9 + i];
   } else {
     // rows with more than 27 blocks (not produced by hexahedral lattices): one slot at a time
     for (int part = 0; part < 3; ++part) {
       const int cnt = part == 0 ? nl : (part == 1 ? 1 : nu);
-      for (int loc = 0; loc < cnt; ++loc) {
-        const int slot = part == 0 ? off_l + lp + loc : (part == 1 ? off_d + r : off_u + up + loc);
-        float sum = (part == 1 && diag_add != nullptr && (k == 0 || k == 4 || k == 8)) ? __ldg(diag_add + r) : 0.f;
-        for (int j = 0; j < 8; ++j) {
-          const int e8 = __ldg(vert_elem + (size_t)v * 8 + j);
-          if (e8 < 0) continue;
-          for (int b = 0; b < 8; ++b)
-            if (__ldg(elem2nnz + (size_t)e8 * 8 + b) == slot) sum += __ldg(elem_k + (size_t)e8 * 72 + 9 * b + k);
+      for (int li = 0; li < cnt; ++li) {
+        const int slot = part == 0 ? off_l + lp + li : (part == 1 ? off_d + r : off_u + up + li);
+        if (lane < 9) {
+          float sum = (part == 1 && diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) ? __ldg(diag_add + r) : 0.f;
+          for (int t = 0; t < 64; ++t)
+            if (s_loc[w][t] == slot) sum += s_stage[w][t >> 3][(t & 7) * 9 + lane];
+          values[(size_t)slot * 9 + lane] = sum;
         }
-        values[(size_t)slot * 9 + k] = sum;
       }
     }
   }
@@ -502,7 +533,7 @@ static int launch_force_gather(const FembLevel* l, const float* x, const float* 
 }
 
 static int launch_assemble(const FembLevel* l, const float* diag_add, const float* elem_k, float* values, cudaStream_t st) {
-  assemble_rows_kernel<<<cdiv(l->n_vert, AS_ROWS), AS_THREADS, 0, st>>>(l->n_vert, l->i2v, l->vert_elem, l->elem2nnz, l->L_ptr,
+  assemble_rows_kernel<<<cdiv(l->n_vert, AS_WARPS), AS_THREADS, 0, st>>>(l->n_vert, l->i2v, l->vert_elem, l->elem2nnz, l->L_ptr,
                                                                         l->U_ptr, l->off_l, l->off_d, l->off_u, elem_k, diag_add,
                                                                         values);
   count_launch();

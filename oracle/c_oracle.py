@@ -1,0 +1,171 @@
+"""ORACLE (test / CPU-baseline infrastructure only): ctypes driver of oracle/femb_oracle.c.
+
+Builds an ``OrcCtx`` from the numpy arrays of a hierarchy (the same integer maps the product uses -- they
+are validated bit-exactly against oracle/ref_setup.py) and rest data computed by the numpy oracle, and runs
+whole Newton-multigrid / FASv3 steps on the host cores.  Only tests/, __graft_entry__ and bench.py's
+CPU-baseline legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+P = C.c_void_p
+
+
+class OrcLevel(C.Structure):
+    _fields_ = [("n_vert", C.c_int), ("n_hex", C.c_int), ("nnz", C.c_int), ("off_l", C.c_int), ("off_d", C.c_int),
+                ("off_u", C.c_int), ("color_start", C.c_int * 9), ("hex", P), ("v2i", P), ("i2v", P), ("L_ptr", P),
+                ("L_col", P), ("U_ptr", P), ("U_col", P), ("elem2nnz", P), ("invJ", P), ("detJ", P), ("mass", P),
+                ("values", P), ("B", P), ("B_fixed", P), ("delta_x", P), ("x_solved", P), ("R", P)]
+
+
+class OrcCsr(C.Structure):
+    _fields_ = [("nrow", C.c_int), ("ncol", C.c_int), ("nnz", C.c_int), ("offsets", P), ("columns", P), ("weights", P)]
+
+
+class OrcPlan(C.Structure):
+    _fields_ = [("t_nnz", C.c_int), ("t_ptr", P), ("t_col", P), ("c_ptr", P), ("c_col", P), ("c_slot", P), ("t_val", P),
+                ("c_val", P)]
+
+
+class OrcCtx(C.Structure):
+    _fields_ = [("layers", C.c_int), ("lv", C.POINTER(OrcLevel)), ("Ut_hat", C.POINTER(OrcCsr)), ("Us_hat", C.POINTER(OrcCsr)),
+                ("Ut_noOrder", C.POINTER(OrcCsr)), ("Ut_noOrder_hat", C.POINTER(OrcCsr)), ("plan", C.POINTER(OrcPlan)),
+                ("x", P), ("grad", P), ("pin", P), ("pin_pos", P), ("diag_fixed", P), ("mu", C.c_float), ("la", C.c_float),
+                ("g", C.c_float), ("control_mag", C.c_float), ("spd_value", C.c_float), ("sfg", C.c_float * 192)]
+
+
+_lib = None
+
+
+def load(native: bool = True):
+    """Compile (host-tuned when ``native``) and load the C oracle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    tag = "portable"
+    flags = "-O3 -fopenmp -fPIC -std=c11 -Wno-unknown-pragmas"
+    if native:
+        try:
+            cpu = [l for l in open("/proc/cpuinfo") if l.startswith("flags")][0]
+        except Exception:
+            cpu = "unknown"
+        tag = hashlib.md5(cpu.encode()).hexdigest()[:10]
+        flags += " -march=native"
+    out = os.path.join(_DIR, "_build", f"libfemb_oracle_{tag}.so")
+    src = os.path.join(_DIR, "femb_oracle.c")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.run([cc] + flags.split() + ["-shared", "-o", out, src, "-lm"], check=True)
+    lib = C.CDLL(out)
+    lib.orc_num_threads.restype = C.c_int
+    lib.orc_energy.restype = C.c_float
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(P)
+
+
+class COracle:
+    """Owns the numpy buffers behind an OrcCtx.  ``H`` is a fem_simulation_b200.hierarchy.Hierarchy (integer maps
+    only), ``rest`` a oracle.ref_solvers.RefObject-like provider of det/inv/mass/x0/pins (numpy oracle)."""
+
+    def __init__(self, H, plans, x0, det, inv, mass, pin, pin_pos, diag_fixed, mu=250.0, la=0.0, g=-4.9, control_mag=100.0,
+                 spd_value=1e-3, native=True):
+        self.lib = load(native)
+        self.keep = []
+        k = lambda a, dt: self._keep(np.ascontiguousarray(a, dtype=dt))
+        L = H.layer
+        self.L = L
+        self.levels = (OrcLevel * L)()
+        self.values, self.vec = [], []
+        for l in range(L):
+            p = H.pattern[l]
+            lv = self.levels[l]
+            lv.n_vert, lv.n_hex, lv.nnz = H.dims[l], H.hexs[l].shape[0], p.nnz
+            lv.off_l, lv.off_d, lv.off_u = p.off_l, p.off_d, p.off_u
+            for c in range(9):
+                lv.color_start[c] = H.color_vertex_num[l][c]
+            lv.hex = _p(k(H.hexs[l], np.int32)); lv.v2i = _p(k(H.vertex2index[l], np.int32)); lv.i2v = _p(k(H.index2vertex[l], np.int32))
+            lv.L_ptr = _p(k(p.L_ptr, np.int32)); lv.L_col = _p(k(p.L_col, np.int32))
+            lv.U_ptr = _p(k(p.U_ptr, np.int32)); lv.U_col = _p(k(p.U_col, np.int32))
+            lv.elem2nnz = _p(k(p.hex_update_offset, np.int32))
+            lv.invJ = _p(k(inv[l], np.float32)); lv.detJ = _p(k(det[l], np.float32)); lv.mass = _p(k(mass[l], np.float32))
+            vals = self._keep(np.zeros((p.nnz, 3, 3), np.float32)); self.values.append(vals); lv.values = _p(vals)
+            vs = {}
+            for nm in ("B", "B_fixed", "delta_x", "x_solved", "R"):
+                vs[nm] = self._keep(np.zeros((H.dims[l], 3), np.float32)); setattr(lv, nm, _p(vs[nm]))
+            self.vec.append(vs)
+
+        def csr_array(lst):
+            arr = (OrcCsr * max(len(lst), 1))()
+            for i, m in enumerate(lst):
+                arr[i].nrow, arr[i].ncol, arr[i].nnz = m.nrow, m.ncol, m.nnz
+                arr[i].offsets = _p(k(m.offsets, np.int32)); arr[i].columns = _p(k(m.columns, np.int32)); arr[i].weights = _p(k(m.weights, np.float32))
+            return arr
+        self.Ut_hat, self.Us_hat = csr_array(H.Ut_hat), csr_array(H.Us_hat)
+        self.Ut_noOrder, self.Ut_noOrder_hat = csr_array(H.Ut_noOrder), csr_array(H.Ut_noOrder_hat)
+        self.plans = (OrcPlan * max(L - 1, 1))()
+        for l in range(L - 1):
+            g_ = plans[l]
+            pl = self.plans[l]
+            pl.t_nnz = len(g_["t_col"])
+            pl.t_ptr = _p(k(g_["t_ptr"], np.int32)); pl.t_col = _p(k(g_["t_col"], np.int32))
+            pl.c_ptr = _p(k(g_["c_ptr"], np.int32)); pl.c_col = _p(k(g_["c_col"], np.int32)); pl.c_slot = _p(k(g_["c_slot"], np.int32))
+            pl.t_val = _p(self._keep(np.zeros(pl.t_nnz * 9, np.float32)))
+            pl.c_val = _p(self._keep(np.zeros(len(g_["c_col"]) * 9, np.float32)))
+        self.x = self._keep(np.ascontiguousarray(x0, np.float32).copy())
+        self.grad = self._keep(np.zeros_like(self.x))
+        ctx = OrcCtx()
+        ctx.layers = L
+        ctx.lv = C.cast(self.levels, C.POINTER(OrcLevel))
+        ctx.Ut_hat = C.cast(self.Ut_hat, C.POINTER(OrcCsr)); ctx.Us_hat = C.cast(self.Us_hat, C.POINTER(OrcCsr))
+        ctx.Ut_noOrder = C.cast(self.Ut_noOrder, C.POINTER(OrcCsr)); ctx.Ut_noOrder_hat = C.cast(self.Ut_noOrder_hat, C.POINTER(OrcCsr))
+        ctx.plan = C.cast(self.plans, C.POINTER(OrcPlan))
+        ctx.x, ctx.grad = _p(self.x), _p(self.grad)
+        ctx.pin = _p(k(pin, np.int32)); ctx.pin_pos = _p(k(pin_pos, np.float32)); ctx.diag_fixed = _p(k(diag_fixed, np.float32))
+        ctx.mu, ctx.la, ctx.g, ctx.control_mag, ctx.spd_value = mu, la, g, control_mag, spd_value
+        sfg = np.ascontiguousarray(H.shapeFuncGrad, np.float32).reshape(-1)
+        for i in range(192):
+            ctx.sfg[i] = float(sfg[i])
+        self.ctx = ctx
+
+    def _keep(self, a):
+        self.keep.append(a)
+        return a
+
+    @property
+    def threads(self):
+        return int(self.lib.orc_num_threads())
+
+    def newton_mg_step(self):
+        self.lib.orc_newton_mg_step(C.byref(self.ctx))
+
+    def fasv3_step(self):
+        self.lib.orc_fasv3_step(C.byref(self.ctx))
+
+    def force(self, x, out, with_gravity_pins=True):
+        self.lib.orc_force(C.byref(self.ctx), 0, _p(x), _p(out), 1 if with_gravity_pins else 0)
+
+    def hessian(self, level, x, values, diag_add=None):
+        self.lib.orc_hessian(C.byref(self.ctx), level, _p(x), _p(values), _p(diag_add) if diag_add is not None else None)
+
+    def energy(self, x):
+        return float(self.lib.orc_energy(C.byref(self.ctx), _p(x)))
+
+
+def from_ref(ref, H, plans, native=True):
+    """COracle whose rest data / pins come from a numpy-oracle RefObject built on the same mesh."""
+    diag = np.zeros(H.dims[0], np.float32)
+    diag[H.vertex2index[0][ref.pin_list]] = ref.control_mag
+    return COracle(H, plans, ref.S["x0"], ref.det, ref.inv, ref.m, ref.pin, ref.all_pin_pos, diag, ref.mu, ref.la, ref.g,
+                   ref.control_mag, ref.spd_value, native)

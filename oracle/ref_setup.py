@@ -68,14 +68,16 @@ def bsr_from_triplets(nrow, ncol, rows, cols, vals):
     (source absent; semantics from sparse.py:184-194 and its callers)."""
     rows = np.asarray(rows, dtype=np.int64)
     cols = np.asarray(cols, dtype=np.int64)
-    vals = np.asarray(vals, dtype=F32)
+    vals = np.asarray(vals)
+    if vals.dtype != np.float64:                      # float64 only for the oracle's float64 twin
+        vals = vals.astype(F32)
     order = np.lexsort((cols, rows))
     r, c, v = rows[order], cols[order], vals[order]
     if len(r):
         new = np.ones(len(r), dtype=bool)
         new[1:] = (r[1:] != r[:-1]) | (c[1:] != c[:-1])
         seg = np.cumsum(new) - 1
-        out_v = np.zeros((seg[-1] + 1,) + v.shape[1:], dtype=F32)
+        out_v = np.zeros((seg[-1] + 1,) + v.shape[1:], dtype=v.dtype)
         np.add.at(out_v, seg, v)
         r, c = r[new], c[new]
     else:

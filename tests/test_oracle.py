@@ -1,0 +1,165 @@
+"""CPU: the oracle against mathematics and against itself.
+
+The reference ships no tests or golden vectors; the numpy oracle is therefore checked with the
+identities the reference's own derivation implies (force = -dE/dx, Hessian = -d force/dx, H_ab = H_ba^T,
+Galerkin product vs dense triple product, Gauss-Seidel sweep vs a dense triangular solve), its float32 path
+against its float64 twin, and the independent C restatement (oracle/femb_oracle.c) against the numpy one.
+"""
+import numpy as np
+import pytest
+
+from fem_simulation_b200 import hierarchy, mesh
+from oracle import ref_kernels as K
+from oracle import ref_solvers
+
+
+@pytest.fixture(scope="module")
+def small():
+    pts, hx = mesh.jagged_mesh(10, 9, 11, 0.05, seed=1)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [], dtype=np.float64)
+    rng = np.random.default_rng(0)
+    x = ref.x_gpu_layer[0] + rng.normal(size=ref.x_gpu_layer[0].shape) * 0.003
+    return ref, x
+
+
+def test_force_is_minus_energy_gradient(small):
+    ref, x = small
+    g = np.zeros_like(x); ref.force(x, g)                       # index order
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        d = rng.normal(size=x.shape)
+        eps = 1e-6
+        fd = (ref.total_energy(x + eps * d) - ref.total_energy(x - eps * d)) / (2 * eps)
+        an = -(g[ref.v2i[0]] * d).sum()
+        assert abs(fd - an) <= 1e-6 * max(1.0, abs(an))
+
+
+def test_hessian_is_minus_force_jacobian_and_symmetric(small):
+    ref, x = small
+    p = ref.pat[0]
+    vals = np.zeros_like(ref.MF_value); ref.hessian(0, x, vals)
+    rng = np.random.default_rng(2)
+    d = rng.normal(size=x.shape)                                # vertex order
+    d_idx = np.zeros_like(d); d_idx[ref.v2i[0]] = d
+    Hd = np.zeros_like(d)
+    np.add.at(Hd, p["row"], np.einsum("nij,nj->ni", vals, d_idx[p["col"]]))
+    eps = 1e-6
+    f1 = np.zeros_like(x); K.elastic_force(x + eps * d, ref.hexs[0], ref.v2i[0], ref.sfg, ref.det[0], ref.inv[0], ref.mu, ref.la, f1, np.float64)
+    f0 = np.zeros_like(x); K.elastic_force(x - eps * d, ref.hexs[0], ref.v2i[0], ref.sfg, ref.det[0], ref.inv[0], ref.mu, ref.la, f0, np.float64)
+    fd = -(f1 - f0) / (2 * eps)
+    assert np.abs(fd - Hd).max() <= 1e-6 * np.abs(Hd).max()
+    # symmetry through the pattern: block (r,c) == block (c,r)^T
+    n = ref.dims[0]
+    key = p["row"].astype(np.int64) * n + p["col"]
+    tkey = p["col"].astype(np.int64) * n + p["row"]
+    order = np.argsort(key); pos = order[np.searchsorted(key[order], tkey)]
+    assert np.abs(vals - np.swapaxes(vals[pos], 1, 2)).max() <= 1e-12 * np.abs(vals).max()
+
+
+def test_closed_form_block_matches_literal_chain(small):
+    """The closed form the CUDA kernel uses (femb_element.cu) vs the literal dF/dE/dP chain of quai_hexagon.py:86-106."""
+    ref, x = small
+    hx = ref.hexs[0][:64]
+    mu, la = 250.0, 30.0
+    for e0, blocks in K.elastic_hessian_blocks(x, hx, ref.sfg, ref.det[0][:64], ref.inv[0][:64], mu, la, np.float64):
+        F, E = K._FE(x, hx, ref.sfg, ref.inv[0][:64])
+        trE = np.trace(E, axis1=-2, axis2=-1)
+        S = 2 * mu * E + la * trE[..., None, None] * np.eye(3)
+        g = np.einsum("bqk,eqkj->eqbj", ref.sfg, ref.inv[0][:64])
+        u = np.einsum("eqij,eqbj->eqbi", F, g)
+        t = np.einsum("eqij,eqbj->eqbi", S, g)
+        FFT = F @ np.swapaxes(F, -1, -2)
+        det = ref.det[0][:64]
+        s1 = np.einsum("eqaj,eqbj->eqab", g, t)
+        s2 = np.einsum("eqaj,eqbj->eqab", g, g)
+        blk = (s1[..., None, None] * np.eye(3) + mu * s2[..., None, None] * FFT[:, :, None, None]
+               + mu * np.einsum("eqbj,eqai->eqabji", u, u) + la * np.einsum("eqaj,eqbi->eqabji", u, u))
+        blk = (blk * det[:, :, None, None, None, None]).sum(axis=1)
+        assert np.abs(blk - blocks).max() <= 1e-12 * np.abs(blocks).max()
+
+
+def test_gauss_seidel_equals_triangular_solves(small):
+    """One symmetric sweep == (D+U) dx1 = b ; (D+L) dx2 = b - U dx1 with the block diagonal inverted exactly."""
+    ref, x = small
+    ref.MF_value[...] = ref.MF_value_fixed; ref.hessian(0, x, ref.MF_value)
+    ref.set_LUD(0)
+    p = ref.pat[0]; n = ref.dims[0]
+    rng = np.random.default_rng(3)
+    b = rng.normal(size=(n, 3)) * 1e3          # large rhs: the 1e-10 cut-offs of solve3x3 (cublas.py:67-86) are negligible
+    ref.dev_B_fixed[0][...] = b
+    ref.PerformGaussSeidel(0, 1)
+    A = np.zeros((3 * n, 3 * n))
+    for s in range(p["nnz"]):
+        r, c = p["row"][s], p["col"][s]
+        A[3 * r:3 * r + 3, 3 * c:3 * c + 3] = ref.MF_value[s]
+    blk = np.kron(np.arange(n)[:, None] >= np.arange(n)[None, :], np.ones((3, 3), bool))      # block lower incl. diagonal
+    DL, DU = np.where(blk, A, 0.0), np.where(blk.T, A, 0.0)
+    U, L = A - DL, A - DU
+    dx1 = np.linalg.solve(DU, b.reshape(-1))
+    dx2 = np.linalg.solve(DL, b.reshape(-1) - U @ dx1)
+    assert np.abs(ref.dev_delta_x[0].reshape(-1) - dx2).max() <= 1e-6 * np.abs(dx2).max()
+    assert L.shape == A.shape
+
+
+def test_galerkin_equals_dense_triple_product(small):
+    ref, x = small
+    ref.MF_value[...] = ref.MF_value_fixed; ref.hessian(0, x, ref.MF_value)
+    spd = K.spd_matrix33f
+    K.spd_matrix33f = lambda blocks, value: blocks            # isolate the triple product from the eigen-clamp
+    try:
+        ref.galerkin()
+    finally:
+        K.spd_matrix33f = spd
+    p, pc = ref.pat[0], ref.pat[1]
+    n, nc = ref.dims[0], ref.dims[1]
+    A = np.zeros((3 * n, 3 * n))
+    for s in range(p["nnz"]):
+        A[3 * p["row"][s]:3 * p["row"][s] + 3, 3 * p["col"][s]:3 * p["col"][s] + 3] = ref.MF_value[s]
+    P = np.zeros((3 * n, 3 * nc))
+    us = ref.Us_hat[0]
+    rows = np.repeat(np.arange(us["nrow"]), np.diff(us["offsets"]))
+    for r, c, w in zip(rows, us["columns"], us["values"]):
+        P[3 * r:3 * r + 3, 3 * c:3 * c + 3] = w * np.eye(3)
+    Ac = P.T @ A @ P
+    for s in range(pc["nnz"]):
+        r, c = pc["row"][s], pc["col"][s]
+        assert np.abs(Ac[3 * r:3 * r + 3, 3 * c:3 * c + 3] - ref.UtAUs_values[0][s]).max() <= 1e-10 * np.abs(Ac).max()
+
+
+def test_spd_matrix33f_on_symmetric_blocks():
+    """On symmetric blocks the restated eig3 must reproduce the block when it is SPD and clamp negative eigenvalues."""
+    rng = np.random.default_rng(4)
+    M = rng.normal(size=(200, 3, 3))
+    S = M @ np.swapaxes(M, 1, 2) + 0.1 * np.eye(3)
+    out = K.spd_matrix33f(S, 1e-3)
+    assert np.abs(out - S).max() <= 5e-3 * np.abs(S).max()     # 4 approximate-Givens sweeps: not exact (McAdams 2011)
+    N = -S
+    out = K.spd_matrix33f(N, 1e-3)
+    w = np.linalg.eigvalsh(out)
+    assert w.min() >= -1e-9 and np.abs(w - 1e-3).max() <= 1e-6
+
+
+def test_fp32_oracle_tracks_fp64_twin():
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    r32 = ref_solvers.RefObject(pts, hx, 0.05, [])
+    r64 = ref_solvers.RefObject(pts, hx, 0.05, [], dtype=np.float64, setup=r32.S)
+    r32.NewtonMultigrid(2); r64.NewtonMultigrid(2)
+    a, b = r32.x_gpu_layer[0], r64.x_gpu_layer[0]
+    assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+    assert r32.not_spd == 0
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import c_oracle
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    H = hierarchy.build_hierarchy(pts, hx, 0.05)
+    plans = [hierarchy.build_galerkin_plan(H, l) for l in range(H.layer - 1)]
+    for method, step in (("NewtonMultigrid", "newton_mg_step"), ("FASv3", "fasv3_step")):
+        ref = ref_solvers.RefObject(pts, hx, 0.05, [])
+        co = c_oracle.from_ref(ref, H, plans, native=False)
+        for _ in range(2):
+            getattr(co, step)()
+        getattr(ref, method)(2)
+        assert np.abs(co.x - ref.x_gpu_layer[0]).max() <= 1e-6 * np.abs(ref.x_gpu_layer[0]).max()
+        disp = ref.x_gpu_layer[0] - ref.S["x0"]
+        assert np.abs((co.x - ref.S["x0"]) - disp).max() <= 1e-3 * np.abs(disp).max()
