@@ -169,3 +169,30 @@ def from_ref(ref, H, plans, native=True):
     diag[H.vertex2index[0][ref.pin_list]] = ref.control_mag
     return COracle(H, plans, ref.S["x0"], ref.det, ref.inv, ref.m, ref.pin, ref.all_pin_pos, diag, ref.mu, ref.la, ref.g,
                    ref.control_mag, ref.spd_value, native)
+
+
+def from_hierarchy(H, plans, points, dx, pin_list=None, mu=250.0, la=0.0, g=-4.9, control_mag=100.0, spd_value=1e-3,
+                   native=True):
+    """COracle for meshes too large for the literal setup of oracle/ref_setup.py: integer maps come from the
+    vectorised hierarchy (bit-exact with the literal one, tests/test_hierarchy.py), rest data from the numpy
+    restatement of prepare_kernal / Sum_8 / prepare_mass (oracle/ref_kernels.py)."""
+    from . import ref_kernels as K
+    x0 = np.ascontiguousarray(points, np.float32)
+    xs = [x0]
+    for l in range(1, H.layer):                               # object.py:730-731
+        m = H.Ut_noOrder[l - 1]
+        y = np.zeros((m.nrow, 3), np.float32)
+        np.add.at(y, m.rows(), m.weights[:, None] * xs[l - 1][m.columns])
+        xs.append(y)
+    det, inv, mass = [], [], []
+    sfg = H.shapeFuncGrad
+    for l in range(H.layer):                                  # object.py:756-759
+        d, iv = K.prepare_kernal(xs[l], H.hexs[l], sfg)
+        det.append(d); inv.append(iv)
+        mass.append(K.prepare_mass(K.sum_8(d), H.hexs[l], H.dims[l]))
+    if pin_list is None:
+        y = x0[:, 1]
+        pin_list = np.nonzero(y >= np.float32(np.float32(y.max() - np.float32(dx)) - np.float32(1e-5)))[0]
+    pin = np.zeros(H.dims[0], np.int32); pin[pin_list] = 1
+    diag = np.zeros(H.dims[0], np.float32); diag[H.vertex2index[0][pin_list]] = control_mag
+    return COracle(H, plans, x0, det, inv, mass, pin, x0, diag, mu, la, g, control_mag, spd_value, native)
