@@ -36,10 +36,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=100, help="voxels per cube edge (100 -> 1 M hexahedra)")
-    ap.add_argument("--method", default="nmg", choices=["nmg", "fasv3"])
+    ap.add_argument("--method", default="fasv3", choices=["nmg", "fasv3"],
+                    help="fasv3 (BASELINE configs[4], the mesh-partitioned series) or nmg (Newton-multigrid, 1 GPU only)")
     ap.add_argument("--layers", type=int, default=0, help="0 = the reference's level-count formula")
     ap.add_argument("--cpu-n", type=int, default=0, help="cube edge of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nmg", action="store_true", help="skip the extra Newton-multigrid timing at N=1")
     return ap.parse_args()
 
 
@@ -140,42 +142,58 @@ def run_ours(args):
     from fem_simulation_b200 import Object, _lib
     lib = _lib.load()
     n = args.n
+    method = args.method
+    if world > 1 and method != "fasv3":
+        raise SystemExit("the mesh-partitioned path implements the FASv3 step (BASELINE configs[4]); use --method fasv3")
     t0 = time.time()
-    obj = Object(f"cube:{n}", 1.0 / n, [], device=str(dev), layers=(args.layers or None), use_graphs=True)
+    if world > 1:
+        # weak scaling: every rank owns an n x n x n block of an n x n x (n*world) box, cut into z-slabs
+        from fem_simulation_b200.distributed import SlabObject
+        so = SlabObject(n, n, n * world, 1.0 / n, device=str(dev))
+        obj = so.obj
+        step = so.fasv3_step
+    else:
+        obj = Object(f"cube:{n}", 1.0 / n, [], device=str(dev), layers=(args.layers or None), use_graphs=True)
+        body = obj._newton_mg_body if method == "nmg" else (lambda: obj._fas_v123_body(obj.x_gpu_layer[0], False, True, True, True))
+        key = "nmg" if method == "nmg" else "fasv3"
+        step = lambda: obj._run_step(key, body)
     setup_s = time.time() - t0
-    body = obj._newton_mg_body if args.method == "nmg" else (lambda: obj._fas_v123_body(obj.x_gpu_layer[0], False, True, True, True))
-    key = "nmg" if args.method == "nmg" else "fasv3"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- warm-up (first call also captures the CUDA graph) ------------------------------------
+    def maxed(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (first call also captures the CUDA graph on the 1-GPU path) --------------------
     for _ in range(max(args.warmup, 3)):
-        obj._run_step(key, body)
+        step()
     barrier()
-    # ---- device-resident timing -------------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = lib.femb_launch_count()
-    obj.use_graphs = False
-    obj._run_step(key, body)                       # one eager step only to count this step's launches
+    if world == 1:
+        obj.use_graphs = False
+        step()                                     # one eager step only to count this step's launches
+        obj.use_graphs = True
+    else:
+        step()
     launches_per_step = lib.femb_launch_count() - l0
-    obj.use_graphs = True
     barrier()
+    # ---- device-resident timing -------------------------------------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        obj._run_step(key, body)
+        step()
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = maxed(ev0.elapsed_time(ev1))
     # ---- end-to-end: state from pinned host memory in, new state back out, every step ------------
     x_host = obj.x_gpu_layer[0].cpu().pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
@@ -183,16 +201,12 @@ def run_ours(args):
     ev0.record()
     for _ in range(args.steps):
         obj.x_gpu_layer[0].copy_(x_host, non_blocking=True)
-        obj._run_step(key, body)
+        step()
         out_host.copy_(obj.x_gpu_layer[0], non_blocking=True)
         x_host, out_host = out_host, x_host
     ev1.record()
     barrier()
-    ms_e2e = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_e2e], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    ms_e2e = maxed(ev0.elapsed_time(ev1))
     # ---- dominant kernel: the row pass inside femb_gauss_seidel on the fine level -----------------
     reps = 5
     obj.PerformGaussSeidel(0, 3)
@@ -203,6 +217,21 @@ def run_ours(args):
     ev1.record()
     torch.cuda.synchronize(dev)
     gs_ms_per_launch = ev0.elapsed_time(ev1) / (reps * 48)
+    # ---- the Newton-multigrid step as well (1 GPU): the other half of BASELINE.json's metric --------
+    nmg = None
+    if world == 1 and method == "fasv3" and not args.no_nmg:
+        for _ in range(3):
+            obj._run_step("nmg", obj._newton_mg_body)
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        for _ in range(args.steps):
+            obj._run_step("nmg", obj._newton_mg_body)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        t_nmg = ev0.elapsed_time(ev1) / args.steps
+        sbn = step_bytes(obj, "nmg")
+        nmg = {"ms_per_step": t_nmg, "steps_per_sec": 1e3 / t_nmg, "algorithmic_bytes_per_step": sbn,
+               "achieved_GBps": sbn / (t_nmg * 1e-3) / 1e9}
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
@@ -215,33 +244,43 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = gs_launch_bytes(obj) / (gs_ms_per_launch * 1e-3) / 1e9
-    sb = step_bytes(obj, args.method)
+    sb = step_bytes(obj, method)
     H = obj.hierarchy
+    hexes_per_rank = n ** 3
+    mhex = hexes_per_rank * world / 1e6
+    steps_per_s = args.steps / (ms * 1e-3)
+    if nmg is not None:
+        nmg["frac_of_peak"] = nmg["achieved_GBps"] / peak
     line = {
-        "metric": "newton_mg_steps_per_sec" if args.method == "nmg" else "fasv3_steps_per_sec",
-        "value": world * args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "metric": "fas_mg_mhex_steps_per_sec" if method == "fasv3" else "newton_mg_mhex_steps_per_sec",
+        "value": steps_per_s * mhex, "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)",
+        "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"voxel cube n={n}: {H.hexs[0].shape[0]} hexahedra, {H.dims[0]} vertices, {H.layer} levels "
-                               f"({'reference level formula' if not args.layers else 'forced'}), "
-                               f"{'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin)' if args.method == 'nmg' else 'FASv3 two-level step'}, "
-                               "mu=250 la=0 g=-4.9 k=100, default top-layer pins",
-                   "levels": H.layer, "dims": H.dims, "nnz_blocks": [p.nnz for p in H.pattern],
-                   "parallelism": f"{world} rank(s), one mesh block per rank, no exchange" if world > 1 else "single GPU",
-                   "l2": "working set (matrix values %.2f GB) >> 126 MB L2, no flush needed" % (H.pattern[0].nnz * 36 / 1e9),
-                   "setup_s": round(setup_s, 1), "timing": "CUDA events around CUDA-graph replays, max over ranks"},
-        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": H.dims[0] * 12,
-                "d2h_bytes_per_step": H.dims[0] * 12},
-        "gpu_launches": int(launches_per_step * args.steps),
-        "step_hbm": {"algorithmic_bytes_per_step": sb, "achieved_GBps": sb / (ms / args.steps * 1e-3) / 1e9,
+        "config": {"workload": (f"voxel box {n}x{n}x{n * world}: {hexes_per_rank * world} hexahedra, "
+                                f"{'FASv3 two-level quasi-static step (object.py:1467-1511)' if method == 'fasv3' else 'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin; object.py:1231-1296)'}, "
+                                "mu=250 la=0 g=-4.9 k=100, default top-layer pins"),
+                   "steps_per_sec": steps_per_s, "hexahedra": hexes_per_rank * world, "local_levels": H.layer, "local_dims": H.dims,
+                   "parallelism": (f"{world} ranks, z-slab domain decomposition ({n} cell layers + 2 overlap layers per rank), "
+                                   "NCCL neighbour halo exchange (6 per step), no all-reduce on the data path") if world > 1 else
+                                  "single GPU, CUDA-graph replay of the step body",
+                   "l2": "working set (matrix values %.2f GB per rank) >> 126 MB L2, no flush needed" % (H.pattern[0].nnz * 36 / 1e9),
+                   "setup_s": round(setup_s, 1), "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
+        "e2e": {"value": args.steps / (ms_e2e * 1e-3) * mhex, "unit": "Mhex-steps/s", "h2d_bytes_per_step": H.dims[0] * 12 * world,
+                "d2h_bytes_per_step": H.dims[0] * 12 * world},
+        "gpu_launches": int(launches_per_step * args.steps * world),
+        "step_hbm": {"algorithmic_bytes_per_step_per_rank": sb, "achieved_GBps_per_rank": sb / (ms / args.steps * 1e-3) / 1e9,
                      "frac_of_peak": sb / (ms / args.steps * 1e-3) / 1e9 / peak},
         "roofline": {"bound": "hbm", "kernel": "row_pass_kernel<GS> (femb_gauss_seidel, fine level, per colour launch)",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 118.9e6,
+                     "traffic_note": "dram__bytes_read+write per launch from profiles/r01_rowpass_tma_ncu_raw.txt (cube n=100)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "us_per_launch": gs_ms_per_launch * 1e3},
+                     "us_per_launch": gs_ms_per_launch * 1e3, "algorithmic_bytes_per_launch": gs_launch_bytes(obj)},
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if nmg is not None:
+        line["newton_mg"] = nmg
+    if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, sample_only=True)
     print(json.dumps(line))
     if world > 1:
@@ -280,14 +319,14 @@ def run_reference(args):
         return
     cb = cpu_baseline(args, steps=max(1, min(args.steps, 5)), warmup=min(args.warmup, 1))
     n = args.n
-    line = {"impl": "reference", "metric": "newton_mg_steps_per_sec" if args.method == "nmg" else "fasv3_steps_per_sec",
-            "value": cb["value"], "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": "fas_mg_mhex_steps_per_sec" if args.method == "fasv3" else "newton_mg_mhex_steps_per_sec",
+            "value": cb["value"] * (n ** 3) / 1e6, "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"voxel cube n={n}: {n ** 3} hexahedra; CPU restatement of the reference algorithm "
                                    "(the reference is GPU-only Warp code and cannot run here)"},
             "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": cb["value"] * (n ** 3) / 1e6, "unit": "Mhex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "femb_spmv": [LV, P, I, F, P, F, P, P],
     "femb_residual": [LV, P, P, P, P, P],
     "femb_gauss_seidel": [LV, P, P, P, I, P, P],
+    "femb_gs_colors": [LV, P, P, P, I, I, I, P, P],
     "femb_jacobi": [LV, P, P, P, P, I, P, P],
     "femb_cg": [LV, P, P, P, P, P, P, P, I, F, I, P],
     "femb_spd_blocks": [P, I, F, P],

@@ -643,6 +643,23 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
   return FEMB_OK;
 }
 
+int femb_gs_colors(const FembLevel* lvl, const float* values, const float* b, float* dx, int first_color, int last_color,
+                   int parts, int* not_spd, void* stream) {
+  FEMB_REQUIRE(lvl && values && b && dx, "null pointer");
+  FEMB_REQUIRE(first_color >= 0 && first_color < 8 && last_color >= 0 && last_color < 8, "colour range");
+  FEMB_REQUIRE(parts == FEMB_PART_U || parts == FEMB_PART_L || parts == (FEMB_PART_L | FEMB_PART_U), "parts");
+  RowArgs a = base_args(lvl, values);
+  a.parts = parts; a.x = dx; a.y = dx; a.b = b; a.not_spd = not_spd;
+  const int step = first_color <= last_color ? 1 : -1;
+  for (int c = first_color;; c += step) {
+    a.row_begin = lvl->color_start[c]; a.row_end = lvl->color_start[c + 1];
+    int rc = launch_rows<RM_GS>(a, as_stream(stream));
+    if (rc) return rc;
+    if (c == last_color) break;
+  }
+  return FEMB_OK;
+}
+
 int femb_jacobi(const FembLevel* lvl, const float* values, const float* b, float* dx, float* scratch, int iterations,
                 int* not_spd, void* stream) {
   FEMB_REQUIRE(lvl && values && b && dx && scratch, "null pointer");

@@ -10,8 +10,10 @@ from __future__ import annotations
 import numpy as np
 
 
-def mesh_from_mask(mask: np.ndarray, dx: float, origin=(0.0, 0.0, 0.0)):
-    """``mask[ix,iy,iz]`` (bool) marks the kept voxels.  Returns (points f32[N,3], hexagons i32[Nh,8])."""
+def mesh_from_mask(mask: np.ndarray, dx: float, origin=(0.0, 0.0, 0.0), index_offset=(0, 0, 0)):
+    """``mask[ix,iy,iz]`` (bool) marks the kept voxels.  Returns (points f32[N,3], hexagons i32[Nh,8]).
+    ``index_offset`` shifts the integer lattice coordinates before they are scaled (a slab of a larger lattice gets
+    bit-identical coordinates to the full mesh)."""
     mask = np.asarray(mask, dtype=bool)
     nx, ny, nz = mask.shape
     iz, iy, ix = np.nonzero(np.transpose(mask, (2, 1, 0)))          # x fastest, then y, then z
@@ -29,7 +31,8 @@ def mesh_from_mask(mask: np.ndarray, dx: float, origin=(0.0, 0.0, 0.0)):
     gy = (used // px) % py
     gz = used // (px * py)
     o = np.asarray(origin, dtype=np.float32)
-    points = np.stack([gx, gy, gz], axis=1).astype(np.float32) * np.float32(dx) + o
+    off = np.asarray(index_offset, dtype=np.int64)
+    points = (np.stack([gx, gy, gz], axis=1) + off).astype(np.float32) * np.float32(dx) + o
     return points.astype(np.float32), hexagons
 
 
@@ -40,8 +43,8 @@ def cube_mesh(n: int, dx: float | None = None, origin=(0.0, 0.0, 0.0)):
     return mesh_from_mask(np.ones((n, n, n), dtype=bool), dx, origin)
 
 
-def box_mesh(nx: int, ny: int, nz: int, dx: float, origin=(0.0, 0.0, 0.0)):
-    return mesh_from_mask(np.ones((nx, ny, nz), dtype=bool), dx, origin)
+def box_mesh(nx: int, ny: int, nz: int, dx: float, origin=(0.0, 0.0, 0.0), index_offset=(0, 0, 0)):
+    return mesh_from_mask(np.ones((nx, ny, nz), dtype=bool), dx, origin, index_offset)
 
 
 def jagged_mesh(nx: int, ny: int, nz: int, dx: float, seed: int = 0, keep: float = 0.8, origin=(0.0, 0.0, 0.0)):

@@ -150,6 +150,11 @@ int femb_residual(const FembLevel* lvl, const float* values, const float* b, con
  * NULL) counts the `print('not spd')` events (cublas.py:79-80). */
 int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b, float* dx, int iterations,
                       int* not_spd, void* stream);
+/* A run of colour launches of the in-place sweep above: colours first_color..last_color (descending if
+ * first > last), dx is NOT zeroed.  femb_gauss_seidel(it=1) == zero dx; colours 7..0 with parts=U; colours 0..7
+ * with parts=L|U.  Lets a caller put a halo exchange between colour groups (domain decomposition). */
+int femb_gs_colors(const FembLevel* lvl, const float* values, const float* b, float* dx, int first_color,
+                   int last_color, int parts, int* not_spd, void* stream);
 /* PerformJacobi (object.py:869-884); scratch [n_vert*3] */
 int femb_jacobi(const FembLevel* lvl, const float* values, const float* b, float* dx, float* scratch,
                 int iterations, int* not_spd, void* stream);

@@ -1,0 +1,121 @@
+"""Runs the UNMODIFIED reference class (``/root/reference/exp1/quasi_simulation/object.py``) under the shims of this
+directory and writes golden fixtures to tests/golden/ref_<case>.npz.   Build-container only (needs /root/reference).
+
+    python oracle/warp_emulator/generate_golden.py [case ...]
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/exp1/quasi_simulation"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(HERE, "shims"))          # shadows warp / sparse / pyvista / OpenGL / cuda / matplotlib
+
+_orig_to = torch.Tensor.to
+
+
+def _to(self, *a, **k):                                  # `.to('cuda:0')` -> stay on the CPU
+    if a and isinstance(a[0], str) and a[0].startswith("cuda"):
+        return self
+    return _orig_to(self, *a, **k)
+
+
+torch.Tensor.to = _to
+
+# torch has already imported the real (namespace) `cuda` package: plant the inert cudart stand-in inside it
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("cuda.cudart", os.path.join(HERE, "shims", "cuda", "cudart.py"))
+_cudart = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_cudart)
+sys.modules["cuda.cudart"] = _cudart
+if "cuda" in sys.modules:
+    sys.modules["cuda"].cudart = _cudart
+
+from fem_simulation_b200 import mesh  # noqa: E402
+
+CASES = {
+    # name: (mesh builder, dx, pinList, {method: steps})
+    "jag9": (lambda: mesh.jagged_mesh(9, 9, 10, 0.05, seed=3, keep=0.75), 0.05, [],
+             {"NewtonMultigrid": 2, "FASv3": 2, "FASv0": 1, "Newton": 2}),
+    "jag9_pin": (lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40], {"FASv2": 2, "FASv1": 1}),
+}
+
+
+def snapshot_setup(obj):
+    out = {"layer": int(obj.layer), "dims": np.array(obj.dims), "N_pin": obj.N_pin}
+    for l in range(int(obj.layer)):
+        out[f"hexs{l}"] = obj.hexs[l].numpy()
+        out[f"x{l}"] = obj.x[l].numpy()
+        out[f"v2i{l}"] = obj.dev_vertex2index[l].numpy()
+        out[f"i2v{l}"] = obj.dev_index2vertex[l].numpy()
+        out[f"cvn{l}"] = np.array(obj.color_vertex_num[l])
+        out[f"hex_update_offset{l}"] = obj.hex_update_offset_gpu[l].numpy()
+        out[f"x_gpu_layer{l}"] = obj.x_gpu_layer[l].numpy().copy()
+        out[f"det{l}"] = obj.det_pX_peps_gpu[l].numpy().copy()
+        out[f"inv{l}"] = obj.inverse_pX_peps_gpu[l].numpy().copy()
+        out[f"m{l}"] = obj.m_gpu[l].numpy().copy()
+    for l in range(int(obj.layer) - 1):
+        out[f"fine_coarse{l}"] = obj.fine_coarse[l].numpy()
+        for nm in ("Ut", "Us", "Ut_noOrder", "Us_noOrder", "Ut_hat", "Us_hat", "Ut_noOrder_hat", "Us_noOrder_hat"):
+            m = getattr(obj, nm)[l]
+            out[f"{nm}{l}_offsets"] = m.offsets.numpy()[:m.nrow + 1]
+            out[f"{nm}{l}_columns"] = m.columns.numpy()[:m.nnz]
+            out[f"{nm}{l}_values"] = m.values.numpy()[:m.nnz]
+        out[f"UtAUs_block_offset{l}"] = obj.UtAUs_block_offset[l].numpy()
+        out[f"UtAUs_GS_U_Ptr{l}"] = np.array(obj.UtAUs_GS_U_Ptr[l]); out[f"UtAUs_GS_L_Ptr{l}"] = np.array(obj.UtAUs_GS_L_Ptr[l])
+        out[f"UtAUs_L_row{l}"] = obj.UtAUs_L_row[l].numpy(); out[f"UtAUs_L_col{l}"] = obj.UtAUs_L_col[l].numpy()
+        out[f"UtAUs_U_row{l}"] = obj.UtAUs_U_row[l].numpy(); out[f"UtAUs_U_col{l}"] = obj.UtAUs_U_col[l].numpy()
+    out["MF_L_row"] = obj.MF_L_row.numpy(); out["MF_L_col"] = obj.MF_L_col.numpy()
+    out["MF_U_row"] = obj.MF_U_row.numpy(); out["MF_U_col"] = obj.MF_U_col.numpy()
+    out["MF_GS_U_Ptr"] = np.array(obj.MF_GS_U_Ptr); out["MF_GS_L_Ptr"] = np.array(obj.MF_GS_L_Ptr)
+    out["MF_GS_U_row"] = obj.MF_GS_U_row_gpu.numpy(); out["MF_GS_U_col"] = obj.MF_GS_U_col_gpu.numpy()
+    out["MF_GS_L_row"] = obj.MF_GS_L_row_gpu.numpy(); out["MF_GS_L_col"] = obj.MF_GS_L_col_gpu.numpy()
+    out["offs"] = np.array([obj.MF_nnz, obj.off_l, obj.off_d, obj.off_u])
+    out["fix_idx"] = obj.fix_idx_gpu.numpy(); out["fix_values"] = obj.fix_values_gpu.numpy()
+    out["pin"] = obj.pin_gpu.numpy(); out["pin_list"] = obj.pin_list_gpu.numpy(); out["pin_pos"] = obj.pin_pos_gpu.numpy()
+    out["MF_value_fixed"] = obj.MF_value_fixed_gpu.numpy()
+    out["shapeFuncGrad"] = obj.shapeFuncGrad_gpu.numpy()
+    return out
+
+
+def run_case(name):
+    import importlib
+    import object as ref_object                           # the reference module, unmodified
+    importlib.reload(ref_object)
+    build, dx, pins, methods = CASES[name]
+    pts, hx = build()
+    path = os.path.join(ROOT, "tests", "golden", f"_mesh_{name}.npz")
+    np.savez(path, points=pts, hexagons=hx)
+    out = {"points": pts, "hexagons": hx, "dx": dx, "pinList": np.array(pins, dtype=np.int64)}
+    for k, (method, steps) in enumerate(methods.items()):
+        t0 = time.time()
+        with contextlib.redirect_stdout(io.StringIO()):
+            obj = ref_object.Object("npz:" + path, dx, list(pins))
+            if k == 0:
+                out.update(snapshot_setup(obj))
+            getattr(obj, method)(steps)
+        xs = obj.dev_x_solved[0] if method in ("FASv0", "FASv1") else obj.x_gpu_layer[0]
+        out[f"{method}_steps"] = steps
+        out[f"{method}_x"] = xs.numpy().copy()
+        out[f"{method}_MF_value"] = obj.MF_value_gpu.numpy().copy()
+        out[f"{method}_delta_x0"] = obj.dev_delta_x[0].numpy().copy()
+        if int(obj.layer) > 1:
+            out[f"{method}_UtAUs_values0"] = obj.UtAUs_values[0].numpy().copy()
+        print(f"{name}: {method} x{steps} done in {time.time() - t0:.0f} s", flush=True)
+    os.remove(path)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"), **out)
+    print("written", name, flush=True)
+
+
+if __name__ == "__main__":
+    for c in (sys.argv[1:] or list(CASES)):
+        run_case(c)

@@ -1,0 +1,11 @@
+"""Inert stand-in for matplotlib.pyplot (the reference's compare() plots its sampled lists)."""
+
+
+class _Ax:
+    def __getattr__(self, n): return lambda *a, **k: None
+
+
+def subplots(n=1, *a, **k): return _Ax(), tuple(_Ax() for _ in range(n))
+def show(*a, **k): pass
+def plot(*a, **k): pass
+def figure(*a, **k): return _Ax()

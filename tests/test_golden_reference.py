@@ -1,0 +1,121 @@
+"""Golden vectors produced by the reference's own Python source (unmodified ``object.py`` / ``quai_hexagon.py`` /
+``cublas.py``) executed under the Warp stand-in of oracle/warp_emulator (tests/golden/README.md).
+
+CPU: pins the oracle (literal setup, numpy kernels/solvers) and the product's vectorised setup against them.
+GPU (``-m gpu``): the CUDA path through ``Object`` against the same files."""
+import os
+
+import numpy as np
+import pytest
+
+from fem_simulation_b200 import hierarchy
+from oracle import ref_solvers
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = [c for c in ("jag9", "jag9_pin") if os.path.exists(os.path.join(GOLD, f"ref_{c}.npz"))]
+INT_KEYS = ["MF_L_row", "MF_L_col", "MF_U_row", "MF_U_col", "MF_GS_U_Ptr", "MF_GS_L_Ptr", "MF_GS_U_row", "MF_GS_U_col",
+            "MF_GS_L_row", "MF_GS_L_col", "fix_idx", "pin", "pin_list"]
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module", params=CASES)
+def gold(request):
+    g = dict(np.load(os.path.join(GOLD, f"ref_{request.param}.npz")))
+    g["pins"] = [int(v) for v in g["pinList"]]
+    return g
+
+
+def test_setup_matches_reference_class(gold):
+    g = gold
+    ref = ref_solvers.RefObject(g["points"], g["hexagons"], float(g["dx"]), g["pins"])
+    H = hierarchy.build_hierarchy(g["points"], g["hexagons"], float(g["dx"]))
+    S = ref.S
+    L = int(g["layer"])
+    assert S["layer"] == L == H.layer and list(g["dims"]) == S["dims"] == H.dims
+    for l in range(L):
+        for key, mine, prod in ((f"hexs{l}", S["hexs"][l], H.hexs[l]), (f"v2i{l}", S["vertex2index"][l], H.vertex2index[l]),
+                                (f"i2v{l}", S["index2vertex"][l], H.index2vertex[l]),
+                                (f"cvn{l}", S["color_vertex_num"][l], H.color_vertex_num[l]),
+                                (f"hex_update_offset{l}", S["pattern"][l]["hex_update_offset"], H.pattern[l].hex_update_offset)):
+            assert np.array_equal(g[key], np.asarray(mine)), key
+            assert np.array_equal(g[key], np.asarray(prod)), key + " (product)"
+        assert np.array_equal(g[f"x{l}"], S["x"][l]) and np.array_equal(g[f"x{l}"], H.x[l])
+        assert rel(ref.det[l], g[f"det{l}"]) <= 1e-6 and rel(ref.inv[l], g[f"inv{l}"]) <= 1e-6 and rel(ref.m[l], g[f"m{l}"]) <= 1e-6
+    for l in range(L - 1):
+        assert np.array_equal(g[f"fine_coarse{l}"], S["fine_coarse"][l]) and np.array_equal(g[f"fine_coarse{l}"], H.fine_coarse[l])
+        for nm in ("Ut", "Us", "Ut_noOrder", "Us_noOrder", "Ut_hat", "Us_hat", "Ut_noOrder_hat", "Us_noOrder_hat"):
+            m, pm = S[nm][l], getattr(H, nm)[l]
+            assert np.array_equal(g[f"{nm}{l}_offsets"], m["offsets"]) and np.array_equal(g[f"{nm}{l}_columns"], m["columns"]), nm
+            assert np.array_equal(g[f"{nm}{l}_offsets"], pm.offsets) and np.array_equal(g[f"{nm}{l}_columns"], pm.columns), nm
+            blocks = g[f"{nm}{l}_values"]                                   # reference stores w * I3 blocks
+            assert np.array_equal(blocks, m["values"][:, None, None] * np.eye(3, dtype=np.float32)), nm + " values"
+            assert np.array_equal(blocks[:, 0, 0], pm.weights), nm + " weights (product)"
+        p = S["pattern"][l + 1]
+        q = H.pattern[l + 1]
+        for key, mine, prod in ((f"UtAUs_block_offset{l}", p["block_offset"], q.block_offset),
+                                (f"UtAUs_GS_U_Ptr{l}", p["GS_U_Ptr"], q.GS_U_Ptr), (f"UtAUs_GS_L_Ptr{l}", p["GS_L_Ptr"], q.GS_L_Ptr),
+                                (f"UtAUs_L_row{l}", p["L_row"], q.L_row), (f"UtAUs_L_col{l}", p["L_col"], q.L_col),
+                                (f"UtAUs_U_row{l}", p["U_row"], q.U_row), (f"UtAUs_U_col{l}", p["U_col"], q.U_col)):
+            assert np.array_equal(g[key], np.asarray(mine)), key
+            assert np.array_equal(g[key], np.asarray(prod)), key + " (product)"
+    p0, q0 = S["pattern"][0], H.pattern[0]
+    mine = dict(MF_L_row=p0["L_row"], MF_L_col=p0["L_col"], MF_U_row=p0["U_row"], MF_U_col=p0["U_col"], MF_GS_U_Ptr=p0["GS_U_Ptr"],
+                MF_GS_L_Ptr=p0["GS_L_Ptr"], MF_GS_U_row=p0["GS_U_row"], MF_GS_U_col=p0["GS_U_col"], MF_GS_L_row=p0["GS_L_row"],
+                MF_GS_L_col=p0["GS_L_col"], fix_idx=S["fix_idx"], pin=S["pin"], pin_list=S["pin_list"])
+    prod = dict(MF_L_row=q0.L_row, MF_L_col=q0.L_col, MF_U_row=q0.U_row, MF_U_col=q0.U_col, MF_GS_U_Ptr=q0.GS_U_Ptr,
+                MF_GS_L_Ptr=q0.GS_L_Ptr, MF_GS_U_row=q0.GS_U_row, MF_GS_U_col=q0.GS_U_col, MF_GS_L_row=q0.GS_L_row,
+                MF_GS_L_col=q0.GS_L_col, fix_idx=H.fix_idx)
+    for k in INT_KEYS:
+        assert np.array_equal(g[k], np.asarray(mine[k])), k
+        if k in prod:
+            assert np.array_equal(g[k], np.asarray(prod[k])), k + " (product)"
+    assert list(g["offs"]) == [p0["nnz"], p0["off_l"], p0["off_d"], p0["off_u"]]
+    assert np.array_equal(g["fix_values"], S["fix_values"]) and np.array_equal(g["fix_values"], H.fix_values)
+    assert np.array_equal(g["shapeFuncGrad"], S["shapeFuncGrad"]) and np.array_equal(g["shapeFuncGrad"], H.shapeFuncGrad)
+    assert np.array_equal(g["MF_value_fixed"], S["MF_value_fixed"])
+    assert np.array_equal(g["pin_pos"], S["pin_pos"])
+    for l in range(L):
+        assert rel(ref.x_gpu_layer[l] if l else S["x0"], g[f"x_gpu_layer{l}"]) <= 1e-6
+
+
+METHODS = ["NewtonMultigrid", "Newton", "FASv3", "FASv2", "FASv1", "FASv0"]
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_oracle_steps_match_reference_class(gold, method):
+    g = gold
+    if f"{method}_x" not in g:
+        pytest.skip("method not in this fixture")
+    ref = ref_solvers.RefObject(g["points"], g["hexagons"], float(g["dx"]), g["pins"])
+    getattr(ref, method)(int(g[f"{method}_steps"]))
+    x = ref.dev_x_solved[0] if method in ("FASv0", "FASv1") else ref.x_gpu_layer[0]
+    assert rel(x, g[f"{method}_x"]) <= 1e-5, "positions"
+    disp_ref = g[f"{method}_x"] - ref.S["x0"]
+    assert np.abs((x - ref.S["x0"]) - disp_ref).max() <= 2e-3 * np.abs(disp_ref).max(), "displacement"
+    assert rel(ref.MF_value, g[f"{method}_MF_value"]) <= 1e-5, "MF_value"
+    assert rel(ref.dev_delta_x[0], g[f"{method}_delta_x0"]) <= 2e-3, "delta_x"
+    if f"{method}_UtAUs_values0" in g:
+        assert rel(ref.UtAUs_values[0], g[f"{method}_UtAUs_values0"]) <= 2e-5, "coarse operator"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", METHODS)
+def test_cuda_steps_match_reference_class(gold, method):
+    torch = pytest.importorskip("torch")
+    from fem_simulation_b200 import Object
+    g = gold
+    if f"{method}_x" not in g:
+        pytest.skip("method not in this fixture")
+    obj = Object((g["points"], g["hexagons"]), float(g["dx"]), g["pins"])
+    getattr(obj, method)(int(g[f"{method}_steps"]))
+    x = (obj.dev_x_solved[0] if method in ("FASv0", "FASv1") else obj.x_gpu_layer[0]).cpu().numpy()
+    assert rel(x, g[f"{method}_x"]) <= 1e-5, "positions"
+    x0 = obj.x_cpu.numpy()
+    disp_ref = g[f"{method}_x"] - x0
+    assert np.abs((x - x0) - disp_ref).max() <= 2e-3 * np.abs(disp_ref).max(), "displacement"
+    assert rel(obj.MF_value_gpu.cpu().numpy(), g[f"{method}_MF_value"]) <= 1e-5, "MF_value"
+    if f"{method}_UtAUs_values0" in g and obj.layer > 1:
+        assert rel(obj.UtAUs_values[0].cpu().numpy(), g[f"{method}_UtAUs_values0"]) <= 2e-5, "coarse operator"
