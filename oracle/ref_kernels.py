@@ -218,10 +218,10 @@ def _approx_givens(a11, a12, a22):
     sh = a12
     t = a11.dtype.type
     b = t(_GAMMA) * sh * sh < ch * ch
-    with np.errstate(divide="ignore", invalid="ignore"):
+    with np.errstate(divide="ignore", invalid="ignore"):     # ch = sh = 0: w = inf, the select takes the constants
         w = t(1.0) / np.sqrt(ch * ch + sh * sh)
-    ch = np.where(b, w * ch, t(_CSTAR))
-    sh = np.where(b, w * sh, t(_SSTAR))
+        ch = np.where(b, w * ch, t(_CSTAR))
+        sh = np.where(b, w * sh, t(_SSTAR))
     return ch, sh
 
 

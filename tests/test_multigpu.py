@@ -3,7 +3,8 @@
 CPU (gloo, world_size 2): slab bookkeeping and halo plans -- every global vertex has exactly one owner, the send /
 recv lists of neighbouring ranks match entry by entry (fine and coarse level, vertex and index ordering), the local
 colouring / coarse cells coincide with the global ones.
-GPU (``-m gpu``, needs >= 2 GPUs, NCCL): the distributed FASv3 step reproduces the single-GPU step bit for bit."""
+GPU (``-m gpu``, needs >= 2 GPUs, NCCL): the distributed FASv3 step reproduces the single-GPU step up to summation-order
+round-off (the local coarse numbering orders the <= 8 parents of a fine vertex differently in the prolongation sum)."""
 import os
 import socket
 
@@ -147,4 +148,6 @@ def test_distributed_fasv3_matches_single_gpu():
         x[ids] = xs
         assert abs(fn - fref) <= 1e-6 * fref
     assert not np.isnan(x).any()
-    assert np.array_equal(x, xref), f"max diff {np.abs(x - xref).max():.3e}"
+    assert np.abs(x - xref).max() <= 1e-6 * np.abs(xref).max(), f"max diff {np.abs(x - xref).max():.3e}"
+    disp = xref - pts
+    assert np.abs((x - pts) - disp).max() <= 1e-4 * np.abs(disp).max()
