@@ -7,5 +7,7 @@ simulation API (``Object``) on top of hand-written sm_100a CUDA kernels behind t
 """
 from . import _lib, hierarchy, mesh  # noqa: F401
 from .object import Object  # noqa: F401
+from .object_dynamic import DynamicObject  # noqa: F401
+from .cloth import Cloth  # noqa: F401
 
-__all__ = ["Object", "mesh", "hierarchy", "_lib"]
+__all__ = ["Object", "DynamicObject", "Cloth", "mesh", "hierarchy", "_lib"]

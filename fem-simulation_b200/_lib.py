@@ -12,7 +12,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libfemb200.so")
-SOURCES = ["femb_api.cu", "femb_element.cu", "femb_sparse.cu"]
+SOURCES = ["femb_api.cu", "femb_element.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -72,6 +72,14 @@ PROTOTYPES = {
     "femb_spd_blocks": [P, I, F, P],
     "femb_transfer_mv": [TR, F, P, F, P, P],
     "femb_galerkin": [LV, LV, P, TR, TR, GP, P, I, F, P, P],
+    "femb_dyn_begin": [I, P, P, P, P, P, P, P, C.POINTER(C.c_float), F, F, P],
+    "femb_dyn_diag": [LV, P, P, P, F, F, P, P],
+    "femb_dyn_force": [LV, P, P, P, P, P, F, F, P, P],
+    "femb_dyn_velocity": [I, P, P, F, P, P],
+    "femb_control": [I, I, P, P, P],
+    "femb_cloth_rest_length": [I, P, P, P, P],
+    "femb_cloth_assemble": [I, I, P, P, F, P, P, F, P, F, P, P, P, P, P, P, P, P, P, P],
+    "femb_cloth_update": [I, P, P, I, I, P],
     "femb_axpby": [I, F, P, F, P, P],
     "femb_copy": [I, P, P, P],
     "femb_fill": [I, F, P, P],

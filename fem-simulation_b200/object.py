@@ -59,7 +59,7 @@ def _dev(a, device):
 
 class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
-                 control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0):
+                 control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.FembError("femb200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -74,6 +74,7 @@ class Object:
         self.spd_value = 1e-3
         self.mu, self.la, self.g = float(mu), float(la), float(g)
         self.dx = dx
+        self.spd_level0 = spd_level0           # exp1/simulation applies spd_matrix33f on level 0 too (object.py:1059,1125 there)
 
         points, hexagons = self._load_mesh(mesh_path, dx)
         self.N_verts, self.N_hexagons = int(points.shape[0]), int(hexagons.shape[0])
@@ -162,7 +163,7 @@ class Object:
         if len(pinList) == 0:
             pinList = hierarchy.default_pins(points, dx).tolist()
         else:
-            self.x_cpu[pinList[0]][1] += 0.1
+            self.x_cpu[pinList[0]][1] += pin_displacement
             self.x_gpu_layer[0].copy_(self.x_cpu)
         self.pinList = pinList
         self.N_pin = len(pinList)
@@ -456,6 +457,8 @@ class Object:
     def _newton_mg_body(self):
         x = self.x_gpu_layer[0]
         self._force_hessian(x, self.grad_gpu, self.MF_value_gpu, self.diag_fixed)       # :1232-1236, 1249
+        if self.spd_level0:
+            self._spd(self.MF_value_gpu)
         self.galerkin()                                                                  # :1252-1264
         self._copy(self.dev_B_fixed[0], self.grad_gpu)                                   # :1266
         self.VCycle(0)                                                                   # :1290
@@ -484,6 +487,8 @@ class Object:
     def _newton_body(self):
         x = self.x_gpu_layer[0]
         self._force_hessian(x, self.grad_gpu, self.MF_value_gpu, self.diag_fixed)
+        if self.spd_level0:
+            self._spd(self.MF_value_gpu)
         self._copy(self.dev_B_fixed[0], self.grad_gpu)
         self.PerformConjugateGradient(layer=0, iterations=5)
         self.update_deltaX(x, self.dev_delta_x[0])

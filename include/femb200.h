@@ -174,6 +174,35 @@ int femb_galerkin(const FembLevel* fine, const FembLevel* coarse, const float* f
                   const FembTransfer* ut_hat, const FembTransfer* us_hat, const FembGalerkinPlan* plan,
                   float* t_values, int spd, float spd_value, float* coarse_values, void* stream);
 
+/* ---- dynamic (implicit Euler) step: exp1/simulation/hexagon.py:174-203, cublas.py:234-299, object.py:1286-1325 ---- */
+/* Fixed_Update_Kernel + x_old = x + Basic_Update_Kernel (v *= damping; x += v dt) + x_inertia = x; dir_host: float[3] on the HOST */
+int femb_dyn_begin(int n_vert, float* x, float* v, float* old_x, float* inertia_x, float* fixed_x, const int* more_fixed,
+                   const int* pin, const float* dir_host, float damping, float dt, void* stream);
+/* Hessian_Diag_Kernel + Hessian_Mass_Kernel as the diag_add vector of femb_hessian: diag[v2i[v]] = (pinned|dragged ? k : 0) + m/dt^2 */
+int femb_dyn_diag(const FembLevel* lvl, const float* mass, const int* more_fixed, const int* pin, float control_mag,
+                  float inv_dt, float* diag, void* stream);
+/* compute_partial_more_fixed_energy_X + compute_Inertia_Gradient_Kernel onto an index-order force */
+int femb_dyn_force(const FembLevel* lvl, const float* x, const float* inertia_x, const int* more_fixed, const float* fixed_x,
+                   const float* mass, float control_mag, float inv_dt, float* grad, void* stream);
+/* updateVelocity: v = (x - x_old) * inv_dt */
+int femb_dyn_velocity(int n_vert, const float* x, const float* old_x, float inv_dt, float* v, void* stream);
+/* Control_Kernel: more_fixed[i] = |x_i - x_select|^2 < 0.002 */
+int femb_control(int n_vert, int select_v, const float* x, int* more_fixed, void* stream);
+
+/* ---- mass-spring cloth: exp1/cloth_simulation/triangle.py:5-79, object.py:657-677 there ------------------------- */
+/* compute_rest_length: rest[e] = |x[p0] - x[p1]|, edge = int[n_edge*2] */
+int femb_cloth_rest_length(int n_edge, const int* edge, const float* x, float* rest, void* stream);
+/* Hessian_Mass_Kernel + compute_elastic_hessian + compute_elastic_gradient + gravity + inertia, without atomics.
+ * inc_ptr/inc: CSR vertex -> (edge*2 + end) incidence; off_p0p1/off_p1p0/d_slot: value slots of the blocks (p0,p1),
+ * (p1,p0) of every edge and of every diagonal block (the reference's `offset`/`d_offset` maps, object.py:139-176 there,
+ * translated to the caller's value layout); edge_h [n_edge*9], edge_g [n_edge*3] scratch; grad in vertex order. */
+int femb_cloth_assemble(int n_vert, int n_edge, const int* edge, const float* rest, float k, const float* x, const float* mass,
+                        float g, const float* inertia_x, float inv_dt, const int* inc_ptr, const int* inc,
+                        const int* off_p0p1, const int* off_p1p0, const int* d_slot, float* edge_h, float* edge_g,
+                        float* values, float* grad, void* stream);
+/* the cloth's update_deltaX_kernel (cublas.py:22-26 there): x += dx except vertices skip0, skip1 (0 and 65) */
+int femb_cloth_update(int n_vert, const float* dx, float* x, int skip0, int skip1, void* stream);
+
 /* ---- vectors ------------------------------------------------------------------------------- */
 int femb_axpby(int n, float a, const float* x, float b, float* y, void* stream);          /* y = a x + b y (cublas.py:160-163) */
 int femb_copy(int n, const float* x, float* y, void* stream);
