@@ -1,5 +1,6 @@
-"""Runs the UNMODIFIED reference class (``/root/reference/exp1/quasi_simulation/object.py``) under the shims of this
-directory and writes golden fixtures to tests/golden/ref_<case>.npz.   Build-container only (needs /root/reference).
+"""Runs the UNMODIFIED reference classes (``/root/reference/exp1/{quasi_simulation,simulation,cloth_simulation}/object.py``)
+under the shims of this directory and writes golden fixtures to tests/golden/ref_<case>.npz.   Build-container only
+(needs /root/reference).
 
     python oracle/warp_emulator/generate_golden.py [case ...]
 """
@@ -14,10 +15,9 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-REF = "/root/reference/exp1/quasi_simulation"
+REF_DIRS = {"quasi": "/root/reference/exp1/quasi_simulation", "dynamic": "/root/reference/exp1/simulation",
+            "cloth": "/root/reference/exp1/cloth_simulation"}
 sys.path.insert(0, ROOT)
-sys.path.insert(0, REF)
-sys.path.insert(0, os.path.join(HERE, "shims"))          # shadows warp / sparse / pyvista / OpenGL / cuda / matplotlib
 
 _orig_to = torch.Tensor.to
 
@@ -43,11 +43,20 @@ if "cuda" in sys.modules:
 from fem_simulation_b200 import mesh  # noqa: E402
 
 CASES = {
-    # name: (mesh builder, dx, pinList, {method: steps})
-    "jag9": (lambda: mesh.jagged_mesh(9, 9, 10, 0.05, seed=3, keep=0.75), 0.05, [],
+    # name: (reference dir, mesh builder, dx, pinList, {method: steps})
+    "jag9": ("quasi", lambda: mesh.jagged_mesh(9, 9, 10, 0.05, seed=3, keep=0.75), 0.05, [],
              {"NewtonMultigrid": 2, "FASv3": 2, "FASv0": 1, "Newton": 2}),
-    "jag9_pin": (lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40], {"FASv2": 2, "FASv1": 1}),
+    "jag9_pin": ("quasi", lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40], {"FASv2": 2, "FASv1": 1}),
+    "dyn5": ("dynamic", lambda: mesh.jagged_mesh(5, 6, 5, 0.05, seed=7, keep=0.8), 0.05, [], {"render": 3}),
+    "cloth": ("cloth", None, None, None, {"render": 3}),
 }
+
+
+def use_reference(kind):
+    """Put ONE reference experiment directory (they all name their modules object / cublas / cpu_function) and the shims
+    on sys.path.  One case per process."""
+    sys.path.insert(0, REF_DIRS[kind])
+    sys.path.insert(0, os.path.join(HERE, "shims"))      # shadows warp / sparse / pyvista / OpenGL / cuda / matplotlib / glm
 
 
 def snapshot_setup(obj):
@@ -87,11 +96,59 @@ def snapshot_setup(obj):
     return out
 
 
+def run_dynamic(name):
+    kind, build, dx, pins, methods = CASES[name]
+    use_reference(kind)
+    import object as ref_object                           # exp1/simulation/object.py, unmodified
+    pts, hx = build()
+    path = os.path.join(ROOT, "tests", "golden", f"_mesh_{name}.npz")
+    np.savez(path, points=pts, hexagons=hx)
+    out = {"points": pts, "hexagons": hx, "dx": dx, "pinList": np.array(pins, dtype=np.int64)}
+    with contextlib.redirect_stdout(io.StringIO()):
+        obj = ref_object.Object("npz:" + path, dx, list(pins))
+        out["m0"] = obj.m_gpu[0].numpy().copy()
+        out["MF_value_fixed"] = obj.MF_value_fixed_gpu.numpy().copy()
+        out["consts"] = np.array([obj.control_mag, obj.dt, obj.inv_dt, obj.damping, obj.g_gpu.numpy()[0]], dtype=np.float64)
+        for f in range(methods["render"]):
+            obj.render(False)
+            out[f"x_frame{f}"] = obj.dev_x.numpy().copy()
+            out[f"v_frame{f}"] = obj.dev_v.numpy().copy()
+        out["MF_value"] = obj.MF_value_gpu.numpy().copy()
+        out["frames"] = methods["render"]
+    os.remove(path)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"), **out)
+    print("written", name, flush=True)
+
+
+def run_cloth(name):
+    kind, _, _, _, methods = CASES[name]
+    use_reference(kind)
+    import object as ref_object                           # exp1/cloth_simulation/object.py, unmodified
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        obj = ref_object.Cloth()
+        out["edge"] = obj.edge.numpy(); out["x_cpu"] = obj.x_cpu.numpy().copy()
+        out["MF_row"] = obj.MF_row.numpy(); out["MF_col"] = obj.MF_col.numpy()
+        out["offset"] = obj.offset_gpu.numpy(); out["d_offset"] = obj.d_offset.numpy()
+        out["rest_length"] = obj.rest_length.numpy().copy()
+        for f in range(methods["render"]):
+            obj.render(False)
+            out[f"x_frame{f}"] = obj.dev_x.numpy().copy()
+            out[f"v_frame{f}"] = obj.dev_v.numpy().copy()
+        out["MF_value"] = obj.MF_value_gpu.numpy().copy()
+        out["frames"] = methods["render"]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"), **out)
+    print("written", name, flush=True)
+
+
 def run_case(name):
-    import importlib
-    import object as ref_object                           # the reference module, unmodified
-    importlib.reload(ref_object)
-    build, dx, pins, methods = CASES[name]
+    if CASES[name][0] == "dynamic":
+        return run_dynamic(name)
+    if CASES[name][0] == "cloth":
+        return run_cloth(name)
+    use_reference(CASES[name][0])
+    import object as ref_object                           # exp1/quasi_simulation/object.py, unmodified
+    _, build, dx, pins, methods = CASES[name]
     pts, hx = build()
     path = os.path.join(ROOT, "tests", "golden", f"_mesh_{name}.npz")
     np.savez(path, points=pts, hexagons=hx)
@@ -117,5 +174,9 @@ def run_case(name):
 
 
 if __name__ == "__main__":
-    for c in (sys.argv[1:] or list(CASES)):
-        run_case(c)
+    if len(sys.argv) == 2:
+        run_case(sys.argv[1])
+    else:                                                 # one process per case: the experiments share module names
+        import subprocess
+        for c in (sys.argv[1:] or list(CASES)):
+            subprocess.run([sys.executable, os.path.abspath(__file__), c], check=True)

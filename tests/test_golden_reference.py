@@ -122,3 +122,67 @@ def test_cuda_steps_match_reference_class(gold, method):
     assert rel(obj.MF_value_gpu.cpu().numpy(), g[f"{method}_MF_value"]) <= 1e-5, "MF_value"
     if f"{method}_UtAUs_values0" in g and obj.layer > 1:
         assert rel(obj.UtAUs_values[0].cpu().numpy(), g[f"{method}_UtAUs_values0"]) <= 2e-5, "coarse operator"
+
+
+# ---- dynamic (exp1/simulation) and cloth (exp1/cloth_simulation) reference classes -------------------------------
+def _load(name):
+    p = os.path.join(GOLD, f"ref_{name}.npz")
+    if not os.path.exists(p):
+        pytest.skip(f"{name} fixture not generated")
+    return dict(np.load(p))
+
+
+def test_cloth_oracle_matches_reference_class():
+    from oracle.ref_cloth import RefCloth
+    g = _load("cloth")
+    r = RefCloth()
+    for k, v in (("edge", r.edge), ("x_cpu", r.x_cpu), ("MF_row", r.MF_row), ("MF_col", r.MF_col), ("offset", r.offset),
+                 ("d_offset", r.d_offset)):
+        assert np.array_equal(g[k], v), k
+    assert rel(r.rest_length, g["rest_length"]) <= 1e-6
+    for f in range(int(g["frames"])):
+        r.render()
+        assert rel(r.dev_x, g[f"x_frame{f}"]) <= 1e-6, f"x frame {f}"
+        assert rel(r.dev_v, g[f"v_frame{f}"]) <= 1e-3, f"v frame {f}"
+    assert rel(r.MF_value, g["MF_value"]) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_cloth_cuda_matches_reference_class():
+    pytest.importorskip("torch")
+    from fem_simulation_b200 import Cloth
+    g = _load("cloth")
+    c = Cloth()
+    assert np.array_equal(c.offset.numpy(), g["offset"]) and np.array_equal(c.d_offset.numpy(), g["d_offset"])
+    assert np.array_equal(c.MF_row.numpy(), g["MF_row"]) and np.array_equal(c.MF_col.numpy(), g["MF_col"])
+    for f in range(int(g["frames"])):
+        c.step()
+        assert rel(c.dev_x.cpu().numpy(), g[f"x_frame{f}"]) <= 1e-6, f"x frame {f}"
+        assert rel(c.dev_v.cpu().numpy(), g[f"v_frame{f}"]) <= 1e-3, f"v frame {f}"
+    assert rel(c.MF_value_gpu.cpu().numpy(), g["MF_value"]) <= 1e-5
+
+
+def test_dynamic_oracle_matches_reference_class():
+    from oracle.ref_dynamic import RefDynamicObject
+    g = _load("dyn5")
+    r = RefDynamicObject(g["points"], g["hexagons"], float(g["dx"]), [int(v) for v in g["pinList"]])
+    assert np.allclose(g["consts"], [r.control_mag, 0.033, 30.0, 0.9995, -9.8], rtol=1e-6)
+    assert rel(r.m[0], g["m0"]) <= 1e-6 and rel(r.MF_value_fixed, g["MF_value_fixed"]) <= 1e-6
+    for f in range(int(g["frames"])):
+        r.render()
+        assert rel(r.dev_x, g[f"x_frame{f}"]) <= 1e-6, f"x frame {f}"
+        assert rel(r.dev_v, g[f"v_frame{f}"]) <= 1e-3, f"v frame {f}"
+    assert rel(r.MF_value, g["MF_value"]) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_dynamic_cuda_matches_reference_class():
+    pytest.importorskip("torch")
+    from fem_simulation_b200 import DynamicObject
+    g = _load("dyn5")
+    d = DynamicObject((g["points"], g["hexagons"]), float(g["dx"]), [int(v) for v in g["pinList"]])
+    for f in range(int(g["frames"])):
+        d.step()
+        assert rel(d.dev_x.cpu().numpy(), g[f"x_frame{f}"]) <= 1e-6, f"x frame {f}"
+        assert rel(d.dev_v.cpu().numpy(), g[f"v_frame{f}"]) <= 1e-3, f"v frame {f}"
+    assert rel(d.MF_value_gpu.cpu().numpy(), g["MF_value"]) <= 1e-5
