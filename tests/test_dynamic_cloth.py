@@ -83,3 +83,31 @@ def test_dynamic_frames(pins):
         r2.PerformConjugateGradient(0, 5); r2.update_deltaX(r2.x_gpu_layer[0], r2.dev_delta_x[0])
     assert rel(d2.x_gpu_layer[0].cpu().numpy(), r2.x_gpu_layer[0]) <= 1e-5
     torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+def test_exp2_compare_forward():
+    """exp2 compare(): classic weights and a perturbed ("trained") weight vector, CUDA vs oracle."""
+    import torch
+    from fem_simulation_b200.object_exp2 import Exp2Object
+    from oracle.ref_exp2 import RefExp2Object
+    pts, hx = mesh.jagged_mesh(10, 9, 11, 0.05, seed=1)
+    o = Exp2Object((pts, hx), 0.05, [])
+    r = RefExp2Object(pts, hx, 0.05, [])
+    pv, pert = 300, (0.0007, -0.0004, 0.0009)
+    rng = np.random.default_rng(11)
+    w_tr = (r.w * (1.0 + 0.05 * rng.standard_normal(len(r.w)))).astype(np.float32)
+    o.compare(4, perturb_vertex=pv, perturbation=pert, trained=torch.from_numpy(w_tr))
+    r.x_gpu_layer[0][pv] += np.array(pert, np.float32)
+    x_start = r.x_gpu_layer[0].copy()
+    r.compare_loop(4, r.w)
+    classic = list(r.plot_InfNorm)
+    x_classic = r.x_gpu_layer[0].copy()
+    r.x_gpu_layer[0][...] = x_start
+    r.plot_InfNorm = []
+    r.compare_loop(4, w_tr)
+    assert rel(np.array(o.plot_InfNorm), np.array(classic)) <= 1e-4
+    assert rel(np.array(o.plot_InfNorm_newton), np.array(r.plot_InfNorm)) <= 1e-4
+    assert rel(o.x_gpu_layer[0].cpu().numpy(), r.x_gpu_layer[0]) <= 1e-5
+    assert np.abs(x_classic - r.x_gpu_layer[0]).max() > 0          # the trained weights do change the iteration
+    assert o.Ut_noOrder_value.numel() == o.Ut_noOrder[0].nnz
