@@ -29,7 +29,11 @@ class FembLevel(C.Structure):
                 ("hex", C.c_void_p), ("v2i", C.c_void_p), ("i2v", C.c_void_p),
                 ("L_ptr", C.c_void_p), ("L_col", C.c_void_p), ("U_ptr", C.c_void_p), ("U_col", C.c_void_p),
                 ("elem2nnz", C.c_void_p),
-                ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p)]
+                ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p),
+                ("fold_plan", C.c_void_p), ("asm_chunk_ptr", C.c_void_p), ("asm_chunk_grp", C.c_void_p), ("asm_expected", C.c_void_p),
+                ("asm_counter", C.c_void_p)]
+
+ASM_CHUNK_HEXES, ASM_GROUP_ROWS = 16, 16
 
 
 class FembTransfer(C.Structure):
@@ -57,15 +61,18 @@ PROTOTYPES = {
     "femb_launch_count": [],
     "femb_check_device": [I],
     "femb_prepare_rest": [I, P, P, P, P, P],
+    "femb_build_fold_plan": [LV, P, P],
     "femb_lumped_mass": [LV, P, P, P],
     "femb_force": [LV, P, F, F, P, F, P, P, F, I, P, P, P],
     "femb_hessian": [LV, P, F, F, P, P, P, P],
+    "femb_set_fused_assembly": [I],
     "femb_force_hessian": [LV, P, F, F, P, F, P, P, F, P, P, P, P, P, P],
     "femb_energy": [LV, P, F, F, P, F, P, P, F, P, P, P],
     "femb_coarse_pin_penalty": [LV, TR, P, F, P, P],
     "femb_spmv": [LV, P, I, F, P, F, P, P],
     "femb_residual": [LV, P, P, P, P, P],
     "femb_gauss_seidel": [LV, P, P, P, I, P, P],
+    "femb_set_pdl": [I],
     "femb_gs_colors": [LV, P, P, P, I, I, I, P, P],
     "femb_jacobi": [LV, P, P, P, P, I, P, P],
     "femb_cg": [LV, P, P, P, P, P, P, P, I, F, I, P],
@@ -134,7 +141,7 @@ def load(rebuild: bool = False):
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported
         fn.argtypes = args
         fn.restype = _RESTYPE.get(name, C.c_int)
-    if lib.femb_abi_version() != 1:
+    if lib.femb_abi_version() != 2:
         raise FembError("libfemb200 ABI version mismatch")
     _lib = lib
     return lib

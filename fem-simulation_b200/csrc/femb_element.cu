@@ -20,19 +20,26 @@
 
 #include "femb_common.cuh"
 
+static int g_no_fuse = 1;   // femb_set_fused_assembly(1) turns the one-kernel (last-arriver) assembly on; measured slower, see DESIGN.md
+
 namespace femb {
 
-constexpr int EPB = 16;            // hexahedra per CTA
+constexpr int EPB = FEMB_ASM_CHUNK_HEXES;            // hexahedra per CTA
 constexpr int ETHREADS = EPB * 8;  // 128 threads
 
 // per (hexahedron, Gauss point) record in shared memory, in floats; written and read as float4:
 //   [0..5] det*mu * F F^T (symmetric: 00 01 02 11 12 22)   [6] det*mu   [7] det*la
-//   [8 + 9 b ..] per node b: g_b[3], u_b[3], det * S g_b[3]                      (72 floats)
+//   [8 + 6 b ..] per node b: g_b[3], u_b[3]          (48 floats; broadcast-read by all 8 lanes)
+//   [56 + 3 b ..] per node b: det * S g_b[3]          (24 floats; lane a reads only its own t_a)
 constexpr int QP_FFT = 0;
 constexpr int QP_C = 6;
-constexpr int QP_GUT = 8;
+constexpr int QP_GU = 8;
+constexpr int QP_T = 56;
+constexpr int QP_BCAST = 56;  // floats every lane loads (14 float4)
 constexpr int QP_SIZE = 84;   // 21 float4: 16-byte accesses of 8 consecutive lanes hit distinct banks (21 is odd)
-constexpr int FQ_SIZE = 25;   // per (hexahedron, Gauss point) nodal forces 8x3, padded
+// floats between the records of consecutive hexahedra: 8*84 + 16 = 16 (mod 32), so the per-lane 8-byte reads of phase B
+// (two hexahedra per half-warp, 16 banks each) are conflict-free
+constexpr int HEX_STRIDE = 8 * QP_SIZE + 16;
 
 struct ElemIn {
   const int* hex;
@@ -126,13 +133,14 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
 #pragma unroll
     for (int r = 0; r < 3; ++r) fq[b][r] = -det * (P[3 * r] * g[0] + P[3 * r + 1] * g[1] + P[3 * r + 2] * g[2]);
     if (want_rec) {
-      float* o = R + QP_GUT + 9 * b;
+      float* o = R + QP_GU + 6 * b;
       o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
 #pragma unroll
       for (int r = 0; r < 3; ++r) o[3 + r] = F[3 * r] * g[0] + F[3 * r + 1] * g[1] + F[3 * r + 2] * g[2];
-      o[6] = det * (S[0] * g[0] + S[1] * g[1] + S[2] * g[2]);
-      o[7] = det * (S[1] * g[0] + S[3] * g[1] + S[4] * g[2]);
-      o[8] = det * (S[2] * g[0] + S[4] * g[1] + S[5] * g[2]);
+      float* t = R + QP_T + 3 * b;
+      t[0] = det * (S[0] * g[0] + S[1] * g[1] + S[2] * g[2]);
+      t[1] = det * (S[1] * g[0] + S[3] * g[1] + S[4] * g[2]);
+      t[2] = det * (S[2] * g[0] + S[4] * g[1] + S[5] * g[2]);
     }
   }
   if (want_rec) {
@@ -142,14 +150,160 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
   }
 }
 
+// ---- row-centric assembly of one row (vertex v, index-order row r) by one warp -------------------------
+// The row needs row `a` of the element matrices of its <= 8 incident hexahedra: 8 blocks = 288 contiguous,
+// 16-byte aligned bytes each, fetched as 18 float4 by 18 lanes (all 8 fetches in flight before the first is
+// consumed).  The blocks are folded into the row's <= 27 value slots through the element->nnz map in shared
+// memory (fixed order: incidence order, then b; no atomics) and the row's L, D and U segments are written
+// with coalesced stores.  kCoherent: the element matrices were written by other CTAs of the SAME launch
+// (fused path), so they are read through L2 (ld.global.cg), never through the non-coherent path.
+constexpr int AS_SLOTS = FEMB_FOLD_SLOTS;       // 27: blocks of a row of a hexahedral lattice
+struct AsmArgs {
+  int n_vert;
+  const int* i2v; const int* v2i; const int* vert_elem; const int* elem2nnz; const int* L_ptr; const int* U_ptr;
+  const unsigned char* fold;     // [n_vert][27][8] fold plan (femb_build_fold_plan)
+  int off_l, off_d, off_u;
+  const float* elem_k; const float* diag_add; float* values;
+};
+struct AsmWarpSmem {
+  alignas(16) float stage[8][72];          // row `a` of the <= 8 incident element matrices: block (j,b) at [j][9b]
+  float out[AS_SLOTS * 9 + 5];             // the folded row: L blocks, D, U blocks
+};
+
+// rows with more than 27 blocks (not produced by hexahedral lattices): one slot at a time through elem2nnz
+__device__ __noinline__ void assemble_row_slow(const AsmArgs& A, int r, int lane, int my_ea, int lp, int nl, int up, int nu,
+                                               const float* stage) {
+  for (int part = 0; part < 3; ++part) {
+    const int cnt = part == 0 ? nl : (part == 1 ? 1 : nu);
+    for (int li = 0; li < cnt; ++li) {
+      const int slot = part == 0 ? A.off_l + lp + li : (part == 1 ? A.off_d + r : A.off_u + up + li);
+      float sum = (part == 1 && A.diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) ? __ldg(A.diag_add + r) : 0.f;
+      for (int t = 0; t < 64; ++t) {
+        const int ea = __shfl_sync(0xffffffffu, my_ea, t >> 3);
+        if (ea < 0) continue;
+        if (__ldg(A.elem2nnz + (size_t)ea * 8 + (t & 7)) == slot && lane < 9)
+          sum += stage[(t >> 3) * 72 + (((t & 7) - (ea & 7)) & 7) * 9 + lane];        // rotated row layout
+      }
+      if (lane < 9) A.values[(size_t)slot * 9 + lane] = sum;
+    }
+  }
+}
+
+template <bool kCoherent>
+__device__ __forceinline__ void assemble_row(const AsmArgs& A, int v, int r, int lane, AsmWarpSmem& sm) {
+  const int lp = __ldg(A.L_ptr + r), nl = __ldg(A.L_ptr + r + 1) - lp;
+  const int up = __ldg(A.U_ptr + r), nu = __ldg(A.U_ptr + r + 1) - up;
+  // incident hexahedra (e*8+a): lane j < 8 holds entry j
+  const int my_ea = lane < 8 ? __ldg(A.vert_elem + (size_t)v * 8 + lane) : -1;
+  // fold plan: lane s < 27 gets the <= 8 contributors (j*8+b, 255 = none) of the row's s-th block, in fold order
+  uint2 plan = make_uint2(0xffffffffu, 0xffffffffu);
+  if (lane < AS_SLOTS) plan = __ldg(reinterpret_cast<const uint2*>(A.fold + (size_t)v * (AS_SLOTS * 8)) + lane);
+  float4 seg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ea = __shfl_sync(0xffffffffu, my_ea, j);
+    seg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ea >= 0 && lane < 18) {
+      const float4* src = reinterpret_cast<const float4*>(A.elem_k + (size_t)ea * 72) + lane;
+      seg[j] = kCoherent ? __ldcg(src) : __ldg(src);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (lane < 18) *reinterpret_cast<float4*>(&sm.stage[j][4 * lane]) = seg[j];
+  __syncwarp();
+  const unsigned first = __shfl_sync(0xffffffffu, plan.x, 0) & 255u;
+  if (first == 254u) {                                       // oversized row (plan not applicable); warp-uniform
+    assemble_row_slow(A, r, lane, my_ea, lp, nl, up, nu, &sm.stage[0][0]);
+    __syncwarp();
+    return;
+  }
+  // lane s folds block s: contributors in incidence order (same order as the reference's scatter would be sorted to)
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* st = &sm.stage[0][0];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const unsigned idx = ((c < 4 ? plan.x : plan.y) >> (8 * (c & 3))) & 255u;
+    if (idx < 64u) {
+      const float* src = st + idx * 9;                       // block (j,b) lives at stage[j][9b] = st + (8j+b)*9
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[k] += src[k];
+    }
+  }
+  if (lane < AS_SLOTS) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sm.out[lane * 9 + k] = acc[k];
+  }
+  __syncwarp();
+  float* outL = A.values + ((size_t)A.off_l + lp) * 9;
+  for (int i = lane; i < nl * 9; i += 32) outL[i] = sm.out[i];
+  if (lane < 9) {
+    float d = sm.out[nl * 9 + lane];
+    if (A.diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) d += __ldg(A.diag_add + r);
+    A.values[((size_t)A.off_d + r) * 9 + lane] = d;
+  }
+  float* outU = A.values + ((size_t)A.off_u + up) * 9;
+  for (int i = lane; i < nu * 9; i += 32) outU[i] = sm.out[(nl + 1) * 9 + i];
+  __syncwarp();                                              // the warp's scratch is reused by its next row
+}
+
+// setup: the fold plan of every row (vertex order).  One warp per vertex.
+__global__ void __launch_bounds__(256) fold_plan_kernel(AsmArgs A, unsigned char* __restrict__ fold) {
+  __shared__ int s_loc[8][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int v = blockIdx.x * 8 + w;
+  if (v >= A.n_vert) return;
+  const int r = __ldg(A.v2i + v);
+  const int lp = __ldg(A.L_ptr + r), nl = __ldg(A.L_ptr + r + 1) - lp;
+  const int up = __ldg(A.U_ptr + r), nu = __ldg(A.U_ptr + r + 1) - up;
+  const int my_ea = lane < 8 ? __ldg(A.vert_elem + (size_t)v * 8 + lane) : -1;
+  unsigned char* out = fold + (size_t)v * (AS_SLOTS * 8);
+  if (nl + 1 + nu > AS_SLOTS) {
+    for (int i = lane; i < AS_SLOTS * 8; i += 32) out[i] = 254;
+    return;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int t = lane + 32 * h, j = t >> 3, b = t & 7;
+    const int ea = __shfl_sync(0xffffffffu, my_ea, j);
+    int loc = -1;
+    if (ea >= 0) {
+      const int s = __ldg(A.elem2nnz + (size_t)ea * 8 + b);
+      loc = s < A.off_d ? (s - A.off_l - lp) : (s < A.off_u ? nl : nl + 1 + (s - A.off_u - up));
+    }
+    // the element kernel stores row a of an element matrix rotated: column node b sits at position (b - a) & 7
+    s_loc[w][(t & ~7) | ((b - (ea & 7)) & 7)] = loc;
+  }
+  __syncwarp();
+  if (lane < AS_SLOTS) {
+    int n = 0;
+    for (int t = 0; t < 64; ++t)
+      if (s_loc[w][t] == lane && n < 8) out[lane * 8 + n++] = (unsigned char)t;
+    for (; n < 8; ++n) out[lane * 8 + n] = 255;
+  }
+}
+
+// Fused ("last arriver") assembly.  Hexahedra are processed in chunks of EPB (one CTA each), rows in groups of
+// FEMB_ASM_GROUP_ROWS consecutive vertices.  After a CTA has published its element matrices it bumps the counter of
+// every row group its chunk touches; the CTA whose increment completes a group (all chunks incident to the group's
+// rows have been published) assembles that group right away, while the element matrices are still in L2.  Nobody
+// waits, so there is no scheduling dependence and no deadlock; the fold order of a row is fixed by the incidence
+// list, so the result is bit-identical to the two-kernel path whichever CTA does the fold.
+struct FuseArgs {
+  const int* chunk_ptr;   // [n_chunks + 1]
+  const int* chunk_grp;   // row groups touched by each chunk
+  const int* expected;    // [n_groups] chunks touching the group
+  int* counter;           // [n_groups] zero between launches (the last arriver resets it)
+};
+
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both
-template <int kMode>
-__global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
+template <int kMode, bool kFused>
+__global__ void __launch_bounds__(ETHREADS, 5) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k,
+                                                              FuseArgs fu, AsmArgs as) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
   extern __shared__ __align__(16) float smem[];
-  float* s_rec = smem;                                                // [EPB][8][QP_SIZE]   (Hessian only)
-  float* s_f = smem + (kHess ? EPB * 8 * QP_SIZE : 0);                // [EPB][8q][8a][3]    (force only)
+  float* s_rec = smem;                                                // [EPB][HEX_STRIDE]: 8 records per hexahedron (Hessian only)
   const int sub = threadIdx.x & 7;
   const int le = threadIdx.x >> 3;
   const int e = blockIdx.x * EPB + le;
@@ -164,187 +318,167 @@ __global__ void __launch_bounds__(ETHREADS) element_kernel(ElemIn in, float* __r
 #pragma unroll
     for (int c = 0; c < 3; ++c) X[a][c] = __shfl_sync(0xffffffffu, xn[c], a, 8);
 
-  float fq[8][3];
-  float energy;
-  float* rec = s_rec + ((size_t)le * 8 + sub) * QP_SIZE;
-  gauss_point(in, ee, sub, X, rec, fq, energy, kHess);
-  if (kForce) {
-    float* o = s_f + ((size_t)le * 8 + sub) * FQ_SIZE;
+  {
+    float fq[8][3];
+    float energy;
+    float* rec = s_rec + (size_t)le * HEX_STRIDE + sub * QP_SIZE;
+    gauss_point(in, ee, sub, X, rec, fq, energy, kHess);
+    if (kForce) {
+      // lane q holds the Gauss-point contributions to all 8 nodes; a reduce-scatter over the 8 lanes of the
+      // hexahedron (xor 4, 2, 1) leaves lane a with the force on node a
+      float h4[4][3], h2[2][3], f[3];
+      const bool up4 = (sub & 4) != 0, up2 = (sub & 2) != 0, up1 = (sub & 1) != 0;
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) o[a * 3 + c] = fq[a][c];
-  }
-  __syncthreads();
-  if (kForce && live) {
-    // lane a sums its node's force over the Gauss points in q order
-    float f[3] = {0.f, 0.f, 0.f};
+        for (int c = 0; c < 3; ++c) {
+          const float give = up4 ? fq[i][c] : fq[i + 4][c], keep = up4 ? fq[i + 4][c] : fq[i][c];
+          h4[i][c] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+        }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float* o = s_f + ((size_t)le * 8 + q) * FQ_SIZE + sub * 3;
-      f[0] += o[0]; f[1] += o[1]; f[2] += o[2];
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float give = up2 ? h4[i][c] : h4[i + 2][c], keep = up2 ? h4[i + 2][c] : h4[i][c];
+          h2[i][c] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float give = up1 ? h2[0][c] : h2[1][c], keep = up1 ? h2[1][c] : h2[0][c];
+        f[c] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+      }
+      if (live) {
+        float* dst = elem_f + ((size_t)e * 8 + sub) * 3;
+        dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];
+      }
     }
-    float* dst = elem_f + ((size_t)e * 8 + sub) * 3;
-    dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];
   }
   if (!kHess) return;
+  __syncthreads();
 
-  // ---- phase B: lane a accumulates K[a][b], b = 0..7 --------------------------------------
-  float K[8][9];
+  // ---- phase B: lane a accumulates the 5 blocks K[a][(a+k) & 7], k = 0..4 ------------------------------
+  // K_ab[j][i] = sum_q  d_ji (t_a . g_b) + (det mu FF^T)_ji (g_a . g_b) + det mu u_b[j] u_a[i] + det la u_a[j] u_b[i]
+  // with t_a = det S g_a (S symmetric: g_a . S g_b == S g_a . g_b); every term is one FFMA into an accumulator.
+  // The element matrix is symmetric (K_ba = K_ab^T), so the cyclic half {(a, a+k)} is enough: the blocks
+  // K[a][(a-m) & 7], m = 1..3, are the transposes of block m of lane (a-m) & 7 and arrive by shuffle.
+  float K[5][9], Ks[5];
 #pragma unroll
-  for (int b = 0; b < 8; ++b)
+  for (int k = 0; k < 5; ++k) {
+    Ks[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) K[b][k] = 0.f;
+    for (int i = 0; i < 9; ++i) K[k][i] = 0.f;
+  }
   const bool has_la = in.la != 0.f;
 #pragma unroll 1
   for (int q = 0; q < 8; ++q) {
-    const float* r = s_rec + ((size_t)le * 8 + q) * QP_SIZE;
-    float G[80];                                           // the whole Gauss-point record, 20 broadcast LDS.128
+    const float* r = s_rec + (size_t)le * HEX_STRIDE + q * QP_SIZE;
     const float4* r4 = reinterpret_cast<const float4*>(r);
+    const float4 h0 = r4[0], h1 = r4[1];                   // broadcast reads (all 8 lanes of a hexahedron, same address)
+    const float FFT[6] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y};
+    const float cmu = h1.z, cla = h1.w;
+    const float2* ga2 = reinterpret_cast<const float2*>(r + QP_GU + 6 * sub);   // own node
+    const float2 o0 = ga2[0], o1 = ga2[1], o2 = ga2[2];
+    const float g_a[3] = {o0.x, o0.y, o1.x};
+    const float ua_mu[3] = {cmu * o1.y, cmu * o2.x, cmu * o2.y};
+    const float ua_la[3] = {cla * o1.y, cla * o2.x, cla * o2.y};
+    const float* tp = r + QP_T + 3 * sub;
+    const float t_a[3] = {tp[0], tp[1], tp[2]};
 #pragma unroll
-    for (int v = 0; v < 20; ++v) {
-      const float4 t4 = r4[v];
-      G[4 * v] = t4.x; G[4 * v + 1] = t4.y; G[4 * v + 2] = t4.z; G[4 * v + 3] = t4.w;
-    }
-    const float* FFT = G + QP_FFT;
-    const float cmu = G[QP_C], cla = G[QP_C + 1];
-    const float* ga = r + QP_GUT + 9 * sub;                // own node: runtime index, scalar loads
-    const float g_a[3] = {ga[0], ga[1], ga[2]};
-    const float ua_mu[3] = {cmu * ga[3], cmu * ga[4], cmu * ga[5]};
-    const float ua_la[3] = {cla * ga[3], cla * ga[4], cla * ga[5]};
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const float* gb = G + QP_GUT + 9 * b;
-      const float g_b[3] = {gb[0], gb[1], gb[2]};
-      const float u_b[3] = {gb[3], gb[4], gb[5]};
-      const float s1 = g_a[0] * gb[6] + g_a[1] * gb[7] + g_a[2] * gb[8];       // det * g_a . S g_b
-      const float s2 = g_a[0] * g_b[0] + g_a[1] * g_b[1] + g_a[2] * g_b[2];    // g_a . g_b
-      // K[j][i] += d_ji s1 + (det mu FF^T)_ji s2 + det mu u_b[j] u_a[i] + det la u_a[j] u_b[i]
-      K[b][0] += s1 + FFT[0] * s2 + u_b[0] * ua_mu[0];
-      K[b][1] += FFT[1] * s2 + u_b[0] * ua_mu[1];
-      K[b][2] += FFT[2] * s2 + u_b[0] * ua_mu[2];
-      K[b][3] += FFT[1] * s2 + u_b[1] * ua_mu[0];
-      K[b][4] += s1 + FFT[3] * s2 + u_b[1] * ua_mu[1];
-      K[b][5] += FFT[4] * s2 + u_b[1] * ua_mu[2];
-      K[b][6] += FFT[2] * s2 + u_b[2] * ua_mu[0];
-      K[b][7] += FFT[4] * s2 + u_b[2] * ua_mu[1];
-      K[b][8] += s1 + FFT[5] * s2 + u_b[2] * ua_mu[2];
+    for (int k = 0; k < 5; ++k) {
+      const float2* gb2 = reinterpret_cast<const float2*>(r + QP_GU + 6 * ((sub + k) & 7));
+      const float2 p0 = gb2[0], p1 = gb2[1], p2 = gb2[2];
+      const float gb[3] = {p0.x, p0.y, p1.x};
+      const float u_b[3] = {p1.y, p2.x, p2.y};
+      Ks[k] = fmaf(t_a[0], gb[0], fmaf(t_a[1], gb[1], fmaf(t_a[2], gb[2], Ks[k])));
+      const float s2 = fmaf(g_a[0], gb[0], fmaf(g_a[1], gb[1], g_a[2] * gb[2]));
+      K[k][0] = fmaf(FFT[0], s2, fmaf(u_b[0], ua_mu[0], K[k][0]));
+      K[k][1] = fmaf(FFT[1], s2, fmaf(u_b[0], ua_mu[1], K[k][1]));
+      K[k][2] = fmaf(FFT[2], s2, fmaf(u_b[0], ua_mu[2], K[k][2]));
+      K[k][3] = fmaf(FFT[1], s2, fmaf(u_b[1], ua_mu[0], K[k][3]));
+      K[k][4] = fmaf(FFT[3], s2, fmaf(u_b[1], ua_mu[1], K[k][4]));
+      K[k][5] = fmaf(FFT[4], s2, fmaf(u_b[1], ua_mu[2], K[k][5]));
+      K[k][6] = fmaf(FFT[2], s2, fmaf(u_b[2], ua_mu[0], K[k][6]));
+      K[k][7] = fmaf(FFT[4], s2, fmaf(u_b[2], ua_mu[1], K[k][7]));
+      K[k][8] = fmaf(FFT[5], s2, fmaf(u_b[2], ua_mu[2], K[k][8]));
       if (has_la) {
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
-          for (int i = 0; i < 3; ++i) K[b][3 * j + i] += ua_la[j] * u_b[i];
+          for (int i = 0; i < 3; ++i) K[k][3 * j + i] = fmaf(ua_la[j], u_b[i], K[k][3 * j + i]);
       }
     }
   }
+  // Row a of the element matrix in ROTATED order: position p holds the block of column (a + p) & 7.
+  //   p = 0..4: own blocks;  p = 8 - m (m = 1..3): transpose of block m of lane (a - m) & 7.
+  float row[72];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    K[k][0] += Ks[k]; K[k][4] += Ks[k]; K[k][8] += Ks[k];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) row[9 * k + i] = K[k][i];
+  }
+#pragma unroll
+  for (int m = 1; m <= 3; ++m) {
+    const int src = (threadIdx.x & 24) | ((sub - m) & 7);    // lane within the warp
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) row[9 * (8 - m) + 3 * i + j] = __shfl_sync(0xffffffffu, K[m][3 * j + i], src);
+  }
   if (live) {
-    float4* dst = reinterpret_cast<float4*>(elem_k + ((size_t)e * 8 + sub) * 72);    // K[e][a][b][3][3], a = sub
+    float4* dst = reinterpret_cast<float4*>(elem_k + ((size_t)e * 8 + sub) * 72);    // K[e][a][p][3][3], a = sub
 #pragma unroll
     for (int v = 0; v < 18; ++v) {
-      const int i0 = 4 * v;
-      dst[v] = make_float4(K[i0 / 9][i0 % 9], K[(i0 + 1) / 9][(i0 + 1) % 9], K[(i0 + 2) / 9][(i0 + 2) % 9],
-                           K[(i0 + 3) / 9][(i0 + 3) % 9]);
+      const float4 o = make_float4(row[4 * v], row[4 * v + 1], row[4 * v + 2], row[4 * v + 3]);
+      if (kFused) __stcg(dst + v, o); else dst[v] = o;
     }
+  }
+  if (!kFused) return;
+
+  // ---- fused tail: publish, count, and assemble the row groups this chunk completed ---------------------
+  __shared__ int s_ready[ETHREADS];
+  __shared__ int s_nready;
+  if (threadIdx.x == 0) s_nready = 0;
+  __threadfence();                                           // this thread's element-matrix stores are visible device-wide
+  __syncthreads();                                           // ... for every thread of the CTA, before any counter moves
+  {
+    const int c0 = __ldg(fu.chunk_ptr + blockIdx.x), nc = __ldg(fu.chunk_ptr + blockIdx.x + 1) - c0;
+    for (int i = threadIdx.x; i < nc; i += ETHREADS) {
+      const int g = __ldg(fu.chunk_grp + c0 + i);
+      const int old = atomicAdd(fu.counter + g, 1);
+      if (old + 1 == __ldg(fu.expected + g)) {
+        fu.counter[g] = 0;                                   // nobody else touches it again in this launch
+        s_ready[atomicAdd(&s_nready, 1)] = g;
+      }
+    }
+  }
+  __syncthreads();
+  const int nready = s_nready;
+  if (nready == 0) return;
+  __threadfence();                                           // acquire side: order the reads below after the counter read
+  AsmWarpSmem* wsm = reinterpret_cast<AsmWarpSmem*>(smem);   // the record area is dead now
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = w; i < nready * FEMB_ASM_GROUP_ROWS; i += ETHREADS / 32) {
+    const int v = s_ready[i / FEMB_ASM_GROUP_ROWS] * FEMB_ASM_GROUP_ROWS + (i % FEMB_ASM_GROUP_ROWS);
+    if (v >= as.n_vert) continue;                            // warp-uniform
+    assemble_row<true>(as, v, __ldg(as.v2i + v), lane, wsm[w]);
   }
 }
 
 template <int kMode>
 static size_t element_smem() {
-  size_t f = 0;
-  if (kMode != 1) f += (size_t)EPB * 8 * FQ_SIZE;
-  if (kMode != 0) f += (size_t)EPB * 8 * QP_SIZE;
-  return f * sizeof(float);
+  return (kMode != 0 ? (size_t)EPB * HEX_STRIDE : 4) * sizeof(float);
 }
 
-// Row-centric assembly, one warp per index-order row.  A row needs row `a` of the element matrices of its
-// <= 8 incident hexahedra: 8 blocks = 288 contiguous, 16-byte aligned bytes each, fetched as 18 float4 by 18
-// lanes (all 8 fetches in flight before the first is consumed).  The blocks are folded into the row's <= 27
-// value slots through the element->nnz map in shared memory (fixed order: incidence order, then b; no
-// atomics) and the row's L, D and U segments are written with coalesced stores.
+// two-kernel path: one warp per index-order row
 constexpr int AS_WARPS = 8;
 constexpr int AS_THREADS = AS_WARPS * 32;
-constexpr int AS_SLOTS = 28;
-__global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(int n_vert, const int* __restrict__ i2v,
-                                                                  const int* __restrict__ vert_elem,
-                                                                  const int* __restrict__ elem2nnz,
-                                                                  const int* __restrict__ L_ptr, const int* __restrict__ U_ptr,
-                                                                  int off_l, int off_d, int off_u,
-                                                                  const float* __restrict__ elem_k,
-                                                                  const float* __restrict__ diag_add, float* __restrict__ values) {
-  __shared__ float s_acc[AS_WARPS][AS_SLOTS * 9 + 4];
-  __shared__ __align__(16) float s_stage[AS_WARPS][8][72];
-  __shared__ int s_loc[AS_WARPS][64];
+__global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(AsmArgs A) {
+  __shared__ AsmWarpSmem sm[AS_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int r = blockIdx.x * AS_WARPS + w;
-  if (r >= n_vert) return;                                   // warp-uniform
-  const int v = __ldg(i2v + r);
-  const int lp = __ldg(L_ptr + r), nl = __ldg(L_ptr + r + 1) - lp;
-  const int up = __ldg(U_ptr + r), nu = __ldg(U_ptr + r + 1) - up;
-  // incident hexahedra (e*8+a): lane j < 8 holds entry j
-  const int my_ea = lane < 8 ? __ldg(vert_elem + (size_t)v * 8 + lane) : -1;
-  float4 seg[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ea = __shfl_sync(0xffffffffu, my_ea, j);
-    seg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ea >= 0 && lane < 18) seg[j] = __ldg(reinterpret_cast<const float4*>(elem_k + (size_t)ea * 72) + lane);
-  }
-  // local slot of every (j,b): lanes handle 2 map entries each
-  const bool fits = nl + 1 + nu <= AS_SLOTS;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int t = lane + 32 * h, j = t >> 3, b = t & 7;
-    const int ea = __shfl_sync(0xffffffffu, my_ea, j);
-    int loc = -1;
-    if (ea >= 0) {
-      const int s = __ldg(elem2nnz + (size_t)ea * 8 + b);
-      loc = s < off_d ? (s - off_l - lp) : (s < off_u ? nl : nl + 1 + (s - off_u - up));
-      if (!fits) loc = s;                                    // oversized rows keep the global slot (slow path below)
-    }
-    s_loc[w][t] = loc;
-  }
-  for (int i = lane; i < AS_SLOTS * 9; i += 32) s_acc[w][i] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (lane < 18) *reinterpret_cast<float4*>(&s_stage[w][j][4 * lane]) = seg[j];
-  __syncwarp();
-  if (fits) {
-    for (int j = 0; j < 8; ++j) {
-      if (s_loc[w][8 * j] < 0) continue;                     // hexahedron slot unused (boundary vertex); warp-uniform
-#pragma unroll
-      for (int h = 0; h < 3; ++h) {
-        const int t = lane + 32 * h;
-        if (t < 72) {
-          const int b = t / 9, k = t - 9 * b;
-          s_acc[w][s_loc[w][8 * j + b] * 9 + k] += s_stage[w][j][t];
-        }
-      }
-      __syncwarp();
-    }
-    float* outL = values + ((size_t)off_l + lp) * 9;
-    for (int i = lane; i < nl * 9; i += 32) outL[i] = s_acc[w][i];
-    if (lane < 9) {
-      float d = s_acc[w][nl * 9 + lane];
-      if (diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) d += __ldg(diag_add + r);
-      values[((size_t)off_d + r) * 9 + lane] = d;
-    }
-    float* outU = values + ((size_t)off_u + up) * 9;
-    for (int i = lane; i < nu * 9; i += 32) outU[i] = s_acc[w][(nl + 1) * 9 + i];
-  } else {
-    // rows with more than 27 blocks (not produced by hexahedral lattices): one slot at a time
-    for (int part = 0; part < 3; ++part) {
-      const int cnt = part == 0 ? nl : (part == 1 ? 1 : nu);
-      for (int li = 0; li < cnt; ++li) {
-        const int slot = part == 0 ? off_l + lp + li : (part == 1 ? off_d + r : off_u + up + li);
-        if (lane < 9) {
-          float sum = (part == 1 && diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) ? __ldg(diag_add + r) : 0.f;
-          for (int t = 0; t < 64; ++t)
-            if (s_loc[w][t] == slot) sum += s_stage[w][t >> 3][(t & 7) * 9 + lane];
-          values[(size_t)slot * 9 + lane] = sum;
-        }
-      }
-    }
-  }
+  if (r >= A.n_vert) return;                                 // warp-uniform
+  assemble_row<false>(A, __ldg(A.i2v + r), r, lane, sm[w]);
 }
 
 // out[row] = sum of the element forces of the incident hexahedra + gravity + pin spring
@@ -508,16 +642,30 @@ static ElemIn make_in(const FembLevel* l, const float* x, float mu, float la) {
   return in;
 }
 
-template <int kMode>
+static AsmArgs make_asm(const FembLevel* l, const float* diag_add, const float* elem_k, float* values) {
+  AsmArgs A;
+  A.n_vert = l->n_vert; A.i2v = l->i2v; A.v2i = l->v2i; A.vert_elem = l->vert_elem; A.elem2nnz = l->elem2nnz;
+  A.L_ptr = l->L_ptr; A.U_ptr = l->U_ptr; A.off_l = l->off_l; A.off_d = l->off_d; A.off_u = l->off_u;
+  A.fold = l->fold_plan; A.elem_k = elem_k; A.diag_add = diag_add; A.values = values;
+  return A;
+}
+
+static bool can_fuse(const FembLevel* l) {
+  return l->asm_chunk_ptr && l->asm_chunk_grp && l->asm_expected && l->asm_counter && l->n_hex > 0;
+}
+
+template <int kMode, bool kFused>
 static int launch_element(const FembLevel* l, const float* x, float mu, float la, float* elem_f, float* elem_k,
-                          cudaStream_t st) {
+                          const AsmArgs& as, cudaStream_t st) {
   static bool configured = false;
   const size_t smem = element_smem<kMode>();
   if (!configured) {
-    cudaFuncSetAttribute(element_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(element_kernel<kMode, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  element_kernel<kMode><<<cdiv(l->n_hex, EPB), ETHREADS, smem, st>>>(make_in(l, x, mu, la), elem_f, elem_k);
+  FuseArgs fu;
+  fu.chunk_ptr = l->asm_chunk_ptr; fu.chunk_grp = l->asm_chunk_grp; fu.expected = l->asm_expected; fu.counter = l->asm_counter;
+  element_kernel<kMode, kFused><<<cdiv(l->n_hex, EPB), ETHREADS, smem, st>>>(make_in(l, x, mu, la), elem_f, elem_k, fu, as);
   count_launch();
   return check_launch("element_kernel");
 }
@@ -532,10 +680,8 @@ static int launch_force_gather(const FembLevel* l, const float* x, const float* 
   return check_launch("force_gather_kernel");
 }
 
-static int launch_assemble(const FembLevel* l, const float* diag_add, const float* elem_k, float* values, cudaStream_t st) {
-  assemble_rows_kernel<<<cdiv(l->n_vert, AS_WARPS), AS_THREADS, 0, st>>>(l->n_vert, l->i2v, l->vert_elem, l->elem2nnz, l->L_ptr,
-                                                                        l->U_ptr, l->off_l, l->off_d, l->off_u, elem_k, diag_add,
-                                                                        values);
+static int launch_assemble(const AsmArgs& as, cudaStream_t st) {
+  assemble_rows_kernel<<<cdiv(as.n_vert, AS_WARPS), AS_THREADS, 0, st>>>(as);
   count_launch();
   return check_launch("assemble_rows_kernel");
 }
@@ -546,12 +692,27 @@ using namespace femb;
 
 extern "C" {
 
+int femb_set_fused_assembly(int enable) {
+  const int old = !g_no_fuse;
+  g_no_fuse = !enable;
+  return old;
+}
+
 int femb_prepare_rest(int n_hex, const int* hex, const float* x_rest, float* detJ, float* invJ, void* stream) {
   FEMB_REQUIRE(n_hex >= 0 && hex && x_rest && detJ && invJ, "null pointer or negative size");
   if (n_hex == 0) return FEMB_OK;
   prepare_rest_kernel<<<cdiv((long long)n_hex * 8, 256), 256, 0, as_stream(stream)>>>(n_hex, hex, x_rest, detJ, invJ);
   count_launch();
   return check_launch("prepare_rest_kernel");
+}
+
+int femb_build_fold_plan(const FembLevel* lvl, unsigned char* fold_plan, void* stream) {
+  FEMB_REQUIRE(lvl && fold_plan, "null pointer");
+  FEMB_REQUIRE(lvl->v2i && lvl->vert_elem && lvl->elem2nnz && lvl->L_ptr && lvl->U_ptr, "level not initialised");
+  if (lvl->n_vert == 0) return FEMB_OK;
+  fold_plan_kernel<<<cdiv(lvl->n_vert, 8), 256, 0, as_stream(stream)>>>(make_asm(lvl, nullptr, nullptr, nullptr), fold_plan);
+  count_launch();
+  return check_launch("fold_plan_kernel");
 }
 
 int femb_lumped_mass(const FembLevel* lvl, float* vol, float* mass, void* stream) {
@@ -572,7 +733,7 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
   FEMB_REQUIRE(lvl && x && elem_f && out, "null pointer");
   FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->vert_elem && lvl->v2i, "level not initialised");
   if (lvl->n_hex > 0) {
-    int rc = launch_element<0>(lvl, x, mu, lambda, elem_f, nullptr, as_stream(stream));
+    int rc = launch_element<0, false>(lvl, x, mu, lambda, elem_f, nullptr, AsmArgs(), as_stream(stream));
     if (rc) return rc;
   }
   if (lvl->n_vert == 0) return FEMB_OK;
@@ -582,29 +743,34 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add, float* elem_k,
                  float* values, void* stream) {
   FEMB_REQUIRE(lvl && x && elem_k && values, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v, "level not initialised");
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan, "level not initialised");
+  const AsmArgs as = make_asm(lvl, diag_add, elem_k, values);
+  if (can_fuse(lvl) && !g_no_fuse) return launch_element<1, true>(lvl, x, mu, lambda, nullptr, elem_k, as, as_stream(stream));
   if (lvl->n_hex > 0) {
-    int rc = launch_element<1>(lvl, x, mu, lambda, nullptr, elem_k, as_stream(stream));
+    int rc = launch_element<1, false>(lvl, x, mu, lambda, nullptr, elem_k, as, as_stream(stream));
     if (rc) return rc;
   }
   if (lvl->nnz == 0) return FEMB_OK;
-  return launch_assemble(lvl, diag_add, elem_k, values, as_stream(stream));
+  return launch_assemble(as, as_stream(stream));
 }
 
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add, float* elem_f,
                        float* elem_k, float* force_out, float* values, void* stream) {
   FEMB_REQUIRE(lvl && x && elem_f && elem_k && force_out && values, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->vert_elem && lvl->v2i,
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan && lvl->v2i,
                "level not initialised");
+  const AsmArgs as = make_asm(lvl, diag_add, elem_k, values);
+  const bool fused = can_fuse(lvl) && !g_no_fuse;
   if (lvl->n_hex > 0) {
-    int rc = launch_element<2>(lvl, x, mu, lambda, elem_f, elem_k, as_stream(stream));
+    int rc = fused ? launch_element<2, true>(lvl, x, mu, lambda, elem_f, elem_k, as, as_stream(stream))
+                   : launch_element<2, false>(lvl, x, mu, lambda, elem_f, elem_k, as, as_stream(stream));
     if (rc) return rc;
   }
   if (lvl->n_vert == 0) return FEMB_OK;
   int rc = launch_force_gather(lvl, x, mass, g, pin, pin_pos, control_mag, 1, elem_f, force_out, as_stream(stream));
-  if (rc) return rc;
-  return launch_assemble(lvl, diag_add, elem_k, values, as_stream(stream));
+  if (rc || fused) return rc;
+  return launch_assemble(as, as_stream(stream));
 }
 
 int femb_energy(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g, const int* pin,

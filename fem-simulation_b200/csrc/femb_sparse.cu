@@ -67,6 +67,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor is still running; griddep_wait() blocks until the predecessor has completed and its
+// writes are visible, griddep_launch() lets the successor start.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct RowSmem {
   alignas(128) float val[RP_CAP * 9 + 16];   // [L chunk | U chunk], each starting on a 16-byte boundary
   alignas(16) int col[RP_CAP + 16];
@@ -80,7 +86,7 @@ struct RowSmem {
 // (cooperative) launch, so it is read through L2 (ld.global.cg) instead of the per-SM L1.
 // The values / L_col / U_col arrays must be 16-byte aligned and readable 16 bytes past their end
 // (the bulk copies are rounded out to 16-byte granules).
-template <int kMode, bool kCoherent>
+template <int kMode, bool kCoherent, bool kPdl = false>
 __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, RowSmem& sm, uint32_t& phase) {
   const int tid = threadIdx.x;
   const bool useL = (a.parts & FEMB_PART_L) != 0, useU = (a.parts & FEMB_PART_U) != 0;
@@ -117,6 +123,12 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
       bulk_g2s(sm.col + cbaseU, a.U_col + (U0 - cpreU), cU, &sm.bar);
     }
     if (needD) bulk_g2s(sm.diag, a.values + (gD - preD), bD, &sm.bar);
+  }
+  if (kPdl) {
+    // Everything above reads only the matrix (constant while a sweep runs): with a programmatic launch it overlaps
+    // the tail of the previous colour.  x / b / y are touched only after the predecessor has completed.
+    griddep_wait();
+    griddep_launch();
   }
   mbar_wait(&sm.bar, phase);
   phase ^= 1u;
@@ -219,6 +231,16 @@ __global__ void __launch_bounds__(RP_THREADS) row_pass_kernel(RowArgs a) {
   row_block<kMode, false>(a, r0, min(RP_ROWS, a.row_end - r0), sm, phase);
 }
 
+// One colour of a Gauss-Seidel sweep, launchable as a programmatic dependent of the previous colour: the matrix
+// staging (pointer reads + bulk copies) runs before griddepcontrol.wait, i.e. during the previous colour's tail.
+__global__ void __launch_bounds__(RP_THREADS) gs_color_kernel(RowArgs a) {
+  __shared__ RowSmem sm;
+  if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
+  uint32_t phase = 0;
+  const int r0 = a.row_begin + blockIdx.x * RP_ROWS;
+  row_block<RM_GS, false, true>(a, r0, min(RP_ROWS, a.row_end - r0), sm, phase);
+}
+
 // Whole femb_gauss_seidel call in ONE cooperative launch (levels whose colour fits the resident grid):
 // iterations x 16 colour phases separated by grid-wide barriers instead of 16 launches per iteration.
 struct GsCoopArgs {
@@ -268,6 +290,26 @@ static int launch_rows(const RowArgs& a, cudaStream_t st) {
   row_pass_kernel<kMode><<<cdiv(n, RP_ROWS), RP_THREADS, 0, st>>>(a);
   count_launch();
   return check_launch("row_pass_kernel");
+}
+
+// pdl: the launch may overlap the tail of the previous kernel in the stream (which must not write the matrix)
+static int g_no_pdl = 0;
+static int launch_gs_color(const RowArgs& a, bool pdl, cudaStream_t st) {
+  const int n = a.row_end - a.row_begin;
+  if (n <= 0) return FEMB_OK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(n, RP_ROWS)); cfg.blockDim = dim3(RP_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl && !g_no_pdl) ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, gs_color_kernel, a);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error("gs_color_kernel: %s", cudaGetErrorString(e));
+    return FEMB_E_CUDA;
+  }
+  return check_launch("gs_color_kernel");
 }
 
 // resident CTAs of gs_coop_kernel on the current device (0 if cooperative launch is unsupported)
@@ -579,6 +621,12 @@ using namespace femb;
 
 extern "C" {
 
+int femb_set_pdl(int enable) {
+  const int old = !g_no_pdl;
+  g_no_pdl = !enable;
+  return old;
+}
+
 int femb_spmv(const FembLevel* lvl, const float* values, int parts, float alpha, const float* x, float beta, float* y,
               void* stream) {
   FEMB_REQUIRE(lvl && values && x && y, "null pointer");
@@ -625,18 +673,20 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
     }
     return FEMB_OK;
   }
+  bool first = true;                 // the first colour follows the memset (and whatever wrote the matrix): ordinary launch
   for (int it = 0; it < iterations; ++it) {
     for (int c = 7; c >= 0; --c) {                                                // backward sweep, object.py:893-898
       a.row_begin = lvl->color_start[c]; a.row_end = lvl->color_start[c + 1];
       // first half-sweep of the first iteration: dx == 0, rows of colour c only see higher colours
       a.parts = (it == 0) ? FEMB_PART_U : (FEMB_PART_L | FEMB_PART_U);
-      int rc = launch_rows<RM_GS>(a, st);
+      int rc = launch_gs_color(a, !first, st);
       if (rc) return rc;
+      first = false;
     }
     a.parts = FEMB_PART_L | FEMB_PART_U;
     for (int c = 0; c < 8; ++c) {                                                 // forward sweep, object.py:903-908
       a.row_begin = lvl->color_start[c]; a.row_end = lvl->color_start[c + 1];
-      int rc = launch_rows<RM_GS>(a, st);
+      int rc = launch_gs_color(a, true, st);
       if (rc) return rc;
     }
   }
@@ -653,7 +703,7 @@ int femb_gs_colors(const FembLevel* lvl, const float* values, const float* b, fl
   const int step = first_color <= last_color ? 1 : -1;
   for (int c = first_color;; c += step) {
     a.row_begin = lvl->color_start[c]; a.row_end = lvl->color_start[c + 1];
-    int rc = launch_rows<RM_GS>(a, as_stream(stream));
+    int rc = launch_gs_color(a, c != first_color, as_stream(stream));   // the first colour follows a halo exchange
     if (rc) return rc;
     if (c == last_color) break;
   }

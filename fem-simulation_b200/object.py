@@ -110,6 +110,7 @@ class Object:
             start = np.cumsum(cnt) - cnt
             ve[flat[o2], np.arange(len(o2)) - start[flat[o2]]] = o2.astype(np.int32)      # e*8+a
             pad = np.zeros(4, np.int32)                                  # bulk copies are rounded out to 16 bytes
+            ap = self._asm_plan(H.hexs[l], n)
             d = dict(L_ptr=_dev(p.L_ptr, dev), L_col=_dev(np.concatenate([p.L_col, pad]), dev)[:p.L_nnz],
                      U_ptr=_dev(p.U_ptr, dev), U_col=_dev(np.concatenate([p.U_col, pad]), dev)[:p.L_nnz],
                      vert_elem=_dev(ve, dev),
@@ -126,6 +127,14 @@ class Object:
             lv.elem2nnz = self.hex_update_offset_gpu[l].data_ptr()
             for k in ("L_ptr", "L_col", "U_ptr", "U_col", "vert_elem", "invJ", "detJ"):
                 setattr(lv, k, d[k].data_ptr())
+            d["fold_plan"] = torch.empty(n * 27 * 8 + 16, dtype=torch.uint8, device=dev)
+            _lib.check(self.lib.femb_build_fold_plan(C.byref(lv), d["fold_plan"].data_ptr(), self._stream()), "femb_build_fold_plan")
+            lv.fold_plan = d["fold_plan"].data_ptr()
+            if ap is not None:                                           # fused ("last arriver") assembly plan
+                d.update(asm_chunk_ptr=_dev(ap[0], dev), asm_chunk_grp=_dev(ap[1], dev), asm_expected=_dev(ap[2], dev),
+                         asm_counter=torch.zeros(len(ap[2]), dtype=torch.int32, device=dev))
+                for k in ("asm_chunk_ptr", "asm_chunk_grp", "asm_expected", "asm_counter"):
+                    setattr(lv, k, d[k].data_ptr())
             self.levels.append(lv)
             self.inverse_pX_peps_gpu.append(d["invJ"])
             self.det_pX_peps_gpu.append(d["detJ"])
@@ -225,6 +234,25 @@ class Object:
             return mesh.box_mesh(nx, ny, nz, dx)
         from . import voxelize
         return voxelize.voxelize_obj(mesh_path, dx)
+
+    @staticmethod
+    def _asm_plan(hexs, n_vert):
+        """Plan of the fused assembly (femb200.h, FembLevel.asm_*): which row groups (16 consecutive vertex ids) every
+        chunk of 16 consecutive hexahedra touches, and how many chunks touch each group."""
+        nh = hexs.shape[0]
+        if nh == 0:
+            return None
+        CH, GR = _lib.ASM_CHUNK_HEXES, _lib.ASM_GROUP_ROWS
+        n_chunks, n_groups = (nh + CH - 1) // CH, (n_vert + GR - 1) // GR
+        key = np.unique((np.repeat(np.arange(nh, dtype=np.int64) // CH, 8)) * n_groups + hexs.reshape(-1).astype(np.int64) // GR)
+        chunk_of, grp_of = key // n_groups, key % n_groups
+        expected = np.bincount(grp_of, minlength=n_groups).astype(np.int32)
+        if expected.min() == 0:                                          # a vertex outside every hexahedron: keep the two-kernel path
+            return None
+        chunk_ptr = np.zeros(n_chunks + 1, dtype=np.int32)
+        chunk_ptr[1:] = np.cumsum(np.bincount(chunk_of, minlength=n_chunks))
+        assert np.diff(chunk_ptr).max() <= 128
+        return chunk_ptr, grp_of.astype(np.int32), expected
 
     def new_values(self, layer):
         """Zeroed block-value array [nnz,3,3] of a level, padded as the bulk-copy kernels require (femb200.h)."""

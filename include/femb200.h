@@ -33,7 +33,12 @@ extern "C" {
 #define FEMB_E_CUDA (-2)      /* a CUDA runtime call or launch failed                 */
 #define FEMB_E_NODEVICE (-3)  /* no usable sm_100 device                              */
 
-#define FEMB_ABI_VERSION 1
+#define FEMB_ABI_VERSION 2
+
+/* granularity of the fused assembly plan (FembLevel.asm_*) */
+#define FEMB_ASM_CHUNK_HEXES 16
+#define FEMB_ASM_GROUP_ROWS 16
+#define FEMB_FOLD_SLOTS 27
 
 /* matrix part selector for femb_spmv (bsr_mv on self.L / self.D / self.U / self.A) */
 #define FEMB_PART_L 1
@@ -60,6 +65,15 @@ typedef struct FembLevel {
   const int* vert_elem;  /* [n_vert*8] e*8+a of the hexes incident to a vertex, -1 pad  */
   const float* invJ;     /* [n_hex*8*9] inverse_pX_peps (quai_hexagon.py:18)            */
   const float* detJ;     /* [n_hex*8]   det_pX_peps     (quai_hexagon.py:17)            */
+  const unsigned char* fold_plan; /* [n_vert*27*8] per vertex, per block of its row (L blocks, D, U blocks): the <= 8   */
+                                  /* contributors j*8+b (j-th incident hexahedron, local node b; 255 = none) in fold order; */
+                                  /* filled by femb_build_fold_plan from vert_elem + elem2nnz                              */
+  /* Optional plan of the fused ("last arriver") assembly, all NULL = two-kernel assembly.  Hexahedra are taken in
+   * chunks of FEMB_ASM_CHUNK_HEXES consecutive ids, rows in groups of FEMB_ASM_GROUP_ROWS consecutive VERTEX ids. */
+  const int* asm_chunk_ptr;  /* [n_chunks+1] CSR: chunk -> row groups holding a vertex of one of its hexahedra */
+  const int* asm_chunk_grp;  /* [asm_chunk_ptr[n_chunks]]                                                      */
+  const int* asm_expected;   /* [n_groups] number of chunks that touch the group                               */
+  int* asm_counter;          /* [n_groups] device scratch, zero on entry to and on exit from every call         */
 } FembLevel;
 
 /* CSR matrix with one scalar weight per entry = BSR matrix with blocks w*I3: the interpolation
@@ -106,6 +120,9 @@ int femb_check_device(int device);
 /* ---- rest state (setup) ------------------------------------------------------------------- */
 /* prepare_kernal (quai_hexagon.py:4-18): rest Jacobian per (hex,q) -> detJ[n_hex*8], invJ[n_hex*72] */
 int femb_prepare_rest(int n_hex, const int* hex, const float* x_rest, float* detJ, float* invJ, void* stream);
+/* setup of FembLevel.fold_plan (all other fields of *lvl must be final): the inverse of the element->nnz map per row, so
+ * that the assembly is a gather in a fixed order (replaces the atomics of quai_hexagon.py:100-106) */
+int femb_build_fold_plan(const FembLevel* lvl, unsigned char* fold_plan, void* stream);
 /* Sum_8 + prepare_mass (cublas.py:215-218, quai_hexagon.py:20-26) as a gather: vol[n_hex], mass[n_vert] */
 int femb_lumped_mass(const FembLevel* lvl, float* vol, float* mass, void* stream);
 
@@ -125,6 +142,11 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
  *   filled as in femb_force (same optional arguments). */
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add,
                  float* elem_k, float* values, void* stream);
+/* Experimental, OFF by default (measured slower than the two-kernel path on B200): with an assembly plan in
+ * the level (asm_* != NULL) and femb_set_fused_assembly(1), femb_hessian / femb_force_hessian run ONE kernel -- the CTA
+ * whose chunk completes a row group folds that group while the element matrices are still in L2 (same fold order, so
+ * bit-identical values).  Returns the old setting. */
+int femb_set_fused_assembly(int enable);
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add,
                        float* elem_f, float* elem_k, float* force_out, float* values, void* stream);
@@ -150,6 +172,9 @@ int femb_residual(const FembLevel* lvl, const float* values, const float* b, con
  * NULL) counts the `print('not spd')` events (cublas.py:79-80). */
 int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b, float* dx, int iterations,
                       int* not_spd, void* stream);
+/* The colour launches of a sweep are programmatic dependent launches (each colour stages its matrix rows while the
+ * previous colour drains); femb_set_pdl(0) makes them ordinary launches (tests).  Returns the old setting. */
+int femb_set_pdl(int enable);
 /* A run of colour launches of the in-place sweep above: colours first_color..last_color (descending if
  * first > last), dx is NOT zeroed.  femb_gauss_seidel(it=1) == zero dx; colours 7..0 with parts=U; colours 0..7
  * with parts=L|U.  Lets a caller put a halo exchange between colour groups (domain decomposition). */

@@ -1,0 +1,41 @@
+"""Micro-benchmark of the assembly stage (element Hessians + fold) on the cube: fused vs two-kernel path."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fem_simulation_b200 import Object
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+modes = [int(c) for c in (sys.argv[3] if len(sys.argv) > 3 else "101")]
+obj = Object(f"cube:{n}", 1.0 / n, [], use_graphs=False, layers=2)
+x = obj.x_gpu_layer[0]
+x.add_(torch.randn_like(x) * 1e-4)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+
+def timed(fn, label):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    print(f"{label:40s} {ev[0].elapsed_time(ev[1]) / reps * 1e3:9.1f} us", flush=True)
+
+
+for fused in modes:
+    obj.lib.femb_set_fused_assembly(fused)
+    timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed), f"hessian level0 fused={fused}")
+    timed(lambda: obj._force_hessian(x, obj.grad_gpu, obj.MF_value_gpu, obj.diag_fixed), f"force+hessian level0 fused={fused}")
+    timed(lambda: obj._hessian(1, obj.x_gpu_layer[1], obj.UtAUs_values[0]), f"hessian level1 fused={fused}")
+timed(lambda: obj._force(x, obj.grad_gpu), "force level0")
+obj._force_hessian(x, obj.dev_B_fixed[0], obj.MF_value_gpu, obj.diag_fixed)
+for pdl in ((1, 0, 1) if len(modes) > 1 else ()):
+    obj.lib.femb_set_pdl(pdl)
+    timed(lambda: obj.PerformGaussSeidel(0, 3), f"GS level0 x3 pdl={pdl} (eager)")
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        obj.PerformGaussSeidel(0, 3)
+    timed(g.replay, f"GS level0 x3 pdl={pdl} (graph)")

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(repo_root):
         assert hasattr(lib, n), f"{n} declared in femb200.h but not exported"
         assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
     assert sorted(_lib.PROTOTYPES) == names
-    assert lib.femb_abi_version() == 1
+    assert lib.femb_abi_version() == 2
 
 
 def test_no_device_is_an_error_not_a_fallback():

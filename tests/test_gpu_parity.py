@@ -267,3 +267,75 @@ def test_empty_and_errors():
     assert lib.femb_axpby(0, 1.0, z.data_ptr(), 1.0, z.data_ptr(), None) == 0
     assert lib.femb_inf_norm(0, z.data_ptr(), z.data_ptr(), None) == 0
     assert lib.femb_launch_count() > 0
+
+
+def test_fused_assembly_is_bit_identical_to_two_kernel_path(pair):
+    """femb_hessian with the FembLevel.asm_* plan (femb_set_fused_assembly(1): one kernel, last-arriver fold) vs the default
+    (element kernel + assemble_rows_kernel): same fold order => identical bits, on every level, repeatedly
+    (the group counters must return to zero after each call)."""
+    obj, ref, xp = pair
+    x0 = torch.from_numpy(xp).to(obj.device)
+    for l in range(min(obj.layer, 2)):
+        x = x0 if l == 0 else obj.x_gpu_layer[l] * 1.01
+        diag = obj.diag_fixed if l == 0 else None
+        assert obj.levels[l].asm_chunk_ptr, "no fused-assembly plan on this level"
+        va, vb = obj.new_values(l), obj.new_values(l)
+        obj.lib.femb_set_fused_assembly(0)
+        obj._hessian(l, x, va, diag)
+        obj.lib.femb_set_fused_assembly(1)
+        try:
+            for rep in range(3):
+                vb.fill_(float("nan"))
+                obj._hessian(l, x, vb, diag)
+                torch.cuda.synchronize()
+                assert torch.equal(va, vb), f"level {l} rep {rep}: fused assembly differs from the two-kernel path"
+                assert int(obj._pat[l]["asm_counter"].abs().sum()) == 0
+        finally:
+            obj.lib.femb_set_fused_assembly(0)
+    # fused force + Hessian entry point
+    f1, f2 = torch.zeros_like(x0), torch.zeros_like(x0)
+    va, vb = obj.new_values(0), obj.new_values(0)
+    obj.lib.femb_set_fused_assembly(0)
+    obj._force_hessian(x0, f1, va, obj.diag_fixed)
+    obj.lib.femb_set_fused_assembly(1)
+    try:
+        obj._force_hessian(x0, f2, vb, obj.diag_fixed)
+    finally:
+        obj.lib.femb_set_fused_assembly(0)
+    torch.cuda.synchronize()
+    assert torch.equal(va, vb) and torch.equal(f1, f2)
+
+
+def test_pdl_gauss_seidel_is_bit_identical():
+    """The colour launches of femb_gauss_seidel are programmatic dependent launches (matrix staging overlaps the
+    previous colour's tail).  Same arithmetic => identical bits with femb_set_pdl(0), eagerly and in a CUDA graph,
+    on a mesh with more CTAs per colour than fit on the device at once."""
+    n = 56
+    obj = Object(f"cube:{n}", 1.0 / n, [], use_graphs=False, layers=2)
+    x = obj.x_gpu_layer[0]
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    x.add_((torch.randn(x.shape, generator=gen) * 2e-4).to(x.device))
+    obj._force_hessian(x, obj.dev_B_fixed[0], obj.MF_value_gpu, obj.diag_fixed)
+    old = obj.lib.femb_set_pdl(0)
+    try:
+        obj.PerformGaussSeidel(0, 2)
+        ref = obj.dev_delta_x[0].clone()
+    finally:
+        obj.lib.femb_set_pdl(old)
+    for rep in range(3):
+        obj.dev_delta_x[0].fill_(float("nan"))
+        obj.PerformGaussSeidel(0, 2)
+        torch.cuda.synchronize()
+        assert torch.equal(ref, obj.dev_delta_x[0]), f"eager PDL sweep differs (rep {rep})"
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        obj.PerformGaussSeidel(0, 2)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            obj.PerformGaussSeidel(0, 2)
+    for rep in range(3):
+        obj.dev_delta_x[0].fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ref, obj.dev_delta_x[0]), f"graph-replayed PDL sweep differs (rep {rep})"
