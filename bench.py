@@ -88,6 +88,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# DRAM bytes (read + write) per launch measured with `ncu --set full` on the cube n=100 (profiles/README.md), per million hexahedra
+ASM_TRAFFIC_PER_MHEX = 4.62e9      # element_kernel<1> 0.364 + 1.484 GB, assemble_rows_kernel 1.81 + 0.96 GB
+GS_TRAFFIC_PER_MHEX = 118.9e6      # one colour launch of the row pass
+
+
 def pass_bytes(V, Z):
     """Algorithmic bytes of one full-matrix pass: values+col of every block, row pointer, b, x, out."""
     return Z * (36 + 4) + V * (4 + 12 + 12 + 12)
@@ -207,8 +212,19 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_e2e = maxed(ev0.elapsed_time(ev1))
-    # ---- dominant kernel: the row pass inside femb_gauss_seidel on the fine level -----------------
+    # ---- dominant stage of the FAS step: femb_hessian = element_kernel + assemble_rows_kernel (timed through the C ABI) ----
     reps = 5
+    vals_tmp = obj.MF_value_gpu
+    for _ in range(2):
+        obj._hessian(0, obj.x_gpu_layer[0], vals_tmp, obj.diag_fixed)
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    for _ in range(reps):
+        obj._hessian(0, obj.x_gpu_layer[0], vals_tmp, obj.diag_fixed)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    asm_ms = ev0.elapsed_time(ev1) / reps
+    # ---- dominant kernel of the smoother: one colour launch of femb_gauss_seidel on the fine level ----------------
     obj.PerformGaussSeidel(0, 3)
     torch.cuda.synchronize(dev)
     ev0.record()
@@ -243,9 +259,10 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach = gs_launch_bytes(obj) / (gs_ms_per_launch * 1e-3) / 1e9
-    sb = step_bytes(obj, method)
     H = obj.hierarchy
+    ach = gs_launch_bytes(obj) / (gs_ms_per_launch * 1e-3) / 1e9
+    asm_bytes = 352 * H.hexs[0].shape[0] + 36 * H.pattern[0].nnz + 256 * H.hexs[0].shape[0]
+    sb = step_bytes(obj, method)
     hexes_per_rank = n ** 3
     mhex = hexes_per_rank * world / 1e6
     steps_per_s = args.steps / (ms * 1e-3)
@@ -271,11 +288,17 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps * world),
         "step_hbm": {"algorithmic_bytes_per_step_per_rank": sb, "achieved_GBps_per_rank": sb / (ms / args.steps * 1e-3) / 1e9,
                      "frac_of_peak": sb / (ms / args.steps * 1e-3) / 1e9 / peak},
-        "roofline": {"bound": "hbm", "kernel": "row_pass_kernel<GS> (femb_gauss_seidel, fine level, per colour launch)",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 118.9e6,
-                     "traffic_note": "dram__bytes_read+write per launch from profiles/r01_rowpass_tma_ncu_raw.txt (cube n=100)",
+        "roofline": {"bound": "hbm", "kernel": "femb_hessian: element_kernel<1> + assemble_rows_kernel (level 0, the two launches of "
+                     "the assembly stage; the element kernel itself is FP32-issue / shared-memory bound, see DESIGN.md)",
+                     "achieved": asm_bytes / (asm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "traffic": ASM_TRAFFIC_PER_MHEX * n ** 3 / 1e6,
+                     "traffic_note": "dram__bytes_read+write of the two kernels, ncu --set full at cube n=100 (profiles/), scaled by hexahedra",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "us_per_launch": gs_ms_per_launch * 1e3, "algorithmic_bytes_per_launch": gs_launch_bytes(obj)},
+                     "us_per_launch": asm_ms * 1e3, "algorithmic_bytes_per_launch": asm_bytes,
+                     "algorithmic_bytes_formula": "352*N_h + 36*Z + 256*N_h (SURVEY.md 8d, Hessian assembly)"},
+        "roofline_smoother": {"bound": "hbm", "kernel": "gs_color_kernel<8> (femb_gauss_seidel, fine level, one colour launch)",
+                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": GS_TRAFFIC_PER_MHEX * n ** 3 / 1e6,
+                              "us_per_launch": gs_ms_per_launch * 1e3, "algorithmic_bytes_per_launch": gs_launch_bytes(obj)},
         "clocks": clocks,
     }
     if nmg is not None:

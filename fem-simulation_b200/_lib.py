@@ -30,10 +30,11 @@ class FembLevel(C.Structure):
                 ("L_ptr", C.c_void_p), ("L_col", C.c_void_p), ("U_ptr", C.c_void_p), ("U_col", C.c_void_p),
                 ("elem2nnz", C.c_void_p),
                 ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p),
-                ("fold_plan", C.c_void_p), ("asm_chunk_ptr", C.c_void_p), ("asm_chunk_grp", C.c_void_p), ("asm_expected", C.c_void_p),
-                ("asm_counter", C.c_void_p)]
+                ("fold_plan", C.c_void_p),
+                ("pipe_chunks", C.c_int), ("pipe_hex_end", C.c_void_p), ("pipe_vert_end", C.c_void_p)]
 
-ASM_CHUNK_HEXES, ASM_GROUP_ROWS = 16, 16
+ASM_CHUNK_HEXES = 16           # FEMB_ASM_CHUNK_HEXES
+ELEM_K_FLOATS = 384            # FEMB_ELEM_K_FLOATS
 
 
 class FembTransfer(C.Structure):
@@ -65,7 +66,7 @@ PROTOTYPES = {
     "femb_lumped_mass": [LV, P, P, P],
     "femb_force": [LV, P, F, F, P, F, P, P, F, I, P, P, P],
     "femb_hessian": [LV, P, F, F, P, P, P, P],
-    "femb_set_fused_assembly": [I],
+    "femb_set_pipeline": [I],
     "femb_force_hessian": [LV, P, F, F, P, F, P, P, F, P, P, P, P, P, P],
     "femb_energy": [LV, P, F, F, P, F, P, P, F, P, P, P],
     "femb_coarse_pin_penalty": [LV, TR, P, F, P, P],
@@ -73,6 +74,7 @@ PROTOTYPES = {
     "femb_residual": [LV, P, P, P, P, P],
     "femb_gauss_seidel": [LV, P, P, P, I, P, P],
     "femb_set_pdl": [I],
+    "femb_set_gs_threads_per_row": [I],
     "femb_gs_colors": [LV, P, P, P, I, I, I, P, P],
     "femb_jacobi": [LV, P, P, P, P, I, P, P],
     "femb_cg": [LV, P, P, P, P, P, P, P, I, F, I, P],

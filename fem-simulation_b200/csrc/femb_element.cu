@@ -20,8 +20,6 @@
 
 #include "femb_common.cuh"
 
-static int g_no_fuse = 1;   // femb_set_fused_assembly(1) turns the one-kernel (last-arriver) assembly on; measured slower, see DESIGN.md
-
 namespace femb {
 
 constexpr int EPB = FEMB_ASM_CHUNK_HEXES;            // hexahedra per CTA
@@ -35,18 +33,18 @@ constexpr int QP_FFT = 0;
 constexpr int QP_C = 6;
 constexpr int QP_GU = 8;
 constexpr int QP_T = 56;
-constexpr int QP_BCAST = 56;  // floats every lane loads (14 float4)
 constexpr int QP_SIZE = 84;   // 21 float4: 16-byte accesses of 8 consecutive lanes hit distinct banks (21 is odd)
 // floats between the records of consecutive hexahedra: 8*84 + 16 = 16 (mod 32), so the per-lane 8-byte reads of phase B
 // (two hexahedra per half-warp, 16 banks each) are conflict-free
 constexpr int HEX_STRIDE = 8 * QP_SIZE + 16;
+constexpr int EK_ROW = FEMB_ELEM_K_FLOATS / 8;   // floats per stored row of an element matrix (5 blocks + 3 pad)
 
 struct ElemIn {
   const int* hex;
   const float* x;
   const float* invJ;
   const float* detJ;
-  int n_hex;
+  int e_begin, n_hex;    // the launch covers hexahedra [e_begin, n_hex)
   float mu, la;
 };
 
@@ -155,8 +153,7 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
 // 16-byte aligned bytes each, fetched as 18 float4 by 18 lanes (all 8 fetches in flight before the first is
 // consumed).  The blocks are folded into the row's <= 27 value slots through the element->nnz map in shared
 // memory (fixed order: incidence order, then b; no atomics) and the row's L, D and U segments are written
-// with coalesced stores.  kCoherent: the element matrices were written by other CTAs of the SAME launch
-// (fused path), so they are read through L2 (ld.global.cg), never through the non-coherent path.
+// with coalesced stores.
 constexpr int AS_SLOTS = FEMB_FOLD_SLOTS;       // 27: blocks of a row of a hexahedral lattice
 struct AsmArgs {
   int n_vert;
@@ -165,85 +162,142 @@ struct AsmArgs {
   int off_l, off_d, off_u;
   const float* elem_k; const float* diag_add; float* values;
 };
+// Stored layout of a half row (EK_ROW = 48 floats): positions 0..4 as 8 floats each (elements 0..7 of the block, 16-byte
+// aligned) at [8p, 8p+8), their ninth elements ("tails") at [40, 45), 3 pad floats.  The staged copy of a row in shared
+// memory keeps that shape per incident hexahedron j: 8 positions x 8 floats, then 8 tails; positions 5..7 are the
+// mirrored blocks as they are stored (position m of row (a-m)&7) -- they are transposed in registers by the fold.
+constexpr int AS_JSTRIDE = 84;                    // 64 + 8 own tails + 12 mirror tails; = 20 (mod 32) spreads the hexahedra over the banks
+constexpr int AS_TAIL = 64;                       // tails of positions 0..4 (two float4 as stored)
+constexpr int AS_MTAIL = 72;                      // tail float4 of rows (a-m)&7, m = 1..3, as stored: tail of position 8-m at +4(m-1)+m
+constexpr int AS_ZERO = 8 * AS_JSTRIDE;           // a block of zeros (+ zero tail at +8): what an absent contributor reads
 struct AsmWarpSmem {
-  alignas(16) float stage[8][72];          // row `a` of the <= 8 incident element matrices: block (j,b) at [j][9b]
-  float out[AS_SLOTS * 9 + 5];             // the folded row: L blocks, D, U blocks
+  alignas(16) float stage[8 * AS_JSTRIDE + 12];   // the folded row (27 x 9 floats) reuses the front of it
 };
+// per-row record of the fold plan: 27 x 8 contributor bytes, then a 16-byte header
+constexpr int FP_ROW = FEMB_FOLD_PLAN_BYTES;       // 232
+// what a warp needs to know about a row before touching the element matrices; one coalesced read of the plan record
+// (+ the incidence list), prefetched one row ahead
+struct AsmMeta {
+  uint2 plan;        // lane s < 27: contributors of block s
+  int my_ea;         // lane j < 8: j-th incident hexahedron*8 + local node, -1 = none
+  int r, lp, up, nl, nu;
+};
+__device__ __forceinline__ AsmMeta asm_meta(const AsmArgs& A, int v, int lane) {
+  AsmMeta M;
+  uint2 w = make_uint2(0xffffffffu, 0xffffffffu);
+  if (lane < AS_SLOTS + 2) w = __ldg(reinterpret_cast<const uint2*>(A.fold + (size_t)v * FP_ROW) + lane);
+  M.plan = lane < AS_SLOTS ? w : make_uint2(0xffffffffu, 0xffffffffu);
+  M.my_ea = lane < 8 ? __ldg(A.vert_elem + (size_t)v * 8 + lane) : -1;
+  M.r = (int)__shfl_sync(0xffffffffu, w.x, AS_SLOTS);          // header: r, lp | up, nl + (nu << 8)
+  M.lp = (int)__shfl_sync(0xffffffffu, w.y, AS_SLOTS);
+  M.up = (int)__shfl_sync(0xffffffffu, w.x, AS_SLOTS + 1);
+  const unsigned nn = __shfl_sync(0xffffffffu, w.y, AS_SLOTS + 1);
+  M.nl = (int)(nn & 255u); M.nu = (int)((nn >> 8) & 255u);
+  return M;
+}
+// what depends only on the lane: computed once per warp, used for every row the warp folds.  Per incident hexahedron one
+// LDG.128 per lane fetches: lanes 0..11 the 12 float4 of the own half row; lanes 12..17 the two float4 of position m of
+// row (a-m)&7 (m = 1..3); lanes 18..20 the tail float4 of those rows.
+struct AsmLane {
+  int nb_m;        // 0: own row, m: row (a - m) & 7
+  int src4;        // float4 index inside that row
+  int dst;         // float offset inside the staged hexahedron where the float4 goes
+};
+__device__ __forceinline__ AsmLane asm_lane(int lane) {
+  AsmLane L;
+  L.nb_m = 0; L.src4 = 0; L.dst = 0;
+  if (lane < 10) { L.src4 = lane; L.dst = 4 * lane; }                                   // positions 0..4, elements 0..7
+  else if (lane < 12) { L.src4 = lane; L.dst = AS_TAIL + 4 * (lane - 10); }              // tails of positions 0..4 (+ pad)
+  else if (lane < 18) { const int m = (lane - 12) / 2 + 1, h = (lane - 12) & 1; L.nb_m = m; L.src4 = 2 * m + h; L.dst = (8 - m) * 8 + 4 * h; }
+  else if (lane < 21) { const int m = lane - 17; L.nb_m = m; L.src4 = 10; L.dst = AS_MTAIL + 4 * (m - 1); }
+  return L;
+}
+// float offset of the ninth element of rotated position p inside a staged hexahedron
+__device__ __forceinline__ int staged_tail(int p) { return p < 5 ? AS_TAIL + p : AS_MTAIL + 36 - 5 * p; }   // m = 8-p: 4(m-1)+m
+// element k of the block at rotated position p of staged hexahedron j (mirrored positions are stored transposed)
+__device__ __forceinline__ float staged_elem(const float* stage, int j, int p, int k) {
+  const int ks = p >= 5 ? 3 * (k % 3) + k / 3 : k;
+  return ks < 8 ? stage[j * AS_JSTRIDE + p * 8 + ks] : stage[j * AS_JSTRIDE + staged_tail(p)];
+}
 
 // rows with more than 27 blocks (not produced by hexahedral lattices): one slot at a time through elem2nnz
-__device__ __noinline__ void assemble_row_slow(const AsmArgs& A, int r, int lane, int my_ea, int lp, int nl, int up, int nu,
+__device__ __noinline__ void assemble_row_slow(const int* elem2nnz, const float* diag_add, float* values, int off_l, int off_d,
+                                               int off_u, int r, int lane, int my_ea, int lp, int nl, int up, int nu,
                                                const float* stage) {
   for (int part = 0; part < 3; ++part) {
     const int cnt = part == 0 ? nl : (part == 1 ? 1 : nu);
     for (int li = 0; li < cnt; ++li) {
-      const int slot = part == 0 ? A.off_l + lp + li : (part == 1 ? A.off_d + r : A.off_u + up + li);
-      float sum = (part == 1 && A.diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) ? __ldg(A.diag_add + r) : 0.f;
+      const int slot = part == 0 ? off_l + lp + li : (part == 1 ? off_d + r : off_u + up + li);
+      float sum = (part == 1 && diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) ? __ldg(diag_add + r) : 0.f;
       for (int t = 0; t < 64; ++t) {
         const int ea = __shfl_sync(0xffffffffu, my_ea, t >> 3);
         if (ea < 0) continue;
-        if (__ldg(A.elem2nnz + (size_t)ea * 8 + (t & 7)) == slot && lane < 9)
-          sum += stage[(t >> 3) * 72 + (((t & 7) - (ea & 7)) & 7) * 9 + lane];        // rotated row layout
+        if (__ldg(elem2nnz + (size_t)ea * 8 + (t & 7)) == slot && lane < 9)
+          sum += staged_elem(stage, t >> 3, ((t & 7) - (ea & 7)) & 7, lane);              // rotated position of column node b
       }
-      if (lane < 9) A.values[(size_t)slot * 9 + lane] = sum;
+      if (lane < 9) values[(size_t)slot * 9 + lane] = sum;
     }
   }
 }
 
-template <bool kCoherent>
-__device__ __forceinline__ void assemble_row(const AsmArgs& A, int v, int r, int lane, AsmWarpSmem& sm) {
-  const int lp = __ldg(A.L_ptr + r), nl = __ldg(A.L_ptr + r + 1) - lp;
-  const int up = __ldg(A.U_ptr + r), nu = __ldg(A.U_ptr + r + 1) - up;
-  // incident hexahedra (e*8+a): lane j < 8 holds entry j
-  const int my_ea = lane < 8 ? __ldg(A.vert_elem + (size_t)v * 8 + lane) : -1;
-  // fold plan: lane s < 27 gets the <= 8 contributors (j*8+b, 255 = none) of the row's s-th block, in fold order
-  uint2 plan = make_uint2(0xffffffffu, 0xffffffffu);
-  if (lane < AS_SLOTS) plan = __ldg(reinterpret_cast<const uint2*>(A.fold + (size_t)v * (AS_SLOTS * 8)) + lane);
-  float4 seg[8];
+__device__ __forceinline__ void assemble_row(const AsmArgs& A, const AsmLane& LN, const AsmMeta& M, int lane, AsmWarpSmem& sm) {
+  const int r = M.r, lp = M.lp, nl = M.nl, up = M.up, nu = M.nu, my_ea = M.my_ea;
+  const uint2 plan = M.plan;
+  // One LDG.128 + one STS.128 per lane and incident hexahedron.  A missing hexahedron (ea < 0, boundary vertex) is read
+  // from hexahedron 0 instead: no contributor of the plan points at it, so what lands in its stage is never looked at.
+  if (lane < 21) {
+    float4 seg[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ea = __shfl_sync(0xffffffffu, my_ea, j);
-    seg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ea >= 0 && lane < 18) {
-      const float4* src = reinterpret_cast<const float4*>(A.elem_k + (size_t)ea * 72) + lane;
-      seg[j] = kCoherent ? __ldcg(src) : __ldg(src);
+    for (int j = 0; j < 8; ++j) {
+      const int ea = max(__shfl_sync(0x001fffffu, my_ea, j), 0);
+      const int rowid = (ea & ~7) | ((ea - LN.nb_m) & 7);
+      seg[j] = __ldg(reinterpret_cast<const float4*>(A.elem_k + (size_t)rowid * EK_ROW) + LN.src4);
     }
-  }
+    float* d = sm.stage + LN.dst;
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (lane < 18) *reinterpret_cast<float4*>(&sm.stage[j][4 * lane]) = seg[j];
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(d + j * AS_JSTRIDE) = seg[j];
+  }
   __syncwarp();
   const unsigned first = __shfl_sync(0xffffffffu, plan.x, 0) & 255u;
   if (first == 254u) {                                       // oversized row (plan not applicable); warp-uniform
-    assemble_row_slow(A, r, lane, my_ea, lp, nl, up, nu, &sm.stage[0][0]);
+    assemble_row_slow(A.elem2nnz, A.diag_add, A.values, A.off_l, A.off_d, A.off_u, r, lane, my_ea, lp, nl, up, nu, sm.stage);
     __syncwarp();
     return;
   }
-  // lane s folds block s: contributors in incidence order (same order as the reference's scatter would be sorted to)
+  // lane s folds block s: contributors in incidence order; a mirrored contributor (position >= 5) is added transposed
   float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float* st = &sm.stage[0][0];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const unsigned idx = ((c < 4 ? plan.x : plan.y) >> (8 * (c & 3))) & 255u;
-    if (idx < 64u) {
-      const float* src = st + idx * 9;                       // block (j,b) lives at stage[j][9b] = st + (8j+b)*9
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc[k] += src[k];
-    }
+    const bool have = idx < 64u;                             // no branch: an absent contributor reads the zero block
+    const unsigned j = idx >> 3, p = idx & 7u;
+    const unsigned off = have ? j * AS_JSTRIDE + p * 8 : (unsigned)AS_ZERO;
+    const unsigned toff = have ? j * AS_JSTRIDE + (p < 5u ? AS_TAIL + p : AS_MTAIL + 36u - 5u * p) : (unsigned)AS_ZERO + 8;
+    const bool tr = have && p >= 5u;
+    const float4* s4 = reinterpret_cast<const float4*>(sm.stage + off);
+    const float4 b0 = s4[0], b1 = s4[1];
+    const float t8 = sm.stage[toff];
+    acc[0] += b0.x; acc[4] += b1.x; acc[8] += t8;
+    acc[1] += tr ? b0.w : b0.y; acc[3] += tr ? b0.y : b0.w;
+    acc[2] += tr ? b1.z : b0.z; acc[6] += tr ? b0.z : b1.z;
+    acc[5] += tr ? b1.w : b1.y; acc[7] += tr ? b1.y : b1.w;
   }
+  __syncwarp();                                              // every lane is done reading the staged blocks
+  float* out = sm.stage;                                     // the folded row: L blocks, D, U blocks
   if (lane < AS_SLOTS) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) sm.out[lane * 9 + k] = acc[k];
+    for (int k = 0; k < 9; ++k) out[lane * 9 + k] = acc[k];
   }
   __syncwarp();
   float* outL = A.values + ((size_t)A.off_l + lp) * 9;
-  for (int i = lane; i < nl * 9; i += 32) outL[i] = sm.out[i];
+  for (int i = lane; i < nl * 9; i += 32) outL[i] = out[i];
   if (lane < 9) {
-    float d = sm.out[nl * 9 + lane];
+    float d = out[nl * 9 + lane];
     if (A.diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) d += __ldg(A.diag_add + r);
     A.values[((size_t)A.off_d + r) * 9 + lane] = d;
   }
   float* outU = A.values + ((size_t)A.off_u + up) * 9;
-  for (int i = lane; i < nu * 9; i += 32) outU[i] = sm.out[(nl + 1) * 9 + i];
+  for (int i = lane; i < nu * 9; i += 32) outU[i] = out[(nl + 1) * 9 + i];
   __syncwarp();                                              // the warp's scratch is reused by its next row
 }
 
@@ -257,7 +311,11 @@ __global__ void __launch_bounds__(256) fold_plan_kernel(AsmArgs A, unsigned char
   const int lp = __ldg(A.L_ptr + r), nl = __ldg(A.L_ptr + r + 1) - lp;
   const int up = __ldg(A.U_ptr + r), nu = __ldg(A.U_ptr + r + 1) - up;
   const int my_ea = lane < 8 ? __ldg(A.vert_elem + (size_t)v * 8 + lane) : -1;
-  unsigned char* out = fold + (size_t)v * (AS_SLOTS * 8);
+  unsigned char* out = fold + (size_t)v * FP_ROW;
+  if (lane == 0) {                                            // header: r, lp, up, nl + (nu << 8)
+    int* h = reinterpret_cast<int*>(out + AS_SLOTS * 8);
+    h[0] = r; h[1] = lp; h[2] = up; h[3] = (nl & 255) | ((nu & 255) << 8);
+  }
   if (nl + 1 + nu > AS_SLOTS) {
     for (int i = lane; i < AS_SLOTS * 8; i += 32) out[i] = 254;
     return;
@@ -283,30 +341,16 @@ __global__ void __launch_bounds__(256) fold_plan_kernel(AsmArgs A, unsigned char
   }
 }
 
-// Fused ("last arriver") assembly.  Hexahedra are processed in chunks of EPB (one CTA each), rows in groups of
-// FEMB_ASM_GROUP_ROWS consecutive vertices.  After a CTA has published its element matrices it bumps the counter of
-// every row group its chunk touches; the CTA whose increment completes a group (all chunks incident to the group's
-// rows have been published) assembles that group right away, while the element matrices are still in L2.  Nobody
-// waits, so there is no scheduling dependence and no deadlock; the fold order of a row is fixed by the incidence
-// list, so the result is bit-identical to the two-kernel path whichever CTA does the fold.
-struct FuseArgs {
-  const int* chunk_ptr;   // [n_chunks + 1]
-  const int* chunk_grp;   // row groups touched by each chunk
-  const int* expected;    // [n_groups] chunks touching the group
-  int* counter;           // [n_groups] zero between launches (the last arriver resets it)
-};
-
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both
-template <int kMode, bool kFused>
-__global__ void __launch_bounds__(ETHREADS, 5) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k,
-                                                              FuseArgs fu, AsmArgs as) {
+template <int kMode>
+__global__ void __launch_bounds__(ETHREADS, 5) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
   extern __shared__ __align__(16) float smem[];
   float* s_rec = smem;                                                // [EPB][HEX_STRIDE]: 8 records per hexahedron (Hessian only)
   const int sub = threadIdx.x & 7;
   const int le = threadIdx.x >> 3;
-  const int e = blockIdx.x * EPB + le;
+  const int e = in.e_begin + blockIdx.x * EPB + le;                   // this launch covers hexahedra [e_begin, n_hex)
   const bool live = e < in.n_hex;
   const int ee = live ? e : in.n_hex - 1;                             // dead lanes shadow a valid hexahedron
   // node positions: lane `sub` loads node `sub`, the group shares them with width-8 shuffles
@@ -408,60 +452,40 @@ __global__ void __launch_bounds__(ETHREADS, 5) element_kernel(ElemIn in, float* 
       }
     }
   }
-  // Row a of the element matrix in ROTATED order: position p holds the block of column (a + p) & 7.
-  //   p = 0..4: own blocks;  p = 8 - m (m = 1..3): transpose of block m of lane (a - m) & 7.
-  float row[72];
+  // Row a of the element matrix is stored ROTATED and HALF: position p = 0..4 holds the block of column (a + p) & 7
+  // (45 floats + 3 pad = 192 bytes).  The blocks of columns (a - m) & 7, m = 1..3, are the transposes of position m of
+  // row (a - m) & 7 and are picked up from there by the assembly.
+  // Layout of the 48 floats: elements 0..7 of position p at [8p, 8p+8), the ninth elements at [40, 45), 3 pad.
+  float row[48];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     K[k][0] += Ks[k]; K[k][4] += Ks[k]; K[k][8] += Ks[k];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) row[9 * k + i] = K[k][i];
+    for (int i = 0; i < 8; ++i) row[8 * k + i] = K[k][i];
+    row[40 + k] = K[k][8];
   }
-#pragma unroll
-  for (int m = 1; m <= 3; ++m) {
-    const int src = (threadIdx.x & 24) | ((sub - m) & 7);    // lane within the warp
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) row[9 * (8 - m) + 3 * i + j] = __shfl_sync(0xffffffffu, K[m][3 * j + i], src);
-  }
-  if (live) {
-    float4* dst = reinterpret_cast<float4*>(elem_k + ((size_t)e * 8 + sub) * 72);    // K[e][a][p][3][3], a = sub
-#pragma unroll
-    for (int v = 0; v < 18; ++v) {
-      const float4 o = make_float4(row[4 * v], row[4 * v + 1], row[4 * v + 2], row[4 * v + 3]);
-      if (kFused) __stcg(dst + v, o); else dst[v] = o;
-    }
-  }
-  if (!kFused) return;
-
-  // ---- fused tail: publish, count, and assemble the row groups this chunk completed ---------------------
-  __shared__ int s_ready[ETHREADS];
-  __shared__ int s_nready;
-  if (threadIdx.x == 0) s_nready = 0;
-  __threadfence();                                           // this thread's element-matrix stores are visible device-wide
-  __syncthreads();                                           // ... for every thread of the CTA, before any counter moves
+  row[45] = 0.f; row[46] = 0.f; row[47] = 0.f;
+  // The warp's 32 half rows are contiguous in elem_k (4 consecutive hexahedra x 8 rows x 192 bytes).  Written straight from
+  // registers every STG.128 would scatter 32 16-byte pieces over 32 sectors (measured: the stores cost as many L1
+  // wavefronts as all shared-memory traffic of the kernel), so the rows are transposed through the warp's own record area
+  // (dead now; read only by this warp) and stored as 12 fully coalesced 512-byte writes.
+  constexpr int WROW = EK_ROW + 4;                                   // padded row: 16-byte stores of 8 lanes hit distinct banks
+  const int lane = threadIdx.x & 31;
+  float* wst = s_rec + (size_t)(threadIdx.x >> 5) * 4 * HEX_STRIDE;  // records of this warp's 4 hexahedra
+  __syncwarp();
   {
-    const int c0 = __ldg(fu.chunk_ptr + blockIdx.x), nc = __ldg(fu.chunk_ptr + blockIdx.x + 1) - c0;
-    for (int i = threadIdx.x; i < nc; i += ETHREADS) {
-      const int g = __ldg(fu.chunk_grp + c0 + i);
-      const int old = atomicAdd(fu.counter + g, 1);
-      if (old + 1 == __ldg(fu.expected + g)) {
-        fu.counter[g] = 0;                                   // nobody else touches it again in this launch
-        s_ready[atomicAdd(&s_nready, 1)] = g;
-      }
-    }
+    float4* my = reinterpret_cast<float4*>(wst + lane * WROW);
+#pragma unroll
+    for (int v = 0; v < EK_ROW / 4; ++v) my[v] = make_float4(row[4 * v], row[4 * v + 1], row[4 * v + 2], row[4 * v + 3]);
   }
-  __syncthreads();
-  const int nready = s_nready;
-  if (nready == 0) return;
-  __threadfence();                                           // acquire side: order the reads below after the counter read
-  AsmWarpSmem* wsm = reinterpret_cast<AsmWarpSmem*>(smem);   // the record area is dead now
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = w; i < nready * FEMB_ASM_GROUP_ROWS; i += ETHREADS / 32) {
-    const int v = s_ready[i / FEMB_ASM_GROUP_ROWS] * FEMB_ASM_GROUP_ROWS + (i % FEMB_ASM_GROUP_ROWS);
-    if (v >= as.n_vert) continue;                            // warp-uniform
-    assemble_row<true>(as, v, __ldg(as.v2i + v), lane, wsm[w]);
+  __syncwarp();
+  const int e_w = in.e_begin + blockIdx.x * EPB + (threadIdx.x >> 5) * 4;   // first hexahedron of the warp
+  float4* gdst = reinterpret_cast<float4*>(elem_k + (size_t)e_w * 8 * EK_ROW);
+#pragma unroll
+  for (int i = 0; i < EK_ROW / 4; ++i) {
+    const int g = i * 32 + lane;                                     // float4 index inside the warp's 6144 bytes
+    const int rw = g / (EK_ROW / 4), c = g - rw * (EK_ROW / 4);
+    if (e_w + (rw >> 3) < in.n_hex) gdst[g] = *reinterpret_cast<const float4*>(wst + rw * WROW + 4 * c);
   }
 }
 
@@ -470,15 +494,29 @@ static size_t element_smem() {
   return (kMode != 0 ? (size_t)EPB * HEX_STRIDE : 4) * sizeof(float);
 }
 
-// two-kernel path: one warp per index-order row
+// two-kernel path: one warp per row
 constexpr int AS_WARPS = 8;
 constexpr int AS_THREADS = AS_WARPS * 32;
-__global__ void __launch_bounds__(AS_THREADS) assemble_rows_kernel(AsmArgs A) {
+constexpr int AS_ROWS_PER_WARP = 4;
+__global__ void __launch_bounds__(AS_THREADS, 4) assemble_rows_kernel(AsmArgs A, int v_begin, int v_end) {
   __shared__ AsmWarpSmem sm[AS_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int r = blockIdx.x * AS_WARPS + w;
-  if (r >= A.n_vert) return;                                 // warp-uniform
-  assemble_row<false>(A, __ldg(A.i2v + r), r, lane, sm[w]);
+  const AsmLane LN = asm_lane(lane);
+  // vertex order: the 8 rows that share a hexahedron are folded close in time, so every stored half row (read by
+  // its own row and, for the mirrored blocks, by up to three other rows of the hexahedron) comes from DRAM once.
+  // A warp folds AS_ROWS_PER_WARP consecutive vertices; the plan record of the next one is fetched while the current
+  // one is folded, which leaves one exposed memory round trip per row (the element matrices) instead of two.
+  const int v0 = v_begin + (blockIdx.x * AS_WARPS + w) * AS_ROWS_PER_WARP;
+  const int v1 = min(v0 + AS_ROWS_PER_WARP, v_end);
+  if (v0 >= v1) return;
+  AsmMeta M = asm_meta(A, v0, lane);
+  if (lane < 12) sm[w].stage[AS_ZERO + lane] = 0.f;
+  for (int v = v0; v < v1; ++v) {
+    AsmMeta Mn = M;
+    if (v + 1 < v1) Mn = asm_meta(A, v + 1, lane);
+    assemble_row(A, LN, M, lane, sm[w]);
+    M = Mn;
+  }
 }
 
 // out[row] = sum of the element forces of the incident hexahedra + gravity + pin spring
@@ -638,7 +676,7 @@ __global__ void __launch_bounds__(256) coarse_pin_kernel(int n_coarse, const int
 
 static ElemIn make_in(const FembLevel* l, const float* x, float mu, float la) {
   ElemIn in;
-  in.hex = l->hex; in.x = x; in.invJ = l->invJ; in.detJ = l->detJ; in.n_hex = l->n_hex; in.mu = mu; in.la = la;
+  in.hex = l->hex; in.x = x; in.invJ = l->invJ; in.detJ = l->detJ; in.e_begin = 0; in.n_hex = l->n_hex; in.mu = mu; in.la = la;
   return in;
 }
 
@@ -650,22 +688,17 @@ static AsmArgs make_asm(const FembLevel* l, const float* diag_add, const float* 
   return A;
 }
 
-static bool can_fuse(const FembLevel* l) {
-  return l->asm_chunk_ptr && l->asm_chunk_grp && l->asm_expected && l->asm_counter && l->n_hex > 0;
-}
-
-template <int kMode, bool kFused>
-static int launch_element(const FembLevel* l, const float* x, float mu, float la, float* elem_f, float* elem_k,
-                          const AsmArgs& as, cudaStream_t st) {
+template <int kMode>
+static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
   static bool configured = false;
   const size_t smem = element_smem<kMode>();
   if (!configured) {
-    cudaFuncSetAttribute(element_kernel<kMode, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(element_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  FuseArgs fu;
-  fu.chunk_ptr = l->asm_chunk_ptr; fu.chunk_grp = l->asm_chunk_grp; fu.expected = l->asm_expected; fu.counter = l->asm_counter;
-  element_kernel<kMode, kFused><<<cdiv(l->n_hex, EPB), ETHREADS, smem, st>>>(make_in(l, x, mu, la), elem_f, elem_k, fu, as);
+  if (e_end <= e_begin) return FEMB_OK;
+  in.e_begin = e_begin; in.n_hex = e_end;
+  element_kernel<kMode><<<cdiv(e_end - e_begin, EPB), ETHREADS, smem, st>>>(in, elem_f, elem_k);
   count_launch();
   return check_launch("element_kernel");
 }
@@ -680,10 +713,81 @@ static int launch_force_gather(const FembLevel* l, const float* x, const float* 
   return check_launch("force_gather_kernel");
 }
 
-static int launch_assemble(const AsmArgs& as, cudaStream_t st) {
-  assemble_rows_kernel<<<cdiv(as.n_vert, AS_WARPS), AS_THREADS, 0, st>>>(as);
+static int launch_assemble(const AsmArgs& as, int v_begin, int v_end, cudaStream_t st) {
+  if (v_end <= v_begin) return FEMB_OK;
+  assemble_rows_kernel<<<cdiv(v_end - v_begin, AS_WARPS * AS_ROWS_PER_WARP), AS_THREADS, 0, st>>>(as, v_begin, v_end);
   count_launch();
   return check_launch("assemble_rows_kernel");
+}
+
+// ---- software pipeline of the two stages through L2 ----------------------------------------------------------------
+// The element kernel is bound by FP32 issue / shared memory, the fold by HBM; run back to back each leaves the other
+// resource idle and the element matrices make a round trip through HBM.  With a pipeline plan (FembLevel.pipe_*) the
+// hexahedra are taken in chunks; the fold of the rows completed by chunk c (vertices below pipe_vert_end[c]: all their
+// hexahedra lie below pipe_hex_end[c]) runs on a side stream concurrently with the element kernel of chunk c+1 and
+// finds its element matrices still in L2.  Fork/join is by events, so the whole thing is capturable into a CUDA graph
+// (parallel branches).  The side stream and the two events are the only objects the library owns; they are created
+// on first use outside of any capture, and without them the stages simply run one after the other.
+struct PipeCtx {
+  int device = -1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_elem = nullptr, ev_fold = nullptr;
+};
+static PipeCtx g_pipe;
+static int g_pipe_enabled = 0;   // measured on B200 (cube n=100): no gain, both stages are SM-side bound; see DESIGN.md
+
+static bool pipe_ready(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (g_pipe.side != nullptr && g_pipe.device == dev) return true;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return false;                                            // never create objects while a capture is in progress
+  }
+  PipeCtx c;
+  c.device = dev;
+  if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c.ev_elem, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c.ev_fold, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  g_pipe = c;                                                // (objects of a previous device, if any, are leaked on purpose)
+  return true;
+}
+
+// element matrices of all hexahedra + fold of all rows; kMode 1 = Hessian only, 2 = element forces as well
+template <int kMode>
+static int hessian_pipeline(const FembLevel* l, const float* x, float mu, float la, const float* diag_add, float* elem_f,
+                            float* elem_k, float* values, cudaStream_t st) {
+  const ElemIn in = make_in(l, x, mu, la);
+  const AsmArgs as = make_asm(l, diag_add, elem_k, values);
+  const int nc = (g_pipe_enabled && l->pipe_hex_end && l->pipe_vert_end) ? l->pipe_chunks : 0;
+  if (nc < 2 || !pipe_ready(st)) {
+    int rc = launch_element<kMode>(in, 0, l->n_hex, elem_f, elem_k, st);
+    if (rc) return rc;
+    return launch_assemble(as, 0, l->n_vert, st);
+  }
+  FEMB_REQUIRE(l->pipe_hex_end[nc - 1] == l->n_hex && l->pipe_vert_end[nc - 1] == l->n_vert, "pipeline plan does not cover the level");
+  cudaStream_t side = g_pipe.side;
+  int e0 = 0, v0 = 0;
+  for (int c = 0; c < nc; ++c) {
+    const int e1 = l->pipe_hex_end[c], v1 = l->pipe_vert_end[c];
+    FEMB_REQUIRE(e1 >= e0 && v1 >= v0 && e1 <= l->n_hex && v1 <= l->n_vert, "pipeline plan is not monotone");
+    int rc = launch_element<kMode>(in, e0, e1, elem_f, elem_k, st);
+    if (rc) return rc;
+    if (v1 > v0) {
+      cudaEventRecord(g_pipe.ev_elem, st);                   // chunk c (and everything before it in `st`) is done
+      cudaStreamWaitEvent(side, g_pipe.ev_elem, 0);
+      rc = launch_assemble(as, v0, v1, side);
+      if (rc) return rc;
+    }
+    e0 = e1; v0 = v1;
+  }
+  cudaEventRecord(g_pipe.ev_fold, side);                     // join
+  cudaStreamWaitEvent(st, g_pipe.ev_fold, 0);
+  return check_launch("hessian_pipeline");
 }
 
 }  // namespace femb
@@ -692,9 +796,9 @@ using namespace femb;
 
 extern "C" {
 
-int femb_set_fused_assembly(int enable) {
-  const int old = !g_no_fuse;
-  g_no_fuse = !enable;
+int femb_set_pipeline(int enable) {
+  const int old = g_pipe_enabled;
+  g_pipe_enabled = enable != 0;
   return old;
 }
 
@@ -733,7 +837,7 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
   FEMB_REQUIRE(lvl && x && elem_f && out, "null pointer");
   FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->vert_elem && lvl->v2i, "level not initialised");
   if (lvl->n_hex > 0) {
-    int rc = launch_element<0, false>(lvl, x, mu, lambda, elem_f, nullptr, AsmArgs(), as_stream(stream));
+    int rc = launch_element<0>(make_in(lvl, x, mu, lambda), 0, lvl->n_hex, elem_f, nullptr, as_stream(stream));
     if (rc) return rc;
   }
   if (lvl->n_vert == 0) return FEMB_OK;
@@ -744,14 +848,8 @@ int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, c
                  float* values, void* stream) {
   FEMB_REQUIRE(lvl && x && elem_k && values, "null pointer");
   FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan, "level not initialised");
-  const AsmArgs as = make_asm(lvl, diag_add, elem_k, values);
-  if (can_fuse(lvl) && !g_no_fuse) return launch_element<1, true>(lvl, x, mu, lambda, nullptr, elem_k, as, as_stream(stream));
-  if (lvl->n_hex > 0) {
-    int rc = launch_element<1, false>(lvl, x, mu, lambda, nullptr, elem_k, as, as_stream(stream));
-    if (rc) return rc;
-  }
-  if (lvl->nnz == 0) return FEMB_OK;
-  return launch_assemble(as, as_stream(stream));
+  if (lvl->n_vert == 0) return FEMB_OK;
+  return hessian_pipeline<1>(lvl, x, mu, lambda, diag_add, nullptr, elem_k, values, as_stream(stream));
 }
 
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
@@ -760,17 +858,10 @@ int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lam
   FEMB_REQUIRE(lvl && x && elem_f && elem_k && force_out && values, "null pointer");
   FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan && lvl->v2i,
                "level not initialised");
-  const AsmArgs as = make_asm(lvl, diag_add, elem_k, values);
-  const bool fused = can_fuse(lvl) && !g_no_fuse;
-  if (lvl->n_hex > 0) {
-    int rc = fused ? launch_element<2, true>(lvl, x, mu, lambda, elem_f, elem_k, as, as_stream(stream))
-                   : launch_element<2, false>(lvl, x, mu, lambda, elem_f, elem_k, as, as_stream(stream));
-    if (rc) return rc;
-  }
   if (lvl->n_vert == 0) return FEMB_OK;
-  int rc = launch_force_gather(lvl, x, mass, g, pin, pin_pos, control_mag, 1, elem_f, force_out, as_stream(stream));
-  if (rc || fused) return rc;
-  return launch_assemble(as, as_stream(stream));
+  int rc = hessian_pipeline<2>(lvl, x, mu, lambda, diag_add, elem_f, elem_k, values, as_stream(stream));
+  if (rc) return rc;
+  return launch_force_gather(lvl, x, mass, g, pin, pin_pos, control_mag, 1, elem_f, force_out, as_stream(stream));
 }
 
 int femb_energy(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g, const int* pin,

@@ -73,21 +73,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-struct RowSmem {
+template <int kSubs>
+struct RowSmemT {
   alignas(128) float val[RP_CAP * 9 + 16];   // [L chunk | U chunk], each starting on a 16-byte boundary
   alignas(16) int col[RP_CAP + 16];
   alignas(16) float diag[RP_ROWS * 9 + 8];
   int ptr[2][RP_ROWS + 1];
-  float red[RP_SUBS][RP_ROWS][3];
   alignas(8) uint64_t bar;
+  // the partial row sums of the kSubs threads of a row are exchanged through `val` once everybody is done reading it
+  static_assert(sizeof(float) * kSubs * RP_ROWS * 3 <= sizeof(float) * (RP_CAP * 9 + 16), "red does not fit");
 };
+using RowSmem = RowSmemT<RP_SUBS>;
 
 // One block of <= RP_ROWS consecutive rows.  kCoherent: x is being updated by other CTAs of the same
 // (cooperative) launch, so it is read through L2 (ld.global.cg) instead of the per-SM L1.
 // The values / L_col / U_col arrays must be 16-byte aligned and readable 16 bytes past their end
 // (the bulk copies are rounded out to 16-byte granules).
-template <int kMode, bool kCoherent, bool kPdl = false>
-__device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, RowSmem& sm, uint32_t& phase) {
+template <int kMode, bool kCoherent, bool kPdl = false, int kSubs = RP_SUBS>
+__device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, RowSmemT<kSubs>& sm, uint32_t& phase) {
   const int tid = threadIdx.x;
   const bool useL = (a.parts & FEMB_PART_L) != 0, useU = (a.parts & FEMB_PART_U) != 0;
   const bool needD = (kMode == RM_GS || kMode == RM_JACOBI) || (a.parts & FEMB_PART_D) != 0;
@@ -130,6 +133,12 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
     griddep_wait();
     griddep_launch();
   }
+  // the right-hand side of this thread's row (epilogue) travels while the staging is in flight
+  float bv[3] = {0.f, 0.f, 0.f};
+  if ((kMode == RM_GS || kMode == RM_JACOBI || kMode == RM_RESIDUAL) && tid < nrow) {
+    const float* bp = a.b + 3 * (size_t)(r0 + tid);
+    bv[0] = __ldg(bp); bv[1] = __ldg(bp + 1); bv[2] = __ldg(bp + 2);
+  }
   mbar_wait(&sm.bar, phase);
   phase ^= 1u;
 
@@ -144,13 +153,13 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
     const int ub = sm.ptr[1][rl] - U0, cntU = sm.ptr[1][rl + 1] - sm.ptr[1][rl];
     const int n = cntL + cntU;
     if (staged) {
-      constexpr int MAXB = 7;                            // ceil(27 / RP_SUBS) blocks per thread: one trip
-      for (int j0 = sub; j0 < n; j0 += MAXB * RP_SUBS) {
+      constexpr int MAXB = (27 + kSubs - 1) / kSubs;     // blocks per thread: one trip
+      for (int j0 = sub; j0 < n; j0 += MAXB * kSubs) {
         const float* m[MAXB];
         float xv[MAXB][3];
 #pragma unroll
         for (int u = 0; u < MAXB; ++u) {                 // issue every x gather of this thread first
-          const int j = j0 + u * RP_SUBS;
+          const int j = j0 + u * kSubs;
           const bool ok = j < n;
           const int jj = ok ? j : j0;
           m[u] = (jj < cntL) ? vL + (lb + jj) * 9 : vU + (ub + jj - cntL) * 9;
@@ -168,7 +177,7 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
         }
       }
     } else {
-      for (int j = sub; j < n; j += RP_SUBS) {           // oversized rows: straight from global memory
+      for (int j = sub; j < n; j += kSubs) {           // oversized rows: straight from global memory
         const bool isL = j < cntL;
         const size_t g = isL ? ((size_t)a.off_l + L0 + lb + j) : ((size_t)a.off_u + U0 + ub + (j - cntL));
         const int col = isL ? __ldg(a.L_col + L0 + lb + j) : __ldg(a.U_col + U0 + ub + (j - cntL));
@@ -182,13 +191,18 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
       }
     }
   }
-  sm.red[sub][rl][0] = acc[0]; sm.red[sub][rl][1] = acc[1]; sm.red[sub][rl][2] = acc[2];
+  __syncthreads();                                         // all reads of the staged blocks are done
+  float (*red)[RP_ROWS][3] = reinterpret_cast<float (*)[RP_ROWS][3]>(sm.val);
+  red[sub][rl][0] = acc[0]; red[sub][rl][1] = acc[1]; red[sub][rl][2] = acc[2];
   __syncthreads();
   if (tid < nrow) {
     const int r = r0 + tid;
     float s[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) s[c] = (sm.red[0][tid][c] + sm.red[1][tid][c]) + (sm.red[2][tid][c] + sm.red[3][tid][c]);
+    for (int c = 0; c < 3; ++c) {
+      s[c] = (red[0][tid][c] + red[1][tid][c]) + (red[2][tid][c] + red[3][tid][c]);
+      if (kSubs == 8) s[c] += (red[4][tid][c] + red[5][tid][c]) + (red[6][tid][c] + red[7][tid][c]);
+    }
     const float* D = sm.diag + preD + tid * 9;
     if (kMode == RM_SPMV || kMode == RM_RESIDUAL) {
       if (a.parts & FEMB_PART_D) {
@@ -207,12 +221,12 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
       }
     } else if (kMode == RM_RESIDUAL) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) a.y[3 * (size_t)r + c] = a.b[3 * (size_t)r + c] - s[c];
+      for (int c = 0; c < 3; ++c) a.y[3 * (size_t)r + c] = bv[c] - s[c];
     } else {
       // x_r = solve3x3(D_r, b_r - sum, 0)                       (Colored_GS_MF_Kernel, cublas.py:129-135)
       float rhs[3], xs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) rhs[c] = a.b[3 * (size_t)r + c] - s[c];
+      for (int c = 0; c < 3; ++c) rhs[c] = bv[c] - s[c];
       const int bad = solve3x3(D, rhs, xs);
       if (bad && a.not_spd != nullptr) atomicAdd(a.not_spd, 1);
 #pragma unroll
@@ -233,12 +247,17 @@ __global__ void __launch_bounds__(RP_THREADS) row_pass_kernel(RowArgs a) {
 
 // One colour of a Gauss-Seidel sweep, launchable as a programmatic dependent of the previous colour: the matrix
 // staging (pointer reads + bulk copies) runs before griddepcontrol.wait, i.e. during the previous colour's tail.
-__global__ void __launch_bounds__(RP_THREADS) gs_color_kernel(RowArgs a) {
-  __shared__ RowSmem sm;
+// kSubs threads per row: 4 (default) or 8.  Measured per colour launch at 1 M hexahedra: 32.8 us with 4, 34.7 us with 8
+// (same CTAs per SM, twice the warps: no gain), 42.6 us for a persistent double-buffered variant with 3 CTAs per SM
+// (removed) -- what bounds the pass is the number of independent row blocks in flight per SM (each one a chain of
+// pointer load -> staging -> L2 gathers of x -> 3x3 solve), which the 36 KB of staging per block limit to 6.
+template <int kSubs>
+__global__ void __launch_bounds__(RP_ROWS * kSubs) gs_color_kernel(RowArgs a) {
+  __shared__ RowSmemT<kSubs> sm;
   if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
   uint32_t phase = 0;
   const int r0 = a.row_begin + blockIdx.x * RP_ROWS;
-  row_block<RM_GS, false, true>(a, r0, min(RP_ROWS, a.row_end - r0), sm, phase);
+  row_block<RM_GS, false, true, kSubs>(a, r0, min(RP_ROWS, a.row_end - r0), sm, phase);
 }
 
 // Whole femb_gauss_seidel call in ONE cooperative launch (levels whose colour fits the resident grid):
@@ -294,16 +313,17 @@ static int launch_rows(const RowArgs& a, cudaStream_t st) {
 
 // pdl: the launch may overlap the tail of the previous kernel in the stream (which must not write the matrix)
 static int g_no_pdl = 0;
+static int g_gs_subs = 4;   // measured: 32.8 us per colour launch with 4 threads per row, 34.7 with 8 (cube n=100)
 static int launch_gs_color(const RowArgs& a, bool pdl, cudaStream_t st) {
   const int n = a.row_end - a.row_begin;
   if (n <= 0) return FEMB_OK;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(n, RP_ROWS)); cfg.blockDim = dim3(RP_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = dim3(cdiv(n, RP_ROWS)); cfg.blockDim = dim3(RP_ROWS * g_gs_subs); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (pdl && !g_no_pdl) ? 1 : 0;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, gs_color_kernel, a);
+  const cudaError_t e = g_gs_subs == 8 ? cudaLaunchKernelEx(&cfg, gs_color_kernel<8>, a) : cudaLaunchKernelEx(&cfg, gs_color_kernel<4>, a);
   count_launch();
   if (e != cudaSuccess) {
     set_error("gs_color_kernel: %s", cudaGetErrorString(e));
@@ -586,8 +606,21 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, c
       const float w = __ldg(r_w + e);
       const int q = ut_q[e];
       const int t1 = __ldg(t_ptr + i + 1);
-      for (int t = __ldg(t_ptr + i); t < t1; ++t)
-        acc[(int)c_slot8[(size_t)t * 8 + q] * GA_THREADS] += w * __ldg(t_val + (size_t)t * 9 + k);
+      int t = __ldg(t_ptr + i);
+      // the slots of one T row are distinct: batches of 4 keep 8 independent global loads in flight per thread
+      for (; t + 4 <= t1; t += 4) {
+        int sl[4];
+        float tv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sl[u] = (int)__ldg(c_slot8 + (size_t)(t + u) * 8 + q);
+          tv[u] = __ldg(t_val + (size_t)(t + u) * 9 + k);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[sl[u] * GA_THREADS] += w * tv[u];
+      }
+      for (; t < t1; ++t)
+        acc[(int)__ldg(c_slot8 + (size_t)t * 8 + q) * GA_THREADS] += w * __ldg(t_val + (size_t)t * 9 + k);
     }
   }
   __syncthreads();
@@ -624,6 +657,12 @@ extern "C" {
 int femb_set_pdl(int enable) {
   const int old = !g_no_pdl;
   g_no_pdl = !enable;
+  return old;
+}
+
+int femb_set_gs_threads_per_row(int subs) {
+  const int old = g_gs_subs;
+  if (subs == 4 || subs == 8) g_gs_subs = subs;
   return old;
 }
 

@@ -59,7 +59,8 @@ def _dev(a, device):
 
 class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
-                 control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False):
+                 control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False,
+                 pipe_chunk_hexes=2 * 740 * 16):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.FembError("femb200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -109,8 +110,8 @@ class Object:
             assert cnt.max(initial=0) <= 8, "a vertex belongs to more than 8 hexahedra"
             start = np.cumsum(cnt) - cnt
             ve[flat[o2], np.arange(len(o2)) - start[flat[o2]]] = o2.astype(np.int32)      # e*8+a
+            ap = self._pipe_plan(nh, ve, pipe_chunk_hexes)
             pad = np.zeros(4, np.int32)                                  # bulk copies are rounded out to 16 bytes
-            ap = self._asm_plan(H.hexs[l], n)
             d = dict(L_ptr=_dev(p.L_ptr, dev), L_col=_dev(np.concatenate([p.L_col, pad]), dev)[:p.L_nnz],
                      U_ptr=_dev(p.U_ptr, dev), U_col=_dev(np.concatenate([p.U_col, pad]), dev)[:p.L_nnz],
                      vert_elem=_dev(ve, dev),
@@ -127,14 +128,14 @@ class Object:
             lv.elem2nnz = self.hex_update_offset_gpu[l].data_ptr()
             for k in ("L_ptr", "L_col", "U_ptr", "U_col", "vert_elem", "invJ", "detJ"):
                 setattr(lv, k, d[k].data_ptr())
-            d["fold_plan"] = torch.empty(n * 27 * 8 + 16, dtype=torch.uint8, device=dev)
+            d["fold_plan"] = torch.empty(n * 232 + 16, dtype=torch.uint8, device=dev)      # FEMB_FOLD_PLAN_BYTES per vertex
             _lib.check(self.lib.femb_build_fold_plan(C.byref(lv), d["fold_plan"].data_ptr(), self._stream()), "femb_build_fold_plan")
             lv.fold_plan = d["fold_plan"].data_ptr()
-            if ap is not None:                                           # fused ("last arriver") assembly plan
-                d.update(asm_chunk_ptr=_dev(ap[0], dev), asm_chunk_grp=_dev(ap[1], dev), asm_expected=_dev(ap[2], dev),
-                         asm_counter=torch.zeros(len(ap[2]), dtype=torch.int32, device=dev))
-                for k in ("asm_chunk_ptr", "asm_chunk_grp", "asm_expected", "asm_counter"):
-                    setattr(lv, k, d[k].data_ptr())
+            if ap is not None:                                           # element/fold software pipeline plan (host arrays)
+                d.update(pipe_hex_end=ap[0], pipe_vert_end=ap[1])
+                lv.pipe_chunks = len(ap[0])
+                lv.pipe_hex_end = ap[0].ctypes.data
+                lv.pipe_vert_end = ap[1].ctypes.data
             self.levels.append(lv)
             self.inverse_pX_peps_gpu.append(d["invJ"])
             self.det_pX_peps_gpu.append(d["detJ"])
@@ -205,7 +206,7 @@ class Object:
         self._cg_state = torch.zeros(16 + 1024, device=dev)
         nh_max = max(h.shape[0] for h in H.hexs)
         self._elem_f = torch.empty(nh_max * 24, device=dev)
-        self._elem_k = torch.empty(nh_max * 576, device=dev)
+        self._elem_k = torch.empty(nh_max * _lib.ELEM_K_FLOATS, device=dev)
         self.L = [self._part_view(l, "L") for l in range(L)]
         self.U = [self._part_view(l, "U") for l in range(L)]
         self.D = [self._part_view(l, "D") for l in range(L)]
@@ -236,23 +237,18 @@ class Object:
         return voxelize.voxelize_obj(mesh_path, dx)
 
     @staticmethod
-    def _asm_plan(hexs, n_vert):
-        """Plan of the fused assembly (femb200.h, FembLevel.asm_*): which row groups (16 consecutive vertex ids) every
-        chunk of 16 consecutive hexahedra touches, and how many chunks touch each group."""
-        nh = hexs.shape[0]
-        if nh == 0:
+    def _pipe_plan(nh, vert_elem, chunk_hexes):
+        """Plan of the element/fold software pipeline (femb200.h, FembLevel.pipe_*): hexahedra in chunks of `chunk_hexes`;
+        after chunk c the rows of all vertices v < vert_end[c] are complete (every hexahedron of every vertex <= v has
+        been processed).  Works for any numbering; it pipelines well when hexahedron and vertex ids grow together."""
+        if nh == 0 or not chunk_hexes or nh <= chunk_hexes:
             return None
-        CH, GR = _lib.ASM_CHUNK_HEXES, _lib.ASM_GROUP_ROWS
-        n_chunks, n_groups = (nh + CH - 1) // CH, (n_vert + GR - 1) // GR
-        key = np.unique((np.repeat(np.arange(nh, dtype=np.int64) // CH, 8)) * n_groups + hexs.reshape(-1).astype(np.int64) // GR)
-        chunk_of, grp_of = key // n_groups, key % n_groups
-        expected = np.bincount(grp_of, minlength=n_groups).astype(np.int32)
-        if expected.min() == 0:                                          # a vertex outside every hexahedron: keep the two-kernel path
-            return None
-        chunk_ptr = np.zeros(n_chunks + 1, dtype=np.int32)
-        chunk_ptr[1:] = np.cumsum(np.bincount(chunk_of, minlength=n_chunks))
-        assert np.diff(chunk_ptr).max() <= 128
-        return chunk_ptr, grp_of.astype(np.int32), expected
+        hex_end = np.minimum(np.arange(1, (nh + chunk_hexes - 1) // chunk_hexes + 1, dtype=np.int64) * chunk_hexes, nh)
+        last = vert_elem.max(axis=1).astype(np.int64) >> 3               # last hexahedron of every vertex (-1: none)
+        pref = np.maximum.accumulate(last)
+        vert_end = np.searchsorted(pref, hex_end, side="left")           # vertices with pref < hex_end
+        vert_end[-1] = vert_elem.shape[0]
+        return np.ascontiguousarray(hex_end, dtype=np.int32), np.ascontiguousarray(vert_end, dtype=np.int32)
 
     def new_values(self, layer):
         """Zeroed block-value array [nnz,3,3] of a level, padded as the bulk-copy kernels require (femb200.h)."""

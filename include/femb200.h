@@ -35,10 +35,13 @@ extern "C" {
 
 #define FEMB_ABI_VERSION 2
 
-/* granularity of the fused assembly plan (FembLevel.asm_*) */
+/* hexahedra per CTA of the element kernel (pipeline chunks should be multiples of it) */
 #define FEMB_ASM_CHUNK_HEXES 16
-#define FEMB_ASM_GROUP_ROWS 16
 #define FEMB_FOLD_SLOTS 27
+#define FEMB_FOLD_PLAN_BYTES 232   /* 27*8 contributor bytes + 16 header bytes per vertex */
+/* floats of element-matrix scratch per hexahedron (elem_k of femb_hessian): 8 rows x (5 blocks of 9 + 3 pad) -- the
+ * symmetric half in rotated order, see femb_element.cu */
+#define FEMB_ELEM_K_FLOATS 384
 
 /* matrix part selector for femb_spmv (bsr_mv on self.L / self.D / self.U / self.A) */
 #define FEMB_PART_L 1
@@ -65,15 +68,16 @@ typedef struct FembLevel {
   const int* vert_elem;  /* [n_vert*8] e*8+a of the hexes incident to a vertex, -1 pad  */
   const float* invJ;     /* [n_hex*8*9] inverse_pX_peps (quai_hexagon.py:18)            */
   const float* detJ;     /* [n_hex*8]   det_pX_peps     (quai_hexagon.py:17)            */
-  const unsigned char* fold_plan; /* [n_vert*27*8] per vertex, per block of its row (L blocks, D, U blocks): the <= 8   */
-                                  /* contributors j*8+b (j-th incident hexahedron, local node b; 255 = none) in fold order; */
-                                  /* filled by femb_build_fold_plan from vert_elem + elem2nnz                              */
-  /* Optional plan of the fused ("last arriver") assembly, all NULL = two-kernel assembly.  Hexahedra are taken in
-   * chunks of FEMB_ASM_CHUNK_HEXES consecutive ids, rows in groups of FEMB_ASM_GROUP_ROWS consecutive VERTEX ids. */
-  const int* asm_chunk_ptr;  /* [n_chunks+1] CSR: chunk -> row groups holding a vertex of one of its hexahedra */
-  const int* asm_chunk_grp;  /* [asm_chunk_ptr[n_chunks]]                                                      */
-  const int* asm_expected;   /* [n_groups] number of chunks that touch the group                               */
-  int* asm_counter;          /* [n_groups] device scratch, zero on entry to and on exit from every call         */
+  const unsigned char* fold_plan; /* [n_vert*FEMB_FOLD_PLAN_BYTES] per vertex: for each of the 27 blocks of its row (L blocks, */
+                                  /* D, U blocks) the <= 8 contributors j*8+p (j-th incident hexahedron, rotated column      */
+                                  /* position p; 255 = none) in fold order, then int32 {row, L_ptr[row], U_ptr[row],         */
+                                  /* nL | nU<<8}; filled by femb_build_fold_plan from vert_elem + elem2nnz                  */
+  /* Optional plan of the two-stage software pipeline of femb_hessian / femb_force_hessian (0 / NULL = one chunk).  HOST
+   * arrays: chunk c ends at hexahedron pipe_hex_end[c] (exclusive); every vertex below pipe_vert_end[c] has all its
+   * hexahedra below pipe_hex_end[c].  Both non-decreasing, last entries n_hex and n_vert. */
+  int pipe_chunks;
+  const int* pipe_hex_end;   /* host [pipe_chunks] */
+  const int* pipe_vert_end;  /* host [pipe_chunks] */
 } FembLevel;
 
 /* CSR matrix with one scalar weight per entry = BSR matrix with blocks w*I3: the interpolation
@@ -137,16 +141,17 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
                float* out, void* stream);
 /* compute_elastic_hessian (quai_hexagon.py:69-106) + the `MF_value = MF_value_fixed` copy (object.py:1233):
  * values[slot] = sum of element blocks (+ diag_add[i]*I3 on the diagonal slot of index-order row i).
- *   elem_k scratch [n_hex*576] (element matrices K[e][a][b][3][3]); diag_add [n_vert] (index order) or NULL.
+ *   elem_k scratch [n_hex*FEMB_ELEM_K_FLOATS] (symmetric half of the element matrices); diag_add [n_vert] (index order) or NULL.
  *   If elem_f != NULL the element forces are produced by the same element pass and `force_out` is
  *   filled as in femb_force (same optional arguments). */
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add,
                  float* elem_k, float* values, void* stream);
-/* Experimental, OFF by default (measured slower than the two-kernel path on B200): with an assembly plan in
- * the level (asm_* != NULL) and femb_set_fused_assembly(1), femb_hessian / femb_force_hessian run ONE kernel -- the CTA
- * whose chunk completes a row group folds that group while the element matrices are still in L2 (same fold order, so
- * bit-identical values).  Returns the old setting. */
-int femb_set_fused_assembly(int enable);
+/* Optional (OFF by default: no gain measured on B200, both stages are bound on the SM side): with femb_set_pipeline(1)
+ * and a plan in the level (pipe_*) both calls run the element kernel and the row fold as a software pipeline -- the fold
+ * of the rows completed by chunk c runs on a library-owned side stream next to the element kernel of chunk c+1 (event
+ * fork/join, graph-capturable) and reads the element matrices from L2.  Results do not depend on the chunking (same
+ * fold order).  Returns the old setting. */
+int femb_set_pipeline(int enable);
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add,
                        float* elem_f, float* elem_k, float* force_out, float* values, void* stream);
@@ -175,6 +180,8 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
 /* The colour launches of a sweep are programmatic dependent launches (each colour stages its matrix rows while the
  * previous colour drains); femb_set_pdl(0) makes them ordinary launches (tests).  Returns the old setting. */
 int femb_set_pdl(int enable);
+/* threads per row of the colour kernel: 4 (default, measured faster) or 8; the summation tree differs, so results differ in rounding */
+int femb_set_gs_threads_per_row(int subs);
 /* A run of colour launches of the in-place sweep above: colours first_color..last_color (descending if
  * first > last), dx is NOT zeroed.  femb_gauss_seidel(it=1) == zero dx; colours 7..0 with parts=U; colours 0..7
  * with parts=L|U.  Lets a caller put a halo exchange between colour groups (domain decomposition). */

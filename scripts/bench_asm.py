@@ -7,7 +7,9 @@ from fem_simulation_b200 import Object
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 modes = [int(c) for c in (sys.argv[3] if len(sys.argv) > 3 else "101")]
-obj = Object(f"cube:{n}", 1.0 / n, [], use_graphs=False, layers=2)
+chunk = int(os.environ.get("PIPE_CHUNK", 2 * 740 * 16))
+obj = Object(f"cube:{n}", 1.0 / n, [], use_graphs=False, layers=2, pipe_chunk_hexes=chunk)
+print("chunks", obj.levels[0].pipe_chunks, "chunk hexes", chunk)
 x = obj.x_gpu_layer[0]
 x.add_(torch.randn_like(x) * 1e-4)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -26,16 +28,20 @@ def timed(fn, label):
 
 
 for fused in modes:
-    obj.lib.femb_set_fused_assembly(fused)
-    timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed), f"hessian level0 fused={fused}")
-    timed(lambda: obj._force_hessian(x, obj.grad_gpu, obj.MF_value_gpu, obj.diag_fixed), f"force+hessian level0 fused={fused}")
-    timed(lambda: obj._hessian(1, obj.x_gpu_layer[1], obj.UtAUs_values[0]), f"hessian level1 fused={fused}")
+    obj.lib.femb_set_pipeline(fused)
+    timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed), f"hessian level0 pipeline={fused}")
+    timed(lambda: obj._force_hessian(x, obj.grad_gpu, obj.MF_value_gpu, obj.diag_fixed), f"force+hessian level0 pipeline={fused}")
+    timed(lambda: obj._hessian(1, obj.x_gpu_layer[1], obj.UtAUs_values[0]), f"hessian level1 pipeline={fused}")
 timed(lambda: obj._force(x, obj.grad_gpu), "force level0")
 obj._force_hessian(x, obj.dev_B_fixed[0], obj.MF_value_gpu, obj.diag_fixed)
-for pdl in ((1, 0, 1) if len(modes) > 1 else ()):
+for subs, pdl in (((8, 1), (4, 1), (8, 0), (8, 1)) if len(modes) > 1 else ()):
     obj.lib.femb_set_pdl(pdl)
-    timed(lambda: obj.PerformGaussSeidel(0, 3), f"GS level0 x3 pdl={pdl} (eager)")
+    obj.lib.femb_set_gs_threads_per_row(subs)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         obj.PerformGaussSeidel(0, 3)
-    timed(g.replay, f"GS level0 x3 pdl={pdl} (graph)")
+    timed(g.replay, f"GS level0 x3 threads/row={subs} pdl={pdl} (graph)")
+obj.lib.femb_set_gs_threads_per_row(8)
+timed(lambda: obj._residual(0, obj.dev_B_fixed[0], obj.dev_delta_x[0], obj.dev_R[0]), "residual level0 (full pass)")
+obj.galerkin()
+timed(obj.galerkin, "galerkin 0->1")

@@ -269,41 +269,54 @@ def test_empty_and_errors():
     assert lib.femb_launch_count() > 0
 
 
-def test_fused_assembly_is_bit_identical_to_two_kernel_path(pair):
-    """femb_hessian with the FembLevel.asm_* plan (femb_set_fused_assembly(1): one kernel, last-arriver fold) vs the default
-    (element kernel + assemble_rows_kernel): same fold order => identical bits, on every level, repeatedly
-    (the group counters must return to zero after each call)."""
-    obj, ref, xp = pair
-    x0 = torch.from_numpy(xp).to(obj.device)
-    for l in range(min(obj.layer, 2)):
+def test_pipelined_assembly_is_bit_identical():
+    """femb_hessian / femb_force_hessian as a chunked two-stream software pipeline (FembLevel.pipe_*) vs the two stages
+    back to back (the default): same fold order => identical bits; eagerly, repeatedly, and replayed from a
+    CUDA graph (event fork/join captured as parallel branches)."""
+    pts, hx = MESHES["jag3"]()
+    obj = Object((pts, hx), 0.05, [], use_graphs=False, pipe_chunk_hexes=160)
+    assert obj.levels[0].pipe_chunks > 4 and obj.levels[1].pipe_chunks >= 2
+    he, ve = obj._pat[0]["pipe_hex_end"], obj._pat[0]["pipe_vert_end"]
+    assert he[-1] == obj.N_hexagons and ve[-1] == obj.N_verts and np.all(np.diff(he) > 0) and np.all(np.diff(ve) >= 0)
+    last = obj._pat[0]["vert_elem"].cpu().numpy().max(axis=1) >> 3
+    for c in range(len(he)):
+        assert last[:ve[c]].max(initial=-1) < he[c]                  # rows below vert_end[c] are complete after chunk c
+    rng = np.random.default_rng(11)
+    x0 = obj.x_gpu_layer[0] + torch.from_numpy(rng.normal(size=(obj.N_verts, 3)).astype(np.float32) * 0.002).to(obj.device)
+    for l in range(2):
         x = x0 if l == 0 else obj.x_gpu_layer[l] * 1.01
         diag = obj.diag_fixed if l == 0 else None
-        assert obj.levels[l].asm_chunk_ptr, "no fused-assembly plan on this level"
         va, vb = obj.new_values(l), obj.new_values(l)
-        obj.lib.femb_set_fused_assembly(0)
         obj._hessian(l, x, va, diag)
-        obj.lib.femb_set_fused_assembly(1)
+        obj.lib.femb_set_pipeline(1)
         try:
             for rep in range(3):
                 vb.fill_(float("nan"))
                 obj._hessian(l, x, vb, diag)
                 torch.cuda.synchronize()
-                assert torch.equal(va, vb), f"level {l} rep {rep}: fused assembly differs from the two-kernel path"
-                assert int(obj._pat[l]["asm_counter"].abs().sum()) == 0
+                assert torch.equal(va, vb), f"level {l} rep {rep}: pipelined assembly differs"
         finally:
-            obj.lib.femb_set_fused_assembly(0)
-    # fused force + Hessian entry point
+            obj.lib.femb_set_pipeline(0)
     f1, f2 = torch.zeros_like(x0), torch.zeros_like(x0)
     va, vb = obj.new_values(0), obj.new_values(0)
-    obj.lib.femb_set_fused_assembly(0)
     obj._force_hessian(x0, f1, va, obj.diag_fixed)
-    obj.lib.femb_set_fused_assembly(1)
+    obj.lib.femb_set_pipeline(1)
     try:
         obj._force_hessian(x0, f2, vb, obj.diag_fixed)
+        torch.cuda.synchronize()
+        assert torch.equal(va, vb) and torch.equal(f1, f2)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                obj._force_hessian(x0, f2, vb, obj.diag_fixed)
+        for rep in range(3):
+            vb.fill_(float("nan")); f2.fill_(float("nan"))
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(va, vb) and torch.equal(f1, f2), f"graph replay {rep} differs"
     finally:
-        obj.lib.femb_set_fused_assembly(0)
-    torch.cuda.synchronize()
-    assert torch.equal(va, vb) and torch.equal(f1, f2)
+        obj.lib.femb_set_pipeline(0)
 
 
 def test_pdl_gauss_seidel_is_bit_identical():
