@@ -310,13 +310,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, sample_only=False, steps=2, warmup=1):
+def cpu_baseline(args, sample_only=False, steps=6, warmup=1):
     """The C/OpenMP restatement of the reference algorithm (oracle/femb_oracle.c; the reference is GPU-only Warp code
     and has no CPU path) on all host cores, on a bounded sample: a smaller cube with the same level formula,
     throughput scaled by hexahedron count to the benchmark's workload."""
     from fem_simulation_b200 import hierarchy, mesh
     from oracle import c_oracle
-    n_s = args.cpu_n or 40
+    n_s = args.cpu_n or 64                     # 262 144 hexahedra: ~1.5-2 s of CPU work per step on 24 threads
     pts, hx = mesh.cube_mesh(n_s)
     H = hierarchy.build_hierarchy(pts, hx, 1.0 / n_s, args.layers or None)
     plans = [hierarchy.build_galerkin_plan(H, l) for l in range(H.layer - 1)]
@@ -340,7 +340,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args, steps=max(1, min(args.steps, 5)), warmup=min(args.warmup, 1))
+    cb = cpu_baseline(args, steps=max(1, min(args.steps, 10)), warmup=min(args.warmup, 1))
     n = args.n
     line = {"impl": "reference", "metric": "fas_mg_mhex_steps_per_sec" if args.method == "fasv3" else "newton_mg_mhex_steps_per_sec",
             "value": cb["value"] * (n ** 3) / 1e6, "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

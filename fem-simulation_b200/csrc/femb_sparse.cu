@@ -475,15 +475,16 @@ __global__ void __launch_bounds__(256) transfer_kernel(int nrow, const int* __re
 //   stage 2  A_c = Ut_hat T : 32 coarse vertices per CTA (vertex order, so the <= 8 parents of a fine row
 //            are processed close in time and T is read from HBM once), 9 threads per coarse row,
 //            spd_matrix33f in the epilogue, output written to the [L;D;U] slot of every block.
-constexpr int GA_ROWS = 32;
+constexpr int GA_ROWS = 16;                 // 16 rows = 37 KB of staging + accumulators per CTA: 6 CTAs per SM (32 rows: 2 CTAs)
 constexpr int GA_THREADS = GA_ROWS * 9;
 constexpr int GA_SLOTS = 27;
+constexpr int GA_CAP = GA_ROWS * 27;        // staged off-diagonal blocks per CTA
 
 struct GaSmem {
-  alignas(128) float val[RP_CAP * 9 + 16];
-  alignas(16) int col[RP_CAP + 16];
+  alignas(128) float val[GA_CAP * 9 + 16];
+  alignas(16) int col[GA_CAP + 16];
   alignas(16) float diag[GA_ROWS * 9 + 8];
-  alignas(16) unsigned char tsl[(RP_CAP + GA_ROWS) * 8 + 64];   // t_slot of the L chunk | U chunk | D chunk
+  alignas(16) unsigned char tsl[(GA_CAP + GA_ROWS) * 8 + 64];   // t_slot of the L chunk | U chunk | D chunk
   int ptr[2][GA_ROWS + 1];
   float acc[GA_ROWS * GA_SLOTS * 9];
   alignas(8) uint64_t bar;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_ap_kernel(RowArgs a, int 
   __syncthreads();
   const int L0 = sm.ptr[0][0], U0 = sm.ptr[1][0];
   const int nL = sm.ptr[0][nrow] - L0, nU = sm.ptr[1][nrow] - U0;
-  const bool staged = (nL + nU) <= RP_CAP;
+  const bool staged = (nL + nU) <= GA_CAP;
   const size_t sL = (size_t)a.off_l + L0, sU = (size_t)a.off_u + U0, sD = (size_t)a.off_d + r0;   // first [L;D;U] slots
   const size_t gL = sL * 9, gU = sU * 9, gD = sD * 9;
   const int preL = (int)(gL & 3), preU = (int)(gU & 3), preD = (int)(gD & 3);

@@ -211,7 +211,7 @@ class Object:
         self.U = [self._part_view(l, "U") for l in range(L)]
         self.D = [self._part_view(l, "D") for l in range(L)]
         self.A = [self._part_view(l, "A") for l in range(L)]
-        self._plans = [self._build_galerkin_plan(l) for l in range(L - 1)]
+        self._plans = [None] * (L - 1)             # Galerkin plans are built on first use (FAS-only runs never need them)
 
         self.plot_x, self.plot_y, self.plot_InfNorm, self.plot_energy = [], [], [], []
         self.plot_InfNorm_newton, self.plot_energy_newton = [], []
@@ -472,6 +472,8 @@ class Object:
     def galerkin(self):
         """object.py:1252-1264 minus the rebuilds: A_i = Ut_hat (A_{i-1} Us_hat), spd_matrix33f, [L;D;U] layout."""
         for i in range(1, self.layer):
+            if self._plans[i - 1] is None:
+                self._plans[i - 1] = self._build_galerkin_plan(i - 1)
             t = self._plans[i - 1]
             _lib.check(self.lib.femb_galerkin(C.byref(self.levels[i - 1]), C.byref(self.levels[i]), self._values(i - 1).data_ptr(),
                                               C.byref(self.Ut_hat[i - 1].c), C.byref(self.Us_hat[i - 1].c), C.byref(t["plan"]),
