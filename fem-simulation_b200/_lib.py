@@ -75,6 +75,8 @@ PROTOTYPES = {
     "femb_gauss_seidel": [LV, P, P, P, I, P, P],
     "femb_set_pdl": [I],
     "femb_set_gs_threads_per_row": [I],
+    "femb_set_gs_rows_per_cta": [I],
+    "femb_set_gs_coop_max_blocks": [I],
     "femb_gs_colors": [LV, P, P, P, I, I, I, P, P],
     "femb_jacobi": [LV, P, P, P, P, I, P, P],
     "femb_cg": [LV, P, P, P, P, P, P, P, I, F, I, P],

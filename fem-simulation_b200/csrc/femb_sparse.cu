@@ -73,15 +73,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-template <int kSubs>
+template <int kSubs, int kRows = RP_ROWS>
 struct RowSmemT {
-  alignas(128) float val[RP_CAP * 9 + 16];   // [L chunk | U chunk], each starting on a 16-byte boundary
-  alignas(16) int col[RP_CAP + 16];
-  alignas(16) float diag[RP_ROWS * 9 + 8];
-  int ptr[2][RP_ROWS + 1];
+  static constexpr int CAP = kRows * 27;     // staged off-diagonal blocks per CTA (26 neighbours + slack)
+  alignas(128) float val[CAP * 9 + 16];      // [L chunk | U chunk], each starting on a 16-byte boundary
+  alignas(16) int col[CAP + 16];
+  alignas(16) float diag[kRows * 9 + 8];
+  int ptr[2][kRows + 1];
   alignas(8) uint64_t bar;
   // the partial row sums of the kSubs threads of a row are exchanged through `val` once everybody is done reading it
-  static_assert(sizeof(float) * kSubs * RP_ROWS * 3 <= sizeof(float) * (RP_CAP * 9 + 16), "red does not fit");
+  static_assert(sizeof(float) * kSubs * kRows * 3 <= sizeof(float) * (CAP * 9 + 16), "red does not fit");
 };
 using RowSmem = RowSmemT<RP_SUBS>;
 
@@ -89,8 +90,8 @@ using RowSmem = RowSmemT<RP_SUBS>;
 // (cooperative) launch, so it is read through L2 (ld.global.cg) instead of the per-SM L1.
 // The values / L_col / U_col arrays must be 16-byte aligned and readable 16 bytes past their end
 // (the bulk copies are rounded out to 16-byte granules).
-template <int kMode, bool kCoherent, bool kPdl = false, int kSubs = RP_SUBS>
-__device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, RowSmemT<kSubs>& sm, uint32_t& phase) {
+template <int kMode, bool kCoherent, bool kPdl = false, int kSubs = RP_SUBS, int kRows = RP_ROWS>
+__device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, RowSmemT<kSubs, kRows>& sm, uint32_t& phase) {
   const int tid = threadIdx.x;
   const bool useL = (a.parts & FEMB_PART_L) != 0, useU = (a.parts & FEMB_PART_U) != 0;
   const bool needD = (kMode == RM_GS || kMode == RM_JACOBI) || (a.parts & FEMB_PART_D) != 0;
@@ -101,7 +102,7 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
   __syncthreads();
   const int L0 = sm.ptr[0][0], U0 = sm.ptr[1][0];
   const int nL = sm.ptr[0][nrow] - L0, nU = sm.ptr[1][nrow] - U0;
-  const bool staged = (nL + nU) <= RP_CAP;
+  const bool staged = (nL + nU) <= (RowSmemT<kSubs, kRows>::CAP);
   // float / int offsets of the wanted data inside the staged (16-byte rounded) chunks
   const size_t gL = ((size_t)a.off_l + L0) * 9, gU = ((size_t)a.off_u + U0) * 9, gD = ((size_t)a.off_d + r0) * 9;
   const int preL = (int)(gL & 3), preU = (int)(gU & 3), preD = (int)(gD & 3);
@@ -146,7 +147,7 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
   const float* vU = sm.val + baseU + preU;
   const int* cLs = sm.col + cpreL;
   const int* cUs = sm.col + cbaseU + cpreU;
-  const int rl = tid % RP_ROWS, sub = tid / RP_ROWS;
+  const int rl = tid % kRows, sub = tid / kRows;
   float acc[3] = {0.f, 0.f, 0.f};
   if (rl < nrow) {
     const int lb = sm.ptr[0][rl] - L0, cntL = sm.ptr[0][rl + 1] - sm.ptr[0][rl];
@@ -192,7 +193,7 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
     }
   }
   __syncthreads();                                         // all reads of the staged blocks are done
-  float (*red)[RP_ROWS][3] = reinterpret_cast<float (*)[RP_ROWS][3]>(sm.val);
+  float (*red)[kRows][3] = reinterpret_cast<float (*)[kRows][3]>(sm.val);
   red[sub][rl][0] = acc[0]; red[sub][rl][1] = acc[1]; red[sub][rl][2] = acc[2];
   __syncthreads();
   if (tid < nrow) {
@@ -235,14 +236,14 @@ __device__ __forceinline__ void row_block(const RowArgs& a, int r0, int nrow, Ro
   }
 }
 
-template <int kMode>
-__global__ void __launch_bounds__(RP_THREADS) row_pass_kernel(RowArgs a) {
+template <int kMode, int kSubs, int kRows>
+__global__ void __launch_bounds__(kRows * kSubs) row_pass_kernel(RowArgs a) {
   if (a.active != nullptr && *a.active == 0.f) return;
-  __shared__ RowSmem sm;
+  __shared__ RowSmemT<kSubs, kRows> sm;
   if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
   uint32_t phase = 0;
-  const int r0 = a.row_begin + blockIdx.x * RP_ROWS;
-  row_block<kMode, false>(a, r0, min(RP_ROWS, a.row_end - r0), sm, phase);
+  const int r0 = a.row_begin + blockIdx.x * kRows;
+  row_block<kMode, false, false, kSubs, kRows>(a, r0, min(kRows, a.row_end - r0), sm, phase);
 }
 
 // One colour of a Gauss-Seidel sweep, launchable as a programmatic dependent of the previous colour: the matrix
@@ -251,13 +252,13 @@ __global__ void __launch_bounds__(RP_THREADS) row_pass_kernel(RowArgs a) {
 // (same CTAs per SM, twice the warps: no gain), 42.6 us for a persistent double-buffered variant with 3 CTAs per SM
 // (removed) -- what bounds the pass is the number of independent row blocks in flight per SM (each one a chain of
 // pointer load -> staging -> L2 gathers of x -> 3x3 solve), which the 36 KB of staging per block limit to 6.
-template <int kSubs>
-__global__ void __launch_bounds__(RP_ROWS * kSubs) gs_color_kernel(RowArgs a) {
-  __shared__ RowSmemT<kSubs> sm;
+template <int kSubs, int kRows>
+__global__ void __launch_bounds__(kRows * kSubs) gs_color_kernel(RowArgs a) {
+  __shared__ RowSmemT<kSubs, kRows> sm;
   if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
   uint32_t phase = 0;
-  const int r0 = a.row_begin + blockIdx.x * RP_ROWS;
-  row_block<RM_GS, false, true, kSubs>(a, r0, min(RP_ROWS, a.row_end - r0), sm, phase);
+  const int r0 = a.row_begin + blockIdx.x * kRows;
+  row_block<RM_GS, false, true, kSubs, kRows>(a, r0, min(kRows, a.row_end - r0), sm, phase);
 }
 
 // Whole femb_gauss_seidel call in ONE cooperative launch (levels whose colour fits the resident grid):
@@ -302,28 +303,44 @@ static RowArgs base_args(const FembLevel* l, const float* values) {
   return a;
 }
 
+// rows per CTA x threads per row of the one-block-per-CTA kernels (measured at 1 M hexahedra, per Gauss-Seidel colour
+// launch: 32x4 32.8 us, 32x8 34.7, 16x4 29.3, 16x8 28.8 -- smaller blocks mean more independent chains in flight per SM)
+static int g_coop_max_blocks = -1;   // -1: twice the resident grid
+static int g_gs_rows = 16;
+static int g_gs_subs = 8;
+#define FEMB_ROWS_DISPATCH(KERNEL_EXPR)                                        \
+  do {                                                                         \
+    if (g_gs_rows == 8 && g_gs_subs == 8) { constexpr int R = 8, S = 8; KERNEL_EXPR; }        \
+    else if (g_gs_rows == 8) { constexpr int R = 8, S = 4; KERNEL_EXPR; }                      \
+    else if (g_gs_rows == 16 && g_gs_subs == 8) { constexpr int R = 16, S = 8; KERNEL_EXPR; }  \
+    else if (g_gs_rows == 16) { constexpr int R = 16, S = 4; KERNEL_EXPR; }                    \
+    else if (g_gs_subs == 8) { constexpr int R = 32, S = 8; KERNEL_EXPR; }                     \
+    else { constexpr int R = 32, S = 4; KERNEL_EXPR; }                                         \
+  } while (0)
+
 template <int kMode>
 static int launch_rows(const RowArgs& a, cudaStream_t st) {
   const int n = a.row_end - a.row_begin;
   if (n <= 0) return FEMB_OK;
-  row_pass_kernel<kMode><<<cdiv(n, RP_ROWS), RP_THREADS, 0, st>>>(a);
+  FEMB_ROWS_DISPATCH((row_pass_kernel<kMode, S, R><<<cdiv(n, R), R * S, 0, st>>>(a)));
   count_launch();
   return check_launch("row_pass_kernel");
 }
 
 // pdl: the launch may overlap the tail of the previous kernel in the stream (which must not write the matrix)
 static int g_no_pdl = 0;
-static int g_gs_subs = 4;   // measured: 32.8 us per colour launch with 4 threads per row, 34.7 with 8 (cube n=100)
 static int launch_gs_color(const RowArgs& a, bool pdl, cudaStream_t st) {
   const int n = a.row_end - a.row_begin;
   if (n <= 0) return FEMB_OK;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(n, RP_ROWS)); cfg.blockDim = dim3(RP_ROWS * g_gs_subs); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  const int rows = g_gs_rows;
+  cfg.gridDim = dim3(cdiv(n, rows)); cfg.blockDim = dim3(rows * g_gs_subs); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (pdl && !g_no_pdl) ? 1 : 0;
-  const cudaError_t e = g_gs_subs == 8 ? cudaLaunchKernelEx(&cfg, gs_color_kernel<8>, a) : cudaLaunchKernelEx(&cfg, gs_color_kernel<4>, a);
+  cudaError_t e = cudaSuccess;
+  FEMB_ROWS_DISPATCH((e = cudaLaunchKernelEx(&cfg, gs_color_kernel<S, R>, a)));
   count_launch();
   if (e != cudaSuccess) {
     set_error("gs_color_kernel: %s", cudaGetErrorString(e));
@@ -550,33 +567,59 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_ap_kernel(RowArgs a, int 
   const int lb = sm.ptr[0][rl] - L0, cntL = sm.ptr[0][rl + 1] - sm.ptr[0][rl];
   const int ub = sm.ptr[1][rl] - U0, cntU = sm.ptr[1][rl + 1] - sm.ptr[1][rl];
   float* acc = sm.acc + tid;                      // acc[slot][tid]: bank == lane, conflict-free
-  const int total = cntL + 1 + cntU;
-  for (int jj = 0; jj < total; ++jj) {                       // column order: L blocks, D, U blocks
-    float v;
-    int j;
-    const unsigned char* ts;
-    if (jj < cntL) {
-      const int loc = lb + jj;
-      if (staged) { v = sm.val[preL + loc * 9 + k]; j = sm.col[cpreL + loc]; ts = sm.tsl + tpreL + loc * 8; }
-      else { v = __ldg(a.values + (sL + loc) * 9 + k); j = __ldg(a.L_col + L0 + loc); ts = t_slot + (sL + loc) * 8; }
-    } else if (jj == cntL) {
-      v = sm.diag[preD + rl * 9 + k]; j = i; ts = sm.tsl + tbaseD + tpreD + rl * 8;
-    } else {
-      const int loc = ub + (jj - cntL - 1);
-      if (staged) { v = sm.val[baseU + preU + loc * 9 + k]; j = sm.col[cbaseU + cpreU + loc]; ts = sm.tsl + tbaseU + tpreU + loc * 8; }
-      else { v = __ldg(a.values + (sU + loc) * 9 + k); j = __ldg(a.U_col + U0 + loc); ts = t_slot + (sU + loc) * 8; }
-    }
-    if (kDyadic) {
-      // weights 2^-e (e = 0..3) travel in bits 5-6 of the plan byte: no global load in the inner loop
+  // one fine block times the <= 8 parents of its column: acc[slot of parent in the T row] += weight * v.  The 8 plan bytes
+  // (valid ones first, 255 = none) arrive in one 8-byte shared load.
+  auto apply_dyadic = [&](float v, const unsigned char* ts) {
+    const uint2 pk = *reinterpret_cast<const uint2*>(ts);
+    unsigned w = pk.x;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const unsigned b8 = ts[p];
-        if (b8 == 255u) break;
-        acc[(int)(b8 & 31u) * GA_THREADS] += v * __int_as_float((127 - (int)(b8 >> 5)) << 23);
+    for (int p = 0; p < 8; ++p) {
+      if (p == 4) w = pk.y;
+      const unsigned b8 = w & 255u;
+      w >>= 8;
+      if (b8 == 255u) break;
+      // weights 2^-e (e = 0..3) travel in bits 5-6 of the plan byte
+      float* d = acc + (b8 & 31u) * GA_THREADS;
+      *d = fmaf(v, __int_as_float(0x3f800000 - (int)((b8 & 0x60u) << 18)), *d);
+    }
+  };
+  if (kDyadic && staged) {
+    // fast path: everything is in shared memory; L blocks, D, U blocks = column order (sparse.py:873-901)
+    const float* vL = sm.val + preL + lb * 9 + k;
+    const unsigned char* tL = sm.tsl + tpreL + lb * 8;
+    for (int jj = 0; jj < cntL; ++jj) apply_dyadic(vL[jj * 9], tL + jj * 8);
+    apply_dyadic(sm.diag[preD + rl * 9 + k], sm.tsl + tbaseD + tpreD + rl * 8);
+    const float* vU = sm.val + baseU + preU + ub * 9 + k;
+    const unsigned char* tU = sm.tsl + tbaseU + tpreU + ub * 8;
+    for (int jj = 0; jj < cntU; ++jj) apply_dyadic(vU[jj * 9], tU + jj * 8);
+  } else {
+    const int total = cntL + 1 + cntU;
+    for (int jj = 0; jj < total; ++jj) {                       // column order: L blocks, D, U blocks
+      float v;
+      int j;
+      const unsigned char* ts;
+      if (jj < cntL) {
+        const int loc = lb + jj;
+        if (staged) { v = sm.val[preL + loc * 9 + k]; j = sm.col[cpreL + loc]; ts = sm.tsl + tpreL + loc * 8; }
+        else { v = __ldg(a.values + (sL + loc) * 9 + k); j = __ldg(a.L_col + L0 + loc); ts = t_slot + (sL + loc) * 8; }
+      } else if (jj == cntL) {
+        v = sm.diag[preD + rl * 9 + k]; j = i; ts = sm.tsl + tbaseD + tpreD + rl * 8;
+      } else {
+        const int loc = ub + (jj - cntL - 1);
+        if (staged) { v = sm.val[baseU + preU + loc * 9 + k]; j = sm.col[cbaseU + cpreU + loc]; ts = sm.tsl + tbaseU + tpreU + loc * 8; }
+        else { v = __ldg(a.values + (sU + loc) * 9 + k); j = __ldg(a.U_col + U0 + loc); ts = t_slot + (sU + loc) * 8; }
       }
-    } else {
-      const int p0 = __ldg(p_off + j), np = __ldg(p_off + j + 1) - p0;
-      for (int p = 0; p < np; ++p) acc[(int)(ts[p] & 31u) * GA_THREADS] += v * __ldg(p_w + p0 + p);
+      if (kDyadic) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const unsigned b8 = ts[p];
+          if (b8 == 255u) break;
+          acc[(int)(b8 & 31u) * GA_THREADS] += v * __int_as_float((127 - (int)(b8 >> 5)) << 23);
+        }
+      } else {
+        const int p0 = __ldg(p_off + j), np = __ldg(p_off + j + 1) - p0;
+        for (int p = 0; p < np; ++p) acc[(int)(ts[p] & 31u) * GA_THREADS] += v * __ldg(p_w + p0 + p);
+      }
     }
   }
   const int t0 = __ldg(t_ptr + i), tn = __ldg(t_ptr + i + 1) - t0;
@@ -667,6 +710,18 @@ int femb_set_gs_threads_per_row(int subs) {
   return old;
 }
 
+int femb_set_gs_coop_max_blocks(int max_blocks) {
+  const int old = g_coop_max_blocks;
+  g_coop_max_blocks = max_blocks;
+  return old;
+}
+
+int femb_set_gs_rows_per_cta(int rows) {
+  const int old = g_gs_rows;
+  if (rows == 8 || rows == 16 || rows == 32) g_gs_rows = rows;
+  return old;
+}
+
 int femb_spmv(const FembLevel* lvl, const float* values, int parts, float alpha, const float* x, float beta, float* y,
               void* stream) {
   FEMB_REQUIRE(lvl && values && x && y, "null pointer");
@@ -698,7 +753,8 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
   int max_blocks = 1;
   for (int c = 0; c < 8; ++c) max_blocks = max(max_blocks, (int)cdiv(lvl->color_start[c + 1] - lvl->color_start[c], RP_ROWS));
   const int cap = coop_capacity();
-  if (cap > 0 && max_blocks <= 2 * cap) {
+  const int coop_limit = g_coop_max_blocks >= 0 ? g_coop_max_blocks : 2 * cap;
+  if (cap > 0 && max_blocks <= coop_limit) {
     // small level: one cooperative launch, grid-wide barrier between the 16 colour phases
     GsCoopArgs g;
     g.base = a; g.iterations = iterations;

@@ -182,6 +182,11 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
 int femb_set_pdl(int enable);
 /* threads per row of the colour kernel: 4 (default, measured faster) or 8; the summation tree differs, so results differ in rounding */
 int femb_set_gs_threads_per_row(int subs);
+/* rows per CTA of the colour kernel: 32 (default) or 16 */
+int femb_set_gs_rows_per_cta(int rows);
+/* femb_gauss_seidel runs as ONE cooperative launch when the largest colour has at most this many 32-row blocks
+ * (-1 = default: twice the resident grid; 0 = never) */
+int femb_set_gs_coop_max_blocks(int max_blocks);
 /* A run of colour launches of the in-place sweep above: colours first_color..last_color (descending if
  * first > last), dx is NOT zeroed.  femb_gauss_seidel(it=1) == zero dx; colours 7..0 with parts=U; colours 0..7
  * with parts=L|U.  Lets a caller put a halo exchange between colour groups (domain decomposition). */

@@ -34,14 +34,27 @@ for fused in modes:
     timed(lambda: obj._hessian(1, obj.x_gpu_layer[1], obj.UtAUs_values[0]), f"hessian level1 pipeline={fused}")
 timed(lambda: obj._force(x, obj.grad_gpu), "force level0")
 obj._force_hessian(x, obj.dev_B_fixed[0], obj.MF_value_gpu, obj.diag_fixed)
-for subs, pdl in (((8, 1), (4, 1), (8, 0), (8, 1)) if len(modes) > 1 else ()):
+for rows, subs, pdl in (((32, 4, 1), (16, 8, 1), (8, 8, 1), (8, 4, 1), (16, 4, 1), (16, 8, 0)) if len(modes) > 1 else ()):
     obj.lib.femb_set_pdl(pdl)
     obj.lib.femb_set_gs_threads_per_row(subs)
+    obj.lib.femb_set_gs_rows_per_cta(rows)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         obj.PerformGaussSeidel(0, 3)
-    timed(g.replay, f"GS level0 x3 threads/row={subs} pdl={pdl} (graph)")
+    timed(g.replay, f"GS level0 x3 rows/CTA={rows} threads/row={subs} pdl={pdl} (graph)")
+    timed(lambda: obj._residual(0, obj.dev_B_fixed[0], obj.dev_delta_x[0], obj.dev_R[0]), f"   residual level0 (full pass) rows/CTA={rows} threads/row={subs}")
 obj.lib.femb_set_gs_threads_per_row(8)
+obj.lib.femb_set_gs_rows_per_cta(16)
 timed(lambda: obj._residual(0, obj.dev_B_fixed[0], obj.dev_delta_x[0], obj.dev_R[0]), "residual level0 (full pass)")
 obj.galerkin()
 timed(obj.galerkin, "galerkin 0->1")
+
+# coarse level: cooperative single launch vs PDL colour launches
+obj.UtAUs_values[0].copy_(obj.UtAUs_values[0])
+obj.dev_B_fixed[1].normal_()
+for lim in (-1, 0, -1):
+    obj.lib.femb_set_gs_coop_max_blocks(lim)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        obj.PerformGaussSeidel(1, 3)
+    timed(g.replay, f"GS level1 x3 coop_max_blocks={lim} (graph)")

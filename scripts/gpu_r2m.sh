@@ -1,0 +1,5 @@
+set -x
+cd $GRAFT_REPO_ROOT
+free -g | head -2; nproc
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+timeout 600 python scripts/bench_asm.py 100 10 01 > gpurun_out/bench_asm.log 2>&1; echo "rc=$?"; grep -i "GS\|galerkin\|residual" gpurun_out/bench_asm.log
