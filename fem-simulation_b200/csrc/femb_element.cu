@@ -173,25 +173,26 @@ constexpr int AS_ZERO = 8 * AS_JSTRIDE;           // a block of zeros (+ zero ta
 struct AsmWarpSmem {
   alignas(16) float stage[8 * AS_JSTRIDE + 12];   // the folded row (27 x 9 floats) reuses the front of it
 };
-// per-row record of the fold plan: 27 x 8 contributor bytes, then a 16-byte header
-constexpr int FP_ROW = FEMB_FOLD_PLAN_BYTES;       // 232
+// per-row record of the fold plan: 28 x 4 contributor bytes, then a 16-byte header
+constexpr int FP_ROW = FEMB_FOLD_PLAN_BYTES;       // 128
 // what a warp needs to know about a row before touching the element matrices; one coalesced read of the plan record
 // (+ the incidence list), prefetched one row ahead
 struct AsmMeta {
-  uint2 plan;        // lane s < 27: contributors of block s
+  unsigned plan;     // lane s < 27: the <= 4 contributors of block s (the diagonal block: its first 4); lane 27: contributors
+                     // 5..8 of the diagonal block; one byte each, j*8+p, 255 = none
   int my_ea;         // lane j < 8: j-th incident hexahedron*8 + local node, -1 = none
   int r, lp, up, nl, nu;
 };
 __device__ __forceinline__ AsmMeta asm_meta(const AsmArgs& A, int v, int lane) {
   AsmMeta M;
-  uint2 w = make_uint2(0xffffffffu, 0xffffffffu);
-  if (lane < AS_SLOTS + 2) w = __ldg(reinterpret_cast<const uint2*>(A.fold + (size_t)v * FP_ROW) + lane);
-  M.plan = lane < AS_SLOTS ? w : make_uint2(0xffffffffu, 0xffffffffu);
+  // the whole record is one 128-byte line: 28 plan words, then {row, L_ptr[row], U_ptr[row], nL | nU << 8}
+  const unsigned w = __ldg(reinterpret_cast<const unsigned*>(A.fold + (size_t)v * FP_ROW) + lane);
+  M.plan = lane < AS_SLOTS + 1 ? w : 0xffffffffu;
   M.my_ea = lane < 8 ? __ldg(A.vert_elem + (size_t)v * 8 + lane) : -1;
-  M.r = (int)__shfl_sync(0xffffffffu, w.x, AS_SLOTS);          // header: r, lp | up, nl + (nu << 8)
-  M.lp = (int)__shfl_sync(0xffffffffu, w.y, AS_SLOTS);
-  M.up = (int)__shfl_sync(0xffffffffu, w.x, AS_SLOTS + 1);
-  const unsigned nn = __shfl_sync(0xffffffffu, w.y, AS_SLOTS + 1);
+  M.r = (int)__shfl_sync(0xffffffffu, w, 28);
+  M.lp = (int)__shfl_sync(0xffffffffu, w, 29);
+  M.up = (int)__shfl_sync(0xffffffffu, w, 30);
+  const unsigned nn = __shfl_sync(0xffffffffu, w, 31);
   M.nl = (int)(nn & 255u); M.nu = (int)((nn >> 8) & 255u);
   return M;
 }
@@ -242,7 +243,7 @@ __device__ __noinline__ void assemble_row_slow(const int* elem2nnz, const float*
 
 __device__ __forceinline__ void assemble_row(const AsmArgs& A, const AsmLane& LN, const AsmMeta& M, int lane, AsmWarpSmem& sm) {
   const int r = M.r, lp = M.lp, nl = M.nl, up = M.up, nu = M.nu, my_ea = M.my_ea;
-  const uint2 plan = M.plan;
+  const unsigned plan = M.plan;
   // One LDG.128 + one STS.128 per lane and incident hexahedron.  A missing hexahedron (ea < 0, boundary vertex) is read
   // from hexahedron 0 instead: no contributor of the plan points at it, so what lands in its stage is never looked at.
   if (lane < 21) {
@@ -258,17 +259,19 @@ __device__ __forceinline__ void assemble_row(const AsmArgs& A, const AsmLane& LN
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(d + j * AS_JSTRIDE) = seg[j];
   }
   __syncwarp();
-  const unsigned first = __shfl_sync(0xffffffffu, plan.x, 0) & 255u;
+  const unsigned first = __shfl_sync(0xffffffffu, plan, 0) & 255u;
   if (first == 254u) {                                       // oversized row (plan not applicable); warp-uniform
     assemble_row_slow(A.elem2nnz, A.diag_add, A.values, A.off_l, A.off_d, A.off_u, r, lane, my_ea, lp, nl, up, nu, sm.stage);
     __syncwarp();
     return;
   }
-  // lane s folds block s: contributors in incidence order; a mirrored contributor (position >= 5) is added transposed
+  // lane s folds block s: contributors in incidence order; a mirrored contributor (position >= 5) is added transposed.
+  // Two vertices share at most 4 hexahedra, so only the diagonal block has more than 4 contributors: lane 27 folds its
+  // second half and hands it over by shuffle.
   float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const unsigned idx = ((c < 4 ? plan.x : plan.y) >> (8 * (c & 3))) & 255u;
+  for (int c = 0; c < 4; ++c) {
+    const unsigned idx = (plan >> (8 * c)) & 255u;
     const bool have = idx < 64u;                             // no branch: an absent contributor reads the zero block
     const unsigned j = idx >> 3, p = idx & 7u;
     const unsigned off = have ? j * AS_JSTRIDE + p * 8 : (unsigned)AS_ZERO;
@@ -281,6 +284,11 @@ __device__ __forceinline__ void assemble_row(const AsmArgs& A, const AsmLane& LN
     acc[1] += tr ? b0.w : b0.y; acc[3] += tr ? b0.y : b0.w;
     acc[2] += tr ? b1.z : b0.z; acc[6] += tr ? b0.z : b1.z;
     acc[5] += tr ? b1.w : b1.y; acc[7] += tr ? b1.y : b1.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float hi = __shfl_sync(0xffffffffu, acc[k], AS_SLOTS);   // second half of the diagonal block
+    if (lane == nl) acc[k] += hi;
   }
   __syncwarp();                                              // every lane is done reading the staged blocks
   float* out = sm.stage;                                     // the folded row: L blocks, D, U blocks
@@ -313,12 +321,8 @@ __global__ void __launch_bounds__(256) fold_plan_kernel(AsmArgs A, unsigned char
   const int my_ea = lane < 8 ? __ldg(A.vert_elem + (size_t)v * 8 + lane) : -1;
   unsigned char* out = fold + (size_t)v * FP_ROW;
   if (lane == 0) {                                            // header: r, lp, up, nl + (nu << 8)
-    int* h = reinterpret_cast<int*>(out + AS_SLOTS * 8);
+    int* h = reinterpret_cast<int*>(out + 28 * 4);
     h[0] = r; h[1] = lp; h[2] = up; h[3] = (nl & 255) | ((nu & 255) << 8);
-  }
-  if (nl + 1 + nu > AS_SLOTS) {
-    for (int i = lane; i < AS_SLOTS * 8; i += 32) out[i] = 254;
-    return;
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -333,12 +337,33 @@ __global__ void __launch_bounds__(256) fold_plan_kernel(AsmArgs A, unsigned char
     s_loc[w][(t & ~7) | ((b - (ea & 7)) & 7)] = loc;
   }
   __syncwarp();
-  if (lane < AS_SLOTS) {
-    int n = 0;
+  // lane s < 27: contributors of block s; more than 4 are allowed only for the diagonal block (slot nl), whose
+  // contributors 5..8 go to lane 27.  Anything else (or a row with more than 27 blocks) takes the slow path: 254.
+  bool bad = nl + 1 + nu > AS_SLOTS;
+  unsigned char mine[8];
+  int n = 0;
+  if (lane < AS_SLOTS && !bad) {
     for (int t = 0; t < 64; ++t)
-      if (s_loc[w][t] == lane && n < 8) out[lane * 8 + n++] = (unsigned char)t;
-    for (; n < 8; ++n) out[lane * 8 + n] = 255;
+      if (s_loc[w][t] == lane) {
+        if (n < 8) mine[n] = (unsigned char)t;
+        ++n;
+      }
+    if (n > (lane == nl ? 8 : 4)) bad = true;
   }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane < AS_SLOTS) {
+    for (int c = 0; c < 4; ++c) out[lane * 4 + c] = bad ? 254 : (c < n ? mine[c] : 255);
+  }
+  // the diagonal lane also writes the overflow word of lane 27
+  const int dn = __shfl_sync(0xffffffffu, n, bad ? 0 : nl);
+  unsigned hi = 0xffffffffu;
+  if (!bad && lane == nl) {
+    hi = 0;
+    for (int c = 0; c < 4; ++c) hi |= (unsigned)(4 + c < n ? mine[4 + c] : 255) << (8 * c);
+  }
+  hi = __shfl_sync(0xffffffffu, hi, bad ? 0 : nl);
+  (void)dn;
+  if (lane == 0) *reinterpret_cast<unsigned*>(out + 27 * 4) = bad ? 0xfefefefeu : hi;
 }
 
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both

@@ -128,7 +128,7 @@ class Object:
             lv.elem2nnz = self.hex_update_offset_gpu[l].data_ptr()
             for k in ("L_ptr", "L_col", "U_ptr", "U_col", "vert_elem", "invJ", "detJ"):
                 setattr(lv, k, d[k].data_ptr())
-            d["fold_plan"] = torch.empty(n * 232 + 16, dtype=torch.uint8, device=dev)      # FEMB_FOLD_PLAN_BYTES per vertex
+            d["fold_plan"] = torch.empty(n * 128 + 16, dtype=torch.uint8, device=dev)      # FEMB_FOLD_PLAN_BYTES per vertex
             _lib.check(self.lib.femb_build_fold_plan(C.byref(lv), d["fold_plan"].data_ptr(), self._stream()), "femb_build_fold_plan")
             lv.fold_plan = d["fold_plan"].data_ptr()
             if ap is not None:                                           # element/fold software pipeline plan (host arrays)

@@ -38,7 +38,7 @@ extern "C" {
 /* hexahedra per CTA of the element kernel (pipeline chunks should be multiples of it) */
 #define FEMB_ASM_CHUNK_HEXES 16
 #define FEMB_FOLD_SLOTS 27
-#define FEMB_FOLD_PLAN_BYTES 232   /* 27*8 contributor bytes + 16 header bytes per vertex */
+#define FEMB_FOLD_PLAN_BYTES 128   /* 28*4 contributor bytes + 16 header bytes per vertex: one cache line */
 /* floats of element-matrix scratch per hexahedron (elem_k of femb_hessian): 8 rows x (5 blocks of 9 + 3 pad) -- the
  * symmetric half in rotated order, see femb_element.cu */
 #define FEMB_ELEM_K_FLOATS 384
@@ -69,9 +69,10 @@ typedef struct FembLevel {
   const float* invJ;     /* [n_hex*8*9] inverse_pX_peps (quai_hexagon.py:18)            */
   const float* detJ;     /* [n_hex*8]   det_pX_peps     (quai_hexagon.py:17)            */
   const unsigned char* fold_plan; /* [n_vert*FEMB_FOLD_PLAN_BYTES] per vertex: for each of the 27 blocks of its row (L blocks, */
-                                  /* D, U blocks) the <= 8 contributors j*8+p (j-th incident hexahedron, rotated column      */
-                                  /* position p; 255 = none) in fold order, then int32 {row, L_ptr[row], U_ptr[row],         */
-                                  /* nL | nU<<8}; filled by femb_build_fold_plan from vert_elem + elem2nnz                  */
+                                  /* D, U blocks) the <= 4 contributors j*8+p (j-th incident hexahedron, rotated column      */
+                                  /* position p; 255 = none) in fold order, a 28th word with contributors 5..8 of the         */
+                                  /* diagonal block, then int32 {row, L_ptr[row], U_ptr[row], nL | nU<<8}; filled by          */
+                                  /* femb_build_fold_plan from vert_elem + elem2nnz                                          */
   /* Optional plan of the two-stage software pipeline of femb_hessian / femb_force_hessian (0 / NULL = one chunk).  HOST
    * arrays: chunk c ends at hexahedron pipe_hex_end[c] (exclusive); every vertex below pipe_vert_end[c] has all its
    * hexahedra below pipe_hex_end[c].  Both non-decreasing, last entries n_hex and n_vert. */
@@ -184,8 +185,9 @@ int femb_set_pdl(int enable);
 int femb_set_gs_threads_per_row(int subs);
 /* rows per CTA of the colour kernel: 32 (default) or 16 */
 int femb_set_gs_rows_per_cta(int rows);
-/* femb_gauss_seidel runs as ONE cooperative launch when the largest colour has at most this many 32-row blocks
- * (-1 = default: twice the resident grid; 0 = never) */
+/* femb_gauss_seidel runs as ONE cooperative launch (grid-wide barrier between colour phases) when the largest colour has
+ * at most this many 32-row blocks: 0 = never (default: PDL colour launches were measured faster at every level size),
+ * -1 = twice the resident grid */
 int femb_set_gs_coop_max_blocks(int max_blocks);
 /* A run of colour launches of the in-place sweep above: colours first_color..last_color (descending if
  * first > last), dx is NOT zeroed.  femb_gauss_seidel(it=1) == zero dx; colours 7..0 with parts=U; colours 0..7

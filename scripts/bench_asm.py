@@ -49,12 +49,22 @@ timed(lambda: obj._residual(0, obj.dev_B_fixed[0], obj.dev_delta_x[0], obj.dev_R
 obj.galerkin()
 timed(obj.galerkin, "galerkin 0->1")
 
-# coarse level: cooperative single launch vs PDL colour launches
-obj.UtAUs_values[0].copy_(obj.UtAUs_values[0])
-obj.dev_B_fixed[1].normal_()
-for lim in (-1, 0, -1):
-    obj.lib.femb_set_gs_coop_max_blocks(lim)
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        obj.PerformGaussSeidel(1, 3)
-    timed(g.replay, f"GS level1 x3 coop_max_blocks={lim} (graph)")
+# coarse levels: cooperative single launch vs PDL colour launches
+del obj
+torch.cuda.empty_cache()
+obj = Object(f"cube:{n}", 1.0 / n, [], use_graphs=False, layers=3)
+obj._force_hessian(obj.x_gpu_layer[0], obj.dev_B_fixed[0], obj.MF_value_gpu, obj.diag_fixed)
+obj.galerkin()
+for lvl in (1, 2):
+    obj.dev_B_fixed[lvl].normal_()
+    for lim in (-1, 0, -1):
+        obj.lib.femb_set_gs_coop_max_blocks(lim)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            obj.PerformGaussSeidel(lvl, 3)
+        timed(g.replay, f"GS level{lvl} x3 coop_max_blocks={lim} (graph)")
+obj.lib.femb_set_gs_coop_max_blocks(-1)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    obj.galerkin()
+timed(g.replay, "galerkin 0->1->2 (graph)")
