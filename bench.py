@@ -89,7 +89,7 @@ class ClockSampler:
 
 
 # DRAM bytes (read + write) per launch measured with `ncu --set full` on the cube n=100 (profiles/README.md), per million hexahedra
-ASM_TRAFFIC_PER_MHEX = 4.62e9      # element_kernel<1> 0.364 + 1.484 GB, assemble_rows_kernel 1.81 + 0.96 GB
+ASM_TRAFFIC_PER_MHEX = 4.55e9      # element_kernel<1> 0.364 + 1.477 GB, assemble_rows_kernel 1.741 + 0.967 GB (profiles/r01b_element_assemble_ncu_raw.txt)
 GS_TRAFFIC_PER_MHEX = 118.9e6      # one colour launch of the row pass
 
 
@@ -296,7 +296,7 @@ def run_ours(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "us_per_launch": asm_ms * 1e3, "algorithmic_bytes_per_launch": asm_bytes,
                      "algorithmic_bytes_formula": "352*N_h + 36*Z + 256*N_h (SURVEY.md 8d, Hessian assembly)"},
-        "roofline_smoother": {"bound": "hbm", "kernel": "gs_color_kernel<8> (femb_gauss_seidel, fine level, one colour launch)",
+        "roofline_smoother": {"bound": "hbm", "kernel": "gs_color_kernel<8,16> (femb_gauss_seidel, fine level, one colour launch)",
                               "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": GS_TRAFFIC_PER_MHEX * n ** 3 / 1e6,
                               "us_per_launch": gs_ms_per_launch * 1e3, "algorithmic_bytes_per_launch": gs_launch_bytes(obj)},
         "clocks": clocks,

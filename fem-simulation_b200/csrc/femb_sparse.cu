@@ -651,17 +651,19 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, c
       const int q = ut_q[e];
       const int t1 = __ldg(t_ptr + i + 1);
       int t = __ldg(t_ptr + i);
-      // the slots of one T row are distinct: batches of 4 keep 8 independent global loads in flight per thread
-      for (; t + 4 <= t1; t += 4) {
-        int sl[4];
-        float tv[4];
+      // the slots of one T row are distinct: batches of 8 keep 16 independent global loads in flight per thread
+      const unsigned char* cs = c_slot8 + (size_t)t * 8 + q;
+      const float* tv_p = t_val + (size_t)t * 9 + k;
+      for (; t + 8 <= t1; t += 8, cs += 64, tv_p += 72) {
+        int sl[8];
+        float tv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          sl[u] = (int)__ldg(c_slot8 + (size_t)(t + u) * 8 + q);
-          tv[u] = __ldg(t_val + (size_t)(t + u) * 9 + k);
+        for (int u = 0; u < 8; ++u) {
+          sl[u] = (int)__ldg(cs + u * 8);
+          tv[u] = __ldg(tv_p + u * 9);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[sl[u] * GA_THREADS] += w * tv[u];
+        for (int u = 0; u < 8; ++u) acc[sl[u] * GA_THREADS] += w * tv[u];
       }
       for (; t < t1; ++t)
         acc[(int)__ldg(c_slot8 + (size_t)t * 8 + q) * GA_THREADS] += w * __ldg(t_val + (size_t)t * 9 + k);

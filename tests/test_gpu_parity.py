@@ -352,3 +352,58 @@ def test_pdl_gauss_seidel_is_bit_identical():
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(ref, obj.dev_delta_x[0]), f"graph-replayed PDL sweep differs (rep {rep})"
+
+
+def _fan_mesh(dx=0.05):
+    """8 unit cubes around the origin that share ONLY vertex 0 (every other corner is a private copy): not a lattice
+    mesh -- row 0 has 57 blocks, and its diagonal block 8 contributors, every other row 8 blocks."""
+    pts, hexs = [(0.0, 0.0, 0.0)], []
+    for ox in (-1, 0):
+        for oy in (-1, 0):
+            for oz in (-1, 0):
+                h = []
+                for bx in (0, 1):
+                    for by in (0, 1):
+                        for bz in (0, 1):
+                            p = ((ox + bx) * dx, (oy + by) * dx, (oz + bz) * dx)
+                            if p == (0.0, 0.0, 0.0):
+                                h.append(0)
+                            else:
+                                pts.append(p); h.append(len(pts) - 1)
+                hexs.append(h)
+    return np.array(pts, np.float32), np.array(hexs, np.int32)
+
+
+def test_rows_with_more_than_27_blocks():
+    """Generality beyond hexahedral lattices (the fast paths assume <= 27 blocks per row): the fold's slow path, the row
+    pass with 56 off-diagonal blocks in one row, and Gauss-Seidel / SpMV on that matrix, against a direct numpy scatter of the
+    oracle's element matrices through the element->nnz map."""
+    pts, hx = _fan_mesh()
+    obj = Object((pts, hx), 0.05, [3], layers=1, use_graphs=False, pin_displacement=0.0)
+    p = obj.hierarchy.pattern[0]
+    assert int(np.diff(p.L_ptr).max() + np.diff(p.U_ptr).max()) >= 56
+    rng = np.random.default_rng(5)
+    xp = (pts + rng.normal(size=pts.shape).astype(np.float32) * 0.002).astype(np.float32)
+    sfg = obj.hierarchy.shapeFuncGrad
+    det, inv = K.prepare_kernal(pts, hx, sfg)
+    ref = np.zeros((p.nnz, 3, 3), np.float32)
+    K.elastic_hessian(xp, hx, sfg, det, inv, obj.mu, obj.la, ref, p.hex_update_offset)
+    ref64 = np.zeros((p.nnz, 3, 3), np.float64)
+    det64, inv64 = K.prepare_kernal(pts.astype(np.float64), hx, sfg, dtype=np.float64)
+    K.elastic_hessian(xp.astype(np.float64), hx, sfg, det64, inv64, obj.mu, obj.la, ref64, p.hex_update_offset, dtype=np.float64)
+    x = torch.from_numpy(xp).to(obj.device)
+    vals = obj.new_values(0)
+    obj._hessian(0, x, vals, None)
+    close64(vals, ref, ref64, what="values of the fan mesh (slow fold path)")
+    # y = A x with the 57-block row, and one symmetric Gauss-Seidel iteration, against dense algebra
+    n = obj.N_verts
+    A = np.zeros((n * 3, n * 3))
+    v = vals.cpu().numpy().astype(np.float64)
+    rows, cols = p.row, p.col
+    for s in range(p.nnz):
+        A[3 * rows[s]:3 * rows[s] + 3, 3 * cols[s]:3 * cols[s] + 3] += v[s]
+    xv = rng.normal(size=(n, 3)).astype(np.float32)
+    y = torch.zeros(n, 3, device=obj.device)
+    obj.MF_value_gpu.copy_(vals)
+    obj._spmv(0, _lib.PART_ALL, 1.0, torch.from_numpy(xv).to(obj.device), 0.0, y)
+    close(y, (A @ xv.reshape(-1).astype(np.float64)).reshape(n, 3), rel=2e-5, what="SpMV with a 57-block row")
