@@ -407,3 +407,29 @@ def test_rows_with_more_than_27_blocks():
     obj.MF_value_gpu.copy_(vals)
     obj._spmv(0, _lib.PART_ALL, 1.0, torch.from_numpy(xv).to(obj.device), 0.0, y)
     close(y, (A @ xv.reshape(-1).astype(np.float64)).reshape(n, 3), rel=2e-5, what="SpMV with a 57-block row")
+
+
+@pytest.mark.parametrize("rows,subs", [(8, 4), (8, 8), (16, 4), (16, 8), (32, 4), (32, 8)])
+def test_row_pass_configurations(pair, rows, subs):
+    """Every rows-per-CTA x threads-per-row instantiation of the row-pass kernels (Gauss-Seidel colour launches as
+    programmatic dependent launches, and the cooperative single-launch sweep; residual) against the oracle."""
+    obj, ref, xp = pair
+    _load_state(obj, ref, xp)
+    ref.PerformGaussSeidel(0, 2)
+    old_r, old_s = obj.lib.femb_set_gs_rows_per_cta(rows), obj.lib.femb_set_gs_threads_per_row(subs)
+    try:
+        for coop in (0, -1):
+            obj.lib.femb_set_gs_coop_max_blocks(coop)
+            obj.dev_delta_x[0].fill_(float("nan"))
+            obj.PerformGaussSeidel(0, 2)
+            close(obj.dev_delta_x[0], ref.dev_delta_x[0], what=f"GS x2 rows={rows} subs={subs} coop={coop}")
+        r = torch.zeros_like(obj.dev_delta_x[0])
+        obj._residual(0, obj.dev_B_fixed[0], obj.dev_delta_x[0], r)
+        acc = np.zeros_like(ref.dev_delta_x[0])
+        for m in (ref.Lm, ref.Um, ref.Dm):
+            ref_solvers.bsr_mv(m[0], ref.dev_delta_x[0], acc, alpha=1.0, beta=1.0)
+        close(r, ref.grad - acc, what=f"residual rows={rows} subs={subs}")
+    finally:
+        obj.lib.femb_set_gs_coop_max_blocks(0)
+        obj.lib.femb_set_gs_rows_per_cta(old_r)
+        obj.lib.femb_set_gs_threads_per_row(old_s)
