@@ -88,17 +88,19 @@ def _cpu_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_halo_plans_gloo_world2():
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_plans_gloo(world):
+    """world 4 (2 cell layers per rank) adds interior ranks, which talk to both neighbours."""
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
-    res = sorted(out.get(timeout=5) for _ in range(2))
-    assert res == [(0, "ok"), (1, "ok")], res
+        p.join(180)
+    res = sorted(out.get(timeout=5) for _ in range(world))
+    assert res == [(r, "ok") for r in range(world)], res
 
 
 def test_slab_planes_validation():
@@ -113,7 +115,7 @@ def _gpu_worker(rank, world, port, steps, out):
     torch.cuda.set_device(rank)
     _init(rank, world, port, "nccl")
     try:
-        so = D.SlabObject(12, 10, 16, DX, device=f"cuda:{rank}")
+        so = D.SlabObject(12, 10, 16, DX, device=f"cuda:{rank}")      # 16 cell layers: 8 per rank at world 2, 4 at world 4
         so.FASv3(steps)
         ids, xs = so.owned_positions()
         out.put((rank, ids.cpu().numpy(), xs.cpu().numpy(), so.force_inf_norm()))
@@ -134,13 +136,14 @@ def test_distributed_fasv3_matches_single_gpu():
     xref = ref.x_gpu_layer[0].cpu().numpy()
     ref._force(ref.x_gpu_layer[0], ref.grad_gpu)
     fref = float(ref.grad_gpu.abs().max())
+    world = 4 if torch.cuda.device_count() >= 4 else 2               # 4 ranks exercise interior slabs (two neighbours)
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, steps, out)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, steps, out)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [out.get(timeout=600) for _ in range(2)]
+    res = [out.get(timeout=600) for _ in range(world)]
     for p in procs:
         p.join(60)
     x = np.full_like(xref, np.nan)
