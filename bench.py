@@ -188,7 +188,9 @@ def run_ours(args):
         step()                                     # one eager step only to count this step's launches
         obj.use_graphs = True
     else:
+        so.graph_segments = False                  # one eager step to count the launches behind the segment graphs
         step()
+        so.graph_segments = True
     launches_per_step = lib.femb_launch_count() - l0
     barrier()
     # ---- device-resident timing -------------------------------------------------------------------
@@ -279,7 +281,8 @@ def run_ours(args):
                                 "mu=250 la=0 g=-4.9 k=100, default top-layer pins"),
                    "steps_per_sec": steps_per_s, "hexahedra": hexes_per_rank * world, "local_levels": H.layer, "local_dims": H.dims,
                    "parallelism": (f"{world} ranks, z-slab domain decomposition ({n} cell layers + 2 overlap layers per rank), "
-                                   "NCCL neighbour halo exchange (6 per step), no all-reduce on the data path") if world > 1 else
+                                   "NCCL neighbour halo exchange (6 per step), no all-reduce on the data path; the 7 exchange-free "
+                                   "segments of a step are CUDA-graph replays") if world > 1 else
                                   "single GPU, CUDA-graph replay of the step body",
                    "l2": "working set (matrix values %.2f GB per rank) >> 126 MB L2, no flush needed" % (H.pattern[0].nnz * 36 / 1e9),
                    "setup_s": round(setup_s, 1), "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},

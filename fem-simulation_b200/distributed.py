@@ -115,7 +115,8 @@ def build_halo_plans(nx, ny, z0, z1, clo, chi, nz_total, rank, world, coarse_xyz
 class SlabObject:
     """One rank of the mesh-partitioned FASv3 step on an nx x ny x nz_total voxel box (dx spacing)."""
 
-    def __init__(self, nx, ny, nz_total, dx, *, rank=None, world=None, device=None, group=None, **object_kwargs):
+    def __init__(self, nx, ny, nz_total, dx, *, rank=None, world=None, device=None, group=None, graph_segments=True,
+                 **object_kwargs):
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.group = group
@@ -137,7 +138,27 @@ class SlabObject:
         exchange(o.x_gpu_layer[1], self.coarse_v, group)
         o._prepare_rest(1)
         self.global_offset = ps * clo                  # local vertex id + offset = vertex id in the full box mesh
+        self.graph_segments, self._graphs = graph_segments, {}
         torch.cuda.synchronize(o.device) if o.device.type == "cuda" else None
+
+    def _seg(self, key, fn):
+        """Run one exchange-free segment of the step.  With `graph_segments` the segment is captured into a CUDA graph the
+        first time it runs (after executing it eagerly once, like Object._run_step) and replayed afterwards: a step is
+        ~300 kernel launches, and with several ranks per host the eager launches -- not the GPUs -- set the pace.  The NCCL
+        exchanges between the segments stay eager."""
+        if not self.graph_segments or self.obj.device.type != "cuda":
+            fn()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            fn()
+            torch.cuda.synchronize(self.obj.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+            return
+        g.replay()
 
     # the FASv3 loop body of object.py:1467-1511 with the halo exchanges in place
     def fasv3_step(self):
@@ -145,26 +166,48 @@ class SlabObject:
         x = o.x_gpu_layer[0]
         lv0 = C.byref(o.levels[0])
         st = o._stream
-        o._fas_fine(x, False, True, True)                                                   # :1468-1481
         dx0 = o.dev_delta_x[0]
-        dx0.zero_()
         vals, b, nspd = o.MF_value_gpu.data_ptr(), o.dev_B_fixed[0].data_ptr(), o.not_spd.data_ptr()
         U, LU = _lib.PART_U, _lib.PART_L | _lib.PART_U
-        for first, last, parts in ((7, 4, U), (3, 0, U), (0, 3, LU), (4, 7, LU)):            # :1483, sweep in colour groups
+
+        def colours(first, last, parts):
             _lib.check(o.lib.femb_gs_colors(lv0, vals, b, dx0.data_ptr(), first, last, parts, nspd, st()), "femb_gs_colors")
-            exchange(dx0, self.fine_i, self.group)
-        o.update_deltaX(x, dx0)                                                             # :1487
-        o._transfer(o.Ut_noOrder[0], 1.0, x, 0.0, o.dev_x_solved[1])                        # :1489
+
+        def seg_fine():
+            o._fas_fine(x, False, True, True)                                               # :1468-1481
+            dx0.zero_()
+            colours(7, 4, U)                                                                # :1483, sweep in colour groups
+
+        def seg_restrict():
+            o.update_deltaX(x, dx0)                                                         # :1487
+            o._transfer(o.Ut_noOrder[0], 1.0, x, 0.0, o.dev_x_solved[1])                    # :1489
+
+        def seg_coarse():
+            o._force(x, o.dev_R[0])                                                         # :1491-1495
+            o._transfer(o.Ut_hat[0], 1.0, o.dev_R[0], 0.0, o.dev_B_fixed[1])                # :1497
+            o._hessian(1, o.dev_x_solved[1], o.UtAUs_values[0])                             # :1499
+            _lib.check(o.lib.femb_coarse_pin_penalty(C.byref(o.levels[1]), C.byref(o.Ut_noOrder_hat[0].c),
+                                                     o.pin_gpu.data_ptr(), o.control_mag, o.UtAUs_values[0].data_ptr(), st()),
+                       "femb_coarse_pin_penalty")
+            o.PerformJacobi(layer=1, iterations=1)                                          # :1506
+
+        def seg_prolong():
+            o._transfer(o.Us_hat[0], 1.0, o.dev_delta_x[1], 0.0, dx0)                       # :1508
+            o.update_deltaX(x, dx0)                                                         # :1509
+
+        self._seg("fine", seg_fine)
+        exchange(dx0, self.fine_i, self.group)
+        self._seg("gs1", lambda: colours(3, 0, U))
+        exchange(dx0, self.fine_i, self.group)
+        self._seg("gs2", lambda: colours(0, 3, LU))
+        exchange(dx0, self.fine_i, self.group)
+        self._seg("gs3", lambda: colours(4, 7, LU))
+        exchange(dx0, self.fine_i, self.group)
+        self._seg("restrict", seg_restrict)
         exchange(o.dev_x_solved[1], self.coarse_v, self.group)
-        o._force(x, o.dev_R[0])                                                             # :1491-1495
-        o._transfer(o.Ut_hat[0], 1.0, o.dev_R[0], 0.0, o.dev_B_fixed[1])                    # :1497
-        o._hessian(1, o.dev_x_solved[1], o.UtAUs_values[0])                                 # :1499
-        _lib.check(o.lib.femb_coarse_pin_penalty(C.byref(o.levels[1]), C.byref(o.Ut_noOrder_hat[0].c), o.pin_gpu.data_ptr(),
-                                                 o.control_mag, o.UtAUs_values[0].data_ptr(), st()), "femb_coarse_pin_penalty")
-        o.PerformJacobi(layer=1, iterations=1)                                              # :1506
+        self._seg("coarse", seg_coarse)
         exchange(o.dev_delta_x[1], self.coarse_i, self.group)
-        o._transfer(o.Us_hat[0], 1.0, o.dev_delta_x[1], 0.0, dx0)                           # :1508
-        o.update_deltaX(x, dx0)                                                             # :1509
+        self._seg("prolong", seg_prolong)
 
     def FASv3(self, iterations=100):
         for _ in range(iterations):

@@ -240,8 +240,12 @@ def build_pattern(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int) -> L
                         hex_update_offset=slot[inv.reshape(-1)].astype(np.int32))
 
 
-def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers: int | None = None) -> Hierarchy:
-    """object.py:116-697.  ``layers`` overrides the reference's level-count formula (benchmarks only)."""
+def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers: int | None = None,
+                    corrected_spacing: bool = False) -> Hierarchy:
+    """object.py:116-697.  ``layers`` overrides the reference's level-count formula (benchmarks only).
+    ``corrected_spacing`` (off by default = the reference's behaviour) fixes object.py:175-179, which coarsens every
+    level >= 1 with spacing 2 dx so that levels >= 3 are copies of level 2: with it level l has spacing dx 2^l and the
+    hierarchy really gets coarser."""
     x0 = np.ascontiguousarray(points, dtype=F32)
     hex0 = np.ascontiguousarray(hexagons, dtype=np.int32)
     box_min = np.minimum(x0.min(axis=0), F32(1000.0)).astype(F32)
@@ -257,6 +261,8 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
     BIG = np.int64(1) << 20
     for lay in range(layer - 1):                                           # object.py:171-241
         fine_size = dx if lay == 0 else dx * 2                             # sic (object.py:175-179)
+        if corrected_spacing:
+            fine_size = dx * (2 ** lay)
         coarse_size = fine_size * 2
         hx, xl = H.hexs[lay], H.x[lay]
         key3 = _ijk(xl[hx[:, 0]], box_min, coarse_size, 0.1).astype(np.int64)        # [Nh,3]

@@ -98,7 +98,7 @@ def bsr_transposed(m):
 # ----------------------------------------------------------------------------------------------
 # object.py:116-697  hierarchy, interpolation, patterns
 # ----------------------------------------------------------------------------------------------
-def build_setup(points, hexagons, dx, pinList, control_mag=100.0):
+def build_setup(points, hexagons, dx, pinList, control_mag=100.0, corrected_spacing=False):
     """Restates object.py:116-865 for (points f32[N,3], hexagons i32[Nh,8] with local node
     4bx+2by+bz, dx, pinList).  Returns a dict of numpy arrays / python lists named like the
     reference attributes."""
@@ -151,6 +151,8 @@ def build_setup(points, hexagons, dx, pinList, control_mag=100.0):
         coarse_hex_num = 0
         coarse_vert_num = 0
         fine_size = dx if lay == 0 else dx * 2          # object.py:175-179 (sic: 2dx for every lay>=1)
+        if corrected_spacing:                            # the spacing of level `lay` is dx * 2^lay
+            fine_size = dx * (2 ** lay)
         coarse_size = fine_size * 2
         hex_hash = {}
         for i in range(hexs[lay].shape[0]):

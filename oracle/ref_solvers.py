@@ -64,9 +64,9 @@ class RefObject:
     """CPU twin of the reference ``Object`` (physics only; GL/plots dropped)."""
 
     def __init__(self, points, hexagons, dx, pinList, dtype=np.float32, control_mag=100.0,
-                 mu=250.0, la=0.0, g=-9.8 / 2.0, spd_value=1e-3, setup=None):
+                 mu=250.0, la=0.0, g=-9.8 / 2.0, spd_value=1e-3, setup=None, corrected_spacing=False):
         self.dtype = dtype
-        S = setup if setup is not None else build_setup(points, hexagons, dx, pinList, control_mag)
+        S = setup if setup is not None else build_setup(points, hexagons, dx, pinList, control_mag, corrected_spacing)
         self.S = S
         self.layer = S["layer"]
         self.dims = S["dims"]

@@ -22,11 +22,30 @@ def _eq(a, b, name):
     assert np.array_equal(a, b), f"{name}: values differ"
 
 
+def test_corrected_spacing_bit_exact_and_really_coarsens():
+    """with `corrected_spacing` level l is coarsened with spacing dx 2^l instead of the reference's 2 dx for
+    every l >= 1 (object.py:175-179).  The literal loops with the same one-line fix and the vectorised setup agree bit for
+    bit on a sparse ragged mesh with a 4-level bounding box, and the corrected level 3 is smaller than level 2."""
+    points, hexs = mesh.jagged_mesh(33, 32, 34, 0.05, seed=4, keep=0.1)
+    Hb = hierarchy.build_hierarchy(points, hexs, 0.05)
+    assert Hb.layer == 4 and Hb.dims[3] == Hb.dims[2]                 # the reference's degenerate top level
+    _check_setup(points, hexs, 0.05, corrected=True)
+    Hc = hierarchy.build_hierarchy(points, hexs, 0.05, corrected_spacing=True)
+    assert Hc.dims[:3] == Hb.dims[:3] and Hc.dims[3] < Hc.dims[2]
+    us_hat = Hc.Us_hat[2]
+    ps = np.zeros(us_hat.nrow, np.float64); np.add.at(ps, us_hat.rows(), us_hat.weights)
+    assert np.allclose(ps, 1.0)                                      # still a partition of unity
+
+
 @pytest.mark.parametrize("case", list(CASES))
 def test_setup_bit_exact(case):
     (points, hexs), dx = CASES[case]()
-    S = ref_setup.build_setup(points, hexs, dx, [])
-    H = hierarchy.build_hierarchy(points, hexs, dx)
+    _check_setup(points, hexs, dx)
+
+
+def _check_setup(points, hexs, dx, corrected=False):
+    S = ref_setup.build_setup(points, hexs, dx, [], corrected_spacing=corrected)
+    H = hierarchy.build_hierarchy(points, hexs, dx, corrected_spacing=corrected)
     assert S["layer"] == H.layer and S["dims"] == H.dims
     for l in range(H.layer):
         for nm in ["hexs", "x", "vertex2index", "index2vertex", "color_vertex_num"]:
