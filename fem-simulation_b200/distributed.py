@@ -54,21 +54,43 @@ class HaloPlan:
 
 
 def exchange(vec: torch.Tensor, plan: HaloPlan, group=None):
-    """vec[recv rows] <- neighbour's vec[send rows] (vec is [n,3] or [n]); all neighbours in one batched P2P call."""
-    ops, recvs = [], []
-    for nb in plan.neighbours():
-        if nb in plan.send and plan.send[nb].numel():
-            ops.append(dist.P2POp(dist.isend, vec.index_select(0, plan.send[nb]).contiguous(), nb, group))
-        if nb in plan.recv and plan.recv[nb].numel():
-            buf = torch.empty((plan.recv[nb].numel(),) + tuple(vec.shape[1:]), dtype=vec.dtype, device=vec.device)
-            ops.append(dist.P2POp(dist.irecv, buf, nb, group))
-            recvs.append((nb, buf))
+    """vec[recv rows] <- neighbour's vec[send rows] (vec is [n,3] or [n]); all neighbours in one batched P2P call.
+    One gather into a reused send buffer, one batched NCCL group, one scatter from a reused receive buffer."""
+    nbs = plan.neighbours()
+    if not nbs:
+        return
+    key = (vec.dtype, tuple(vec.shape[1:]), vec.device)
+    cache = plan.__dict__.setdefault("_cache", {})
+    c = cache.get(key)
+    if c is None:
+        s_nb = [nb for nb in nbs if nb in plan.send and plan.send[nb].numel()]
+        r_nb = [nb for nb in nbs if nb in plan.recv and plan.recv[nb].numel()]
+        s_idx = torch.cat([plan.send[nb] for nb in s_nb]) if s_nb else None
+        r_idx = torch.cat([plan.recv[nb] for nb in r_nb]) if r_nb else None
+        tail = tuple(vec.shape[1:])
+        c = dict(s_nb=s_nb, r_nb=r_nb, s_idx=s_idx, r_idx=r_idx,
+                 s_len=[plan.send[nb].numel() for nb in s_nb], r_len=[plan.recv[nb].numel() for nb in r_nb],
+                 s_buf=torch.empty((s_idx.numel(),) + tail, dtype=vec.dtype, device=vec.device) if s_nb else None,
+                 r_buf=torch.empty((r_idx.numel(),) + tail, dtype=vec.dtype, device=vec.device) if r_nb else None)
+        cache[key] = c
+    ops = []
+    if c["s_nb"]:
+        torch.index_select(vec, 0, c["s_idx"], out=c["s_buf"])
+        o = 0
+        for nb, n in zip(c["s_nb"], c["s_len"]):
+            ops.append(dist.P2POp(dist.isend, c["s_buf"][o:o + n], nb, group))
+            o += n
+    if c["r_nb"]:
+        o = 0
+        for nb, n in zip(c["r_nb"], c["r_len"]):
+            ops.append(dist.P2POp(dist.irecv, c["r_buf"][o:o + n], nb, group))
+            o += n
     if not ops:
         return
     for r in dist.batch_isend_irecv(ops):
         r.wait()
-    for nb, buf in recvs:
-        vec.index_copy_(0, plan.recv[nb], buf)
+    if c["r_nb"]:
+        vec.index_copy_(0, c["r_idx"], c["r_buf"])
 
 
 def build_halo_plans(nx, ny, z0, z1, clo, chi, nz_total, rank, world, coarse_xyz, coarse_v2i, fine_v2i, dx, device):

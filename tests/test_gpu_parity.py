@@ -433,3 +433,16 @@ def test_row_pass_configurations(pair, rows, subs):
         obj.lib.femb_set_gs_coop_max_blocks(0)
         obj.lib.femb_set_gs_rows_per_cta(old_r)
         obj.lib.femb_set_gs_threads_per_row(old_s)
+
+
+def test_corrected_hierarchy_newton_multigrid():
+    """`Object(..., corrected_hierarchy=True)` (level l coarsened with spacing dx 2^l, so the 4th level really is
+    coarser) against the oracle with the same one-line fix, two Newton-multigrid steps on a sparse ragged 4-level mesh."""
+    pts, hx = mesh.jagged_mesh(33, 32, 34, 0.05, seed=4, keep=0.1)
+    obj = Object((pts, hx), 0.05, [], use_graphs=False, corrected_hierarchy=True)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [], corrected_spacing=True)
+    assert obj.layer == 4 and obj.dims == ref.dims and obj.dims[3] < obj.dims[2]
+    obj.NewtonMultigrid(2)
+    ref.NewtonMultigrid(2)
+    close(obj.x_gpu_layer[0], ref.x_gpu_layer[0], what="positions after 2 Newton-MG steps on the corrected hierarchy")
+    close(obj.UtAUs_values[2], ref.UtAUs_values[2], rel=2e-5, what="Galerkin operator of the corrected level 3")
