@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=0, help="cube edge of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-nmg", action="store_true", help="skip the extra Newton-multigrid timing at N=1")
+    ap.add_argument("--corrected-hierarchy", action="store_true",
+                    help="coarsen level l with spacing dx*2^l (SURVEY 8f-3) instead of the reference's 2*dx for every l>=1; labelled in config")
     return ap.parse_args()
 
 
@@ -158,7 +160,8 @@ def run_ours(args):
         obj = so.obj
         step = so.fasv3_step
     else:
-        obj = Object(f"cube:{n}", 1.0 / n, [], device=str(dev), layers=(args.layers or None), use_graphs=True)
+        obj = Object(f"cube:{n}", 1.0 / n, [], device=str(dev), layers=(args.layers or None), use_graphs=True,
+                     corrected_hierarchy=args.corrected_hierarchy)
         body = obj._newton_mg_body if method == "nmg" else (lambda: obj._fas_v123_body(obj.x_gpu_layer[0], False, True, True, True))
         key = "nmg" if method == "nmg" else "fasv3"
         step = lambda: obj._run_step(key, body)
@@ -280,6 +283,8 @@ def run_ours(args):
                                 f"{'FASv3 two-level quasi-static step (object.py:1467-1511)' if method == 'fasv3' else 'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin; object.py:1231-1296)'}, "
                                 "mu=250 la=0 g=-4.9 k=100, default top-layer pins"),
                    "steps_per_sec": steps_per_s, "hexahedra": hexes_per_rank * world, "local_levels": H.layer, "local_dims": H.dims,
+                   "hierarchy": ("corrected spacing dx*2^l (not the reference's behaviour)" if args.corrected_hierarchy else
+                                 "reference coarsening (object.py:175-179: levels >= 3 repeat level 2)"),
                    "parallelism": (f"{world} ranks, z-slab domain decomposition ({n} cell layers + 2 overlap layers per rank), "
                                    "NCCL neighbour halo exchange (6 per step), no all-reduce on the data path; the 7 exchange-free "
                                    "segments of a step are CUDA-graph replays") if world > 1 else
