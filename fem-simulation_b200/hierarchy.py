@@ -330,6 +330,36 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
     return H
 
 
+HEX_EDGES = np.array([[0, 1], [0, 2], [1, 3], [2, 3], [4, 5], [4, 6], [5, 7], [6, 7], [0, 4], [1, 5], [2, 6], [3, 7]], dtype=np.int64)
+
+
+def edge_index(hexagons: np.ndarray) -> np.ndarray:
+    """exp3/simulation/object.py:258-276: the undirected edges (id0 < id1) of a hexahedral mesh, [2, E] int64, numbered in
+    the order the reference's dictionary first meets them (hexahedra ascending, the 12 local edges in `hex_edge` order)."""
+    h = np.asarray(hexagons, dtype=np.int64)
+    a, b = h[:, HEX_EDGES[:, 0]].reshape(-1), h[:, HEX_EDGES[:, 1]].reshape(-1)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    n = int(h.max(initial=-1)) + 1
+    _, uniq = _first_seen_ids(lo * n + hi)
+    return np.stack([uniq // max(n, 1), uniq % max(n, 1)]).astype(np.int64)
+
+
+def prolongation_chain(H: "Hierarchy"):
+    """exp3/simulation/object.py:294, 429, 438-441: A_noOrder[l] = the un-normalised interpolation weights as a scalar CSR
+    matrix dims[l] x dims[l+1] (vertex order), chained so that entry l maps level l+1 straight to level 0
+    (A_noOrder[l+1] = A_noOrder[l] A_noOrder[l+1]).  Returns scipy CSR matrices with sorted columns (bsr_mm's order)."""
+    import scipy.sparse as sp
+    out = []
+    for l in range(H.layer - 1):
+        u = H.Us_noOrder_hat[l]
+        m = sp.csr_matrix((u.weights.astype(F32), u.columns, u.offsets), shape=(u.nrow, u.ncol))
+        if l > 0:
+            m = (out[l - 1] @ m).tocsr()
+        m.sort_indices()
+        out.append(m.astype(F32))
+    return out
+
+
 def default_pins(points: np.ndarray, dx: float) -> np.ndarray:
     """object.py:762-773: every vertex with y >= y_max - dx - 1e-5 (float32 arithmetic)."""
     y = np.asarray(points, dtype=F32)[:, 1]

@@ -250,6 +250,25 @@ class Object:
         vert_end[-1] = vert_elem.shape[0]
         return np.ascontiguousarray(hex_end, dtype=np.int32), np.ascontiguousarray(vert_end, dtype=np.int32)
 
+    # hooks of the exp3 drivers (exp3/simulation/object.py:258-276, 294-295, 438-441), built on first use
+    @property
+    def edge_index(self):
+        """Per level: the mesh edges as a [2, E] int64 tensor on the device, in the reference's first-seen order."""
+        if getattr(self, "_edge_index", None) is None:
+            self._edge_index = [torch.from_numpy(hierarchy.edge_index(h)).to(self.device) for h in self.hierarchy.hexs]
+        return self._edge_index
+
+    @property
+    def torch_A(self):
+        """Per coarse level l+1: torch sparse CSR [dims[0], dims[l+1]] of the chained un-normalised prolongation."""
+        if getattr(self, "_torch_A", None) is None:
+            self._torch_A = [torch.sparse_csr_tensor(torch.from_numpy(m.indptr.astype(np.int32)).to(self.device),
+                                                     torch.from_numpy(m.indices.astype(np.int32)).to(self.device),
+                                                     torch.from_numpy(m.data.astype(np.float32)).to(self.device),
+                                                     size=m.shape, dtype=torch.float32)
+                             for m in hierarchy.prolongation_chain(self.hierarchy)]
+        return self._torch_A
+
     def new_values(self, layer):
         """Zeroed block-value array [nnz,3,3] of a level, padded as the bulk-copy kernels require (femb200.h)."""
         nnz = self.hierarchy.pattern[layer].nnz

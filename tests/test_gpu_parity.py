@@ -446,3 +446,19 @@ def test_corrected_hierarchy_newton_multigrid():
     ref.NewtonMultigrid(2)
     close(obj.x_gpu_layer[0], ref.x_gpu_layer[0], what="positions after 2 Newton-MG steps on the corrected hierarchy")
     close(obj.UtAUs_values[2], ref.UtAUs_values[2], rel=2e-5, what="Galerkin operator of the corrected level 3")
+
+
+def test_exp3_hooks_on_device(pair):
+    """`edge_index` and `torch_A` (what the exp3 GNN drivers read, exp3/simulation/object.py:258-276, 438-441) live on the
+    device; torch_A[0] is the un-normalised prolongation in vertex order, so it must agree with femb_transfer_mv."""
+    obj, ref, _ = pair
+    ei = obj.edge_index
+    assert len(ei) == obj.layer and all(e.device.type == "cuda" and e.shape[0] == 2 and e.dtype == torch.int64 for e in ei)
+    assert bool((ei[0][0] < ei[0][1]).all())
+    tA = obj.torch_A
+    assert len(tA) == obj.layer - 1 and tuple(tA[0].shape) == (obj.dims[0], obj.dims[1])
+    rng = np.random.default_rng(2)
+    xc = torch.from_numpy(rng.normal(size=(obj.dims[1], 3)).astype(np.float32)).to(obj.device)
+    y = torch.zeros(obj.dims[0], 3, device=obj.device)
+    obj._transfer(obj.Us_noOrder_hat[0], 1.0, xc, 0.0, y)
+    close(tA[0] @ xc, y.cpu().numpy(), what="torch_A[0] @ x vs femb_transfer_mv(Us_noOrder_hat[0])")

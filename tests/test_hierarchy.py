@@ -186,3 +186,31 @@ def test_pipeline_plan_is_prefix_closed():
             for c in range(len(he)):
                 assert last[:vend[c]].max(initial=-1) < he[c]
     assert Object._pipe_plan(0, np.zeros((0, 8), np.int32), 16) is None
+
+
+def test_exp3_hooks_edge_index_and_prolongation_chain():
+    """exp3/simulation/object.py:258-276 (edge_index, dictionary order) and :294,429,438-441 (A_noOrder chain behind torch_A),
+    vectorised vs the literal loops."""
+    points, hexs = mesh.jagged_mesh(18, 17, 19, 0.05, seed=2, keep=0.7, origin=(-0.3, 0.1, 0.2))
+    H = hierarchy.build_hierarchy(points, hexs, 0.05)
+    hex_edge = [[0, 1], [0, 2], [1, 3], [2, 3], [4, 5], [4, 6], [5, 7], [6, 7], [0, 4], [1, 5], [2, 6], [3, 7]]
+    for l in range(H.layer):
+        seen = {}
+        for h in H.hexs[l]:
+            for e0, e1 in hex_edge:
+                a, b = int(h[e0]), int(h[e1])
+                if a > b:
+                    a, b = b, a
+                seen.setdefault((a, b), 1)
+        lit = np.array(list(seen.keys()), dtype=np.int64).T
+        _eq(hierarchy.edge_index(H.hexs[l]), lit, f"edge_index[{l}]")
+    chain = hierarchy.prolongation_chain(H)
+    assert len(chain) == H.layer - 1
+    dense = None
+    for l, m in enumerate(chain):
+        u = H.Us_noOrder_hat[l]
+        d = np.zeros((u.nrow, u.ncol), np.float64)
+        d[u.rows(), u.columns] = u.weights
+        dense = d if dense is None else dense @ d
+        assert m.shape == (H.dims[0], H.dims[l + 1]) and m.has_sorted_indices
+        assert np.array_equal(m.toarray().astype(np.float64), dense), f"A_noOrder[{l}]"      # dyadic weights: exact
