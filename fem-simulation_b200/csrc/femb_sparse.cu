@@ -11,7 +11,7 @@
 //
 // B200 design.  All of the above are one "row pass": for a contiguous range of index-order rows the
 // CTA streams the rows' L blocks, U blocks (both contiguous in the [L;D;U] layout) and D blocks from
-// HBM into shared memory with fully coalesced loads, then 4 threads per row walk the staged blocks
+// HBM into shared memory with bulk copies, then 4 or 8 threads per row walk the staged blocks
 // (lanes = consecutive rows, so the x[col] gathers of a lattice mesh coalesce), and an epilogue turns
 // the row sum into y / residual / a solve3x3 update.  A colour of the 8-colouring is a contiguous row
 // range, so one symmetric Gauss-Seidel iteration is 16 such launches that update dx in place: rows of
@@ -22,8 +22,8 @@
 
 namespace femb {
 
-constexpr int RP_ROWS = 32;                 // rows per CTA
-constexpr int RP_SUBS = 4;                  // threads per row
+constexpr int RP_ROWS = 32;                 // rows per CTA   } of the cooperative kernel and the defaults of the templates;
+constexpr int RP_SUBS = 4;                  // threads per row } the launchers pick 16 x 8 (FEMB_ROWS_DISPATCH)
 constexpr int RP_THREADS = RP_ROWS * RP_SUBS;
 constexpr int RP_CAP = RP_ROWS * 27;        // staged off-diagonal blocks per CTA (26 neighbours + slack)
 
@@ -248,10 +248,11 @@ __global__ void __launch_bounds__(kRows * kSubs) row_pass_kernel(RowArgs a) {
 
 // One colour of a Gauss-Seidel sweep, launchable as a programmatic dependent of the previous colour: the matrix
 // staging (pointer reads + bulk copies) runs before griddepcontrol.wait, i.e. during the previous colour's tail.
-// kSubs threads per row: 4 (default) or 8.  Measured per colour launch at 1 M hexahedra: 32.8 us with 4, 34.7 us with 8
-// (same CTAs per SM, twice the warps: no gain), 42.6 us for a persistent double-buffered variant with 3 CTAs per SM
-// (removed) -- what bounds the pass is the number of independent row blocks in flight per SM (each one a chain of
-// pointer load -> staging -> L2 gathers of x -> 3x3 solve), which the 36 KB of staging per block limit to 6.
+// kRows rows per CTA x kSubs threads per row.  Measured per colour launch at 1 M hexahedra: 32x4 32.8 us, 32x8 34.7 us
+// (same CTAs per SM, twice the warps: no gain), 16x8 28.7 us (default), 16x4 29.1, 8x4 28.4, 8x8 29.2, and 42.6 us for a
+// persistent double-buffered variant with 3 CTAs per SM (removed) -- what bounds the pass is the number of independent
+// row blocks in flight per SM (each one a chain of pointer load -> staging -> L2 gathers of x -> 3x3 solve), so smaller
+// blocks win until the per-block overheads take over.
 template <int kSubs, int kRows>
 __global__ void __launch_bounds__(kRows * kSubs) gs_color_kernel(RowArgs a) {
   __shared__ RowSmemT<kSubs, kRows> sm;
