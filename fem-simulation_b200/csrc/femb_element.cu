@@ -522,17 +522,18 @@ static size_t element_smem() {
 // two-kernel path: one warp per row
 constexpr int AS_WARPS = 8;
 constexpr int AS_THREADS = AS_WARPS * 32;
-constexpr int AS_ROWS_PER_WARP = 4;
-__global__ void __launch_bounds__(AS_THREADS, 4) assemble_rows_kernel(AsmArgs A, int v_begin, int v_end) {
+// kMinBlocks CTAs per SM: 4 -> 64 registers, no spills, 32 warps per SM; 5 -> 48 registers, a few spilled words, 40 warps
+template <int kMinBlocks>
+__global__ void __launch_bounds__(AS_THREADS, kMinBlocks) assemble_rows_kernel(AsmArgs A, int v_begin, int v_end, int rows_per_warp) {
   __shared__ AsmWarpSmem sm[AS_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const AsmLane LN = asm_lane(lane);
   // vertex order: the 8 rows that share a hexahedron are folded close in time, so every stored half row (read by
   // its own row and, for the mirrored blocks, by up to three other rows of the hexahedron) comes from DRAM once.
-  // A warp folds AS_ROWS_PER_WARP consecutive vertices; the plan record of the next one is fetched while the current
+  // A warp folds `rows_per_warp` consecutive vertices; the plan record of the next one is fetched while the current
   // one is folded, which leaves one exposed memory round trip per row (the element matrices) instead of two.
-  const int v0 = v_begin + (blockIdx.x * AS_WARPS + w) * AS_ROWS_PER_WARP;
-  const int v1 = min(v0 + AS_ROWS_PER_WARP, v_end);
+  const int v0 = v_begin + (blockIdx.x * AS_WARPS + w) * rows_per_warp;
+  const int v1 = min(v0 + rows_per_warp, v_end);
   if (v0 >= v1) return;
   AsmMeta M = asm_meta(A, v0, lane);
   if (lane < 12) sm[w].stage[AS_ZERO + lane] = 0.f;
@@ -738,9 +739,13 @@ static int launch_force_gather(const FembLevel* l, const float* x, const float* 
   return check_launch("force_gather_kernel");
 }
 
+static int g_fold_rows_per_warp = 4, g_fold_min_blocks = 4;
 static int launch_assemble(const AsmArgs& as, int v_begin, int v_end, cudaStream_t st) {
   if (v_end <= v_begin) return FEMB_OK;
-  assemble_rows_kernel<<<cdiv(v_end - v_begin, AS_WARPS * AS_ROWS_PER_WARP), AS_THREADS, 0, st>>>(as, v_begin, v_end);
+  const int rpw = g_fold_rows_per_warp;
+  const unsigned grid = cdiv(v_end - v_begin, AS_WARPS * rpw);
+  if (g_fold_min_blocks == 5) assemble_rows_kernel<5><<<grid, AS_THREADS, 0, st>>>(as, v_begin, v_end, rpw);
+  else assemble_rows_kernel<4><<<grid, AS_THREADS, 0, st>>>(as, v_begin, v_end, rpw);
   count_launch();
   return check_launch("assemble_rows_kernel");
 }
@@ -820,6 +825,12 @@ static int hessian_pipeline(const FembLevel* l, const float* x, float mu, float 
 using namespace femb;
 
 extern "C" {
+
+int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm) {
+  if (rows_per_warp >= 1 && rows_per_warp <= 64) g_fold_rows_per_warp = rows_per_warp;
+  if (min_blocks_per_sm == 4 || min_blocks_per_sm == 5) g_fold_min_blocks = min_blocks_per_sm;
+  return FEMB_OK;
+}
 
 int femb_set_pipeline(int enable) {
   const int old = g_pipe_enabled;

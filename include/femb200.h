@@ -153,6 +153,8 @@ int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, c
  * fork/join, graph-capturable) and reads the element matrices from L2.  Results do not depend on the chunking (same
  * fold order).  Returns the old setting. */
 int femb_set_pipeline(int enable);
+/* tuning of the row fold: consecutive rows per warp (default 4) and the occupancy target of the kernel (4 or 5 CTAs per SM) */
+int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm);
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add,
                        float* elem_f, float* elem_k, float* force_out, float* values, void* stream);

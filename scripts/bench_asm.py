@@ -32,7 +32,14 @@ for fused in modes:
     timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed), f"hessian level0 pipeline={fused}")
     timed(lambda: obj._force_hessian(x, obj.grad_gpu, obj.MF_value_gpu, obj.diag_fixed), f"force+hessian level0 pipeline={fused}")
     timed(lambda: obj._hessian(1, obj.x_gpu_layer[1], obj.UtAUs_values[0]), f"hessian level1 pipeline={fused}")
+obj.lib.femb_set_pipeline(0)
+for rpw, mb in ((4, 4), (2, 4), (8, 4), (1, 4), (4, 5), (2, 5), (8, 5), (4, 4)):
+    obj.lib.femb_set_fold_config(rpw, mb)
+    timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed), f"hessian level0 fold rows/warp={rpw} min_blocks={mb}")
+obj.lib.femb_set_fold_config(4, 4)
 timed(lambda: obj._force(x, obj.grad_gpu), "force level0")
+if os.environ.get("ASM_ONLY"):
+    sys.exit(0)
 obj._force_hessian(x, obj.dev_B_fixed[0], obj.MF_value_gpu, obj.diag_fixed)
 for rows, subs, pdl in (((32, 4, 1), (16, 8, 1), (8, 8, 1), (8, 4, 1), (16, 4, 1), (16, 8, 0)) if len(modes) > 1 else ()):
     obj.lib.femb_set_pdl(pdl)
