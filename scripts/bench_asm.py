@@ -40,6 +40,10 @@ obj.lib.femb_set_fold_config(4, 4)
 timed(lambda: obj._force(x, obj.grad_gpu), "force level0")
 if os.environ.get("ASM_ONLY"):
     sys.exit(0)
+if os.environ.get("GALERKIN_ONLY"):
+    obj.galerkin()
+    timed(obj.galerkin, "galerkin 0->1")
+    sys.exit(0)
 obj._force_hessian(x, obj.dev_B_fixed[0], obj.MF_value_gpu, obj.diag_fixed)
 for rows, subs, pdl in (((32, 4, 1), (16, 8, 1), (8, 8, 1), (8, 4, 1), (16, 4, 1), (16, 8, 0)) if len(modes) > 1 else ()):
     obj.lib.femb_set_pdl(pdl)
