@@ -646,12 +646,23 @@ __global__ void __launch_bounds__(GA_THREADS) galerkin_rt_kernel(int n_coarse, c
   float* acc = s_acc + tid;                       // acc[slot][tid]
   if (live) {
     I = __ldg(v2i_c + v);
-    for (int e = __ldg(r_off + I); e < __ldg(r_off + I + 1); ++e) {     // children of I in column order
-      const int i = __ldg(r_col + e);
-      const float w = __ldg(r_w + e);
-      const int q = ut_q[e];
-      const int t1 = __ldg(t_ptr + i + 1);
-      int t = __ldg(t_ptr + i);
+    // children of I in column order.  The metadata of the next child (its fine row, weight, parent position and T-row
+    // range: a chain of two dependent loads) is fetched while the T row of the current child is being accumulated.
+    const int e0 = __ldg(r_off + I), e1 = __ldg(r_off + I + 1);
+    int i_n = 0, q_n = 0, t_n = 0, t1_n = 0;
+    float w_n = 0.f;
+    if (e0 < e1) {
+      i_n = __ldg(r_col + e0); w_n = __ldg(r_w + e0); q_n = ut_q[e0];
+      t_n = __ldg(t_ptr + i_n); t1_n = __ldg(t_ptr + i_n + 1);
+    }
+    for (int e = e0; e < e1; ++e) {
+      const float w = w_n;
+      const int q = q_n, t1 = t1_n;
+      int t = t_n;
+      if (e + 1 < e1) {
+        i_n = __ldg(r_col + e + 1); w_n = __ldg(r_w + e + 1); q_n = ut_q[e + 1];
+        t_n = __ldg(t_ptr + i_n); t1_n = __ldg(t_ptr + i_n + 1);
+      }
       // the slots of one T row are distinct: batches of 8 keep 16 independent global loads in flight per thread
       const unsigned char* cs = c_slot8 + (size_t)t * 8 + q;
       const float* tv_p = t_val + (size_t)t * 9 + k;
