@@ -550,14 +550,16 @@ class Object:
     # -- FAS family (object.py:1308-1511) ---------------------------------------------------------
     def _fas_fine(self, x, spd, gravity_pins, fixed_diag):
         self.dev_B_fixed[1].zero_()
+        g, pn = gravity_pins if isinstance(gravity_pins, tuple) else (gravity_pins, gravity_pins)
         self._force_hessian(x, self.dev_B_fixed[0], self.MF_value_gpu, self.diag_fixed if fixed_diag else None,
-                            gravity=gravity_pins, pins=gravity_pins)
+                            gravity=g, pins=pn)
         if spd:
             self._spd(self.MF_value_gpu)
 
     def _fas_coarse_setup(self, x, spd, gravity_pins, coarse_pin_penalty):
         self._transfer(self.Ut_noOrder[0], 1.0, x, 0.0, self.dev_x_solved[1])            # :1489
-        self._force(x, self.dev_R[0], gravity=gravity_pins, pins=gravity_pins)           # :1491-1495
+        g, pn = gravity_pins if isinstance(gravity_pins, tuple) else (gravity_pins, gravity_pins)
+        self._force(x, self.dev_R[0], gravity=g, pins=pn)                                # :1491-1495
         self._transfer(self.Ut_hat[0], 1.0, self.dev_R[0], 0.0, self.dev_B_fixed[1])     # :1497
         self._hessian(1, self.dev_x_solved[1], self.UtAUs_values[0])                     # :1499
         if coarse_pin_penalty:                                                           # :1501
@@ -647,6 +649,59 @@ class Object:
             if sampled:
                 # dev_B_fixed[0] still holds the force evaluated at the start of the step (:1565)
                 self._record(step, e, self.inf_norm(self.dev_B_fixed[0]), "fas")
+
+    def compare_withoutGravity(self, iterations=100):
+        """object.py:1630-1741 (plots left to the caller): the two-level FAS body without gravity (pin springs only), first
+        with the coarse pin penalty ("add attachment" -> plot_*_newton), then from the rest state again without it
+        (-> plot_*_newtonMultigrid); sampled every iterations/10 steps."""
+        x = self.x_gpu_layer[0]
+        for tag, penalty in (("newton", True), ("without", False)):
+            if tag == "without":
+                x.copy_(self.x_cpu)                                                      # :1686
+            for step in range(1, iterations + 1):
+                sampled = step % (iterations / 10) == 0
+                e = self.total_energy() if sampled else None
+                self._run_step("cmp_nograv_" + tag, lambda: self._fas_v123_body(x, False, (False, True), True, penalty))
+                if sampled:
+                    # dev_B_fixed[0] still holds the force evaluated at the start of the step (:1640-1652)
+                    self._record(step, e, self.inf_norm(self.dev_B_fixed[0]), tag)
+
+    def _drag_linearise(self):
+        x = self.x_gpu_layer[0]
+        self._force_hessian(x, self.grad_gpu, self.MF_value_gpu, self.diag_fixed, gravity=False, pins=True)
+        self._spd(self.MF_value_gpu)
+        self._copy(self.dev_B_fixed[0], self.grad_gpu)
+
+    def _residual_norm(self, layer):
+        self._residual(layer, self.dev_B_fixed[layer], self.dev_delta_x[layer], self.dev_B[layer])
+        return self.inf_norm(self.dev_B[layer])
+
+    def drag(self, n=10):
+        """object.py:1770-1852 without the plots: log10 of the residual infinity norm after i = 0..n-1 iterations of
+        Gauss-Seidel, of CG, and after i V-cycles (Newton-MG), linearised at the rest state with the pin springs only.
+        Returns {"GS": [...], "CG": [...], "NewtonMG": [...]} (the three curves the reference plots)."""
+        out = {"GS": [], "CG": [], "NewtonMG": []}
+        for i in range(n):
+            self._drag_linearise()
+            self.PerformGaussSeidel(layer=0, iterations=i)
+            out["GS"].append(float(np.log10(self._residual_norm(0))))
+        for i in range(n):
+            self.x_gpu_layer[0].copy_(self.x_cpu)
+            self._drag_linearise()
+            self.PerformConjugateGradient(layer=0, iterations=i)
+            out["CG"].append(float(np.log10(self._residual_norm(0))))
+        for it in range(n):
+            self.x_gpu_layer[0].copy_(self.x_cpu)
+            self._drag_linearise()
+            self.galerkin()
+            norm = self.inf_norm(self.grad_gpu)
+            for _ in range(it):
+                self.VCycle(0)
+                norm = self._residual_norm(0)
+            self.finish()
+            out["NewtonMG"].append(float(np.log10(norm)))
+        self.drag_curves = out
+        return out
 
     def gradientDescent(self, iterations=100, lr=1e-3):
         """object.py:1097-1125 (vertex-order force, energy backtracking x0.2, <= 20 tries; host sync per try)."""

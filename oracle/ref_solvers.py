@@ -309,9 +309,9 @@ class RefObject:
         self.showError(layer)
 
     # ------------------------------------------------------------------ non-linear drivers
-    def _sample(self, step, iterations, grad, tag=""):
+    def _sample(self, step, iterations, grad, tag="", every=100):
         """The 'step % (iterations/100) == 0' block, e.g. object.py:1238-1248."""
-        if step % (iterations / 100) == 0:
+        if step % (iterations / every) == 0:
             e = self.total_energy(self.x_gpu_layer[0])
             n = K.inf_norm(grad)
             if tag == "":
@@ -377,13 +377,15 @@ class RefObject:
         self.hessian(0, x, self.MF_value)
         if spd:
             self.MF_value[...] = K.spd_matrix33f(self.MF_value, self.spd_value)
-        self.force(x, self.dev_B_fixed[0], gravity=gravity_pins, pins=gravity_pins)
+        g, pn = gravity_pins if isinstance(gravity_pins, tuple) else (gravity_pins, gravity_pins)
+        self.force(x, self.dev_B_fixed[0], gravity=g, pins=pn)
 
     def _fas_coarse_setup(self, x, spd, gravity_pins, coarse_pin_penalty):
         """object.py:1489-1504: restrict state and re-evaluated residual, re-discretised coarse Hessian."""
         bsr_mv(self.Ut_noOrder[0], x, self.dev_x_solved[1], alpha=1.0, beta=0.0)
         self.dev_R[0][...] = 0
-        self.force(x, self.dev_R[0], gravity=gravity_pins, pins=gravity_pins)
+        g, pn = gravity_pins if isinstance(gravity_pins, tuple) else (gravity_pins, gravity_pins)
+        self.force(x, self.dev_R[0], gravity=g, pins=pn)
         bsr_mv(self.Ut_hat[0], self.dev_R[0], self.dev_B_fixed[1], alpha=1.0, beta=0.0)
         self.hessian(1, self.dev_x_solved[1], self.UtAUs_values[0])
         if coarse_pin_penalty:
@@ -467,3 +469,61 @@ class RefObject:
             self.PerformJacobi(layer=1, iterations=1)
             bsr_mv(self.Us_hat[0], self.dev_delta_x[1], self.dev_delta_x[0], alpha=1.0, beta=0.0)
             self.update_deltaX(x, self.dev_delta_x[0])
+
+    def compare_withoutGravity(self, iterations=100):
+        """object.py:1630-1741: the two-level FAS body without gravity (pin springs only), first with the coarse pin
+        penalty ("add attachment"), then from the rest state again without it; sampled every iterations/10 steps."""
+        x = self.x_gpu_layer[0]
+        for tag, penalty in (("newton", True), ("without", False)):
+            if tag == "without":
+                x[...] = self.x_cpu                                                       # :1686
+            for step in range(1, iterations + 1):
+                self._fas_fine(x, spd=False, gravity_pins=(False, True), fixed_diag=True)
+                self._sample(step, iterations, self.dev_B_fixed[0], tag, every=10)
+                self.set_LUD(0)
+                self.PerformGaussSeidel(layer=0, iterations=1)
+                self.update_deltaX(x, self.dev_delta_x[0])
+                self._fas_coarse_setup(x, spd=False, gravity_pins=(False, True), coarse_pin_penalty=penalty)
+                self.PerformJacobi(layer=1, iterations=1)
+                bsr_mv(self.Us_hat[0], self.dev_delta_x[1], self.dev_delta_x[0], alpha=1.0, beta=0.0)
+                self.update_deltaX(x, self.dev_delta_x[0])
+
+    def _drag_linearise(self):
+        x = self.x_gpu_layer[0]
+        self.MF_value[...] = self.MF_value_fixed
+        self.grad[...] = 0
+        self.force(x, self.grad, gravity=False, pins=True)
+        self.hessian(0, x, self.MF_value)
+        self.MF_value[...] = K.spd_matrix33f(self.MF_value, self.spd_value)
+        self.set_LUD(0)
+        self.dev_B_fixed[0][...] = self.grad
+
+    def _residual_norm(self, layer):
+        self.dev_B[layer][...] = self.dev_B_fixed[layer]
+        self._A_mv_sub(layer)
+        return float(K.inf_norm(self.dev_B[layer]))
+
+    def drag(self, n=10):
+        """object.py:1770-1852 without the plots: log10 of the residual infinity norm after i = 0..n-1 iterations of
+        Gauss-Seidel, of CG, and after i V-cycles (Newton-MG), linearised at the rest state with the pin springs only."""
+        out = {"GS": [], "CG": [], "NewtonMG": []}
+        for i in range(n):
+            self._drag_linearise()
+            self.PerformGaussSeidel(layer=0, iterations=i)
+            out["GS"].append(np.log10(self._residual_norm(0)))
+        for i in range(n):
+            self.x_gpu_layer[0][...] = self.x_cpu
+            self._drag_linearise()
+            self.PerformConjugateGradient(layer=0, iterations=i)
+            out["CG"].append(np.log10(self._residual_norm(0)))
+        for it in range(n):
+            self.x_gpu_layer[0][...] = self.x_cpu
+            self._drag_linearise()
+            self.galerkin()
+            norm = float(K.inf_norm(self.grad))
+            for _ in range(it):
+                self.VCycle(0)
+                norm = self._residual_norm(0)
+            self.finish()
+            out["NewtonMG"].append(np.log10(norm))
+        return out

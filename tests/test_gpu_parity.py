@@ -462,3 +462,27 @@ def test_exp3_hooks_on_device(pair):
     y = torch.zeros(obj.dims[0], 3, device=obj.device)
     obj._transfer(obj.Us_noOrder_hat[0], 1.0, xc, 0.0, y)
     close(tA[0] @ xc, y.cpu().numpy(), what="torch_A[0] @ x vs femb_transfer_mv(Us_noOrder_hat[0])")
+
+
+def test_compare_without_gravity_and_drag():
+    """The remaining diagnostic drivers of the reference API (object.py:1630-1741 compare_withoutGravity, :1770-1852 drag;
+    plots dropped) against the oracle twin, with one displaced pinned vertex as in exp1/quasi_simulation/main.py."""
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    obj = Object((pts, hx), 0.05, [444], use_graphs=True)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [444])
+    d, r = obj.drag(5), ref.drag(5)
+    for key in ("GS", "CG", "NewtonMG"):
+        a, b = np.asarray(d[key]), np.asarray(r[key], dtype=np.float64)
+        live = b > -4.0                                        # below that the residual is at fp32 round-off of the rhs
+        assert live[0] and np.abs(a[live] - b[live]).max() < 2e-3, (key, a, b)
+        assert np.all(a[~live] < -3.5)
+    obj.x_gpu_layer[0].copy_(obj.x_cpu)
+    ref.x_gpu_layer[0][...] = ref.x_cpu
+    obj.compare_withoutGravity(20)
+    ref.compare_withoutGravity(20)
+    assert obj.plot_x == ref.plot_x == list(range(2, 21, 2))
+    for name in ("plot_InfNorm_newton", "plot_InfNorm_newtonMultigrid"):
+        assert np.abs(np.asarray(getattr(obj, name)) - np.asarray(getattr(ref, name), dtype=np.float64)).max() < 2e-3, name
+    for name in ("plot_energy_newton", "plot_energy_newtonMultigrid"):
+        close(np.asarray(getattr(obj, name), dtype=np.float64), np.asarray(getattr(ref, name), dtype=np.float64), rel=2e-5, what=name)
+    close(obj.x_gpu_layer[0], ref.x_gpu_layer[0], what="positions after compare_withoutGravity")
