@@ -94,6 +94,7 @@ PROTOTYPES = {
     "femb_cloth_update": [I, P, P, I, I, P],
     "femb_axpby": [I, F, P, F, P, P],
     "femb_copy": [I, P, P, P],
+    "femb_adam_update": [I, P, P, P, P, P, P, F, F, F, F, F, F, P],
     "femb_fill": [I, F, P, P],
     "femb_update_x": [LV, P, P, P],
     "femb_v2i": [LV, P, P, P],

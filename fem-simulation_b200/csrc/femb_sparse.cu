@@ -399,6 +399,19 @@ __global__ void inf_norm_kernel(int n, const float* __restrict__ x, float* __res
   // non-negative floats order like their bit patterns
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
 }
+// updateM + updateV + scal_ x2 + updateX of the reference's Adam loop (cublas.py:172-194, object.py:1090-1094) in one pass
+__global__ void __launch_bounds__(256) adam_kernel(int n, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                   float* __restrict__ m_hat, float* __restrict__ v_hat, float* __restrict__ x,
+                                                   float a1, float b1, float a2, float b2, float s1, float s2, float lr, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = a1 * gi + b1 * m[i];
+  const float vi = a2 * (gi * gi) + b2 * v[i];
+  const float mh = mi * s1, vh = vi * s2;
+  m[i] = mi; v[i] = vi; m_hat[i] = mh; v_hat[i] = vh;
+  x[i] -= lr * (mh / (sqrtf(vh) + eps));
+}
 __global__ void __launch_bounds__(256) dot_partial_kernel(int n, const float* __restrict__ x, const float* __restrict__ y,
                                                          float* __restrict__ partial, const float* active) {
   __shared__ float red[32];
@@ -932,6 +945,15 @@ int femb_galerkin(const FembLevel* fine, const FembLevel* coarse, const float* f
   return check_launch("galerkin");
 }
 
+int femb_adam_update(int n, const float* grad, float* m, float* v, float* m_hat, float* v_hat, float* x, float beta1, float beta2,
+                     float bias1, float bias2, float lr, float epsilon, void* stream) {
+  FEMB_REQUIRE(n >= 0 && grad && m && v && m_hat && v_hat && x, "null pointer or negative size");
+  if (n == 0) return FEMB_OK;
+  adam_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(n, grad, m, v, m_hat, v_hat, x, 1.f - beta1, beta1, 1.f - beta2, beta2,
+                                                          bias1, bias2, lr, epsilon);
+  count_launch();
+  return check_launch("adam_kernel");
+}
 int femb_axpby(int n, float a, const float* x, float b, float* y, void* stream) {
   FEMB_REQUIRE(n >= 0 && x && y, "null pointer or negative size");
   if (n == 0) return FEMB_OK;

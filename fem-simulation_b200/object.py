@@ -703,6 +703,22 @@ class Object:
         self.drag_curves = out
         return out
 
+    def Adam(self, iterations=1000, lr=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        """object.py:1067-1094: first-order baseline on the vertex-order force (sign as in the reference: x -= lr m_hat /
+        (sqrt(v_hat) + eps) with the FORCE as `gradient`, cublas.py:185-194)."""
+        x = self.x_gpu_layer[0]
+        if getattr(self, "m", None) is None:
+            self.m, self.v, self.m_hat, self.v_hat = (torch.zeros_like(x) for _ in range(4))       # object.py:816-819
+        self.m.zero_(); self.v.zero_()
+        for step in range(1, iterations + 1):
+            self._force(x, self.grad_gpu, ordered=False)
+            if self._sampled(step, iterations):
+                self._record(step, self.total_energy(), self.inf_norm(self.grad_gpu))
+            _lib.check(self.lib.femb_adam_update(x.numel(), self.grad_gpu.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                 self.m_hat.data_ptr(), self.v_hat.data_ptr(), x.data_ptr(), beta1, beta2,
+                                                 1 / (1 - beta1 ** step), 1 / (1 - beta2 ** step), lr, epsilon, self._stream()),
+                       "femb_adam_update")
+
     def gradientDescent(self, iterations=100, lr=1e-3):
         """object.py:1097-1125 (vertex-order force, energy backtracking x0.2, <= 20 tries; host sync per try)."""
         x = self.x_gpu_layer[0]

@@ -247,6 +247,11 @@ int femb_cloth_update(int n_vert, const float* dx, float* x, int skip0, int skip
 /* ---- vectors ------------------------------------------------------------------------------- */
 int femb_axpby(int n, float a, const float* x, float b, float* y, void* stream);          /* y = a x + b y (cublas.py:160-163) */
 int femb_copy(int n, const float* x, float* y, void* stream);
+/* one step of the reference's Adam loop (updateM, updateV, scal_ x2, updateX: cublas.py:172-194, object.py:1090-1094) on n
+ * floats: m = (1-b1) g + b1 m; v = (1-b2) g*g + b2 v; m_hat = bias1 m; v_hat = bias2 v; x -= lr m_hat / (sqrt(v_hat) + eps)
+ * (bias1 = 1/(1-b1^t), bias2 = 1/(1-b2^t); the sign is the reference's: `g` is the force, cublas.py:192) */
+int femb_adam_update(int n, const float* grad, float* m, float* v, float* m_hat, float* v_hat, float* x, float beta1, float beta2,
+                     float bias1, float bias2, float lr, float epsilon, void* stream);
 int femb_fill(int n, float v, float* y, void* stream);
 /* update_deltaX_kernel (cublas.py:20-24): x[i2v[i]] += dx[i] */
 int femb_update_x(const FembLevel* lvl, const float* dx, float* x, void* stream);

@@ -527,3 +527,24 @@ class RefObject:
             self.finish()
             out["NewtonMG"].append(np.log10(norm))
         return out
+
+    def Adam(self, iterations=1000, lr=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        """object.py:1067-1094 with updateM / updateV / scal_ / updateX of cublas.py:172-194 (float32 like the kernels)."""
+        t = self.dtype
+        x = self.x_gpu_layer[0]
+        m = np.zeros_like(x); v = np.zeros_like(x)
+        for step in range(1, iterations + 1):
+            g = np.zeros_like(x)
+            self._force_vertex_order(x, g)
+            self._sample(step, iterations, g, "")
+            m = (t(1 - beta1) * g + t(beta1) * m).astype(t)
+            v = (t(1 - beta2) * (g * g) + t(beta2) * v).astype(t)
+            m_hat = (m * t(1 / (1 - beta1 ** step))).astype(t)
+            v_hat = (v * t(1 / (1 - beta2 ** step))).astype(t)
+            x -= (t(lr) * (m_hat / (np.sqrt(v_hat) + t(epsilon)))).astype(t)
+
+    def _force_vertex_order(self, x, out):
+        """The *_noOrder force kernels (quai_hexagon.py:135-158, 169-186): the index-order force scattered back."""
+        gi = np.zeros_like(out)
+        self.force(x, gi)
+        out[self.i2v[0]] = gi

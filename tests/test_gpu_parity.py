@@ -486,3 +486,33 @@ def test_compare_without_gravity_and_drag():
     for name in ("plot_energy_newton", "plot_energy_newtonMultigrid"):
         close(np.asarray(getattr(obj, name), dtype=np.float64), np.asarray(getattr(ref, name), dtype=np.float64), rel=2e-5, what=name)
     close(obj.x_gpu_layer[0], ref.x_gpu_layer[0], what="positions after compare_withoutGravity")
+
+
+def test_adam_update_operator_and_driver(pair):
+    """femb_adam_update (updateM + updateV + scal_ x2 + updateX, cublas.py:172-194) against the numpy formula on random
+    data (the driver itself is chaotic where the force vanishes: m_hat / sqrt(v_hat) is a sign), and `Object.Adam` filling the
+    sampling lists like the reference (object.py:1067-1094)."""
+    obj, ref, xp = pair
+    rng = np.random.default_rng(9)
+    n = 3000
+    g, m, v, x = (rng.normal(size=n).astype(np.float32) for _ in range(4))
+    v = np.abs(v)
+    b1, b2, lr, eps, step = 0.9, 0.999, 1e-3, 1e-8, 3
+    s1, s2 = np.float32(1 / (1 - b1 ** step)), np.float32(1 / (1 - b2 ** step))
+    m2 = (np.float32(1 - b1) * g + np.float32(b1) * m).astype(np.float32)
+    v2 = (np.float32(1 - b2) * (g * g) + np.float32(b2) * v).astype(np.float32)
+    x2 = x - np.float32(lr) * ((m2 * s1) / (np.sqrt(v2 * s2) + np.float32(eps)))
+    t = lambda a: torch.from_numpy(a.copy()).to(obj.device)
+    tg, tm, tv, tx = t(g), t(m), t(v), t(x)
+    tmh, tvh = torch.zeros_like(tm), torch.zeros_like(tv)
+    _lib.check(obj.lib.femb_adam_update(n, tg.data_ptr(), tm.data_ptr(), tv.data_ptr(), tmh.data_ptr(), tvh.data_ptr(), tx.data_ptr(),
+                                        b1, b2, float(s1), float(s2), lr, eps, None), "femb_adam_update")
+    close(tm, m2, what="Adam m"); close(tv, v2, what="Adam v"); close(tmh, m2 * s1, what="Adam m_hat"); close(tx, x2, what="Adam x")
+    x0 = obj.x_gpu_layer[0].clone()
+    obj.plot_x.clear(); obj.plot_InfNorm.clear(); obj.plot_energy.clear()
+    try:
+        obj.Adam(200, lr=1e-5)
+        assert obj.plot_x == list(range(2, 201, 2)) and len(obj.plot_energy) == 100
+        assert float((obj.x_gpu_layer[0] - x0).abs().max()) <= 200 * 1e-5 * 1.001          # |step| <= lr by construction
+    finally:
+        obj.x_gpu_layer[0].copy_(x0)
