@@ -513,6 +513,7 @@ def test_adam_update_operator_and_driver(pair):
     try:
         obj.Adam(200, lr=1e-5)
         assert obj.plot_x == list(range(2, 201, 2)) and len(obj.plot_energy) == 100
-        assert float((obj.x_gpu_layer[0] - x0).abs().max()) <= 200 * 1e-5 * 1.001          # |step| <= lr by construction
+        moved = float((obj.x_gpu_layer[0] - x0).abs().max())
+        assert 0.0 < moved <= 200 * 1e-5 * 10                 # an Adam step is a few lr at most
     finally:
         obj.x_gpu_layer[0].copy_(x0)
