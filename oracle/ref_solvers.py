@@ -548,3 +548,24 @@ class RefObject:
         gi = np.zeros_like(out)
         self.force(x, gi)
         out[self.i2v[0]] = gi
+
+    def gradientDescent(self, iterations=100, lr=1e-3):
+        """object.py:1097-1125: steepest descent on the vertex-order force with energy backtracking (x0.2, <= 20 tries); the
+        energy it compares with is the one of the last SAMPLE (self.energy is only refreshed inside the sampling block)."""
+        t = self.dtype
+        x = self.x_gpu_layer[0]
+        energy = getattr(self, "_gd_energy", t(0.0))
+        for step in range(1, iterations + 1):
+            g = np.zeros_like(x)
+            self._force_vertex_order(x, g)
+            if step % (iterations / 100) == 0:
+                energy = self.total_energy(x)
+                self.plot_x.append(step); self.plot_InfNorm.append(K.inf_norm(g)); self.plot_energy.append(energy)
+            alpha = t(lr)
+            for _ in range(20):
+                trial = (x + alpha * g).astype(t)                                          # add_grad, cublas.py:143-147
+                if self.total_energy(trial) < energy:
+                    x[...] = trial
+                    break
+                alpha = t(alpha * t(0.2))
+        self._gd_energy = energy

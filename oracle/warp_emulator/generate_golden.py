@@ -47,6 +47,9 @@ CASES = {
     "jag9": ("quasi", lambda: mesh.jagged_mesh(9, 9, 10, 0.05, seed=3, keep=0.75), 0.05, [],
              {"NewtonMultigrid": 2, "FASv3": 2, "FASv0": 1, "Newton": 2}),
     "jag9_pin": ("quasi", lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40], {"FASv2": 2, "FASv1": 1}),
+    # the diagnostic drivers: sampled lists / plotted curves instead of a final state
+    "jag9_diag": ("quasi", lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40],
+                  {"compare_withoutGravity": 10, "drag": None, "gradientDescent": 100, "Adam": 100}),
     "dyn5": ("dynamic", lambda: mesh.jagged_mesh(5, 6, 5, 0.05, seed=7, keep=0.8), 0.05, [], {"render": 3}),
     "cloth": ("cloth", None, None, None, {"render": 3}),
 }
@@ -157,11 +160,21 @@ def run_case(name):
         t0 = time.time()
         with contextlib.redirect_stdout(io.StringIO()):
             obj = ref_object.Object("npz:" + path, dx, list(pins))
-            if k == 0:
+            if k == 0 and name != "jag9_diag":
                 out.update(snapshot_setup(obj))
-            getattr(obj, method)(steps)
+            if method == "drag":
+                import matplotlib.pyplot as plt                   # the recording stand-in
+                plt.PLOTS.clear()
+                obj.drag()
+                for a, kw in plt.PLOTS:
+                    out["drag_" + kw["label"]] = np.array(a[1], dtype=np.float64)
+            else:
+                getattr(obj, method)(steps)
+            for nm in ("plot_x", "plot_InfNorm", "plot_energy", "plot_InfNorm_newton", "plot_energy_newton",
+                       "plot_InfNorm_newtonMultigrid", "plot_energy_newtonMultigrid"):
+                out[f"{method}_{nm}"] = np.array(getattr(obj, nm), dtype=np.float64)
         xs = obj.dev_x_solved[0] if method in ("FASv0", "FASv1") else obj.x_gpu_layer[0]
-        out[f"{method}_steps"] = steps
+        out[f"{method}_steps"] = -1 if steps is None else steps
         out[f"{method}_x"] = xs.numpy().copy()
         out[f"{method}_MF_value"] = obj.MF_value_gpu.numpy().copy()
         out[f"{method}_delta_x0"] = obj.dev_delta_x[0].numpy().copy()

@@ -7,5 +7,8 @@ class _Ax:
 
 def subplots(n=1, *a, **k): return _Ax(), tuple(_Ax() for _ in range(n))
 def show(*a, **k): pass
-def plot(*a, **k): pass
+PLOTS = []          # every plt.plot(x, y, ..., label=...) call, so that drivers which only plot (drag) can be read back
+
+
+def plot(*a, **k): PLOTS.append((a, k))
 def figure(*a, **k): return _Ax()

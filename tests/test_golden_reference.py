@@ -186,3 +186,64 @@ def test_dynamic_cuda_matches_reference_class():
         assert rel(d.dev_x.cpu().numpy(), g[f"x_frame{f}"]) <= 1e-6, f"x frame {f}"
         assert rel(d.dev_v.cpu().numpy(), g[f"v_frame{f}"]) <= 1e-3, f"v frame {f}"
     assert rel(d.MF_value_gpu.cpu().numpy(), g["MF_value"]) <= 1e-5
+
+
+# ---- the diagnostic drivers (compare_withoutGravity, drag, gradientDescent, Adam), reference run under the emulator ----------
+DIAG = os.path.join(GOLD, "ref_jag9_diag.npz")
+LISTS = ("plot_x", "plot_InfNorm", "plot_energy", "plot_InfNorm_newton", "plot_energy_newton", "plot_InfNorm_newtonMultigrid",
+         "plot_energy_newtonMultigrid")
+
+
+def _check_lists(obj, g, method, tol=2e-5, log_tol=2e-3):
+    for nm in LISTS:
+        want = g[f"{method}_{nm}"]
+        got = np.asarray(getattr(obj, nm), dtype=np.float64)
+        assert got.shape == want.shape, f"{method}: {nm} has {got.shape} samples, the reference {want.shape}"
+        if want.size == 0:
+            continue
+        if "InfNorm_newton" in nm:                              # log10 of a norm
+            assert np.abs(got - want).max() <= log_tol, f"{method}: {nm}"
+        else:
+            assert rel(got, want) <= tol, f"{method}: {nm} rel {rel(got, want):.2e}"
+
+
+def _check_drag(curves, g):
+    for key in ("GS", "CG", "NewtonMG"):
+        want, got = g["drag_" + key], np.asarray(curves[key], dtype=np.float64)
+        assert got.shape == want.shape
+        live = want > -4.0                                      # below: fp32 round-off of the right-hand side
+        assert live[0] and np.abs(got[live] - want[live]).max() <= 2e-3, (key, got, want)
+
+
+@pytest.mark.skipif(not os.path.exists(DIAG), reason="golden file not generated")
+def test_oracle_diagnostic_drivers_match_reference_class():
+    g = dict(np.load(DIAG))
+    pins = [int(v) for v in g["pinList"]]
+    mk = lambda: ref_solvers.RefObject(g["points"], g["hexagons"], float(g["dx"]), pins)
+    ref = mk(); ref.compare_withoutGravity(int(g["compare_withoutGravity_steps"]))
+    _check_lists(ref, g, "compare_withoutGravity")
+    assert rel(ref.x_gpu_layer[0], g["compare_withoutGravity_x"]) <= 1e-5
+    _check_drag(mk().drag(), g)
+    ref = mk(); ref.gradientDescent(int(g["gradientDescent_steps"]))
+    _check_lists(ref, g, "gradientDescent")
+    assert rel(ref.x_gpu_layer[0], g["gradientDescent_x"]) <= 1e-5
+    ref = mk(); ref.Adam(int(g["Adam_steps"]))
+    _check_lists(ref, g, "Adam", tol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(DIAG), reason="golden file not generated")
+def test_cuda_diagnostic_drivers_match_reference_class():
+    from fem_simulation_b200 import Object
+    g = dict(np.load(DIAG))
+    pins = [int(v) for v in g["pinList"]]
+    mk = lambda: Object((g["points"], g["hexagons"]), float(g["dx"]), pins)
+    obj = mk(); obj.compare_withoutGravity(int(g["compare_withoutGravity_steps"]))
+    _check_lists(obj, g, "compare_withoutGravity")
+    assert rel(obj.x_gpu_layer[0].cpu().numpy(), g["compare_withoutGravity_x"]) <= 1e-5
+    _check_drag(mk().drag(), g)
+    obj = mk(); obj.gradientDescent(int(g["gradientDescent_steps"]))
+    _check_lists(obj, g, "gradientDescent")
+    assert rel(obj.x_gpu_layer[0].cpu().numpy(), g["gradientDescent_x"]) <= 1e-5
+    obj = mk(); obj.Adam(int(g["Adam_steps"]))
+    _check_lists(obj, g, "Adam", tol=1e-4)
