@@ -47,9 +47,12 @@ CASES = {
     "jag9": ("quasi", lambda: mesh.jagged_mesh(9, 9, 10, 0.05, seed=3, keep=0.75), 0.05, [],
              {"NewtonMultigrid": 2, "FASv3": 2, "FASv0": 1, "Newton": 2}),
     "jag9_pin": ("quasi", lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40], {"FASv2": 2, "FASv1": 1}),
-    # the diagnostic drivers: sampled lists / plotted curves instead of a final state
-    "jag9_diag": ("quasi", lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40],
-                  {"compare_withoutGravity": 10, "drag": None, "gradientDescent": 100, "Adam": 100}),
+    # the diagnostic drivers: sampled lists / plotted curves instead of a final state; one case (= one process, one file)
+    # per driver because the emulator needs tens of minutes for each
+    "diag_cmpng": ("quasi", lambda: mesh.jagged_mesh(8, 9, 8, 0.05, seed=11, keep=0.7), 0.05, [40], {"compare_withoutGravity": 10}),
+    "diag_drag": ("quasi", lambda: mesh.jagged_mesh(8, 9, 8, 0.05, seed=11, keep=0.7), 0.05, [40], {"drag": None}),
+    "diag_gd": ("quasi", lambda: mesh.jagged_mesh(8, 9, 8, 0.05, seed=11, keep=0.7), 0.05, [40], {"gradientDescent": 100}),
+    "diag_adam": ("quasi", lambda: mesh.jagged_mesh(8, 9, 8, 0.05, seed=11, keep=0.7), 0.05, [40], {"Adam": 100}),
     "dyn5": ("dynamic", lambda: mesh.jagged_mesh(5, 6, 5, 0.05, seed=7, keep=0.8), 0.05, [], {"render": 3}),
     "cloth": ("cloth", None, None, None, {"render": 3}),
 }
@@ -160,7 +163,7 @@ def run_case(name):
         t0 = time.time()
         with contextlib.redirect_stdout(io.StringIO()):
             obj = ref_object.Object("npz:" + path, dx, list(pins))
-            if k == 0 and name != "jag9_diag":
+            if k == 0 and not name.startswith("diag_"):
                 out.update(snapshot_setup(obj))
             if method == "drag":
                 import matplotlib.pyplot as plt                   # the recording stand-in
