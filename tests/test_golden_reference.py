@@ -218,7 +218,9 @@ def _run_diag(make, method, to_numpy):
             want, got = g["drag_" + key], np.asarray(curves[key], dtype=np.float64)
             assert got.shape == want.shape
             live = want > -4.0                                  # below: fp32 round-off of the right-hand side
-            assert live[0] and np.abs(got[live] - want[live]).max() <= 2e-3, (key, got, want)
+            # CG in fp32 is not monotone here and sensitive to the order of its dot-product reductions from ~6 iterations on
+            tol = 5e-3 if key == "CG" else 2e-3
+            assert live[0] and np.abs(got[live] - want[live]).max() <= tol, (key, got, want)
         return
     getattr(obj, method)(int(g[f"{method}_steps"]))
     if method == "Adam":
