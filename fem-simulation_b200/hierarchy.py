@@ -115,6 +115,7 @@ class Hierarchy:
     fix_idx: np.ndarray = None
     fix_values: np.ndarray = None
     pattern: list = field(default_factory=list)
+    fine_hex_parent: list = field(default_factory=list)   # [layer-1] int32 [N_h(l)]: coarse hexahedron that contains fine hexahedron e
     shapeFuncGrad: np.ndarray = None
 
 
@@ -285,6 +286,7 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
         ccolor = 4 * (vk[:, 2] % 2) + 2 * (vk[:, 1] % 2) + (vk[:, 0] % 2)
         cv2i, ci2v, ccvn = _color_order(ccolor)
         H.dims.append(n_cv); H.hexs.append(coarse_hex); H.x.append(coarse_vert); H.fine_coarse.append(fc)
+        H.fine_hex_parent.append(hex_id.astype(np.int32))
         H.color_vertex_num.append(ccvn); H.vertex2index.append(cv2i); H.index2vertex.append(ci2v)
 
     n0 = H.dims[0]

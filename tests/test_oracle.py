@@ -163,3 +163,63 @@ def test_c_oracle_matches_numpy_oracle():
         assert np.abs(co.x - ref.x_gpu_layer[0]).max() <= 1e-6 * np.abs(ref.x_gpu_layer[0]).max()
         disp = ref.x_gpu_layer[0] - ref.S["x0"]
         assert np.abs((co.x - ref.S["x0"]) - disp).max() <= 1e-3 * np.abs(disp).max()
+
+
+def test_galerkin_from_element_matrices_identity():
+    """Ground work for the next optimisation: on level 0 (no eigen-clamp between assembly and product)
+    the Galerkin operator Ut_hat A Us_hat equals the sum over fine hexahedra e of P_e^T K_e P_e (+ P^T D_pin P), where P_e
+    only involves the 8 corners of the coarse hexahedron that contains e (`Hierarchy.fine_hex_parent`) with plain trilinear
+    weights 1, 1/2, 1/4, 1/8.  Checked against the oracle's bsr_mm product on a ragged mesh."""
+    import scipy.sparse as sp
+    from fem_simulation_b200 import hierarchy, mesh
+    from oracle import ref_kernels as K
+    pts, hx = mesh.jagged_mesh(8, 9, 8, 0.05, seed=11, keep=0.7)
+    H = hierarchy.build_hierarchy(pts, hx, 0.05)
+    assert H.layer == 2 and len(H.fine_hex_parent) == 1
+    par = H.fine_hex_parent[0]
+    chex = H.hexs[1]
+    ut = H.Ut_noOrder_hat[0]                                      # coarse x fine, vertex order, un-normalised weights
+    P = sp.csr_matrix((ut.weights.astype(np.float64), ut.columns, ut.offsets), shape=(ut.nrow, ut.ncol)).T.tocsr()   # fine x coarse
+    # (1) every parent of every node of a fine hexahedron is a corner of its coarse hexahedron, with trilinear weights
+    fc = H.fine_coarse[0]
+    for e in range(0, hx.shape[0], 7):
+        corners = set(int(c) for c in chex[par[e]])
+        for a in range(8):
+            v = int(hx[e, a])
+            row = P.getrow(v)
+            assert set(int(c) for c in row.indices) <= corners
+            slot = int(np.nonzero(fc[par[e]] == v)[0][0])
+            r = np.array([slot // 9, (slot // 3) % 3, slot % 3])
+            for c, w in zip(row.indices, row.data):
+                b = int(np.nonzero(chex[par[e]] == c)[0][0])
+                bits = np.array([(b >> 2) & 1, (b >> 1) & 1, b & 1])
+                assert w == np.prod(1.0 - np.abs(r / 2.0 - bits))
+    # (2) the identity itself, in float64
+    rng = np.random.default_rng(0)
+    x = (pts + rng.normal(size=pts.shape) * 0.002).astype(np.float64)
+    det, inv = K.prepare_kernal(pts.astype(np.float64), hx, H.shapeFuncGrad, dtype=np.float64)
+    p0, p1 = H.pattern[0], H.pattern[1]
+    vals = np.zeros((p0.nnz, 3, 3))
+    K.elastic_hessian(x, hx, H.shapeFuncGrad, det, inv, 250.0, 0.0, vals, p0.hex_update_offset, dtype=np.float64)
+    d_pin = np.zeros(H.dims[0]); d_pin[hierarchy.default_pins(pts, 0.05)] = 100.0
+    vals[p0.off_d + H.vertex2index[0]] += d_pin[:, None, None] * np.eye(3)
+    n0, n1 = H.dims[0], H.dims[1]
+    i2v0, i2v1 = H.index2vertex[0], H.index2vertex[1]
+    rows_v, cols_v = i2v0[p0.row], i2v0[p0.col]                   # the blocks in VERTEX order
+    want = np.zeros((n1, n1, 3, 3))
+    for a in range(3):
+        for b in range(3):
+            Aab = sp.csr_matrix((vals[:, a, b], (rows_v, cols_v)), shape=(n0, n0))
+            want[:, :, a, b] = (P.T @ Aab @ P).toarray()           # Ut_hat A Us_hat
+    Pd = P.toarray()
+    got = np.zeros((n1, n1, 3, 3))
+    for e0, blocks in K.elastic_hessian_blocks(x, hx, H.shapeFuncGrad, det, inv, 250.0, 0.0, dtype=np.float64):
+        for k in range(blocks.shape[0]):
+            e = e0 + k
+            cs = chex[par[e]]
+            Pe = Pd[np.ix_(hx[e], cs)]                             # 8 fine nodes x 8 coarse corners
+            got[np.ix_(cs, cs)] += np.einsum("aA,abij,bB->ABij", Pe, blocks[k], Pe)
+    got += np.einsum("iI,i,iJ->IJ", Pd, d_pin, Pd)[:, :, None, None] * np.eye(3)
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    # and it is the matrix the oracle's Galerkin produces on the coarse pattern
+    assert np.count_nonzero(np.abs(want).sum(axis=(2, 3))) <= p1.nnz
