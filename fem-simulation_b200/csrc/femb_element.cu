@@ -10,12 +10,12 @@
 //
 // B200 design: 8 lanes per hexahedron (4 hexahedra per warp).  In phase A lane q evaluates everything
 // that depends only on the Gauss point q (F, S, F F^T, g_b = J^-T dN_b, u_b = F g_b, t_b = S g_b) once
-// and parks it in shared memory; in phase B lane a accumulates the 8 blocks K[a][b] over the 8 Gauss
-// points with the closed form
+// and parks it in shared memory; in phase B lane a accumulates, over the 8 Gauss points, the 5 blocks
+// K[a][(a+k) & 7], k = 0..4 (the element matrix is symmetric: the cyclic half is enough) with the closed form
 //     K_ab[j][i] = det * ( (g_a . S g_b) d_ji + mu (g_a . g_b)(F F^T)_ji + mu u_b[j] u_a[i] + la u_a[j] u_b[i] )
-// (== d(P g_a det)_j / d x_b,i of quai_hexagon.py:86-106).  Element results go to a scratch array and
-// are summed into the fixed [L;D;U] value layout by a gather over a precomputed inverse of the
-// element->nnz map (segmented sum, fixed order, no atomics).
+// (== d(P g_a det)_j / d x_b,i of quai_hexagon.py:86-106).  The half rows go to a scratch array (192 bytes per
+// row, written as coalesced 512-byte stores) and are summed into the fixed [L;D;U] value layout by a per-row
+// gather over the fold plan, the precomputed inverse of the element->nnz map (fixed order, no atomics).
 #include <cstdio>
 
 #include "femb_common.cuh"
