@@ -92,7 +92,7 @@ class ClockSampler:
 
 # DRAM bytes (read + write) per launch measured with `ncu --set full` on the cube n=100 (profiles/README.md), per million hexahedra
 ASM_TRAFFIC_PER_MHEX = 4.55e9      # element_kernel<1> 0.364 + 1.477 GB, assemble_rows_kernel 1.741 + 0.967 GB (profiles/r01b_element_assemble_ncu_raw.txt)
-GS_TRAFFIC_PER_MHEX = 118.9e6      # one colour launch of the row pass
+GS_TRAFFIC_PER_MHEX = 142e6        # average colour launch of a 3-iteration sweep: 154.8 MB per L|U launch (profiles/r01b_gs_color_ncu_raw.txt), ~80 MB per U-only launch
 
 
 def pass_bytes(V, Z):
