@@ -46,6 +46,8 @@ CASES = {
     # name: (reference dir, mesh builder, dx, pinList, {method: steps})
     "jag9": ("quasi", lambda: mesh.jagged_mesh(9, 9, 10, 0.05, seed=3, keep=0.75), 0.05, [],
              {"NewtonMultigrid": 2, "FASv3": 2, "FASv0": 1, "Newton": 2}),
+    # 3 levels (what the reference's hierarchy effectively is): Galerkin chain 0 -> 1 -> 2 and the 3-level V-cycle
+    "jag17": ("quasi", lambda: mesh.jagged_mesh(16, 17, 16, 0.05, seed=13, keep=0.12), 0.05, [], {"NewtonMultigrid": 1}),
     "jag9_pin": ("quasi", lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40], {"FASv2": 2, "FASv1": 1}),
     # the diagnostic drivers: sampled lists / plotted curves instead of a final state; one case (= one process, one file)
     # per driver because the emulator needs tens of minutes for each
@@ -181,8 +183,8 @@ def run_case(name):
         out[f"{method}_x"] = xs.numpy().copy()
         out[f"{method}_MF_value"] = obj.MF_value_gpu.numpy().copy()
         out[f"{method}_delta_x0"] = obj.dev_delta_x[0].numpy().copy()
-        if int(obj.layer) > 1:
-            out[f"{method}_UtAUs_values0"] = obj.UtAUs_values[0].numpy().copy()
+        for l in range(int(obj.layer) - 1):
+            out[f"{method}_UtAUs_values{l}"] = obj.UtAUs_values[l].numpy().copy()
         print(f"{name}: {method} x{steps} done in {time.time() - t0:.0f} s", flush=True)
     os.remove(path)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"), **out)

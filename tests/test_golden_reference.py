@@ -12,7 +12,7 @@ from fem_simulation_b200 import hierarchy
 from oracle import ref_solvers
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = [c for c in ("jag9", "jag9_pin") if os.path.exists(os.path.join(GOLD, f"ref_{c}.npz"))]
+CASES = [c for c in ("jag9", "jag9_pin", "jag17") if os.path.exists(os.path.join(GOLD, f"ref_{c}.npz"))]
 INT_KEYS = ["MF_L_row", "MF_L_col", "MF_U_row", "MF_U_col", "MF_GS_U_Ptr", "MF_GS_L_Ptr", "MF_GS_U_row", "MF_GS_U_col",
             "MF_GS_L_row", "MF_GS_L_col", "fix_idx", "pin", "pin_list"]
 
@@ -100,8 +100,9 @@ def test_oracle_steps_match_reference_class(gold, method):
     assert np.abs((x - ref.S["x0"]) - disp_ref).max() <= 2e-3 * np.abs(disp_ref).max(), "displacement"
     assert rel(ref.MF_value, g[f"{method}_MF_value"]) <= 1e-5, "MF_value"
     assert rel(ref.dev_delta_x[0], g[f"{method}_delta_x0"]) <= 2e-3, "delta_x"
-    if f"{method}_UtAUs_values0" in g:
-        assert rel(ref.UtAUs_values[0], g[f"{method}_UtAUs_values0"]) <= 2e-5, "coarse operator"
+    for l in range(len(ref.UtAUs_values)):
+        if f"{method}_UtAUs_values{l}" in g:
+            assert rel(ref.UtAUs_values[l], g[f"{method}_UtAUs_values{l}"]) <= 2e-5, f"coarse operator {l}"
 
 
 @pytest.mark.gpu
@@ -120,8 +121,9 @@ def test_cuda_steps_match_reference_class(gold, method):
     disp_ref = g[f"{method}_x"] - x0
     assert np.abs((x - x0) - disp_ref).max() <= 2e-3 * np.abs(disp_ref).max(), "displacement"
     assert rel(obj.MF_value_gpu.cpu().numpy(), g[f"{method}_MF_value"]) <= 1e-5, "MF_value"
-    if f"{method}_UtAUs_values0" in g and obj.layer > 1:
-        assert rel(obj.UtAUs_values[0].cpu().numpy(), g[f"{method}_UtAUs_values0"]) <= 2e-5, "coarse operator"
+    for l in range(obj.layer - 1):
+        if f"{method}_UtAUs_values{l}" in g:
+            assert rel(obj.UtAUs_values[l].cpu().numpy(), g[f"{method}_UtAUs_values{l}"]) <= 2e-5, f"coarse operator {l}"
 
 
 # ---- dynamic (exp1/simulation) and cloth (exp1/cloth_simulation) reference classes -------------------------------
