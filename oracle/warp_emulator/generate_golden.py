@@ -48,6 +48,8 @@ CASES = {
              {"NewtonMultigrid": 2, "FASv3": 2, "FASv0": 1, "Newton": 2}),
     # 3 levels (what the reference's hierarchy effectively is): Galerkin chain 0 -> 1 -> 2 and the 3-level V-cycle
     "jag17": ("quasi", lambda: mesh.jagged_mesh(16, 17, 16, 0.05, seed=13, keep=0.12), 0.05, [], {"NewtonMultigrid": 1}),
+    "jag17_pin": ("quasi", lambda: mesh.jagged_mesh(17, 16, 16, 0.05, seed=17, keep=0.12), 0.05, [25],
+                  {"NewtonMultigrid": 2, "FASv3": 1}),
     "jag9_pin": ("quasi", lambda: mesh.jagged_mesh(9, 10, 9, 0.05, seed=5, keep=0.75), 0.05, [40], {"FASv2": 2, "FASv1": 1}),
     # the diagnostic drivers: sampled lists / plotted curves instead of a final state; one case (= one process, one file)
     # per driver because the emulator needs tens of minutes for each

@@ -12,7 +12,7 @@ from fem_simulation_b200 import hierarchy
 from oracle import ref_solvers
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = [c for c in ("jag9", "jag9_pin", "jag17") if os.path.exists(os.path.join(GOLD, f"ref_{c}.npz"))]
+CASES = [c for c in ("jag9", "jag9_pin", "jag17", "jag17_pin") if os.path.exists(os.path.join(GOLD, f"ref_{c}.npz"))]
 INT_KEYS = ["MF_L_row", "MF_L_col", "MF_U_row", "MF_U_col", "MF_GS_U_Ptr", "MF_GS_L_Ptr", "MF_GS_U_row", "MF_GS_U_col",
             "MF_GS_L_row", "MF_GS_L_col", "fix_idx", "pin", "pin_list"]
 
