@@ -1,18 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- Newton-multigrid quasi-static steps/s on the synthetic voxel cube (BASELINE.json metric).
+"""bench.py -- FAS-multigrid (default) / Newton-multigrid quasi-static step throughput on the synthetic voxel cube
+(BASELINE.json metric: "Newton/FAS-MG steps/sec and HBM GB/s", configs[4]).
 
-    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--n 100] [--method nmg|fasv3]
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--n 100] [--method fasv3|nmg]
 
-One "step" = one loop body of ``Object.NewtonMultigrid`` (object.py:1231-1296 of the reference): force +
-element Hessians + assembly, Galerkin coarse operators, one V-cycle (3+3 symmetric 8-colour GS per
-level), full Newton update.  Workload at N=1: cube n=100 (1 000 000 hexahedra, 1 030 301 vertices,
-3.09 M dof), the reference's level-count formula (5 levels).  ``value`` = steps/s with all inputs
-resident in HBM (CUDA-graph replay, CUDA events); ``e2e`` = the same step through the public API with the
-state vector coming from pinned host memory and going back every step.  N>1: one process per GPU, each
-rank owns one mesh block (weak scaling; see DESIGN.md "multi-GPU").
+One "step" = one loop body of ``Object.FASv3`` (object.py:1467-1511 of the reference: fine force + Hessian assembly,
+3 symmetric 8-colour GS, restriction, coarse re-discretised solve, prolongation, post-smoothing) or, with
+``--method nmg``, of ``Object.NewtonMultigrid`` (object.py:1231-1296: force + element Hessians + assembly, Galerkin
+coarse operators, one V-cycle with 3+3 symmetric GS per level, full Newton update; also reported in the default line as
+``newton_mg``).  Workload at N=1: cube n=100 (1 000 000 hexahedra, 1 030 301 vertices, 3.09 M dof), the reference's
+level-count formula (5 levels).  ``value`` = million hexahedron-steps per second (= steps/s on the 1 M-hexahedron cube)
+with all inputs resident in HBM (CUDA-graph replay, CUDA events); ``e2e`` = the same step through the public API with
+the state vector coming from pinned host memory and going back every step.  N>1: one process per GPU, each rank owns
+one z-slab of an N-times-longer box (weak scaling, NCCL halo exchange; see DESIGN.md "multi-GPU").
 
-``--impl reference`` times the CPU restatement of the reference algorithm (the reference has no CPU
-path and cannot run here: SURVEY.md 8c) on the box's host cores on a bounded sample of the workload.
+``--impl reference`` times the C/OpenMP restatement of the reference algorithm (the reference has no CPU path and
+cannot run here: SURVEY.md 8c) on the box's host cores on a bounded sample of the workload.
 """
 from __future__ import annotations
 
@@ -336,11 +339,10 @@ def cpu_baseline(args, sample_only=False, steps=6, warmup=1):
     for _ in range(steps):
         fn()
     dt = (time.time() - t0) / steps
-    scale = hx.shape[0] / float(args.n ** 3)
-    return {"value": scale / dt, "unit": "steps/s", "cores": co.threads, "kind": "port",
+    return {"value": hx.shape[0] / 1e6 / dt, "unit": "Mhex-steps/s", "cores": co.threads, "kind": "port",
             "sample": f"oracle/femb_oracle.c (C + OpenMP, {co.threads} threads), {steps} timed step(s) on cube n={n_s} "
-                      f"({hx.shape[0]} hexahedra, {H.layer} levels), {dt:.3f} s/step; steps/s scaled by hexahedron count "
-                      f"({hx.shape[0]}/{args.n ** 3}) to the n={args.n} workload",
+                      f"({hx.shape[0]} hexahedra, {H.layer} levels), {dt:.3f} s/step; "
+                      f"hexahedra per step / s per step (= {hx.shape[0] / float(args.n ** 3) / dt:.4f} steps/s on the n={args.n} workload)",
             "s_per_sample_step": dt}
 
 
@@ -351,13 +353,16 @@ def run_reference(args):
     cb = cpu_baseline(args, steps=max(1, min(args.steps, 10)), warmup=min(args.warmup, 1))
     n = args.n
     line = {"impl": "reference", "metric": "fas_mg_mhex_steps_per_sec" if args.method == "fasv3" else "newton_mg_mhex_steps_per_sec",
-            "value": cb["value"] * (n ** 3) / 1e6, "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "value": cb["value"], "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (n ** 3 * args.gpus) / 1e6 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"voxel cube n={n}: {n ** 3} hexahedra; CPU restatement of the reference algorithm "
-                                   "(the reference is GPU-only Warp code and cannot run here)"},
+            "config": {"workload": (f"voxel box {n}x{n}x{n * args.gpus}: {n ** 3 * args.gpus} hexahedra, "
+                                    f"{'FASv3 two-level quasi-static step (object.py:1467-1511)' if args.method == 'fasv3' else 'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin; object.py:1231-1296)'}, "
+                                    "mu=250 la=0 g=-4.9 k=100, default top-layer pins"),
+                       "arm": "C/OpenMP restatement of the reference algorithm on the host cores, bounded sample (cpu_baseline.sample); "
+                              "the reference itself is GPU-only Warp code and cannot run here (SURVEY.md 8c)"},
             "cpu_baseline": cb,
-            "e2e": {"value": cb["value"] * (n ** 3) / 1e6, "unit": "Mhex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": cb["value"], "unit": "Mhex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
