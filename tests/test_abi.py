@@ -38,3 +38,29 @@ def test_sass_has_bulk_copy_and_no_legacy_tensor_path():
     out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in out            # cp.async.bulk staging of the row pass
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_ctypes_mirrors_match_header_layout(repo_root, tmp_path):
+    """The header compiles as plain C (no CUDA/torch types in the signatures) and the ctypes mirrors in _lib.py have
+    the same sizeof / offsetof as the C structs, field by field."""
+    import ctypes as C
+    import subprocess
+    structs = {"FembLevel": _lib.FembLevel, "FembTransfer": _lib.FembTransfer, "FembGalerkinPlan": _lib.FembGalerkinPlan}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "femb200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for f, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines += ['  printf("consts %d %d %d %d %d\\n", FEMB_ABI_VERSION, FEMB_ASM_CHUNK_HEXES, FEMB_ELEM_K_FLOATS, '
+              'FEMB_FOLD_PLAN_BYTES, FEMB_PART_ALL);', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(repo_root, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    got = dict(l.split(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == C.sizeof(cls), name
+        for f, _ in cls._fields_:
+            assert int(got[f"{name}.{f}"]) == getattr(cls, f).offset, f"{name}.{f}"
+    assert got["consts"].split() == ["2", str(_lib.ASM_CHUNK_HEXES), str(_lib.ELEM_K_FLOATS), "128", str(_lib.PART_ALL)]
