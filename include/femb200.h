@@ -183,9 +183,9 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
 /* The colour launches of a sweep are programmatic dependent launches (each colour stages its matrix rows while the
  * previous colour drains); femb_set_pdl(0) makes them ordinary launches (tests).  Returns the old setting. */
 int femb_set_pdl(int enable);
-/* threads per row of the colour kernel: 4 (default, measured faster) or 8; the summation tree differs, so results differ in rounding */
+/* threads per row of the colour kernel: 8 (default, measured faster with 16-row blocks) or 4; the summation tree differs, so results differ in rounding */
 int femb_set_gs_threads_per_row(int subs);
-/* rows per CTA of the colour kernel: 32 (default) or 16 */
+/* rows per CTA of the colour kernel: 16 (default: more independent row blocks in flight per SM) or 32 */
 int femb_set_gs_rows_per_cta(int rows);
 /* femb_gauss_seidel runs as ONE cooperative launch (grid-wide barrier between colour phases) when the largest colour has
  * at most this many 32-row blocks: 0 = never (default: PDL colour launches were measured faster at every level size),

@@ -64,3 +64,26 @@ def test_ctypes_mirrors_match_header_layout(repo_root, tmp_path):
         for f, _ in cls._fields_:
             assert int(got[f"{name}.{f}"]) == getattr(cls, f).offset, f"{name}.{f}"
     assert got["consts"].split() == ["2", str(_lib.ASM_CHUNK_HEXES), str(_lib.ELEM_K_FLOATS), "128", str(_lib.PART_ALL)]
+
+
+def test_prototypes_match_header_signatures(repo_root):
+    """Every ctypes prototype has the arity and per-argument class (int / float / pointer) of its declaration."""
+    import ctypes as C
+    txt = open(os.path.join(repo_root, "include", "femb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    decls = dict(re.findall(r"\b(femb_\w+)\s*\(([^)]*)\)\s*;", txt))
+    assert sorted(decls) == sorted(_lib.PROTOTYPES)
+
+    def klass_c(param):
+        param = " ".join(param.split())
+        if "*" in param:
+            return "p"
+        return {"int": "i", "float": "f"}[param.rsplit(" ", 1)[0].replace("const ", "")]
+
+    def klass_ct(t):
+        return "i" if t is C.c_int else "f" if t is C.c_float else "p"
+
+    for name, params in decls.items():
+        params = params.strip()
+        want = [] if params in ("", "void") else [klass_c(q) for q in params.split(",")]
+        assert [klass_ct(t) for t in _lib.PROTOTYPES[name]] == want, name
