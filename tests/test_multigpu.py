@@ -30,13 +30,13 @@ def _init(rank, world, port, backend):
     dist.init_process_group(backend, rank=rank, world_size=world)
 
 
-def _cpu_worker(rank, world, port, out):
+def _cpu_worker(rank, world, port, out, nz):
     _init(rank, world, port, "gloo")
     try:
-        z0, z1, clo, chi = D.slab_planes(NZ, world, rank)
+        z0, z1, clo, chi = D.slab_planes(nz, world, rank)
         pts, hx = mesh.box_mesh(NX, NY, chi - clo, DX, index_offset=(0, 0, clo))
         H = hierarchy.build_hierarchy(pts, hx, DX, layers=2)
-        gpts, ghx = mesh.box_mesh(NX, NY, NZ, DX)
+        gpts, ghx = mesh.box_mesh(NX, NY, nz, DX)
         G = hierarchy.build_hierarchy(gpts, ghx, DX, layers=2)
         ps = (NX + 1) * (NY + 1)
         off = ps * clo
@@ -44,12 +44,12 @@ def _cpu_worker(rank, world, port, out):
         assert np.array_equal(pts, gpts[off:off + len(pts)])
         col = lambda Hh: np.searchsorted(np.asarray(Hh.color_vertex_num[0]), Hh.vertex2index[0], side="right") - 1
         assert np.array_equal(col(H), col(G)[off:off + len(pts)])
-        fv, fi, cv, ci = D.build_halo_plans(NX, NY, z0, z1, clo, chi, NZ, rank, world, H.x[1], H.vertex2index[1],
+        fv, fi, cv, ci = D.build_halo_plans(NX, NY, z0, z1, clo, chi, nz, rank, world, H.x[1], H.vertex2index[1],
                                             H.vertex2index[0], DX, torch.device("cpu"))
         # fine level, vertex order: payload = global vertex id
         gid = torch.arange(len(pts), dtype=torch.float32) + off
         gz = np.arange(len(pts)) // ps + clo
-        owned = (gz >= z0) & ((gz < z1) | ((gz == NZ) & (rank == world - 1)))
+        owned = (gz >= z0) & ((gz < z1) | ((gz == nz) & (rank == world - 1)))
         v = torch.stack([gid, gid * 2, gid * 3], dim=1)
         v[torch.from_numpy(~owned)] = -1.0
         D.exchange(v, fv)
@@ -65,7 +65,7 @@ def _cpu_worker(rank, world, port, out):
         key = np.rint(cx / np.float32(2 * DX)).astype(np.int64)
         gkey = torch.from_numpy((key[:, 0] + 100 * key[:, 1] + 10000 * key[:, 2]).astype(np.float32))
         cgz = np.rint(cx[:, 2] / np.float32(DX)).astype(np.int64)
-        cown = (cgz >= z0) & ((cgz < z1) | ((cgz == NZ) & (rank == world - 1)))
+        cown = (cgz >= z0) & ((cgz < z1) | ((cgz == nz) & (rank == world - 1)))
         c = torch.stack([gkey, gkey, gkey], dim=1).clone()
         c[torch.from_numpy(~cown)] = -1.0
         D.exchange(c, cv)
@@ -88,13 +88,14 @@ def _cpu_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_halo_plans_gloo(world):
-    """world 4 (2 cell layers per rank) adds interior ranks, which talk to both neighbours."""
+@pytest.mark.parametrize("world,nz", [(2, NZ), (4, NZ), (8, 2 * NZ)])
+def test_halo_plans_gloo(world, nz):
+    """world 4 and 8 (2 cell layers per rank) add interior ranks, which talk to both neighbours; 8 is the size of the
+    round-end scaling run."""
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, out, nz)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
