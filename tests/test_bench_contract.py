@@ -1,0 +1,35 @@
+"""bench.py's reference arm (the only arm that runs without a GPU): one JSON line with the contract's keys, and the
+non-zero ranks of a torchrun launch exit without work."""
+import json
+import os
+import subprocess
+import sys
+
+
+def _run(repo_root, extra_env=None):
+    env = dict(os.environ, **(extra_env or {}))
+    return subprocess.run([sys.executable, os.path.join(repo_root, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "0", "--cpu-n", "8"], capture_output=True, text=True, env=env, timeout=300)
+
+
+def test_reference_arm_line(repo_root):
+    r = _run(repo_root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "fas_mg_mhex_steps_per_sec" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "Mhex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # value [Mhex-steps/s] and ms_per_step describe the same rate on the named 1 M-hexahedron workload
+    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - 1.0) < 1e-9
+
+
+def test_reference_arm_other_ranks_exit_quietly(repo_root):
+    r = _run(repo_root, {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
