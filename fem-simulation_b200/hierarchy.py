@@ -241,6 +241,11 @@ def build_pattern(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int) -> L
                         hex_update_offset=slot[inv.reshape(-1)].astype(np.int32))
 
 
+class MeshTooSmallError(ValueError, IndexError):
+    """The reference's level formula gives no level at all (object.py:143: layer = int(log2(min extent / dx)) - 1 < 1);
+    its constructor then dies with ``IndexError: list index out of range`` -- same class of error here, with a message."""
+
+
 def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers: int | None = None,
                     corrected_spacing: bool = False) -> Hierarchy:
     """object.py:116-697.  ``layers`` overrides the reference's level-count formula (benchmarks only).
@@ -252,6 +257,9 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
     box_min = np.minimum(x0.min(axis=0), F32(1000.0)).astype(F32)
     box_max = np.maximum(x0.max(axis=0), F32(-1000.0)).astype(F32)
     layer = level_count(box_min, box_max, dx) if layers is None else int(layers)
+    if layer < 1:
+        raise MeshTooSmallError(f"level count {layer} < 1: the smallest bounding-box extent must be at least (about) 4 dx "
+                                f"(extent {float((box_max - box_min).min()):.6g}, dx {dx:.6g}; object.py:143)")
 
     t = _ijk(x0, box_min, dx, 0.5) % 2                                     # object.py:147-149
     color = (t[:, 0] + 2 * t[:, 1] + 4 * t[:, 2]).astype(np.int64)

@@ -214,3 +214,18 @@ def test_exp3_hooks_edge_index_and_prolongation_chain():
         dense = d if dense is None else dense @ d
         assert m.shape == (H.dims[0], H.dims[l + 1]) and m.has_sorted_indices
         assert np.array_equal(m.toarray().astype(np.float64), dense), f"A_noOrder[{l}]"      # dyadic weights: exact
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 3, 3), (9, 1, 9)])
+def test_mesh_below_the_level_formula_is_an_error(shape):
+    """object.py:143 gives layer < 1 when the thinnest extent is under ~4 dx; the reference constructor (and its literal
+    restatement) then dies with IndexError.  The product raises the same class of error, with a message, instead of
+    returning a hierarchy without levels."""
+    pts, hx = mesh.box_mesh(*shape, 0.05)
+    with pytest.raises(IndexError):
+        ref_setup.build_setup(pts, hx, 0.05, [])
+    with pytest.raises(IndexError, match="level count"):
+        hierarchy.build_hierarchy(pts, hx, 0.05)
+    with pytest.raises(ValueError):
+        hierarchy.build_hierarchy(pts, hx, 0.05)
+    assert hierarchy.build_hierarchy(pts, hx, 0.05, layers=1).layer == 1       # explicit override still works
