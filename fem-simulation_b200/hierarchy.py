@@ -254,6 +254,14 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
     hierarchy really gets coarser."""
     x0 = np.ascontiguousarray(points, dtype=F32)
     hex0 = np.ascontiguousarray(hexagons, dtype=np.int32)
+    if x0.ndim != 2 or x0.shape[1] != 3 or hex0.ndim != 2 or hex0.shape[1] != 8:
+        raise ValueError(f"points must be [N,3] and hexagons [M,8], got {x0.shape} and {hex0.shape}")
+    if x0.shape[0] == 0 or hex0.shape[0] == 0:
+        raise ValueError("empty mesh: no vertices or no hexahedra")
+    if hex0.min() < 0 or hex0.max() >= x0.shape[0]:
+        raise ValueError(f"hexagon vertex ids must lie in [0, {x0.shape[0]}), got [{hex0.min()}, {hex0.max()}]")
+    if not np.isfinite(x0).all():
+        raise ValueError("non-finite vertex coordinates")
     box_min = np.minimum(x0.min(axis=0), F32(1000.0)).astype(F32)
     box_max = np.maximum(x0.max(axis=0), F32(-1000.0)).astype(F32)
     layer = level_count(box_min, box_max, dx) if layers is None else int(layers)

@@ -229,3 +229,16 @@ def test_mesh_below_the_level_formula_is_an_error(shape):
     with pytest.raises(ValueError):
         hierarchy.build_hierarchy(pts, hx, 0.05)
     assert hierarchy.build_hierarchy(pts, hx, 0.05, layers=1).layer == 1       # explicit override still works
+
+
+def test_malformed_meshes_are_rejected():
+    """Host-side validation before anything reaches the device: empty, mis-shaped, out-of-range and non-finite input."""
+    pts, hx = mesh.cube_mesh(5, 0.05)
+    bad = [(np.zeros((0, 3), np.float32), np.zeros((0, 8), np.int32)), (pts, hx[:0]), (pts[:, :2], hx), (pts, hx[:, :4])]
+    h2 = hx.copy(); h2[3, 5] = len(pts)
+    h3 = hx.copy(); h3[0, 0] = -1
+    p2 = pts.copy(); p2[7, 1] = np.nan
+    bad += [(pts, h2), (pts, h3), (p2, hx)]
+    for p, h in bad:
+        with pytest.raises(ValueError):
+            hierarchy.build_hierarchy(p, h, 0.05)
