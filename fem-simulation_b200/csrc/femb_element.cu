@@ -882,19 +882,29 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
 
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add, float* elem_k,
                  float* values, void* stream) {
-  FEMB_REQUIRE(lvl && x && elem_k && values, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan, "level not initialised");
+  FEMB_REQUIRE(lvl && x && values, "null pointer");
   if (lvl->n_vert == 0) return FEMB_OK;
+  if (fused_available(lvl)) {
+    FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ, "level not initialised");
+    return launch_fused(lvl, x, mu, lambda, diag_add, values, nullptr, 0.f, nullptr, nullptr, 0.f, nullptr, as_stream(stream));
+  }
+  FEMB_REQUIRE(elem_k, "null pointer");
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan, "level not initialised");
   return hessian_pipeline<1>(lvl, x, mu, lambda, diag_add, nullptr, elem_k, values, as_stream(stream));
 }
 
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add, float* elem_f,
                        float* elem_k, float* force_out, float* values, void* stream) {
-  FEMB_REQUIRE(lvl && x && elem_f && elem_k && force_out && values, "null pointer");
+  FEMB_REQUIRE(lvl && x && force_out && values, "null pointer");
+  if (lvl->n_vert == 0) return FEMB_OK;
+  if (fused_available(lvl)) {
+    FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ, "level not initialised");
+    return launch_fused(lvl, x, mu, lambda, diag_add, values, mass, g, pin, pin_pos, control_mag, force_out, as_stream(stream));
+  }
+  FEMB_REQUIRE(elem_f && elem_k, "null pointer");
   FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan && lvl->v2i,
                "level not initialised");
-  if (lvl->n_vert == 0) return FEMB_OK;
   int rc = hessian_pipeline<2>(lvl, x, mu, lambda, diag_add, elem_f, elem_k, values, as_stream(stream));
   if (rc) return rc;
   return launch_force_gather(lvl, x, mass, g, pin, pin_pos, control_mag, 1, elem_f, force_out, as_stream(stream));

@@ -60,7 +60,7 @@ def _dev(a, device):
 class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
                  control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False,
-                 pipe_chunk_hexes=2 * 740 * 16, corrected_hierarchy=False):
+                 pipe_chunk_hexes=2 * 740 * 16, corrected_hierarchy=False, fused_assembly=False, fused_chunks=0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.FembError("femb200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -136,6 +136,8 @@ class Object:
                 lv.pipe_chunks = len(ap[0])
                 lv.pipe_hex_end = ap[0].ctypes.data
                 lv.pipe_vert_end = ap[1].ctypes.data
+            if fused_assembly:
+                self._attach_lattice_plan(l, lv, d, fused_chunks)
             self.levels.append(lv)
             self.inverse_pX_peps_gpu.append(d["invJ"])
             self.det_pX_peps_gpu.append(d["detJ"])
@@ -235,6 +237,37 @@ class Object:
             return mesh.box_mesh(nx, ny, nz, dx)
         from . import voxelize
         return voxelize.voxelize_obj(mesh_path, dx)
+
+    def _attach_lattice_plan(self, l, lv, d, chunks):
+        """FembLevel.lat_*: the dense lattice view that lets femb_hessian / femb_force_hessian run as one kernel
+        (csrc/femb_fused.cu).  Levels that are not lattice subsets keep the element-kernel + row-fold path."""
+        H = self.hierarchy
+        lp = hierarchy.lattice_plan(H.x[l], H.hexs[l], H.box_min, H.spacing[l], _lib.FUSED_TILE)
+        if lp is None:
+            return
+        dev = self.device
+        d["lat_cell_elem"] = _dev(lp["cell_elem"].reshape(-1), dev)
+        n_lat = lp["vx"] * lp["vy"] * lp["vz"]
+        d["lat_row_rec"] = torch.empty(n_lat * _lib.ROW_REC_BYTES, dtype=torch.uint8, device=dev)
+        vert_lat = _dev(lp["vert_lat"], dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        lv.lat_vx, lv.lat_vy, lv.lat_vz, lv.lat_chunks = lp["vx"], lp["vy"], lp["vz"], int(chunks)
+        _lib.check(self.lib.femb_build_lattice_plan(C.byref(lv), vert_lat.data_ptr(), d["lat_row_rec"].data_ptr(), bad.data_ptr(),
+                                                    self._stream()), "femb_build_lattice_plan")
+        if int(bad.item()) != 0:                                         # a row with more than 27 blocks
+            lv.lat_vx = lv.lat_vy = lv.lat_vz = 0
+            return
+        lv.lat_cell_elem = d["lat_cell_elem"].data_ptr()
+        lv.lat_row_rec = d["lat_row_rec"].data_ptr()
+
+    def level_without_lattice(self, l):
+        """A copy of FembLevel l without the lattice plan: the element-kernel + row-fold assembly path (tests, measurements)."""
+        lv = _lib.FembLevel()
+        C.memmove(C.byref(lv), C.byref(self.levels[l]), C.sizeof(_lib.FembLevel))
+        lv.lat_cell_elem = None
+        lv.lat_row_rec = None
+        lv.lat_vz = 0
+        return lv
 
     @staticmethod
     def _pipe_plan(nh, vert_elem, chunk_hexes):
@@ -357,14 +390,15 @@ class Object:
                                        1 if ordered else 0, self._elem_f.data_ptr(), out.data_ptr(), self._stream()),
                    "femb_force")
 
-    def _hessian(self, layer, x, values, diag_add=None):
-        """compute_elastic_hessian onto (a copy of MF_value_fixed | zeros), e.g. object.py:1233,1249."""
-        _lib.check(self.lib.femb_hessian(C.byref(self.levels[layer]), x.data_ptr(), self.mu, self.la,
+    def _hessian(self, layer, x, values, diag_add=None, level=None):
+        """compute_elastic_hessian onto (a copy of MF_value_fixed | zeros), e.g. object.py:1233,1249.
+        `level`: a FembLevel to use instead of self.levels[layer] (level_without_lattice)."""
+        _lib.check(self.lib.femb_hessian(C.byref(level if level is not None else self.levels[layer]), x.data_ptr(), self.mu, self.la,
                                          diag_add.data_ptr() if diag_add is not None else None,
                                          self._elem_k.data_ptr(), values.data_ptr(), self._stream()), "femb_hessian")
 
-    def _force_hessian(self, x, force_out, values, diag_add, gravity=True, pins=True):
-        lv = self.levels[0]
+    def _force_hessian(self, x, force_out, values, diag_add, gravity=True, pins=True, level=None):
+        lv = level if level is not None else self.levels[0]
         _lib.check(self.lib.femb_force_hessian(C.byref(lv), x.data_ptr(), self.mu, self.la,
                                                self.m_gpu[0].data_ptr() if gravity else None, self.g,
                                                self.pin_gpu.data_ptr() if pins else None,

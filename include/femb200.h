@@ -33,7 +33,7 @@ extern "C" {
 #define FEMB_E_CUDA (-2)      /* a CUDA runtime call or launch failed                 */
 #define FEMB_E_NODEVICE (-3)  /* no usable sm_100 device                              */
 
-#define FEMB_ABI_VERSION 2
+#define FEMB_ABI_VERSION 3
 
 /* hexahedra per CTA of the element kernel (pipeline chunks should be multiples of it) */
 #define FEMB_ASM_CHUNK_HEXES 16
@@ -42,6 +42,9 @@ extern "C" {
 /* floats of element-matrix scratch per hexahedron (elem_k of femb_hessian): 8 rows x (5 blocks of 9 + 3 pad) -- the
  * symmetric half in rotated order, see femb_element.cu */
 #define FEMB_ELEM_K_FLOATS 384
+/* one-kernel assembly on lattice meshes (femb_fused.cu): vertex columns per tile edge, bytes of a row record */
+#define FEMB_FUSED_TILE 7
+#define FEMB_ROW_REC_BYTES 48
 
 /* matrix part selector for femb_spmv (bsr_mv on self.L / self.D / self.U / self.A) */
 #define FEMB_PART_L 1
@@ -79,6 +82,19 @@ typedef struct FembLevel {
   int pipe_chunks;
   const int* pipe_hex_end;   /* host [pipe_chunks] */
   const int* pipe_vert_end;  /* host [pipe_chunks] */
+  /* Optional lattice plan (0 / NULL = none): the mesh is a subset of a regular lattice (every voxel mesh of the reference,
+   * object.py:28-45, and every coarse mesh built from one, object.py:171-241).  With it femb_hessian / femb_force_hessian
+   * run as ONE kernel that never writes element matrices to memory (femb_fused.cu); without it they run the element
+   * kernel + row fold.  lat_vx, lat_vy: vertex planes along x, y rounded up to multiples of FEMB_FUSED_TILE; lat_vz
+   * along z.  Lattice point (i,j,k) has index (k*lat_vy + j)*lat_vx + i. */
+  int lat_vx, lat_vy, lat_vz;
+  int lat_chunks;                 /* z-chunks per tile column (0 = chosen from the SM count)                          */
+  const int* lat_cell_elem;       /* [(lat_vz+1)*(lat_vy+1)*(lat_vx+1)] hexahedron whose node 0 is lattice point        */
+                                  /* (i-1, j-1, k-1), at index (k*(lat_vy+1) + j)*(lat_vx+1) + i; -1 = empty cell      */
+  const unsigned char* lat_row_rec; /* [lat_vz*lat_vy*lat_vx*FEMB_ROW_REC_BYTES] per lattice point: bytes 0..26 sorted  */
+                                  /* position in the row (L blocks, D, U blocks) -> lattice offset 9(dx+1)+3(dy+1)+dz+1, */
+                                  /* int32 words 7..11 {vertex, row or -1, L_ptr[row], U_ptr[row], nL | nU<<8}; filled  */
+                                  /* by femb_build_lattice_plan                                                        */
 } FembLevel;
 
 /* CSR matrix with one scalar weight per entry = BSR matrix with blocks w*I3: the interpolation
@@ -128,6 +144,9 @@ int femb_prepare_rest(int n_hex, const int* hex, const float* x_rest, float* det
 /* setup of FembLevel.fold_plan (all other fields of *lvl must be final): the inverse of the element->nnz map per row, so
  * that the assembly is a gather in a fixed order (replaces the atomics of quai_hexagon.py:100-106) */
 int femb_build_fold_plan(const FembLevel* lvl, unsigned char* fold_plan, void* stream);
+/* setup of FembLevel.lat_row_rec (lat_vx/vy/vz and all non-lattice fields of *lvl must be final): vert_lat [n_vert] = lattice
+ * index of every vertex; bad (int[1], zeroed by the caller) is set if a row has more than 27 blocks (not a lattice mesh) */
+int femb_build_lattice_plan(const FembLevel* lvl, const int* vert_lat, unsigned char* row_rec, int* bad, void* stream);
 /* Sum_8 + prepare_mass (cublas.py:215-218, quai_hexagon.py:20-26) as a gather: vol[n_hex], mass[n_vert] */
 int femb_lumped_mass(const FembLevel* lvl, float* vol, float* mass, void* stream);
 
