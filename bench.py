@@ -5,7 +5,8 @@
     python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--n 100] [--method fasv3|nmg]
 
 One "step" = one loop body of ``Object.FASv3`` (object.py:1467-1511 of the reference: fine force + Hessian assembly,
-3 symmetric 8-colour GS, restriction, coarse re-discretised solve, prolongation, post-smoothing) or, with
+ONE symmetric 8-colour GS iteration on the fine level, state and residual restriction, re-discretised coarse Hessian with
+the coarse pin penalty, ONE Jacobi iteration on the coarse level, prolongation; no post-smoothing) or, with
 ``--method nmg``, of ``Object.NewtonMultigrid`` (object.py:1231-1296: force + element Hessians + assembly, Galerkin
 coarse operators, one V-cycle with 3+3 symmetric GS per level, full Newton update; also reported in the default line as
 ``newton_mg``).  Workload at N=1: cube n=100 (1 000 000 hexahedra, 1 030 301 vertices, 3.09 M dof), the reference's
@@ -15,7 +16,13 @@ the state vector coming from pinned host memory and going back every step.  N>1:
 one z-slab of an N-times-longer box (weak scaling, NCCL halo exchange; see DESIGN.md "multi-GPU").
 
 ``--impl reference`` times the C/OpenMP restatement of the reference algorithm (the reference has no CPU path and
-cannot run here: SURVEY.md 8c) on the box's host cores on a bounded sample of the workload.
+cannot run here: SURVEY.md 8c) on ALL host cores of the box (the thread count is set explicitly: torchrun exports
+OMP_NUM_THREADS=1) on the stated workload at N=1 (a few steps of the same n^3 cube) and, at N>1, on one rank's n^3 block
+of the N-times-longer box (labelled ``extrapolated``).
+
+Every ``ours`` line carries ``parity``: the state after 2 steps from the rest state on the GPU path vs the same 2 steps of
+the C oracle on the same mesh (positions, max-norm relative), so that a throughput number never travels without a
+correctness number measured in the same process.
 """
 from __future__ import annotations
 
@@ -42,8 +49,9 @@ def parse():
     ap.add_argument("--method", default="fasv3", choices=["nmg", "fasv3"],
                     help="fasv3 (BASELINE configs[4], the mesh-partitioned series) or nmg (Newton-multigrid, 1 GPU only)")
     ap.add_argument("--layers", type=int, default=0, help="0 = the reference's level-count formula")
-    ap.add_argument("--cpu-n", type=int, default=0, help="cube edge of the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--cpu-n", type=int, default=0, help="cube edge of the CPU-baseline sample (0 = the benchmark's own n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 2-step comparison with the C oracle after the timed region")
     ap.add_argument("--no-nmg", action="store_true", help="skip the extra Newton-multigrid timing at N=1")
     ap.add_argument("--corrected-hierarchy", action="store_true",
                     help="coarsen level l with spacing dx*2^l (SURVEY 8f-3) instead of the reference's 2*dx for every l>=1; labelled in config")
@@ -314,53 +322,109 @@ def run_ours(args):
     }
     if nmg is not None:
         line["newton_mg"] = nmg
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(args, sample_only=True)
+    if world == 1 and not args.no_parity:
+        line["parity"], co = parity_check(args, obj, step, H)
+        if not args.no_cpu_baseline:
+            co.x[...] = obj.x_cpu.numpy()
+            line["cpu_baseline"] = cpu_baseline(args, H, co=co if not args.cpu_n else None)
+    elif not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, H)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, sample_only=False, steps=6, warmup=1):
-    """The C/OpenMP restatement of the reference algorithm (oracle/femb_oracle.c; the reference is GPU-only Warp code
-    and has no CPU path) on all host cores, on a bounded sample: a smaller cube with the same level formula,
-    throughput scaled by hexahedron count to the benchmark's workload."""
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_oracle(args, n, H=None):
+    """The C/OpenMP restatement of the reference algorithm (oracle/femb_oracle.c) on the n^3 cube, on all host cores."""
     from fem_simulation_b200 import hierarchy, mesh
     from oracle import c_oracle
-    n_s = args.cpu_n or 64                     # 262 144 hexahedra: ~1.5-2 s of CPU work per step on 24 threads
-    pts, hx = mesh.cube_mesh(n_s)
-    H = hierarchy.build_hierarchy(pts, hx, 1.0 / n_s, args.layers or None)
-    plans = [hierarchy.build_galerkin_plan(H, l) for l in range(H.layer - 1)]
-    co = c_oracle.from_hierarchy(H, plans, pts, 1.0 / n_s)
+    pts, hx = mesh.cube_mesh(n)
+    if H is None:
+        H = hierarchy.build_hierarchy(pts, hx, 1.0 / n, args.layers or None, corrected_spacing=args.corrected_hierarchy)
+    plans = [hierarchy.build_galerkin_plan(H, l) for l in range(H.layer - 1)] if args.method == "nmg" else []
+    co = c_oracle.from_hierarchy(H, plans, pts, 1.0 / n)
+    co.set_threads(host_threads())
+    return co, H, hx.shape[0]
+
+
+def cpu_baseline(args, H=None, steps=3, warmup=1, budget_s=30.0, co=None):
+    """CPU baseline on a bounded sample: `steps` steps (fewer if the time budget runs out) of the benchmark's own n^3 cube
+    -- the N=1 workload itself; at N>1 one rank's block of the longer box."""
+    n = args.cpu_n or args.n
+    if co is None:
+        co, H, nh = cpu_oracle(args, n, H if n == args.n else None)
+    else:
+        nh = n ** 3
     fn = co.newton_mg_step if args.method == "nmg" else co.fasv3_step
     for _ in range(warmup):
         fn()
     t0 = time.time()
+    done = 0
+    while done < steps and (done == 0 or time.time() - t0 < budget_s):
+        fn()
+        done += 1
+    dt = (time.time() - t0) / done
+    return {"value": nh / 1e6 / dt, "unit": "Mhex-steps/s", "cores": co.threads, "kind": "port",
+            "sample": f"oracle/femb_oracle.c (C + OpenMP, {co.threads} threads, atomics-free fixed-pattern assembly), {done} timed "
+                      f"step(s) after {warmup} warm-up on cube n={n} ({nh} hexahedra, {co.L} levels), {dt:.3f} s/step",
+            "s_per_sample_step": dt, "sample_steps": done, "sample_n": n}
+
+
+def parity_check(args, obj, step, H, steps=2):
+    """State after `steps` steps from the rest state: GPU path vs the C oracle on the same mesh (1 GPU)."""
+    import numpy as np
+    import torch
+    obj.x_gpu_layer[0].copy_(obj.x_cpu)
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    xg = obj.x_gpu_layer[0].cpu().numpy().astype(np.float64)
+    fg = obj.inf_norm(obj.grad_gpu if args.method == "nmg" else obj.dev_B_fixed[0])
+    co, _, _ = cpu_oracle(args, args.n, H)
+    fn = co.newton_mg_step if args.method == "nmg" else co.fasv3_step
     for _ in range(steps):
         fn()
-    dt = (time.time() - t0) / steps
-    return {"value": hx.shape[0] / 1e6 / dt, "unit": "Mhex-steps/s", "cores": co.threads, "kind": "port",
-            "sample": f"oracle/femb_oracle.c (C + OpenMP, {co.threads} threads), {steps} timed step(s) on cube n={n_s} "
-                      f"({hx.shape[0]} hexahedra, {H.layer} levels), {dt:.3f} s/step; "
-                      f"hexahedra per step / s per step (= {hx.shape[0] / float(args.n ** 3) / dt:.4f} steps/s on the n={args.n} workload)",
-            "s_per_sample_step": dt}
+    xc = co.x.astype(np.float64)
+    fc = float(np.abs(co.grad if args.method == "nmg" else co.vec[0]["B_fixed"]).max())
+    x0 = obj.x_cpu.numpy().astype(np.float64)
+    return {"steps": steps, "x_rel_err": float(np.abs(xg - xc).max() / np.abs(xc).max()),
+            "displacement_rel_err": float(np.abs(xg - xc).max() / max(np.abs(xc - x0).max(), 1e-30)),
+            "force_inf_norm": fg, "force_inf_norm_ref": fc, "x_checksum": float(np.abs(xg).sum()),
+            "x_checksum_ref": float(np.abs(xc).sum()),
+            "ref": "oracle/femb_oracle.c, same mesh, same steps from the rest state (force norm: at the start of the last step)"}, co
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args, steps=max(1, min(args.steps, 10)), warmup=min(args.warmup, 1))
+    t_all = time.time()
+    cb = cpu_baseline(args, steps=max(1, min(args.steps, 5)), warmup=1 if args.warmup > 0 else 0, budget_s=60.0)
     n = args.n
+    hexes = n ** 3 * args.gpus
+    extrapolated = args.gpus > 1 or cb["sample_n"] != n
+    what = ('FASv3 two-level quasi-static step (object.py:1467-1511)' if args.method == 'fasv3' else
+            'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin; object.py:1231-1296)')
     line = {"impl": "reference", "metric": "fas_mg_mhex_steps_per_sec" if args.method == "fasv3" else "newton_mg_mhex_steps_per_sec",
-            "value": cb["value"], "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * (n ** 3 * args.gpus) / 1e6 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": (f"voxel box {n}x{n}x{n * args.gpus}: {n ** 3 * args.gpus} hexahedra, "
-                                    f"{'FASv3 two-level quasi-static step (object.py:1467-1511)' if args.method == 'fasv3' else 'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin; object.py:1231-1296)'}, "
+            "value": cb["value"], "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)",
+            "n_gpus": args.gpus, "steps": cb["sample_steps"], "warmup": 1 if args.warmup > 0 else 0,
+            "ms_per_step": 1e3 * cb["s_per_sample_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "extrapolated": extrapolated,
+            "config": {"workload": (f"voxel box {n}x{n}x{n * args.gpus}: {hexes} hexahedra, {what}, "
                                     "mu=250 la=0 g=-4.9 k=100, default top-layer pins"),
-                       "arm": "C/OpenMP restatement of the reference algorithm on the host cores, bounded sample (cpu_baseline.sample); "
-                              "the reference itself is GPU-only Warp code and cannot run here (SURVEY.md 8c)"},
+                       "timed": (f"cube n={cb['sample_n']} ({cb['sample_n'] ** 3} hexahedra), {cb['sample_steps']} steps; ms_per_step is that "
+                                 "sample's; value = sample hexahedra / sample time" +
+                                 ("" if not extrapolated else " (one rank's block of the longer box: throughput is size-independent to first order)")),
+                       "arm": "C/OpenMP restatement of the reference algorithm on all host cores (thread count set explicitly); "
+                              "the reference itself is GPU-only Warp code and cannot run here (SURVEY.md 8c)",
+                       "wall_s": round(time.time() - t_all, 1)},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "Mhex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -22,7 +22,8 @@ class OrcLevel(C.Structure):
     _fields_ = [("n_vert", C.c_int), ("n_hex", C.c_int), ("nnz", C.c_int), ("off_l", C.c_int), ("off_d", C.c_int),
                 ("off_u", C.c_int), ("color_start", C.c_int * 9), ("hex", P), ("v2i", P), ("i2v", P), ("L_ptr", P),
                 ("L_col", P), ("U_ptr", P), ("U_col", P), ("elem2nnz", P), ("invJ", P), ("detJ", P), ("mass", P),
-                ("values", P), ("B", P), ("B_fixed", P), ("delta_x", P), ("x_solved", P), ("R", P)]
+                ("values", P), ("B", P), ("B_fixed", P), ("delta_x", P), ("x_solved", P), ("R", P),
+                ("vert_elem", P), ("elem_k", P), ("elem_f", P)]
 
 
 class OrcCsr(C.Structure):
@@ -75,6 +76,17 @@ def _p(a):
     return a.ctypes.data_as(P)
 
 
+def vertex_incidence(hexagons, n_vert):
+    """[n_vert, 8] int32: e*8+a of the hexahedra incident to every vertex in ascending order, -1 padded."""
+    ve = np.full((n_vert, 8), -1, dtype=np.int32)
+    flat = np.asarray(hexagons).reshape(-1).astype(np.int64)
+    o2 = np.argsort(flat, kind="stable")
+    cnt = np.bincount(flat, minlength=n_vert)
+    start = np.cumsum(cnt) - cnt
+    ve[flat[o2], np.arange(len(o2)) - start[flat[o2]]] = o2.astype(np.int32)
+    return ve
+
+
 class COracle:
     """Owns the numpy buffers behind an OrcCtx.  ``H`` is a fem_simulation_b200.hierarchy.Hierarchy (integer maps
     only), ``rest`` a oracle.ref_solvers.RefObject-like provider of det/inv/mass/x0/pins (numpy oracle)."""
@@ -100,6 +112,9 @@ class COracle:
             lv.U_ptr = _p(k(p.U_ptr, np.int32)); lv.U_col = _p(k(p.U_col, np.int32))
             lv.elem2nnz = _p(k(p.hex_update_offset, np.int32))
             lv.invJ = _p(k(inv[l], np.float32)); lv.detJ = _p(k(det[l], np.float32)); lv.mass = _p(k(mass[l], np.float32))
+            lv.vert_elem = _p(k(vertex_incidence(H.hexs[l], H.dims[l]), np.int32))
+            lv.elem_k = _p(self._keep(np.zeros(H.hexs[l].shape[0] * 576, np.float32)))
+            lv.elem_f = _p(self._keep(np.zeros(H.hexs[l].shape[0] * 24, np.float32)))
             vals = self._keep(np.zeros((p.nnz, 3, 3), np.float32)); self.values.append(vals); lv.values = _p(vals)
             vs = {}
             for nm in ("B", "B_fixed", "delta_x", "x_solved", "R"):
@@ -115,7 +130,8 @@ class COracle:
         self.Ut_hat, self.Us_hat = csr_array(H.Ut_hat), csr_array(H.Us_hat)
         self.Ut_noOrder, self.Ut_noOrder_hat = csr_array(H.Ut_noOrder), csr_array(H.Ut_noOrder_hat)
         self.plans = (OrcPlan * max(L - 1, 1))()
-        for l in range(L - 1):
+        self.has_plans = len(plans) >= L - 1                   # the Galerkin plans are needed by newton_mg_step only
+        for l in range(L - 1 if self.has_plans else 0):
             g_ = plans[l]
             pl = self.plans[l]
             pl.t_nnz = len(g_["t_col"])
@@ -148,6 +164,7 @@ class COracle:
         return int(self.lib.orc_num_threads())
 
     def newton_mg_step(self):
+        assert self.has_plans, "COracle built without Galerkin plans"
         self.lib.orc_newton_mg_step(C.byref(self.ctx))
 
     def fasv3_step(self):
@@ -158,6 +175,13 @@ class COracle:
 
     def hessian(self, level, x, values, diag_add=None):
         self.lib.orc_hessian(C.byref(self.ctx), level, _p(x), _p(values), _p(diag_add) if diag_add is not None else None)
+
+    def hessian_literal(self, level, x, values, diag_add=None):
+        self.lib.orc_hessian_literal(C.byref(self.ctx), level, _p(x), _p(values), _p(diag_add) if diag_add is not None else None)
+
+    def set_threads(self, n):
+        """Use n OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1)."""
+        self.lib.orc_set_threads(int(n))
 
     def energy(self, x):
         return float(self.lib.orc_energy(C.byref(self.ctx), _p(x)))

@@ -5,8 +5,11 @@
  * bench.py reports next to the GPU numbers and (b) a second, independent check of the numpy oracle
  * (tests/test_oracle.py compares the two at 1e-5).  The reference is GPU-only NVIDIA-Warp Python; each
  * function below is the loop form of the cited Warp kernel (paths relative to
- * /root/reference/exp1/quasi_simulation/), one loop iteration per Warp thread, `#pragma omp atomic`
- * where the kernel uses wp.atomic_*.  The per-step COO->BSR rebuilds (bsr_set_from_triplets, a cub
+ * /root/reference/exp1/quasi_simulation/).  Where the Warp kernels scatter with wp.atomic_* (element forces and
+ * element Hessian blocks) this baseline does what a CPU implementation would: one pass over the hexahedra into an
+ * element scratch, then a gather per vertex / per row through the fixed element->nnz map -- no atomics, fixed summation
+ * order -- and the element Hessian uses the closed form of the dF/dE/dP chain (same blocks to round-off; the literal
+ * chain lives on in orc_hessian_literal for the cross-check against the numpy oracle).  The per-step COO->BSR rebuilds (bsr_set_from_triplets, a cub
  * sort + host sync per call) and the symbolic half of bsr_mm are NOT reproduced -- patterns are fixed --
  * which only makes this baseline faster than a literal port would be.
  *
@@ -37,6 +40,9 @@ typedef struct OrcLevel {
   const float* mass;    /* m_gpu [n_vert]                   */
   float* values;        /* MF_value_gpu / UtAUs_values      */
   float *B, *B_fixed, *delta_x, *x_solved, *R;   /* dev_B, dev_B_fixed, dev_delta_x, dev_x_solved, dev_R */
+  const int* vert_elem; /* [n_vert*8] e*8+a of the hexahedra incident to a vertex, -1 pad (inverse of hex)          */
+  float* elem_k;        /* scratch [n_hex*576]: element matrices, block (a,b) at (a*8+b)*9                            */
+  float* elem_f;        /* scratch [n_hex*24]: element forces                                                         */
 } OrcLevel;
 
 typedef struct OrcCsr {     /* interpolation operator, blocks w*I3 */
@@ -75,6 +81,14 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the baseline must say how many threads it uses and set them itself */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* ---------------------------------------------------------------- small dense helpers */
 static void mat_mul(const float* a, const float* b, float* c) {      /* c = a b, row-major 3x3 */
@@ -102,42 +116,109 @@ static void compute_FE(const OrcCtx* c, const OrcLevel* l, const float* x, int e
   for (int k = 0; k < 9; ++k) E[k] = 0.5f * (C[k] - ((k % 4 == 0) ? 1.f : 0.f));
 }
 
-/* compute_partial_elastic_energy_X (quai_hexagon.py:109-133) + gravity (:176-180) + pin springs (:160-165) */
+/* compute_partial_elastic_energy_X (quai_hexagon.py:109-133) + gravity (:176-180) + pin springs (:160-165).
+ * One pass over the hexahedra into elem_f, then a gather per vertex (incidence order) instead of the kernel's atomics. */
 void orc_force(const OrcCtx* c, int level, const float* x, float* grad, int with_gravity_pins) {
   const OrcLevel* l = &c->lv[level];
-  memset(grad, 0, sizeof(float) * 3 * (size_t)l->n_vert);
 #pragma omp parallel for schedule(static)
-  for (long t = 0; t < (long)l->n_hex * 8; ++t) {
-    const int e = (int)(t >> 3), q = (int)(t & 7);
-    float F[9], E[9], S[9], P[9], iT[9], PiT[9];
-    compute_FE(c, l, x, e, q, F, E);
-    const float tr = E[0] + E[4] + E[8];
-    for (int k = 0; k < 9; ++k) S[k] = 2.0f * c->mu * E[k] + ((k % 4 == 0) ? c->la * tr : 0.f);
-    mat_mul(F, S, P);
-    mat_T(l->invJ + ((size_t)e * 8 + q) * 9, iT);
-    mat_mul(P, iT, PiT);
-    const float det = l->detJ[(size_t)e * 8 + q];
-    for (int i = 0; i < 8; ++i) {
-      const int row = l->v2i[l->hex[8 * e + i]];
-      for (int r = 0; r < 3; ++r) {
-        const float v = (PiT[3 * r] * c->sfg[i][q][0] + PiT[3 * r + 1] * c->sfg[i][q][1] + PiT[3 * r + 2] * c->sfg[i][q][2]) * det;
-#pragma omp atomic
-        grad[3 * row + r] -= v;
-      }
+  for (int e = 0; e < l->n_hex; ++e) {
+    float fe[24];
+    for (int k = 0; k < 24; ++k) fe[k] = 0.f;
+    for (int q = 0; q < 8; ++q) {
+      float F[9], E[9], S[9], P[9], iT[9], PiT[9];
+      compute_FE(c, l, x, e, q, F, E);
+      const float tr = E[0] + E[4] + E[8];
+      for (int k = 0; k < 9; ++k) S[k] = 2.0f * c->mu * E[k] + ((k % 4 == 0) ? c->la * tr : 0.f);
+      mat_mul(F, S, P);
+      mat_T(l->invJ + ((size_t)e * 8 + q) * 9, iT);
+      mat_mul(P, iT, PiT);
+      const float det = l->detJ[(size_t)e * 8 + q];
+      for (int i = 0; i < 8; ++i)
+        for (int r = 0; r < 3; ++r)
+          fe[3 * i + r] -= (PiT[3 * r] * c->sfg[i][q][0] + PiT[3 * r + 1] * c->sfg[i][q][1] + PiT[3 * r + 2] * c->sfg[i][q][2]) * det;
     }
+    memcpy(l->elem_f + (size_t)e * 24, fe, sizeof(fe));
   }
-  if (!with_gravity_pins) return;
 #pragma omp parallel for schedule(static)
   for (int idx = 0; idx < l->n_vert; ++idx) {
     const int v = l->i2v[idx];
-    grad[3 * idx + 1] += l->mass[v] * c->g;
-    if (c->pin[v] == 1)
-      for (int r = 0; r < 3; ++r) grad[3 * idx + r] += c->control_mag * (c->pin_pos[3 * v + r] - x[3 * v + r]);
+    float f[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < 8; ++j) {
+      const int ea = l->vert_elem[(size_t)v * 8 + j];
+      if (ea < 0) continue;
+      for (int r = 0; r < 3; ++r) f[r] += l->elem_f[(size_t)ea * 3 + r];
+    }
+    if (with_gravity_pins) {
+      f[1] += l->mass[v] * c->g;
+      if (c->pin[v] == 1)
+        for (int r = 0; r < 3; ++r) f[r] += c->control_mag * (c->pin_pos[3 * v + r] - x[3 * v + r]);
+    }
+    for (int r = 0; r < 3; ++r) grad[3 * idx + r] = f[r];
   }
 }
 
-/* compute_elastic_hessian (quai_hexagon.py:69-106): literal dF/dE/dP chain, F/E hoisted per (e,q) */
+/* compute_elastic_hessian (quai_hexagon.py:69-106): element matrices by the closed form of the dF/dE/dP chain
+ *   K_ab[j][i] = sum_q det ( d_ji (S g_a . g_b) + mu (g_a . g_b)(F F^T)_ji + mu u_b[j] u_a[i] + la u_a[j] u_b[i] ),
+ *   g_a = J^-T dN_a, u_a = F g_a, S = 2 mu E + la tr(E) I
+ * into elem_k, then every row gathers its blocks through the fixed element->nnz map (hex_update_offset) -- the
+ * fixed-pattern, atomics-free assembly a CPU implementation would use; only the row's owner touches the row's slots. */
 void orc_hessian(const OrcCtx* c, int level, const float* x, float* values, const float* diag_add) {
+  const OrcLevel* l = &c->lv[level];
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < l->n_hex; ++e) {
+    float Ke[576];
+    for (int k = 0; k < 576; ++k) Ke[k] = 0.f;
+    for (int q = 0; q < 8; ++q) {
+      float F[9], E[9], S[9], M[9], g[8][3], u[8][3], t[8][3];
+      compute_FE(c, l, x, e, q, F, E);
+      const float* iJ = l->invJ + ((size_t)e * 8 + q) * 9;
+      const float det = l->detJ[(size_t)e * 8 + q];
+      const float tr = E[0] + E[4] + E[8];
+      for (int k = 0; k < 9; ++k) S[k] = 2.0f * c->mu * E[k] + ((k % 4 == 0) ? c->la * tr : 0.f);
+      const float cmu = det * c->mu, cla = det * c->la;
+      for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) M[3 * j + i] = cmu * (F[3 * j] * F[3 * i] + F[3 * j + 1] * F[3 * i + 1] + F[3 * j + 2] * F[3 * i + 2]);
+      for (int b = 0; b < 8; ++b) {
+        for (int j = 0; j < 3; ++j) g[b][j] = c->sfg[b][q][0] * iJ[j] + c->sfg[b][q][1] * iJ[3 + j] + c->sfg[b][q][2] * iJ[6 + j];
+        for (int r = 0; r < 3; ++r) u[b][r] = F[3 * r] * g[b][0] + F[3 * r + 1] * g[b][1] + F[3 * r + 2] * g[b][2];
+        for (int r = 0; r < 3; ++r) t[b][r] = det * (S[3 * r] * g[b][0] + S[3 * r + 1] * g[b][1] + S[3 * r + 2] * g[b][2]);
+      }
+      for (int a = 0; a < 8; ++a)
+        for (int b = 0; b < 8; ++b) {
+          float* K = Ke + (a * 8 + b) * 9;
+          const float s1 = t[a][0] * g[b][0] + t[a][1] * g[b][1] + t[a][2] * g[b][2];
+          const float s2 = g[a][0] * g[b][0] + g[a][1] * g[b][1] + g[a][2] * g[b][2];
+          for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i)
+              K[3 * j + i] += M[3 * j + i] * s2 + cmu * u[b][j] * u[a][i] + cla * u[a][j] * u[b][i] + ((i == j) ? s1 : 0.f);
+        }
+    }
+    memcpy(l->elem_k + (size_t)e * 576, Ke, sizeof(Ke));
+  }
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < l->n_vert; ++r) {
+    const int v = l->i2v[r];
+    for (int p = l->L_ptr[r]; p < l->L_ptr[r + 1]; ++p) memset(values + ((size_t)l->off_l + p) * 9, 0, 9 * sizeof(float));
+    for (int p = l->U_ptr[r]; p < l->U_ptr[r + 1]; ++p) memset(values + ((size_t)l->off_u + p) * 9, 0, 9 * sizeof(float));
+    float* d = values + ((size_t)l->off_d + r) * 9;
+    memset(d, 0, 9 * sizeof(float));
+    if (diag_add) { d[0] = diag_add[r]; d[4] = diag_add[r]; d[8] = diag_add[r]; }
+    for (int j = 0; j < 8; ++j) {
+      const int ea = l->vert_elem[(size_t)v * 8 + j];
+      if (ea < 0) continue;
+      const float* Ka = l->elem_k + (size_t)(ea >> 3) * 576 + (size_t)(ea & 7) * 72;
+      const int* slot = l->elem2nnz + (size_t)ea * 8;
+      for (int b = 0; b < 8; ++b) {
+        float* dst = values + (size_t)slot[b] * 9;
+        for (int k = 0; k < 9; ++k) dst[k] += Ka[b * 9 + k];
+      }
+    }
+  }
+}
+
+/* the same operator as the literal dF/dE/dP chain of quai_hexagon.py:86-106 with the kernel's atomic scatter (one loop
+ * iteration per Warp thread): the cross-check of orc_hessian and of the numpy oracle (tests/test_oracle.py) */
+void orc_hessian_literal(const OrcCtx* c, int level, const float* x, float* values, const float* diag_add) {
   const OrcLevel* l = &c->lv[level];
   memset(values, 0, sizeof(float) * 9 * (size_t)l->nnz);
   if (diag_add)

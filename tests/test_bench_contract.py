@@ -26,8 +26,17 @@ def test_reference_arm_line(repo_root):
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "Mhex-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    # value [Mhex-steps/s] and ms_per_step describe the same rate on the named 1 M-hexahedron workload
-    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - 1.0) < 1e-9
+    # ms_per_step is the time of the steps that were really timed (the cpu-n sample), value their throughput
+    assert d["extrapolated"] is True and cb["sample_n"] == 8
+    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - 8 ** 3 / 1e6) < 1e-9
+
+
+def test_reference_arm_sets_its_own_thread_count(repo_root):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must use the host's cores anyway and say how many."""
+    r = _run(repo_root, {"OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 def test_reference_arm_other_ranks_exit_quietly(repo_root):
