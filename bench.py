@@ -47,7 +47,11 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=100, help="voxels per cube edge (100 -> 1 M hexahedra)")
     ap.add_argument("--method", default="fasv3", choices=["nmg", "fasv3"],
-                    help="fasv3 (BASELINE configs[4], the mesh-partitioned series) or nmg (Newton-multigrid, 1 GPU only)")
+                    help="fasv3 (BASELINE configs[4], the mesh-partitioned series) or nmg (Newton-multigrid, the north-star target)")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: partition ONE n^3 cube over the ranks (strong scaling) instead of an n x n x (n N) box (weak)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "torch"],
+                    help="auto: C-ABI NCCL exchanges inside one CUDA graph per rank; torch: torch.distributed exchanges between segment graphs")
     ap.add_argument("--layers", type=int, default=0, help="0 = the reference's level-count formula")
     ap.add_argument("--cpu-n", type=int, default=0, help="cube edge of the CPU-baseline sample (0 = the benchmark's own n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,15 +165,19 @@ def run_ours(args):
     lib = _lib.load()
     n = args.n
     method = args.method
-    if world > 1 and method != "fasv3":
-        raise SystemExit("the mesh-partitioned path implements the FASv3 step (BASELINE configs[4]); use --method fasv3")
     t0 = time.time()
+    nz_total = n if (args.strong or world == 1) else n * world
     if world > 1:
-        # weak scaling: every rank owns an n x n x n block of an n x n x (n*world) box, cut into z-slabs
+        # weak scaling: every rank owns an n x n x n block of an n x n x (n*world) box, cut into z-slabs;
+        # strong scaling: the n^3 cube itself is cut
+        from fem_simulation_b200 import hierarchy as _h
         from fem_simulation_b200.distributed import SlabObject
-        so = SlabObject(n, n, n * world, 1.0 / n, device=str(dev))
+        import numpy as _np
+        glayers = 2 if method == "fasv3" else (args.layers or _h.level_count(_np.zeros(3, _np.float32), _np.array([1.0, 1.0, nz_total / n], _np.float32), 1.0 / n))
+        so = SlabObject(n, n, nz_total, 1.0 / n, device=str(dev), layers=glayers, comm=args.comm,
+                        corrected_hierarchy=args.corrected_hierarchy)
         obj = so.obj
-        step = so.fasv3_step
+        step = so.fasv3_step if method == "fasv3" else so.nmg_step
     else:
         obj = Object(f"cube:{n}", 1.0 / n, [], device=str(dev), layers=(args.layers or None), use_graphs=True,
                      corrected_hierarchy=args.corrected_hierarchy)
@@ -202,9 +210,11 @@ def run_ours(args):
         step()                                     # one eager step only to count this step's launches
         obj.use_graphs = True
     else:
-        so.graph_segments = False                  # one eager step to count the launches behind the segment graphs
+        so.graph_segments = False                  # one eager step to count the launches behind the graphs
+        so.n_exchanges = 0
         step()
         so.graph_segments = True
+        exchanges_per_step = so.n_exchanges
     launches_per_step = lib.femb_launch_count() - l0
     barrier()
     # ---- device-resident timing -------------------------------------------------------------------
@@ -264,6 +274,9 @@ def run_ours(args):
         sbn = step_bytes(obj, "nmg")
         nmg = {"ms_per_step": t_nmg, "steps_per_sec": 1e3 / t_nmg, "algorithmic_bytes_per_step": sbn,
                "achieved_GBps": sbn / (t_nmg * 1e-3) / 1e9}
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = parity_check_distributed(args, so, step, dev, rank, world)
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
@@ -279,8 +292,9 @@ def run_ours(args):
     ach = gs_launch_bytes(obj) / (gs_ms_per_launch * 1e-3) / 1e9
     asm_bytes = 352 * H.hexs[0].shape[0] + 36 * H.pattern[0].nnz + 256 * H.hexs[0].shape[0]
     sb = step_bytes(obj, method)
-    hexes_per_rank = n ** 3
-    mhex = hexes_per_rank * world / 1e6
+    total_hexes = n * n * nz_total
+    hexes_per_rank = total_hexes // world
+    mhex = total_hexes / 1e6
     steps_per_s = args.steps / (ms * 1e-3)
     if nmg is not None:
         nmg["frac_of_peak"] = nmg["achieved_GBps"] / peak
@@ -288,17 +302,19 @@ def run_ours(args):
         "metric": "fas_mg_mhex_steps_per_sec" if method == "fasv3" else "newton_mg_mhex_steps_per_sec",
         "value": steps_per_s * mhex, "unit": "Mhex-steps/s (million hexahedron-steps per second; = steps/s on a 1 M-hexahedron mesh)",
         "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (args.strong and world > 1) else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"voxel box {n}x{n}x{n * world}: {hexes_per_rank * world} hexahedra, "
+        "config": {"workload": (f"voxel box {n}x{n}x{nz_total}: {total_hexes} hexahedra, "
                                 f"{'FASv3 two-level quasi-static step (object.py:1467-1511)' if method == 'fasv3' else 'Newton-multigrid step (V-cycle 3+3 sym. 8-colour GS, Galerkin; object.py:1231-1296)'}, "
                                 "mu=250 la=0 g=-4.9 k=100, default top-layer pins"),
-                   "steps_per_sec": steps_per_s, "hexahedra": hexes_per_rank * world, "local_levels": H.layer, "local_dims": H.dims,
+                   "steps_per_sec": steps_per_s, "hexahedra": total_hexes, "local_levels": H.layer, "local_dims": H.dims,
                    "hierarchy": ("corrected spacing dx*2^l (not the reference's behaviour)" if args.corrected_hierarchy else
                                  "reference coarsening (object.py:175-179: levels >= 3 repeat level 2)"),
-                   "parallelism": (f"{world} ranks, z-slab domain decomposition ({n} cell layers + 2 overlap layers per rank), "
-                                   "NCCL neighbour halo exchange (6 per step), no all-reduce on the data path; the 7 exchange-free "
-                                   "segments of a step are CUDA-graph replays") if world > 1 else
+                   "parallelism": (f"{world} ranks, z-slab domain decomposition (cuts {so.cuts}, {so.overlap} overlap cell layers below each slab), "
+                                   f"{exchanges_per_step} neighbour halo exchanges per step (vector ghosts only, no matrix entries), no all-reduce "
+                                   "on the data path; " + ("C-ABI NCCL send/recv + pack/unpack kernels on the step's stream, ONE CUDA graph per "
+                                   "rank per step" if so.comm is not None else "torch.distributed exchanges between CUDA-graph segments")) if world > 1 else
                                   "single GPU, CUDA-graph replay of the step body",
                    "l2": "working set (matrix values %.2f GB per rank) >> 126 MB L2, no flush needed" % (H.pattern[0].nnz * 36 / 1e9),
                    "setup_s": round(setup_s, 1), "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
@@ -310,18 +326,20 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "femb_hessian: element_kernel<1> + assemble_rows_kernel (level 0, the two launches of "
                      "the assembly stage; the element kernel itself is FP32-issue / shared-memory bound, see DESIGN.md)",
                      "achieved": asm_bytes / (asm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "traffic": ASM_TRAFFIC_PER_MHEX * n ** 3 / 1e6,
+                     "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "traffic": ASM_TRAFFIC_PER_MHEX * H.hexs[0].shape[0] / 1e6,
                      "traffic_note": "dram__bytes_read+write of the two kernels, ncu --set full at cube n=100 (profiles/), scaled by hexahedra",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "us_per_launch": asm_ms * 1e3, "algorithmic_bytes_per_launch": asm_bytes,
                      "algorithmic_bytes_formula": "352*N_h + 36*Z + 256*N_h (SURVEY.md 8d, Hessian assembly)"},
         "roofline_smoother": {"bound": "hbm", "kernel": "gs_color_kernel<8,16> (femb_gauss_seidel, fine level, one colour launch)",
-                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": GS_TRAFFIC_PER_MHEX * n ** 3 / 1e6,
+                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": GS_TRAFFIC_PER_MHEX * H.hexs[0].shape[0] / 1e6,
                               "us_per_launch": gs_ms_per_launch * 1e3, "algorithmic_bytes_per_launch": gs_launch_bytes(obj)},
         "clocks": clocks,
     }
     if nmg is not None:
         line["newton_mg"] = nmg
+    if world > 1 and not args.no_parity:
+        line["parity"] = parity
     if world == 1 and not args.no_parity:
         line["parity"], co = parity_check(args, obj, step, H)
         if not args.no_cpu_baseline:
@@ -375,6 +393,41 @@ def cpu_baseline(args, H=None, steps=3, warmup=1, budget_s=30.0, co=None):
             "sample": f"oracle/femb_oracle.c (C + OpenMP, {co.threads} threads, atomics-free fixed-pattern assembly), {done} timed "
                       f"step(s) after {warmup} warm-up on cube n={n} ({nh} hexahedra, {co.L} levels), {dt:.3f} s/step",
             "s_per_sample_step": dt, "sample_steps": done, "sample_n": n}
+
+
+def parity_check_distributed(args, so, step, dev, rank, world, steps=3):
+    """N > 1: (a) the same code path on a SMALL box cut over the N ranks vs rank 0 solving that box alone on its GPU (max-norm
+    relative difference of the positions after `steps` steps); (b) fingerprints of the full-size run (owned-vertex checksum,
+    |f|inf) so that the throughput line carries the state it was measured on."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fem_simulation_b200 import Object, mesh
+    from fem_simulation_b200.distributed import SlabObject, hierarchy_align
+    method = args.method
+    layers = 2 if method == "fasv3" else 3
+    m = 12
+    nz = max(hierarchy_align(layers) * 2, 8) * world
+    small = SlabObject(m, m, nz, 1.0 / m, device=str(dev), layers=layers, comm=args.comm)
+    for _ in range(steps):
+        small.fasv3_step() if method == "fasv3" else small.nmg_step()
+    ids, xs = small.owned_positions()
+    n_glob = (m + 1) * (m + 1) * (nz + 1)
+    xg = torch.zeros((n_glob, 3), device=dev)
+    xg[ids] = xs
+    dist.all_reduce(xg)
+    out = {"small_box": f"{m}x{m}x{nz}, {layers} levels, {steps} steps, {world} ranks vs 1 GPU"}
+    if rank == 0:
+        pts, hx = mesh.box_mesh(m, m, nz, 1.0 / m)
+        ref = Object((pts, hx), 1.0 / m, [], device=str(dev), layers=layers, use_graphs=False)
+        ref.FASv3(steps) if method == "fasv3" else ref.NewtonMultigrid(steps)
+        xr = ref.x_gpu_layer[0]
+        out["x_rel_err_vs_1gpu"] = float((xg - xr).abs().max() / xr.abs().max())
+        out["displacement_rel_err_vs_1gpu"] = float((xg - xr).abs().max() / (xr - torch.from_numpy(pts).to(dev)).abs().max())
+    dist.barrier()
+    out["full_size_x_checksum"] = so.checksum()
+    out["full_size_force_inf_norm"] = so.force_inf_norm()
+    return out
 
 
 def parity_check(args, obj, step, H, steps=2):

@@ -12,9 +12,9 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libfemb200.so")
-SOURCES = ["femb_api.cu", "femb_element.cu", "femb_fused.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
+SOURCES = ["femb_api.cu", "femb_element.cu", "femb_fused.cu", "femb_comm.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 PART_L, PART_D, PART_U, PART_ALL = 1, 2, 4, 7
 
@@ -53,7 +53,18 @@ class FembGalerkinPlan(C.Structure):
                 ("ut_q", C.c_void_p), ("dyadic", C.c_int)]
 
 
+MAX_NEIGHBOURS = 8             # FEMB_MAX_NEIGHBOURS
+COMM_ID_BYTES = 128            # FEMB_COMM_ID_BYTES
+
+
+class FembHalo(C.Structure):
+    _fields_ = [("n_nb", C.c_int), ("nb", C.c_int * MAX_NEIGHBOURS), ("n_send", C.c_int * MAX_NEIGHBOURS),
+                ("n_recv", C.c_int * MAX_NEIGHBOURS), ("send_rows", C.c_void_p), ("recv_rows", C.c_void_p),
+                ("send_buf", C.c_void_p), ("recv_buf", C.c_void_p)]
+
+
 P = C.c_void_p
+HL = C.POINTER(FembHalo)
 LV = C.POINTER(FembLevel)
 TR = C.POINTER(FembTransfer)
 GP = C.POINTER(FembGalerkinPlan)
@@ -97,6 +108,11 @@ PROTOTYPES = {
     "femb_cloth_rest_length": [I, P, P, P, P],
     "femb_cloth_assemble": [I, I, P, P, F, P, P, F, P, F, P, P, P, P, P, P, P, P, P, P],
     "femb_cloth_update": [I, P, P, I, I, P],
+    "femb_comm_unique_id": [P],
+    "femb_comm_init": [C.POINTER(C.c_void_p), P, I, I],
+    "femb_comm_destroy": [P],
+    "femb_halo_exchange": [P, HL, P, I, P],
+    "femb_comm_allreduce": [P, P, I, I, P],
     "femb_axpby": [I, F, P, F, P, P],
     "femb_copy": [I, P, P, P],
     "femb_adam_update": [I, P, P, P, P, P, P, F, F, F, F, F, F, P],

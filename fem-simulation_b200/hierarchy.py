@@ -248,11 +248,14 @@ class MeshTooSmallError(ValueError, IndexError):
 
 
 def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers: int | None = None,
-                    corrected_spacing: bool = False) -> Hierarchy:
+                    corrected_spacing: bool = False, origin=None) -> Hierarchy:
     """object.py:116-697.  ``layers`` overrides the reference's level-count formula (benchmarks only).
     ``corrected_spacing`` (off by default = the reference's behaviour) fixes object.py:175-179, which coarsens every
     level >= 1 with spacing 2 dx so that levels >= 3 are copies of level 2: with it level l has spacing dx 2^l and the
-    hierarchy really gets coarser."""
+    hierarchy really gets coarser.
+    ``origin`` (default: the mesh's own bounding-box minimum, like the reference) is the lattice origin the colours and
+    the coarse cells are counted from; a slab of a partitioned mesh passes the GLOBAL minimum so that its colours and
+    coarse cells coincide with the global ones whatever plane it starts on (distributed.py)."""
     x0 = np.ascontiguousarray(points, dtype=F32)
     hex0 = np.ascontiguousarray(hexagons, dtype=np.int32)
     if x0.ndim != 2 or x0.shape[1] != 3 or hex0.ndim != 2 or hex0.shape[1] != 8:
@@ -266,6 +269,8 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
     box_min = np.minimum(x0.min(axis=0), F32(1000.0)).astype(F32)
     box_max = np.maximum(x0.max(axis=0), F32(-1000.0)).astype(F32)
     layer = level_count(box_min, box_max, dx) if layers is None else int(layers)
+    if origin is not None:
+        box_min = np.asarray(origin, dtype=F32).reshape(3)
     if layer < 1:
         raise MeshTooSmallError(f"level count {layer} < 1: the smallest bounding-box extent must be at least (about) 4 dx "
                                 f"(extent {float((box_max - box_min).min()):.6g}, dx {dx:.6g}; object.py:143)")

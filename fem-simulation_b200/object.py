@@ -60,7 +60,8 @@ def _dev(a, device):
 class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
                  control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False,
-                 pipe_chunk_hexes=2 * 740 * 16, corrected_hierarchy=False, fused_assembly=False, fused_chunks=0):
+                 pipe_chunk_hexes=2 * 740 * 16, corrected_hierarchy=False, fused_assembly=False, fused_chunks=0,
+                 lattice_origin=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.FembError("femb200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -79,7 +80,7 @@ class Object:
 
         points, hexagons = self._load_mesh(mesh_path, dx)
         self.N_verts, self.N_hexagons = int(points.shape[0]), int(hexagons.shape[0])
-        H = hierarchy.build_hierarchy(points, hexagons, dx, layers, corrected_spacing=corrected_hierarchy)
+        H = hierarchy.build_hierarchy(points, hexagons, dx, layers, corrected_spacing=corrected_hierarchy, origin=lattice_origin)
         self.hierarchy = H
         self.layer = H.layer
         self.dims = H.dims

@@ -263,6 +263,41 @@ int femb_cloth_assemble(int n_vert, int n_edge, const int* edge, const float* re
 /* the cloth's update_deltaX_kernel (cublas.py:22-26 there): x += dx except vertices skip0, skip1 (0 and 65) */
 int femb_cloth_update(int n_vert, const float* dx, float* x, int skip0, int skip1, void* stream);
 
+/* ---- multi-GPU: communicator, halo exchange, scalar all-reduce (csrc/femb_comm.cu) -------------------------------
+ * The reference is single-GPU (no NCCL / MPI call site anywhere); a mesh-partitioned caller of this ABI
+ * (fem-simulation_b200/distributed.py) needs exactly these.  One FembComm per rank = one NCCL communicator on the
+ * calling thread's current device; NCCL is loaded at femb_comm_init (dlopen("libnccl.so.2")), the library does not
+ * link against it.  All calls only enqueue on `stream` (graph-capturable once the communicator's connections exist,
+ * i.e. after one eager exchange with every neighbour). */
+#define FEMB_COMM_ID_BYTES 128          /* sizeof(ncclUniqueId) */
+#define FEMB_MAX_NEIGHBOURS 8
+#define FEMB_REDUCE_SUM 0
+#define FEMB_REDUCE_MAX 1
+typedef struct FembComm FembComm;
+/* Ghost-row exchange plan of one vector layout: for neighbour k (rank nb[k]) the rows this rank sends and the ghost
+ * rows it receives; the lists of all neighbours are concatenated in neighbour order.  Both sides order a message by
+ * the lattice position of its rows.  send_buf / recv_buf: device staging, (sum n_send) * width and (sum n_recv) * width
+ * floats. */
+typedef struct FembHalo {
+  int n_nb;
+  int nb[FEMB_MAX_NEIGHBOURS];
+  int n_send[FEMB_MAX_NEIGHBOURS];
+  int n_recv[FEMB_MAX_NEIGHBOURS];
+  const int* send_rows;
+  const int* recv_rows;
+  float* send_buf;
+  float* recv_buf;
+} FembHalo;
+/* id_host: FEMB_COMM_ID_BYTES bytes on the host; created on one rank, handed to the others by the caller (any channel) */
+int femb_comm_unique_id(unsigned char* id_host);
+int femb_comm_init(FembComm** comm, const unsigned char* id_host, int rank, int nranks);
+int femb_comm_destroy(FembComm* comm);
+/* vec[recv rows] <- the neighbours' vec[send rows]; vec is float[n * width] (width 3: a level vector, 1: a scalar field):
+ * pack kernel, one NCCL group of send / recv pairs, unpack kernel, all on `stream` */
+int femb_halo_exchange(FembComm* comm, const FembHalo* halo, float* vec, int width, void* stream);
+/* in-place all-reduce of n floats (batch the scalars of a step into one call): FEMB_REDUCE_SUM or FEMB_REDUCE_MAX */
+int femb_comm_allreduce(FembComm* comm, float* buf, int n, int op, void* stream);
+
 /* ---- vectors ------------------------------------------------------------------------------- */
 int femb_axpby(int n, float a, const float* x, float b, float* y, void* stream);          /* y = a x + b y (cublas.py:160-163) */
 int femb_copy(int n, const float* x, float* y, void* stream);

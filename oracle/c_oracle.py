@@ -35,23 +35,28 @@ class OrcPlan(C.Structure):
                 ("c_val", P)]
 
 
-class OrcCtx(C.Structure):
-    _fields_ = [("layers", C.c_int), ("lv", C.POINTER(OrcLevel)), ("Ut_hat", C.POINTER(OrcCsr)), ("Us_hat", C.POINTER(OrcCsr)),
-                ("Ut_noOrder", C.POINTER(OrcCsr)), ("Ut_noOrder_hat", C.POINTER(OrcCsr)), ("plan", C.POINTER(OrcPlan)),
-                ("x", P), ("grad", P), ("pin", P), ("pin_pos", P), ("diag_fixed", P), ("mu", C.c_float), ("la", C.c_float),
-                ("g", C.c_float), ("control_mag", C.c_float), ("spd_value", C.c_float), ("sfg", C.c_float * 192)]
+def _ctx_type(real):
+    class OrcCtx(C.Structure):
+        _fields_ = [("layers", C.c_int), ("lv", C.POINTER(OrcLevel)), ("Ut_hat", C.POINTER(OrcCsr)), ("Us_hat", C.POINTER(OrcCsr)),
+                    ("Ut_noOrder", C.POINTER(OrcCsr)), ("Ut_noOrder_hat", C.POINTER(OrcCsr)), ("plan", C.POINTER(OrcPlan)),
+                    ("x", P), ("grad", P), ("pin", P), ("pin_pos", P), ("diag_fixed", P), ("mu", real), ("la", real),
+                    ("g", real), ("control_mag", real), ("spd_value", real), ("sfg", real * 192)]
+    return OrcCtx
 
 
-_lib = None
+OrcCtx = _ctx_type(C.c_float)
+OrcCtx64 = _ctx_type(C.c_double)
+
+_libs = {}
 
 
-def load(native: bool = True):
-    """Compile (host-tuned when ``native``) and load the C oracle."""
-    global _lib
-    if _lib is not None:
-        return _lib
+def load(native: bool = True, double: bool = False):
+    """Compile (host-tuned when ``native``) and load the C oracle; ``double`` = the float64 twin (-DORC_DOUBLE)."""
+    key = (native, double)
+    if key in _libs:
+        return _libs[key]
     tag = "portable"
-    flags = "-O3 -fopenmp -fPIC -std=c11 -Wno-unknown-pragmas"
+    flags = "-O3 -fopenmp -fPIC -std=c11 -Wno-unknown-pragmas" + (" -DORC_DOUBLE" if double else "")
     if native:
         try:
             cpu = [l for l in open("/proc/cpuinfo") if l.startswith("flags")][0]
@@ -59,7 +64,7 @@ def load(native: bool = True):
             cpu = "unknown"
         tag = hashlib.md5(cpu.encode()).hexdigest()[:10]
         flags += " -march=native"
-    out = os.path.join(_DIR, "_build", f"libfemb_oracle_{tag}.so")
+    out = os.path.join(_DIR, "_build", f"libfemb_oracle_{tag}{'_f64' if double else ''}.so")
     src = os.path.join(_DIR, "femb_oracle.c")
     if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -67,8 +72,9 @@ def load(native: bool = True):
         subprocess.run([cc] + flags.split() + ["-shared", "-o", out, src, "-lm"], check=True)
     lib = C.CDLL(out)
     lib.orc_num_threads.restype = C.c_int
-    lib.orc_energy.restype = C.c_float
-    _lib = lib
+    lib.orc_energy.restype = C.c_double if double else C.c_float
+    lib.orc_inf_norm.restype = C.c_double if double else C.c_float
+    _libs[key] = lib
     return lib
 
 
@@ -92,10 +98,12 @@ class COracle:
     only), ``rest`` a oracle.ref_solvers.RefObject-like provider of det/inv/mass/x0/pins (numpy oracle)."""
 
     def __init__(self, H, plans, x0, det, inv, mass, pin, pin_pos, diag_fixed, mu=250.0, la=0.0, g=-4.9, control_mag=100.0,
-                 spd_value=1e-3, native=True):
-        self.lib = load(native)
+                 spd_value=1e-3, native=True, dtype=np.float32):
+        self.double = np.dtype(dtype) == np.float64
+        self.lib = load(native, self.double)
         self.keep = []
-        k = lambda a, dt: self._keep(np.ascontiguousarray(a, dtype=dt))
+        rt = np.float64 if self.double else np.float32
+        k = lambda a, dt: self._keep(np.ascontiguousarray(a, dtype=(rt if dt == np.float32 else dt)))
         L = H.layer
         self.L = L
         self.levels = (OrcLevel * L)()
@@ -113,12 +121,12 @@ class COracle:
             lv.elem2nnz = _p(k(p.hex_update_offset, np.int32))
             lv.invJ = _p(k(inv[l], np.float32)); lv.detJ = _p(k(det[l], np.float32)); lv.mass = _p(k(mass[l], np.float32))
             lv.vert_elem = _p(k(vertex_incidence(H.hexs[l], H.dims[l]), np.int32))
-            lv.elem_k = _p(self._keep(np.zeros(H.hexs[l].shape[0] * 576, np.float32)))
-            lv.elem_f = _p(self._keep(np.zeros(H.hexs[l].shape[0] * 24, np.float32)))
-            vals = self._keep(np.zeros((p.nnz, 3, 3), np.float32)); self.values.append(vals); lv.values = _p(vals)
+            lv.elem_k = _p(self._keep(np.zeros(H.hexs[l].shape[0] * 576, rt)))
+            lv.elem_f = _p(self._keep(np.zeros(H.hexs[l].shape[0] * 24, rt)))
+            vals = self._keep(np.zeros((p.nnz, 3, 3), rt)); self.values.append(vals); lv.values = _p(vals)
             vs = {}
             for nm in ("B", "B_fixed", "delta_x", "x_solved", "R"):
-                vs[nm] = self._keep(np.zeros((H.dims[l], 3), np.float32)); setattr(lv, nm, _p(vs[nm]))
+                vs[nm] = self._keep(np.zeros((H.dims[l], 3), rt)); setattr(lv, nm, _p(vs[nm]))
             self.vec.append(vs)
 
         def csr_array(lst):
@@ -137,11 +145,12 @@ class COracle:
             pl.t_nnz = len(g_["t_col"])
             pl.t_ptr = _p(k(g_["t_ptr"], np.int32)); pl.t_col = _p(k(g_["t_col"], np.int32))
             pl.c_ptr = _p(k(g_["c_ptr"], np.int32)); pl.c_col = _p(k(g_["c_col"], np.int32)); pl.c_slot = _p(k(g_["c_slot"], np.int32))
-            pl.t_val = _p(self._keep(np.zeros(pl.t_nnz * 9, np.float32)))
-            pl.c_val = _p(self._keep(np.zeros(len(g_["c_col"]) * 9, np.float32)))
-        self.x = self._keep(np.ascontiguousarray(x0, np.float32).copy())
+            pl.t_val = _p(self._keep(np.zeros(pl.t_nnz * 9, rt)))
+            pl.c_val = _p(self._keep(np.zeros(len(g_["c_col"]) * 9, rt)))
+        self.x = self._keep(np.ascontiguousarray(x0, rt).copy())
+        self.x0 = self.x.copy()
         self.grad = self._keep(np.zeros_like(self.x))
-        ctx = OrcCtx()
+        ctx = (OrcCtx64 if self.double else OrcCtx)()
         ctx.layers = L
         ctx.lv = C.cast(self.levels, C.POINTER(OrcLevel))
         ctx.Ut_hat = C.cast(self.Ut_hat, C.POINTER(OrcCsr)); ctx.Us_hat = C.cast(self.Us_hat, C.POINTER(OrcCsr))
@@ -150,7 +159,7 @@ class COracle:
         ctx.x, ctx.grad = _p(self.x), _p(self.grad)
         ctx.pin = _p(k(pin, np.int32)); ctx.pin_pos = _p(k(pin_pos, np.float32)); ctx.diag_fixed = _p(k(diag_fixed, np.float32))
         ctx.mu, ctx.la, ctx.g, ctx.control_mag, ctx.spd_value = mu, la, g, control_mag, spd_value
-        sfg = np.ascontiguousarray(H.shapeFuncGrad, np.float32).reshape(-1)
+        sfg = np.ascontiguousarray(H.shapeFuncGrad, np.float32).reshape(-1)      # the table is float32 in the reference (object.py:701-722)
         for i in range(192):
             ctx.sfg[i] = float(sfg[i])
         self.ctx = ctx
@@ -179,6 +188,33 @@ class COracle:
     def hessian_literal(self, level, x, values, diag_add=None):
         self.lib.orc_hessian_literal(C.byref(self.ctx), level, _p(x), _p(values), _p(diag_add) if diag_add is not None else None)
 
+    def fasv2_step(self):
+        self.lib.orc_fasv2_step(C.byref(self.ctx))
+
+    def compare_newton_step(self):
+        self.lib.orc_compare_newton_step(C.byref(self.ctx))
+
+    def inf_norm(self, v):
+        return float(self.lib.orc_inf_norm(_p(v), int(v.size)))
+
+    def compare(self, iterations=100):
+        """Object.compare (object.py:1514-1598) on the C oracle: returns dict(plot_x, energy_newton, lognorm_newton,
+        energy_fas, lognorm_fas); sampling `step % (iterations/100) == 0`, energy before the step, |f|inf of the force
+        evaluated at the start of the step."""
+        out = dict(plot_x=[], energy_newton=[], lognorm_newton=[], energy_fas=[], lognorm_fas=[])
+        for tag, fn in (("newton", self.compare_newton_step), ("fas", self.fasv2_step)):
+            self.x[...] = self.x0                                 # object.py:1546
+            for step in range(1, iterations + 1):
+                sampled = step % (iterations / 100) == 0
+                e = self.energy(self.x) if sampled else None
+                fn()
+                if sampled:
+                    if tag == "newton":
+                        out["plot_x"].append(step)
+                    out["energy_" + tag].append(e)
+                    out["lognorm_" + tag].append(float(np.log10(self.inf_norm(self.vec[0]["B_fixed"]))))
+        return out
+
     def set_threads(self, n):
         """Use n OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1)."""
         self.lib.orc_set_threads(int(n))
@@ -196,22 +232,22 @@ def from_ref(ref, H, plans, native=True):
 
 
 def from_hierarchy(H, plans, points, dx, pin_list=None, mu=250.0, la=0.0, g=-4.9, control_mag=100.0, spd_value=1e-3,
-                   native=True):
+                   native=True, dtype=np.float32):
     """COracle for meshes too large for the literal setup of oracle/ref_setup.py: integer maps come from the
     vectorised hierarchy (bit-exact with the literal one, tests/test_hierarchy.py), rest data from the numpy
     restatement of prepare_kernal / Sum_8 / prepare_mass (oracle/ref_kernels.py)."""
     from . import ref_kernels as K
-    x0 = np.ascontiguousarray(points, np.float32)
+    x0 = np.ascontiguousarray(points, np.float32).astype(dtype)
     xs = [x0]
     for l in range(1, H.layer):                               # object.py:730-731
         m = H.Ut_noOrder[l - 1]
-        y = np.zeros((m.nrow, 3), np.float32)
+        y = np.zeros((m.nrow, 3), dtype)
         np.add.at(y, m.rows(), m.weights[:, None] * xs[l - 1][m.columns])
         xs.append(y)
     det, inv, mass = [], [], []
     sfg = H.shapeFuncGrad
     for l in range(H.layer):                                  # object.py:756-759
-        d, iv = K.prepare_kernal(xs[l], H.hexs[l], sfg)
+        d, iv = K.prepare_kernal(xs[l], H.hexs[l], sfg, dtype=dtype)
         det.append(d); inv.append(iv)
         mass.append(K.prepare_mass(K.sum_8(d), H.hexs[l], H.dims[l]))
     if pin_list is None:
@@ -219,4 +255,4 @@ def from_hierarchy(H, plans, points, dx, pin_list=None, mu=250.0, la=0.0, g=-4.9
         pin_list = np.nonzero(y >= np.float32(np.float32(y.max() - np.float32(dx)) - np.float32(1e-5)))[0]
     pin = np.zeros(H.dims[0], np.int32); pin[pin_list] = 1
     diag = np.zeros(H.dims[0], np.float32); diag[H.vertex2index[0][pin_list]] = control_mag
-    return COracle(H, plans, x0, det, inv, mass, pin, x0, diag, mu, la, g, control_mag, spd_value, native)
+    return COracle(H, plans, x0, det, inv, mass, pin, x0, diag, mu, la, g, control_mag, spd_value, native, dtype)

@@ -3,8 +3,9 @@
 CPU (gloo, world_size 2): slab bookkeeping and halo plans -- every global vertex has exactly one owner, the send /
 recv lists of neighbouring ranks match entry by entry (fine and coarse level, vertex and index ordering), the local
 colouring / coarse cells coincide with the global ones.
-GPU (``-m gpu``, needs >= 2 GPUs, NCCL): the distributed FASv3 step reproduces the single-GPU step up to summation-order
-round-off (the local coarse numbering orders the <= 8 parents of a fine vertex differently in the prolongation sum)."""
+GPU (``-m gpu``, needs >= 2 GPUs, NCCL): the distributed FASv3 and Newton-multigrid steps reproduce the single-GPU steps
+up to summation-order round-off (the local coarse numbering orders the <= 8 parents of a fine vertex differently in the
+prolongation sum)."""
 import os
 import socket
 
@@ -30,56 +31,55 @@ def _init(rank, world, port, backend):
     dist.init_process_group(backend, rank=rank, world_size=world)
 
 
-def _cpu_worker(rank, world, port, out, nz):
+def _cpu_worker(rank, world, port, out, nz, layers):
     _init(rank, world, port, "gloo")
     try:
-        z0, z1, clo, chi = D.slab_planes(nz, world, rank)
+        align = D.hierarchy_align(layers)
+        cuts = D.slab_cuts(nz, world, align)
+        z0, z1, clo, chi = D.slab_planes(nz, world, rank, align)
         pts, hx = mesh.box_mesh(NX, NY, chi - clo, DX, index_offset=(0, 0, clo))
-        H = hierarchy.build_hierarchy(pts, hx, DX, layers=2)
+        H = hierarchy.build_hierarchy(pts, hx, DX, layers=layers, origin=(0.0, 0.0, 0.0))
         gpts, ghx = mesh.box_mesh(NX, NY, nz, DX)
-        G = hierarchy.build_hierarchy(gpts, ghx, DX, layers=2)
+        G = hierarchy.build_hierarchy(gpts, ghx, DX, layers=layers)
         ps = (NX + 1) * (NY + 1)
         off = ps * clo
         # local slab == slice of the global mesh: coordinates bit-identical, colours identical
         assert np.array_equal(pts, gpts[off:off + len(pts)])
-        col = lambda Hh: np.searchsorted(np.asarray(Hh.color_vertex_num[0]), Hh.vertex2index[0], side="right") - 1
-        assert np.array_equal(col(H), col(G)[off:off + len(pts)])
-        fv, fi, cv, ci = D.build_halo_plans(NX, NY, z0, z1, clo, chi, nz, rank, world, H.x[1], H.vertex2index[1],
-                                            H.vertex2index[0], DX, torch.device("cpu"))
-        # fine level, vertex order: payload = global vertex id
-        gid = torch.arange(len(pts), dtype=torch.float32) + off
-        gz = np.arange(len(pts)) // ps + clo
-        owned = (gz >= z0) & ((gz < z1) | ((gz == nz) & (rank == world - 1)))
-        v = torch.stack([gid, gid * 2, gid * 3], dim=1)
-        v[torch.from_numpy(~owned)] = -1.0
-        D.exchange(v, fv)
-        assert torch.equal(v[:, 0], gid), "fine ghosts (vertex order)"
-        # fine level, index order
-        v2i = torch.from_numpy(H.vertex2index[0]).long()
-        w = torch.full((len(pts), 3), -1.0)
-        w[v2i[torch.from_numpy(owned)]] = torch.stack([gid, gid, gid], dim=1)[torch.from_numpy(owned)]
-        D.exchange(w, fi)
-        assert torch.equal(w[v2i, 0], gid), "fine ghosts (index order)"
-        # coarse level: payload = global coarse lattice key
-        cx = H.x[1]
-        key = np.rint(cx / np.float32(2 * DX)).astype(np.int64)
-        gkey = torch.from_numpy((key[:, 0] + 100 * key[:, 1] + 10000 * key[:, 2]).astype(np.float32))
-        cgz = np.rint(cx[:, 2] / np.float32(DX)).astype(np.int64)
-        cown = (cgz >= z0) & ((cgz < z1) | ((cgz == nz) & (rank == world - 1)))
-        c = torch.stack([gkey, gkey, gkey], dim=1).clone()
-        c[torch.from_numpy(~cown)] = -1.0
-        D.exchange(c, cv)
-        assert torch.equal(c[:, 0], gkey), "coarse ghosts (vertex order)"
-        cv2i = torch.from_numpy(H.vertex2index[1]).long()
-        ci_vec = torch.full((len(cx), 3), -1.0)
-        ci_vec[cv2i[torch.from_numpy(cown)]] = torch.stack([gkey, gkey, gkey], dim=1)[torch.from_numpy(cown)]
-        D.exchange(ci_vec, ci)
-        assert torch.equal(ci_vec[cv2i, 0], gkey), "coarse ghosts (index order)"
-        # ownership is a partition of the global vertex set
-        cnt = torch.zeros(len(gpts))
-        cnt[off:off + len(pts)][torch.from_numpy(owned)] = 1
-        dist.all_reduce(cnt)
-        assert torch.all(cnt == 1)
+        col = lambda Hh, l: np.searchsorted(np.asarray(Hh.color_vertex_num[l]), Hh.vertex2index[l], side="right") - 1
+        assert np.array_equal(col(H, 0), col(G, 0)[off:off + len(pts)])
+        plans = D.build_level_plans(H, DX, z0, z1, cuts, rank, world, align)
+        n_owned_levels = []
+        for l in range(H.layer):
+            pv, pi, owned = plans[l]
+            ijk = D.level_planes(H.x[l], DX)
+            stride = int(round(H.spacing[l] / DX))
+            # the local level is the matching slice of the global level: same lattice points, same colours
+            gijk = D.level_planes(G.x[l], DX)
+            gkey = {tuple(k): i for i, k in enumerate(gijk.tolist())}
+            gid_np = np.array([gkey[tuple(k)] for k in ijk.tolist()])
+            assert np.array_equal(col(H, l), col(G, l)[gid_np]), f"level {l} colours"
+            gid = torch.from_numpy(gid_np.astype(np.float32))
+            # vertex order: payload = global id of the lattice point at this level; every ghost row a local owned row reads
+            # (one level plane below the slab -- all overlap planes on level 0 -- and the plane above) must end up current
+            v = torch.stack([gid, gid * 2, gid * 3], dim=1)
+            v[torch.from_numpy(~owned)] = -1.0
+            D.exchange(v, pv)
+            span = align if l == 0 else stride
+            need = ((ijk[:, 2] >= z0 - span) & (ijk[:, 2] <= z1)) if rank < world - 1 else (ijk[:, 2] >= z0 - span)
+            need_t = torch.from_numpy(need)
+            assert torch.equal(v[need_t, 0], gid[need_t]), f"level {l} ghosts (vertex order)"
+            v2i = torch.from_numpy(H.vertex2index[l]).long()
+            w = torch.full((len(gid), 3), -1.0)
+            own_t = torch.from_numpy(owned)
+            w[v2i[own_t]] = torch.stack([gid, gid, gid], dim=1)[own_t]
+            D.exchange(w, pi)
+            assert torch.equal(w[v2i[need_t], 0], gid[need_t]), f"level {l} ghosts (index order)"
+            # ownership is a partition of the global level
+            cnt = torch.zeros(len(gijk))
+            cnt[torch.from_numpy(gid_np[owned])] = 1
+            dist.all_reduce(cnt)
+            assert torch.all(cnt == 1), f"level {l} ownership"
+            n_owned_levels.append(int(owned.sum()))
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         out.put((rank, repr(e)))
@@ -88,14 +88,15 @@ def _cpu_worker(rank, world, port, out, nz):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nz", [(2, NZ), (4, NZ), (8, 2 * NZ)])
-def test_halo_plans_gloo(world, nz):
+@pytest.mark.parametrize("world,nz,layers", [(2, NZ, 2), (4, NZ, 2), (8, 2 * NZ, 2), (2, 16, 3), (3, 28, 4)])
+def test_halo_plans_gloo(world, nz, layers):
     """world 4 and 8 (2 cell layers per rank) add interior ranks, which talk to both neighbours; 8 is the size of the
-    round-end scaling run."""
+    round-end scaling run; layers 3 / 4 are the Newton-multigrid decomposition (cuts on multiples of 4 planes, overlap 4,
+    per-level ghost planes; 28 planes over 3 ranks: uneven slabs 12 / 8 / 8)."""
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, out, nz)) for r in range(world)]
+    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, out, nz, layers)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -107,17 +108,24 @@ def test_halo_plans_gloo(world, nz):
 def test_slab_planes_validation():
     assert D.slab_planes(8, 2, 0) == (0, 4, 0, 4) and D.slab_planes(8, 2, 1) == (4, 8, 2, 8)
     with pytest.raises(ValueError):
-        D.slab_planes(9, 2, 0)
+        D.slab_planes(9, 2, 0)             # not a multiple of the cut alignment
+    assert D.slab_cuts(12, 4, 2) == [0, 4, 8, 10, 12]                # uneven slabs are fine
+    # the metric's 10 M cube on 8 ranks: cuts on multiples of 4 planes, six slabs of 28 and two of 24
+    cuts = D.slab_cuts(216, 8, D.hierarchy_align(6))
+    assert cuts[0] == 0 and cuts[-1] == 216 and all(c % 4 == 0 for c in cuts)
+    assert sorted(set(np.diff(cuts).tolist())) == [24, 28]
+    assert D.slab_planes(216, 8, 3, 4) == (84, 112, 80, 112)
     with pytest.raises(ValueError):
-        D.slab_planes(12, 4, 0)            # 3 planes per rank: odd
+        D.slab_cuts(8, 4, 4)               # fewer aligned groups than ranks
 
 
-def _gpu_worker(rank, world, port, steps, out):
+def _gpu_worker(rank, world, port, steps, out, method, layers, comm, graphs):
     torch.cuda.set_device(rank)
     _init(rank, world, port, "nccl")
     try:
-        so = D.SlabObject(12, 10, 16, DX, device=f"cuda:{rank}")      # 16 cell layers: 8 per rank at world 2, 4 at world 4
-        so.FASv3(steps)
+        so = D.SlabObject(12, 10, 32, DX, device=f"cuda:{rank}", layers=layers, comm=comm, graph_segments=graphs)
+        for _ in range(steps):
+            so.fasv3_step() if method == "fasv3" else so.nmg_step()
         ids, xs = so.owned_positions()
         out.put((rank, ids.cpu().numpy(), xs.cpu().numpy(), so.force_inf_norm()))
         dist.barrier()
@@ -126,14 +134,18 @@ def _gpu_worker(rank, world, port, steps, out):
 
 
 @pytest.mark.gpu
-def test_distributed_fasv3_matches_single_gpu():
+@pytest.mark.parametrize("method,layers,comm,graphs", [("fasv3", 2, "auto", True), ("nmg", 3, "auto", True), ("nmg", 4, "torch", False),
+                                                       ("fasv3", 2, "torch", True)])
+def test_distributed_step_matches_single_gpu(method, layers, comm, graphs):
+    """The mesh-partitioned FASv3 / Newton-multigrid step (C-ABI NCCL exchanges inside one CUDA graph per rank, or the
+    torch.distributed exchange between segment graphs) vs the single-GPU step on the same global mesh."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from fem_simulation_b200 import Object
-    steps = 3
-    pts, hx = mesh.box_mesh(12, 10, 16, DX)
-    ref = Object((pts, hx), DX, [], layers=2, use_graphs=False)
-    ref.FASv3(steps)
+    steps = 4
+    pts, hx = mesh.box_mesh(12, 10, 32, DX)
+    ref = Object((pts, hx), DX, [], layers=layers, use_graphs=False)
+    ref.FASv3(steps) if method == "fasv3" else ref.NewtonMultigrid(steps)
     xref = ref.x_gpu_layer[0].cpu().numpy()
     ref._force(ref.x_gpu_layer[0], ref.grad_gpu)
     fref = float(ref.grad_gpu.abs().max())
@@ -141,16 +153,26 @@ def test_distributed_fasv3_matches_single_gpu():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, steps, out)) for r in range(world)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, steps, out, method, layers, comm, graphs)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [out.get(timeout=600) for _ in range(world)]
+    import queue
+    import time
+    res, t_end = [], time.time() + 240
+    while len(res) < world:                                          # a crashed rank must not stall the test for minutes
+        try:
+            res.append(out.get(timeout=2))
+        except queue.Empty:
+            if time.time() > t_end or any(p.exitcode not in (None, 0) for p in procs):
+                for p in procs:
+                    p.kill()
+                pytest.fail(f"ranks exited {[p.exitcode for p in procs]} with {len(res)} of {world} results")
     for p in procs:
         p.join(60)
     x = np.full_like(xref, np.nan)
     for rank, ids, xs, fn in res:
         x[ids] = xs
-        assert abs(fn - fref) <= 1e-6 * fref
+        assert abs(fn - fref) <= 1e-5 * fref
     assert not np.isnan(x).any()
     assert np.abs(x - xref).max() <= 1e-6 * np.abs(xref).max(), f"max diff {np.abs(x - xref).max():.3e}"
     disp = xref - pts
