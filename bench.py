@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=100, help="voxels per cube edge (100 -> 1 M hexahedra)")
+    ap.add_argument("--n", "--edge", dest="n", type=int, default=100,
+                    help="voxels per cube edge (100 -> 1 M hexahedra); use the spelling --edge under torchrun (its parser claims --n)")
     ap.add_argument("--method", default="fasv3", choices=["nmg", "fasv3"],
                     help="fasv3 (BASELINE configs[4], the mesh-partitioned series) or nmg (Newton-multigrid, the north-star target)")
     ap.add_argument("--strong", action="store_true",

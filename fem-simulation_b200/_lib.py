@@ -12,9 +12,9 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libfemb200.so")
-SOURCES = ["femb_api.cu", "femb_element.cu", "femb_fused.cu", "femb_comm.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
+SOURCES = ["femb_api.cu", "femb_element.cu", "femb_fused.cu", "femb_comm.cu", "femb_steps.cu", "femb_setup.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-ldl", "-lgomp"]
 
 PART_L, PART_D, PART_U, PART_ALL = 1, 2, 4, 7
 
@@ -63,8 +63,39 @@ class FembHalo(C.Structure):
                 ("send_buf", C.c_void_p), ("recv_buf", C.c_void_p)]
 
 
+class FembContext(C.Structure):
+    _fields_ = [("layers", C.c_int), ("levels", C.c_void_p), ("Ut_hat", C.c_void_p), ("Us_hat", C.c_void_p),
+                ("Ut_noOrder", C.c_void_p), ("Ut_noOrder_hat", C.c_void_p), ("plans", C.c_void_p),
+                ("values", C.c_void_p), ("t_values", C.c_void_p), ("B", C.c_void_p), ("B_fixed", C.c_void_p),
+                ("delta_x", C.c_void_p), ("x_solved", C.c_void_p), ("R", C.c_void_p),
+                ("x", C.c_void_p), ("grad", C.c_void_p), ("diag_fixed", C.c_void_p), ("mass0", C.c_void_p),
+                ("pin", C.c_void_p), ("pin_pos", C.c_void_p), ("elem_f", C.c_void_p), ("elem_k", C.c_void_p),
+                ("not_spd", C.c_void_p),
+                ("mu", C.c_float), ("la", C.c_float), ("g", C.c_float), ("control_mag", C.c_float), ("spd_value", C.c_float),
+                ("spd_level0", C.c_int)]
+
+
+class FembDynamic(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("v", C.c_void_p), ("old_x", C.c_void_p), ("inertia_x", C.c_void_p),
+                ("more_fixed", C.c_void_p), ("diag_dyn", C.c_void_p), ("cg_p", C.c_void_p), ("cg_ap", C.c_void_p),
+                ("cg_state", C.c_void_p), ("dir_host", C.c_void_p),
+                ("dt", C.c_float), ("inv_dt", C.c_float), ("damping", C.c_float)]
+
+
+class FembCloth(C.Structure):
+    _fields_ = [("level", C.c_void_p), ("n_edge", C.c_int), ("edge", C.c_void_p), ("rest", C.c_void_p), ("mass", C.c_void_p),
+                ("inc_ptr", C.c_void_p), ("inc", C.c_void_p), ("off_p0p1", C.c_void_p), ("off_p1p0", C.c_void_p),
+                ("d_slot", C.c_void_p), ("zeros_i", C.c_void_p),
+                ("x", C.c_void_p), ("v", C.c_void_p), ("old_x", C.c_void_p), ("inertia_x", C.c_void_p),
+                ("values", C.c_void_p), ("grad", C.c_void_p), ("B", C.c_void_p), ("B_fixed", C.c_void_p),
+                ("delta_x", C.c_void_p), ("cg_p", C.c_void_p), ("cg_ap", C.c_void_p), ("cg_state", C.c_void_p),
+                ("edge_h", C.c_void_p), ("edge_g", C.c_void_p),
+                ("k", C.c_float), ("g", C.c_float), ("dt", C.c_float), ("inv_dt", C.c_float), ("damping", C.c_float)]
+
+
 P = C.c_void_p
 HL = C.POINTER(FembHalo)
+CX = C.POINTER(FembContext)
 LV = C.POINTER(FembLevel)
 TR = C.POINTER(FembTransfer)
 GP = C.POINTER(FembGalerkinPlan)
@@ -76,6 +107,11 @@ PROTOTYPES = {
     "femb_last_error": [],
     "femb_launch_count": [],
     "femb_check_device": [I],
+    "femb_setup_incidence_host": [I, I, P, P],
+    "femb_setup_pattern_count_host": [I, P, P, P, P, P, P],
+    "femb_setup_pattern_fill_host": [I, I, P, P, P, P, P, P, P, P, P, P],
+    "femb_setup_galerkin_count_host": [I, P, P, P, P, P, P, P],
+    "femb_setup_galerkin_fill_host": [I, I] + [P] * 22,
     "femb_prepare_rest": [I, P, P, P, P, P],
     "femb_build_fold_plan": [LV, P, P],
     "femb_build_lattice_plan": [LV, P, P, P, P],
@@ -108,6 +144,12 @@ PROTOTYPES = {
     "femb_cloth_rest_length": [I, P, P, P, P],
     "femb_cloth_assemble": [I, I, P, P, F, P, P, F, P, F, P, P, P, P, P, P, P, P, P, P],
     "femb_cloth_update": [I, P, P, I, I, P],
+    "femb_vcycle": [CX, I, P],
+    "femb_galerkin_chain": [CX, P],
+    "femb_newton_mg_step": [CX, P],
+    "femb_fas_step": [CX, I, P, P],
+    "femb_dynamic_step": [CX, C.POINTER(FembDynamic), P],
+    "femb_cloth_step": [C.POINTER(FembCloth), P],
     "femb_comm_unique_id": [P],
     "femb_comm_init": [C.POINTER(C.c_void_p), P, I, I],
     "femb_comm_destroy": [P],

@@ -17,7 +17,7 @@ from . import _lib
 
 
 class Cloth:
-    def __init__(self, *, res_x=64, res_y=64, device="cuda:0", use_graphs=True):
+    def __init__(self, *, res_x=64, res_y=64, device="cuda:0", use_graphs=True, use_c_steps=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.FembError("femb200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -25,6 +25,7 @@ class Cloth:
         _lib.check(self.lib.femb_check_device(self.device.index or 0), "femb_check_device")
         torch.cuda.set_device(self.device)
         self.use_graphs = use_graphs
+        self.use_c_steps = use_c_steps        # a frame as ONE C-ABI call (femb_cloth_step)
         self._graph = None
         self.layer = 1
         self.control_mag, self.spd_value = 10.0, 1e-3
@@ -91,7 +92,29 @@ class Cloth:
         """Block values in the reference's (row,col)-sorted order (object.py:129-158 there)."""
         return self._values[self._slot_of_sorted]
 
+    def _cloth_struct(self):
+        a = self._arrs
+        k = _lib.FembCloth()
+        k.level = C.cast(C.pointer(self.level), C.c_void_p)
+        k.n_edge = self.N_edge
+        k.edge, k.rest, k.mass = self.edge_gpu.data_ptr(), self.rest_length.data_ptr(), self.m_gpu.data_ptr()
+        k.inc_ptr, k.inc = a["inc_ptr"].data_ptr(), a["inc"].data_ptr()
+        k.off_p0p1, k.off_p1p0, k.d_slot = a["off01"].data_ptr(), a["off10"].data_ptr(), a["dslot"].data_ptr()
+        k.zeros_i = self._zeros_i.data_ptr()
+        k.x, k.v, k.old_x, k.inertia_x = (t.data_ptr() for t in (self.dev_x, self.dev_v, self.dev_old_x, self.dev_inertia_x))
+        k.values, k.grad = self._values.data_ptr(), self.grad_gpu.data_ptr()
+        k.B, k.B_fixed, k.delta_x = self.dev_B.data_ptr(), self.dev_B_fixed.data_ptr(), self.dev_delta_x.data_ptr()
+        k.cg_p, k.cg_ap, k.cg_state = self.dev_P.data_ptr(), self.dev_AP.data_ptr(), self._cg_state.data_ptr()
+        k.edge_h, k.edge_g = self._edge_h.data_ptr(), self._edge_g.data_ptr()
+        k.k, k.g, k.dt, k.inv_dt, k.damping = self.k, self.g, self.dt, self.inv_dt, self.damping
+        return k
+
     def _frame_body(self):
+        if self.use_c_steps:
+            if getattr(self, "_cloth", None) is None:
+                self._cloth = self._cloth_struct()
+            _lib.check(self.lib.femb_cloth_step(C.byref(self._cloth), self._stream()), "femb_cloth_step")
+            return
         st, a = self._stream, self._arrs
         n = self.N_verts
         x = self.dev_x

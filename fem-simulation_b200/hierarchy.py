@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -204,8 +206,59 @@ def level_count(box_min, box_max, dx) -> int:
     return int(mb.int() - 1)
 
 
-def build_pattern(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int) -> LevelPattern:
-    """object.py:485-697 for one level."""
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def vertex_incidence(hexagons: np.ndarray, n: int) -> np.ndarray:
+    """[n, 8] int32: e*8+a of the hexahedra incident to every vertex in ascending order, -1 padded (femb_setup_incidence_host)."""
+    from . import _lib
+    lib = _lib.load()
+    hx = np.ascontiguousarray(hexagons, dtype=np.int32)
+    ve = np.empty((n, 8), dtype=np.int32)
+    _lib.check(lib.femb_setup_incidence_host(n, hx.shape[0], _hp(hx), _hp(ve)), "femb_setup_incidence_host")
+    return ve
+
+
+def build_pattern(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int, vert_elem: np.ndarray | None = None) -> LevelPattern:
+    """object.py:485-697 for one level, through the host routines of the C ABI (csrc/femb_setup.cu: per-row sorted unions
+    instead of one global sort); `build_pattern_numpy` is the numpy restatement the tests compare it with."""
+    from . import _lib
+    lib = _lib.load()
+    hx = np.ascontiguousarray(hexagons, dtype=np.int32)
+    v2i = np.ascontiguousarray(v2i, dtype=np.int32)
+    i2v = np.empty_like(v2i)
+    i2v[v2i] = np.arange(n, dtype=np.int32)
+    ve = vertex_incidence(hx, n) if vert_elem is None else vert_elem
+    L_ptr, U_ptr = np.empty(n + 1, np.int32), np.empty(n + 1, np.int32)
+    _lib.check(lib.femb_setup_pattern_count_host(n, _hp(hx), _hp(v2i), _hp(i2v), _hp(ve), _hp(L_ptr), _hp(U_ptr)),
+               "femb_setup_pattern_count_host")
+    L_nnz = int(L_ptr[n])
+    assert int(U_ptr[n]) == L_nnz
+    nnz = 2 * L_nnz + n
+    L_col, U_col = np.empty(L_nnz, np.int32), np.empty(L_nnz, np.int32)
+    e2n = np.empty(hx.shape[0] * 64, np.int32)
+    block_offset = np.empty(nnz, np.int32)
+    _lib.check(lib.femb_setup_pattern_fill_host(n, hx.shape[0], _hp(hx), _hp(v2i), _hp(i2v), _hp(ve), _hp(L_ptr), _hp(U_ptr), _hp(L_col),
+                                                _hp(U_col), _hp(e2n), _hp(block_offset)), "femb_setup_pattern_fill_host")
+    rows = np.arange(n, dtype=np.int32)
+    L_row, U_row = np.repeat(rows, np.diff(L_ptr)), np.repeat(rows, np.diff(U_ptr))
+    cv = np.asarray(cvn, dtype=np.int64)
+    row_colour = (np.searchsorted(cv, rows, side="right") - 1).astype(np.int64)
+    colU, colL = np.repeat(row_colour, np.diff(U_ptr)), np.repeat(row_colour, np.diff(L_ptr))
+    GS_U_row = (U_row - cv[colU]).astype(np.int32)
+    GS_U_col = (U_col - cv[colU + 1]).astype(np.int32)
+    GS_L_row = (L_row - cv[colL]).astype(np.int32)
+    GS_U_Ptr = [int(U_ptr[min(cv[p], n)]) for p in range(8)] + [0]
+    GS_L_Ptr = [int(L_ptr[min(cv[p + 1], n)]) for p in range(8)] + [0]
+    return LevelPattern(n=n, nnz=nnz, L_nnz=L_nnz, off_l=0, off_d=L_nnz, off_u=L_nnz + n,
+                        L_row=L_row, L_col=L_col, U_row=U_row, U_col=U_col, L_ptr=L_ptr, U_ptr=U_ptr,
+                        GS_L_row=GS_L_row, GS_L_col=L_col.copy(), GS_U_row=GS_U_row, GS_U_col=GS_U_col,
+                        GS_L_Ptr=GS_L_Ptr, GS_U_Ptr=GS_U_Ptr, block_offset=block_offset, hex_update_offset=e2n)
+
+
+def build_pattern_numpy(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int) -> LevelPattern:
+    """object.py:485-697 for one level (numpy restatement: one global sort of the 64 n_hex (row, col) keys)."""
     ih = v2i[hexagons].astype(np.int64)                                   # [Nh,8] index-order ids
     keys = (ih[:, :, None] * np.int64(n) + ih[:, None, :]).reshape(-1)    # (r,c) for e,j,k
     uniq, inv = np.unique(keys, return_inverse=True)
@@ -429,7 +482,39 @@ def default_pins(points: np.ndarray, dx: float) -> np.ndarray:
 
 
 def build_galerkin_plan(H: Hierarchy, l: int) -> dict:
-    """Fixed patterns and slot plans of the Galerkin product A_{l+1} = Ut_hat[l] (A_l Us_hat[l]).
+    """Fixed patterns and slot plans of the Galerkin product A_{l+1} = Ut_hat[l] (A_l Us_hat[l]) through the host routines of
+    the C ABI (csrc/femb_setup.cu); same arrays as `build_galerkin_plan_numpy` (tests/test_hierarchy.py)."""
+    from . import _lib
+    lib = _lib.load()
+    p, pc = H.pattern[l], H.pattern[l + 1]
+    nf, nc = H.dims[l], H.dims[l + 1]
+    us, ut = H.Us_hat[l], H.Ut_hat[l]
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    fL_ptr, fL_col, fU_ptr, fU_col = i32(p.L_ptr), i32(p.L_col), i32(p.U_ptr), i32(p.U_col)
+    cL_ptr, cL_col, cU_ptr, cU_col = i32(pc.L_ptr), i32(pc.L_col), i32(pc.U_ptr), i32(pc.U_col)
+    us_off, us_col, us_w = i32(us.offsets), i32(us.columns), np.ascontiguousarray(us.weights, dtype=np.float32)
+    ut_off, ut_col = i32(ut.offsets), i32(ut.columns)
+    t_ptr = np.empty(nf + 1, np.int32)
+    _lib.check(lib.femb_setup_galerkin_count_host(nf, _hp(fL_ptr), _hp(fL_col), _hp(fU_ptr), _hp(fU_col), _hp(us_off), _hp(us_col),
+                                                  _hp(t_ptr)), "femb_setup_galerkin_count_host")
+    t_nnz = int(t_ptr[nf])
+    t_col = np.empty(t_nnz, np.int32)
+    c_ptr = np.empty(nc + 1, np.int32)
+    c_col, c_slot = np.empty(pc.nnz, np.int32), np.empty(pc.nnz, np.int32)
+    t_slot = np.empty((p.nnz, 8), np.uint8)
+    c_slot8 = np.empty((t_nnz, 8), np.uint8)
+    ut_q = np.empty(ut.nnz, np.uint8)
+    dyadic = C.c_int(0)
+    _lib.check(lib.femb_setup_galerkin_fill_host(nf, nc, _hp(fL_ptr), _hp(fL_col), _hp(fU_ptr), _hp(fU_col), _hp(cL_ptr), _hp(cL_col),
+                                                 _hp(cU_ptr), _hp(cU_col), _hp(us_off), _hp(us_col), _hp(us_w), _hp(ut_off), _hp(ut_col),
+                                                 _hp(t_ptr), _hp(t_col), _hp(c_ptr), _hp(c_col), _hp(c_slot), _hp(t_slot), _hp(c_slot8),
+                                                 _hp(ut_q), C.cast(C.byref(dyadic), C.c_void_p)), "femb_setup_galerkin_fill_host")
+    return dict(n_fine=nf, n_coarse=nc, t_ptr=t_ptr, t_col=t_col, c_ptr=c_ptr, c_col=c_col, c_slot=c_slot, t_slot=t_slot,
+                c_slot8=c_slot8, ut_q=ut_q, dyadic=bool(dyadic.value))
+
+
+def build_galerkin_plan_numpy(H: Hierarchy, l: int) -> dict:
+    """Fixed patterns and slot plans of the Galerkin product A_{l+1} = Ut_hat[l] (A_l Us_hat[l]) (numpy / scipy restatement).
 
     Replaces the symbolic half of ``bsr_mm`` (sparse.py:1018-1091), which the reference repeats every step
     (object.py:1259).  Returns numpy arrays:

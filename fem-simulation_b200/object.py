@@ -61,7 +61,7 @@ class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
                  control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False,
                  pipe_chunk_hexes=2 * 740 * 16, corrected_hierarchy=False, fused_assembly=False, fused_chunks=0,
-                 lattice_origin=None):
+                 lattice_origin=None, use_c_steps=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.FembError("femb200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -70,6 +70,7 @@ class Object:
         torch.cuda.set_device(self.device)
         self.verbose = verbose
         self.use_graphs = use_graphs
+        self.use_c_steps = use_c_steps        # step bodies as ONE C-ABI call (femb_newton_mg_step / femb_fas_step) instead of ~25
         self._graphs = {}
         # object.py:23-25, 743-748
         self.control_mag = float(control_mag)
@@ -104,13 +105,7 @@ class Object:
         for l in range(L):
             p = H.pattern[l]
             n, nh = H.dims[l], H.hexs[l].shape[0]
-            ve = np.full((n, 8), -1, dtype=np.int32)
-            flat = H.hexs[l].reshape(-1).astype(np.int64)
-            o2 = np.argsort(flat, kind="stable")
-            cnt = np.bincount(flat, minlength=n)
-            assert cnt.max(initial=0) <= 8, "a vertex belongs to more than 8 hexahedra"
-            start = np.cumsum(cnt) - cnt
-            ve[flat[o2], np.arange(len(o2)) - start[flat[o2]]] = o2.astype(np.int32)      # e*8+a
+            ve = hierarchy.vertex_incidence(H.hexs[l], n)                # e*8+a of the incident hexahedra, -1 padded
             ap = self._pipe_plan(nh, ve, pipe_chunk_hexes)
             pad = np.zeros(4, np.int32)                                  # bulk copies are rounded out to 16 bytes
             d = dict(L_ptr=_dev(p.L_ptr, dev), L_col=_dev(np.concatenate([p.L_col, pad]), dev)[:p.L_nnz],
@@ -216,6 +211,7 @@ class Object:
         self.A = [self._part_view(l, "A") for l in range(L)]
         self._plans = [None] * (L - 1)             # Galerkin plans are built on first use (FAS-only runs never need them)
 
+        self._build_context()
         self.plot_x, self.plot_y, self.plot_InfNorm, self.plot_energy = [], [], [], []
         self.plot_InfNorm_newton, self.plot_energy_newton = [], []
         self.plot_InfNorm_newtonMultigrid, self.plot_energy_newtonMultigrid = [], []
@@ -260,6 +256,45 @@ class Object:
             return
         lv.lat_cell_elem = d["lat_cell_elem"].data_ptr()
         lv.lat_row_rec = d["lat_row_rec"].data_ptr()
+
+    def _build_context(self):
+        """FembContext (include/femb200.h): the arrays of this object as one host struct for the whole-step entry points."""
+        L = self.layer
+        P = C.c_void_p
+        k = self._ctx_keep = {}
+        k["levels"] = (_lib.FembLevel * L)(*self.levels)
+        for name in ("Ut_hat", "Us_hat", "Ut_noOrder", "Ut_noOrder_hat"):
+            k[name] = (_lib.FembTransfer * max(L - 1, 1))(*[m.c for m in getattr(self, name)])
+        k["plans"] = (_lib.FembGalerkinPlan * max(L - 1, 1))()
+        k["t_values"] = (P * max(L - 1, 1))()
+        ptrs = lambda ts: (P * L)(*[t.data_ptr() for t in ts])
+        k["values"] = ptrs([self._values(l) for l in range(L)])
+        for name, ts in (("B", self.dev_B), ("B_fixed", self.dev_B_fixed), ("delta_x", self.dev_delta_x),
+                         ("x_solved", self.dev_x_solved), ("R", self.dev_R)):
+            k[name] = ptrs(ts)
+        c = _lib.FembContext()
+        c.layers = L
+        addr = lambda a: C.cast(a, P)
+        c.levels = addr(k["levels"])
+        c.Ut_hat, c.Us_hat = addr(k["Ut_hat"]), addr(k["Us_hat"])
+        c.Ut_noOrder, c.Ut_noOrder_hat = addr(k["Ut_noOrder"]), addr(k["Ut_noOrder_hat"])
+        c.plans, c.t_values = addr(k["plans"]), addr(k["t_values"])
+        for name in ("values", "B", "B_fixed", "delta_x", "x_solved", "R"):
+            setattr(c, name, addr(k[name]))
+        c.x, c.grad = self.x_gpu_layer[0].data_ptr(), self.grad_gpu.data_ptr()
+        c.diag_fixed, c.mass0 = self.diag_fixed.data_ptr(), self.m_gpu[0].data_ptr()
+        c.pin, c.pin_pos = self.pin_gpu.data_ptr(), self.all_pin_pos_gpu.data_ptr()
+        c.elem_f, c.elem_k, c.not_spd = self._elem_f.data_ptr(), self._elem_k.data_ptr(), self.not_spd.data_ptr()
+        c.mu, c.la, c.g, c.control_mag, c.spd_value = self.mu, self.la, self.g, self.control_mag, self.spd_value
+        c.spd_level0 = 1 if self.spd_level0 else 0
+        self.ctx = c
+
+    def _ensure_plans(self):
+        for i in range(1, self.layer):
+            if self._plans[i - 1] is None:
+                self._plans[i - 1] = t = self._build_galerkin_plan(i - 1)
+                self._ctx_keep["plans"][i - 1] = t["plan"]
+                self._ctx_keep["t_values"][i - 1] = t["t_values"].data_ptr()
 
     def level_without_lattice(self, l):
         """A copy of FembLevel l without the lattice plan: the element-kernel + row-fold assembly path (tests, measurements)."""
@@ -525,9 +560,8 @@ class Object:
 
     def galerkin(self):
         """object.py:1252-1264 minus the rebuilds: A_i = Ut_hat (A_{i-1} Us_hat), spd_matrix33f, [L;D;U] layout."""
+        self._ensure_plans()
         for i in range(1, self.layer):
-            if self._plans[i - 1] is None:
-                self._plans[i - 1] = self._build_galerkin_plan(i - 1)
             t = self._plans[i - 1]
             _lib.check(self.lib.femb_galerkin(C.byref(self.levels[i - 1]), C.byref(self.levels[i]), self._values(i - 1).data_ptr(),
                                               C.byref(self.Ut_hat[i - 1].c), C.byref(self.Us_hat[i - 1].c), C.byref(t["plan"]),
@@ -535,6 +569,11 @@ class Object:
                                               self._stream()), "femb_galerkin")
 
     def _newton_mg_body(self):
+        if self.use_c_steps and not self.verbose:
+            self._ensure_plans()
+            self.ctx.diag_fixed = self.diag_fixed.data_ptr()                             # (DynamicObject replaces the tensor)
+            _lib.check(self.lib.femb_newton_mg_step(C.byref(self.ctx), self._stream()), "femb_newton_mg_step")
+            return
         x = self.x_gpu_layer[0]
         self._force_hessian(x, self.grad_gpu, self.MF_value_gpu, self.diag_fixed)       # :1232-1236, 1249
         if self.spd_level0:
@@ -606,6 +645,12 @@ class Object:
             self._spd(self.UtAUs_values[0])
 
     def _fas_v123_body(self, x, spd, gravity_pins, fixed_diag, coarse_pin_penalty):
+        variant = {(True, False, False, False): 1, (False, True, True, False): 2, (False, True, True, True): 3}.get(
+            (spd, gravity_pins, fixed_diag, coarse_pin_penalty)) if not isinstance(gravity_pins, tuple) else None
+        if self.use_c_steps and variant is not None:
+            self.ctx.diag_fixed = self.diag_fixed.data_ptr()
+            _lib.check(self.lib.femb_fas_step(C.byref(self.ctx), variant, x.data_ptr(), self._stream()), "femb_fas_step")
+            return
         self._fas_fine(x, spd, gravity_pins, fixed_diag)
         self.PerformGaussSeidel(layer=0, iterations=1)                                   # :1483
         self.update_deltaX(x, self.dev_delta_x[0])                                       # :1487

@@ -64,7 +64,21 @@ class DynamicObject(Object):
         d = d * min(ln, 0.5)
         return tuple(float(v) for v in d)
 
+    def _dyn_struct(self):
+        d = _lib.FembDynamic()
+        d.x, d.v, d.old_x, d.inertia_x = (t.data_ptr() for t in (self.dev_x, self.dev_v, self.dev_old_x, self.dev_inertia_x))
+        d.more_fixed, d.diag_dyn = self.more_fixed_gpu.data_ptr(), self.diag_dyn.data_ptr()
+        d.cg_p, d.cg_ap, d.cg_state = self.dev_P[0].data_ptr(), self.dev_AP[0].data_ptr(), self._cg_state.data_ptr()
+        d.dir_host = C.cast(self._dir, C.c_void_p)
+        d.dt, d.inv_dt, d.damping = self.dt, self.inv_dt, self.damping
+        return d
+
     def _frame_body(self):
+        if self.use_c_steps:
+            if getattr(self, "_dyn", None) is None:
+                self._dyn = self._dyn_struct()
+            _lib.check(self.lib.femb_dynamic_step(C.byref(self.ctx), C.byref(self._dyn), self._stream()), "femb_dynamic_step")
+            return
         lv0 = C.byref(self.levels[0])
         st = self._stream
         x = self.dev_x

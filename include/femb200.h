@@ -138,6 +138,30 @@ long long femb_launch_count(void);
 /* 0 if device `device` exists and is compute capability 10.x */
 int femb_check_device(int device);
 
+/* ---- setup of the fixed patterns on the HOST (csrc/femb_setup.cu, OpenMP; every pointer is a host pointer) ----------------
+ * Object.__init__ builds these maps with per-element Python loops and dictionaries (object.py:485-697) and bsr_mm repeats
+ * the symbolic product every step (sparse.py:1018-1091); here they are built once, with the reference's numbering. */
+/* vert_elem[n_vert*8]: e*8+a of the hexahedra incident to every vertex, ascending, -1 padded (the inverse of `hex`) */
+int femb_setup_incidence_host(int n_vert, int n_hex, const int* hex, int* vert_elem);
+/* pattern of one level = sorted set {(v2i[a], v2i[b]) : a, b in one hexahedron} in the [L;D;U] layout (object.py:485-599):
+ * first the row pointers L_ptr / U_ptr [n_vert+1] (L_ptr[n_vert] = L_nnz = U_nnz), then, into arrays the caller sizes from
+ * them, the columns, hex_update_offset (elem2nnz [n_hex*64], object.py:563-569) and UtAUs_block_offset (block_offset
+ * [2 L_nnz + n_vert]: [L;D;U] slot -> rank in (row,col)-sorted order, object.py:633-683) */
+int femb_setup_pattern_count_host(int n_vert, const int* hex, const int* v2i, const int* i2v, const int* vert_elem, int* L_ptr,
+                                  int* U_ptr);
+int femb_setup_pattern_fill_host(int n_vert, int n_hex, const int* hex, const int* v2i, const int* i2v, const int* vert_elem,
+                                 const int* L_ptr, const int* U_ptr, int* L_col, int* U_col, int* elem2nnz, int* block_offset);
+/* symbolic plan of A_c = Ut_hat (A_f Us_hat) (FembGalerkinPlan): t_ptr [n_fine+1] first, then the arrays sized from it:
+ * t_col [t_nnz], c_ptr [n_coarse+1], c_col / c_slot [nnz_c], t_slot [nnz_f*8], c_slot8 [t_nnz*8], ut_q [nnz(Ut_hat)];
+ * fails if the product pattern is not the coarse hexahedral adjacency (block_values_reorder relies on it, object.py:1261) */
+int femb_setup_galerkin_count_host(int n_fine, const int* fL_ptr, const int* fL_col, const int* fU_ptr, const int* fU_col,
+                                   const int* us_off, const int* us_col, int* t_ptr);
+int femb_setup_galerkin_fill_host(int n_fine, int n_coarse, const int* fL_ptr, const int* fL_col, const int* fU_ptr, const int* fU_col,
+                                  const int* cL_ptr, const int* cL_col, const int* cU_ptr, const int* cU_col, const int* us_off,
+                                  const int* us_col, const float* us_w, const int* ut_off, const int* ut_col, const int* t_ptr,
+                                  int* t_col, int* c_ptr, int* c_col, int* c_slot, unsigned char* t_slot, unsigned char* c_slot8,
+                                  unsigned char* ut_q, int* dyadic_out);
+
 /* ---- rest state (setup) ------------------------------------------------------------------- */
 /* prepare_kernal (quai_hexagon.py:4-18): rest Jacobian per (hex,q) -> detJ[n_hex*8], invJ[n_hex*72] */
 int femb_prepare_rest(int n_hex, const int* hex, const float* x_rest, float* detJ, float* invJ, void* stream);
@@ -262,6 +286,77 @@ int femb_cloth_assemble(int n_vert, int n_edge, const int* edge, const float* re
                         float* values, float* grad, void* stream);
 /* the cloth's update_deltaX_kernel (cublas.py:22-26 there): x += dx except vertices skip0, skip1 (0 and 65) */
 int femb_cloth_update(int n_vert, const float* dx, float* x, int skip0, int skip1, void* stream);
+
+/* ---- whole steps (csrc/femb_steps.cu): one call = one loop body of a solver method of `class Object` ---------------------
+ * The context structs are HOST structs of device pointers (the arrays the reference allocates in Object.__init__,
+ * object.py:797-855); arrays indexed by level are host arrays of `layers` (or `layers - 1`) entries.  Every call only
+ * enqueues on `stream`: capture it into a CUDA graph and replay it per step. */
+typedef struct FembContext {
+  int layers;                        /* self.layer                                                                    */
+  const FembLevel* levels;           /* [layers]                                                                      */
+  const FembTransfer* Ut_hat;        /* [layers-1] residual restriction  (index order, un-normalised; object.py:1027)  */
+  const FembTransfer* Us_hat;        /* [layers-1] prolongation          (index order; object.py:1032)                */
+  const FembTransfer* Ut_noOrder;    /* [layers-1] state restriction     (vertex order, row-normalised; :1489) or NULL */
+  const FembTransfer* Ut_noOrder_hat;/* [layers-1] (vertex order, un-normalised; coarse pin penalty :1501) or NULL     */
+  const FembGalerkinPlan* plans;     /* [layers-1] or NULL (steps without Galerkin products)                           */
+  float* const* values;              /* [layers] MF_value_gpu, UtAUs_values[0..]                                      */
+  float* const* t_values;            /* [layers-1] scratch of femb_galerkin (plans[l].t_nnz * 9 floats) or NULL        */
+  float* const* B;                   /* [layers] dev_B                                                                */
+  float* const* B_fixed;             /* [layers] dev_B_fixed                                                          */
+  float* const* delta_x;             /* [layers] dev_delta_x                                                          */
+  float* const* x_solved;            /* [layers] dev_x_solved                                                         */
+  float* const* R;                   /* [layers] dev_R                                                                */
+  float* x;                          /* x_gpu_layer[0]: the state, vertex order                                       */
+  float* grad;                       /* grad_gpu                                                                      */
+  const float* diag_fixed;           /* the k*I pin blocks of MF_value_fixed as a per-row diagonal (index order)      */
+  const float* mass0;                /* m_gpu[0]                                                                      */
+  const int* pin;                    /* pin_gpu                                                                       */
+  const float* pin_pos;              /* all_pin_pos_gpu                                                               */
+  float* elem_f;                     /* scratch [max n_hex * 24]                                                      */
+  float* elem_k;                     /* scratch [max n_hex * FEMB_ELEM_K_FLOATS]                                      */
+  int* not_spd;                      /* int[1] counter of solve3x3 'not spd' events, or NULL                          */
+  float mu, la, g, control_mag, spd_value;
+  int spd_level0;                    /* exp1/simulation applies spd_matrix33f on level 0 as well                      */
+} FembContext;
+/* VCycle(layer) (object.py:1216-1226): 3 pre + 3 post symmetric GS per level, 3 on the coarsest; reads dev_B_fixed[layer] */
+int femb_vcycle(const FembContext* ctx, int layer, void* stream);
+/* the Galerkin chain A_i = Ut_hat (A_{i-1} Us_hat) + spd_matrix33f for i = 1 .. layers-1 (object.py:1252-1264) */
+int femb_galerkin_chain(const FembContext* ctx, void* stream);
+/* the loop body of NewtonMultigrid (object.py:1231-1296): force + Hessian, Galerkin chain, one V-cycle, finish(), x update */
+int femb_newton_mg_step(const FembContext* ctx, void* stream);
+/* the loop body of FASv1 / FASv2 / FASv3 (object.py:1373-1511; variant 1..3) on the state `x` (NULL = ctx->x; FASv1 iterates
+ * on dev_x_solved[0]) */
+int femb_fas_step(const FembContext* ctx, int variant, float* x, void* stream);
+
+/* dynamic (implicit Euler) frame: exp1/simulation/object.py:1286-1325 = one Newton iteration with 5 CG iterations */
+typedef struct FembDynamic {
+  float* x;               /* dev_x (the state the frame advances)                  */
+  float* v;               /* dev_v                                                 */
+  float* old_x;           /* dev_old_x                                             */
+  float* inertia_x;       /* dev_inertia_x                                         */
+  int* more_fixed;        /* more_fixed_gpu (drag constraint flags)                */
+  float* diag_dyn;        /* scratch [n_vert]: pin / drag / mass diagonal          */
+  float* cg_p;            /* dev_P[0]                                              */
+  float* cg_ap;           /* dev_AP[0]                                             */
+  float* cg_state;        /* float[>= 1040] scratch of femb_cg                     */
+  const float* dir_host;  /* float[3] on the HOST: drag direction of this frame    */
+  float dt, inv_dt, damping;
+} FembDynamic;
+int femb_dynamic_step(const FembContext* ctx, const FembDynamic* dyn, void* stream);
+
+/* cloth frame: exp1/cloth_simulation/object.py:657-677 (arguments as in femb_cloth_assemble / femb_cg) */
+typedef struct FembCloth {
+  const FembLevel* level;      /* pattern of the cloth matrix ([L;D;U] view, identity ordering)                    */
+  int n_edge;
+  const int* edge; const float* rest; const float* mass;
+  const int* inc_ptr; const int* inc; const int* off_p0p1; const int* off_p1p0; const int* d_slot;
+  const int* zeros_i;          /* int[n_vert] of zeros (no pins / drags in the cloth)                              */
+  float* x; float* v; float* old_x; float* inertia_x;
+  float* values; float* grad; float* B; float* B_fixed; float* delta_x; float* cg_p; float* cg_ap; float* cg_state;
+  float* edge_h; float* edge_g;
+  float k, g, dt, inv_dt, damping;
+} FembCloth;
+int femb_cloth_step(const FembCloth* cloth, void* stream);
 
 /* ---- multi-GPU: communicator, halo exchange, scalar all-reduce (csrc/femb_comm.cu) -------------------------------
  * The reference is single-GPU (no NCCL / MPI call site anywhere); a mesh-partitioned caller of this ABI

@@ -149,6 +149,74 @@ def _load_state(obj, ref, xp):
     obj.dev_B_fixed[0].copy_(torch.from_numpy(ref.grad))
 
 
+def test_whole_step_exports_match_operator_sequences():
+    """femb_newton_mg_step / femb_fas_step(1..3) / femb_vcycle / femb_dynamic_step / femb_cloth_step (csrc/femb_steps.cu), driven
+    through ctypes from a context struct built HERE, vs the same step issued operator by operator by the Python drivers:
+    identical kernels in identical order => identical bits."""
+    from fem_simulation_b200 import Cloth, DynamicObject
+    pts, hx = MESHES["jag3"]()
+    a = Object((pts, hx), 0.05, [], use_graphs=False, use_c_steps=False)
+    b = Object((pts, hx), 0.05, [], use_graphs=False, use_c_steps=False)
+    assert a.layer == 3
+    b._ensure_plans()
+    st = lambda o: C.c_void_p(torch.cuda.current_stream(o.device).cuda_stream)
+    for _ in range(2):
+        a._newton_mg_body()
+        _lib.check(b.lib.femb_newton_mg_step(C.byref(b.ctx), st(b)), "femb_newton_mg_step")
+    assert torch.equal(a.x_gpu_layer[0], b.x_gpu_layer[0]) and torch.equal(a.UtAUs_values[1], b.UtAUs_values[1])
+    for variant, args in ((2, (False, True, True, False)), (3, (False, True, True, True))):
+        a._fas_v123_body(a.x_gpu_layer[0], *args)
+        _lib.check(b.lib.femb_fas_step(C.byref(b.ctx), variant, None, st(b)), "femb_fas_step")
+        assert torch.equal(a.x_gpu_layer[0], b.x_gpu_layer[0]), f"FASv{variant}"
+    a.dev_x_solved[0].copy_(a.x_gpu_layer[0]); b.dev_x_solved[0].copy_(b.x_gpu_layer[0])
+    a._fas_v123_body(a.dev_x_solved[0], True, False, False, False)
+    _lib.check(b.lib.femb_fas_step(C.byref(b.ctx), 1, b.dev_x_solved[0].data_ptr(), st(b)), "femb_fas_step")
+    assert torch.equal(a.dev_x_solved[0], b.dev_x_solved[0]), "FASv1"
+    for o in (a, b):
+        o.dev_B_fixed[0].normal_(generator=torch.Generator(device=o.device).manual_seed(5))
+    a.VCycle(0)
+    _lib.check(b.lib.femb_vcycle(C.byref(b.ctx), 0, st(b)), "femb_vcycle")
+    assert torch.equal(a.dev_delta_x[0], b.dev_delta_x[0]) and torch.equal(a.dev_x_solved[0], b.dev_x_solved[0])
+    da = DynamicObject((pts, hx), 0.05, [], use_graphs=False, use_c_steps=False)
+    db = DynamicObject((pts, hx), 0.05, [], use_graphs=True, use_c_steps=True)
+    ca, cb = Cloth(use_graphs=False, use_c_steps=False), Cloth(use_graphs=True, use_c_steps=True)
+    for _ in range(3):
+        da.step(); db.step(); ca.step(); cb.step()
+    assert torch.equal(da.dev_x, db.dev_x) and torch.equal(da.dev_v, db.dev_v)
+    assert torch.equal(ca.dev_x, cb.dev_x) and torch.equal(ca.dev_v, cb.dev_v)
+
+
+def test_bsr_views_match_oracle_bsrs(pair):
+    """The drop-in A / L / U / D attributes (object.py:291-311: BsrMatrix objects rebuilt by bsr_set_from_triplets every
+    step) as views of the fixed [L;D;U] layout: .nrow/.ncol/.nnz/.offsets/.columns bit-exact and .values identical to the
+    oracle's BSRs built from the same value array, every level; the transfer operators likewise."""
+    from oracle.ref_setup import bsr_from_triplets
+    obj, ref, xp = pair
+    _load_state(obj, ref, xp)
+    for l in range(obj.layer):
+        if l > 0:
+            vals = np.random.default_rng(l).normal(size=ref.values(l).shape).astype(np.float32)
+            ref.values(l)[...] = vals
+            obj._values(l).copy_(torch.from_numpy(vals))
+        ref.set_LUD(l)
+        p = ref.pat[l]
+        n = ref.dims[l]
+        full = bsr_from_triplets(n, n, np.concatenate([p["L_row"], p["D_row"], p["U_row"]]),
+                                 np.concatenate([p["L_col"], p["D_col"], p["U_col"]]), ref.values(l))       # object.py:1254
+        for mine, theirs, nm in ((obj.L[l], ref.Lm[l], "L"), (obj.U[l], ref.Um[l], "U"), (obj.D[l], ref.Dm[l], "D"), (obj.A[l], full, "A")):
+            assert (mine.nrow, mine.ncol, mine.nnz) == (theirs["nrow"], theirs["ncol"], theirs["nnz"]), f"{nm}[{l}] shape"
+            assert np.array_equal(mine.offsets.cpu().numpy(), theirs["offsets"]), f"{nm}[{l}].offsets"
+            assert np.array_equal(mine.columns.cpu().numpy(), theirs["columns"]), f"{nm}[{l}].columns"
+            assert np.array_equal(mine.values.cpu().numpy().reshape(-1, 3, 3), theirs["values"].reshape(-1, 3, 3)), f"{nm}[{l}].values"
+    for name in ("Ut", "Us", "Ut_noOrder", "Us_noOrder", "Ut_hat", "Us_hat", "Ut_noOrder_hat", "Us_noOrder_hat"):
+        for l in range(obj.layer - 1):
+            mine, theirs = getattr(obj, name)[l], getattr(ref, name)[l]
+            assert (mine.nrow, mine.ncol, mine.nnz) == (theirs["nrow"], theirs["ncol"], theirs["nnz"]), f"{name}[{l}] shape"
+            assert np.array_equal(mine.offsets.cpu().numpy(), theirs["offsets"]) and np.array_equal(mine.columns.cpu().numpy(), theirs["columns"])
+            tv = theirs["values"] if theirs["values"].ndim == 3 else theirs["values"][:, None, None] * np.eye(3, dtype=np.float32)
+            assert np.array_equal(mine.values.cpu().numpy(), tv), f"{name}[{l}].values"
+
+
 def test_spmv_parts(pair):
     obj, ref, xp = pair
     _load_state(obj, ref, xp)

@@ -242,3 +242,28 @@ def test_malformed_meshes_are_rejected():
     for p, h in bad:
         with pytest.raises(ValueError):
             hierarchy.build_hierarchy(p, h, 0.05)
+
+
+def test_host_setup_routines_match_numpy_restatements():
+    """csrc/femb_setup.cu (femb_setup_incidence/pattern/galerkin_*_host: per-row sorted unions, OpenMP) vs the numpy / scipy
+    restatements (one global sort, scipy products), array by array, on ragged 3-level meshes and a box."""
+    for pts, hx, dx in (mesh.jagged_mesh(18, 17, 19, 0.05, seed=2, keep=0.7) + (0.05,), mesh.box_mesh(7, 12, 9, 0.1) + (0.1,),
+                        mesh.jagged_mesh(10, 9, 11, 0.05, seed=1, origin=(-0.3, 0.1, 0.2)) + (0.05,)):
+        H = hierarchy.build_hierarchy(pts, hx, dx)
+        for l in range(H.layer):
+            a = H.pattern[l]
+            b = hierarchy.build_pattern_numpy(H.hexs[l], H.vertex2index[l], H.color_vertex_num[l], H.dims[l])
+            assert (a.n, a.nnz, a.L_nnz, a.off_l, a.off_d, a.off_u) == (b.n, b.nnz, b.L_nnz, b.off_l, b.off_d, b.off_u)
+            for f in ("L_row", "L_col", "U_row", "U_col", "L_ptr", "U_ptr", "GS_L_row", "GS_L_col", "GS_U_row", "GS_U_col",
+                      "block_offset", "hex_update_offset"):
+                assert np.array_equal(getattr(a, f), getattr(b, f)), (l, f)
+            assert a.GS_L_Ptr == b.GS_L_Ptr and a.GS_U_Ptr == b.GS_U_Ptr
+            ve = hierarchy.vertex_incidence(H.hexs[l], H.dims[l])
+            flat = H.hexs[l].reshape(-1)
+            for v in range(0, H.dims[l], max(1, H.dims[l] // 50)):
+                assert ve[v][ve[v] >= 0].tolist() == np.nonzero(flat == v)[0].tolist()
+        for l in range(H.layer - 1):
+            g1, g2 = hierarchy.build_galerkin_plan(H, l), hierarchy.build_galerkin_plan_numpy(H, l)
+            assert set(g1) == set(g2)
+            for k in g2:
+                assert np.array_equal(np.asarray(g1[k]), np.asarray(g2[k])), (l, k)
