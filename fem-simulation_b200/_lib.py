@@ -31,7 +31,6 @@ class FembLevel(C.Structure):
                 ("elem2nnz", C.c_void_p),
                 ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p),
                 ("fold_plan", C.c_void_p),
-                ("pipe_chunks", C.c_int), ("pipe_hex_end", C.c_void_p), ("pipe_vert_end", C.c_void_p),
                 ("lat_vx", C.c_int), ("lat_vy", C.c_int), ("lat_vz", C.c_int), ("lat_chunks", C.c_int),
                 ("lat_cell_elem", C.c_void_p), ("lat_row_rec", C.c_void_p)]
 
@@ -118,7 +117,6 @@ PROTOTYPES = {
     "femb_lumped_mass": [LV, P, P, P],
     "femb_force": [LV, P, F, F, P, F, P, P, F, I, P, P, P],
     "femb_hessian": [LV, P, F, F, P, P, P, P],
-    "femb_set_pipeline": [I],
     "femb_set_fold_config": [I, I],
     "femb_force_hessian": [LV, P, F, F, P, F, P, P, F, P, P, P, P, P, P],
     "femb_energy": [LV, P, F, F, P, F, P, P, F, P, P, P],
@@ -129,7 +127,6 @@ PROTOTYPES = {
     "femb_set_pdl": [I],
     "femb_set_gs_threads_per_row": [I],
     "femb_set_gs_rows_per_cta": [I],
-    "femb_set_gs_coop_max_blocks": [I],
     "femb_gs_colors": [LV, P, P, P, I, I, I, P, P],
     "femb_jacobi": [LV, P, P, P, P, I, P, P],
     "femb_cg": [LV, P, P, P, P, P, P, P, I, F, I, P],
@@ -210,7 +207,7 @@ def load(rebuild: bool = False):
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported
         fn.argtypes = args
         fn.restype = _RESTYPE.get(name, C.c_int)
-    if lib.femb_abi_version() != 3:
+    if lib.femb_abi_version() != 4:
         raise FembError("libfemb200 ABI version mismatch")
     _lib = lib
     return lib

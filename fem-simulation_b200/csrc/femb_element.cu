@@ -716,7 +716,10 @@ static AsmArgs make_asm(const FembLevel* l, const float* diag_add, const float* 
 
 template <int kMode>
 static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_dev[64] = {};                         // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   const size_t smem = element_smem<kMode>();
   if (!configured) {
     cudaFuncSetAttribute(element_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -750,74 +753,18 @@ static int launch_assemble(const AsmArgs& as, int v_begin, int v_end, cudaStream
   return check_launch("assemble_rows_kernel");
 }
 
-// ---- software pipeline of the two stages through L2 ----------------------------------------------------------------
-// The element kernel is bound by FP32 issue / shared memory, the fold by HBM; run back to back each leaves the other
-// resource idle and the element matrices make a round trip through HBM.  With a pipeline plan (FembLevel.pipe_*) the
-// hexahedra are taken in chunks; the fold of the rows completed by chunk c (vertices below pipe_vert_end[c]: all their
-// hexahedra lie below pipe_hex_end[c]) runs on a side stream concurrently with the element kernel of chunk c+1 and
-// finds its element matrices still in L2.  Fork/join is by events, so the whole thing is capturable into a CUDA graph
-// (parallel branches).  The side stream and the two events are the only objects the library owns; they are created
-// on first use outside of any capture, and without them the stages simply run one after the other.
-struct PipeCtx {
-  int device = -1;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_elem = nullptr, ev_fold = nullptr;
-};
-static PipeCtx g_pipe;
-static int g_pipe_enabled = 0;   // measured on B200 (cube n=100): no gain, both stages are SM-side bound; see DESIGN.md
-
-static bool pipe_ready(cudaStream_t st) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (g_pipe.side != nullptr && g_pipe.device == dev) return true;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
-    cudaGetLastError();
-    return false;                                            // never create objects while a capture is in progress
-  }
-  PipeCtx c;
-  c.device = dev;
-  if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c.ev_elem, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c.ev_fold, cudaEventDisableTiming) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  g_pipe = c;                                                // (objects of a previous device, if any, are leaked on purpose)
-  return true;
-}
-
 // element matrices of all hexahedra + fold of all rows; kMode 1 = Hessian only, 2 = element forces as well
 template <int kMode>
 static int hessian_pipeline(const FembLevel* l, const float* x, float mu, float la, const float* diag_add, float* elem_f,
                             float* elem_k, float* values, cudaStream_t st) {
   const ElemIn in = make_in(l, x, mu, la);
   const AsmArgs as = make_asm(l, diag_add, elem_k, values);
-  const int nc = (g_pipe_enabled && l->pipe_hex_end && l->pipe_vert_end) ? l->pipe_chunks : 0;
-  if (nc < 2 || !pipe_ready(st)) {
-    int rc = launch_element<kMode>(in, 0, l->n_hex, elem_f, elem_k, st);
-    if (rc) return rc;
-    return launch_assemble(as, 0, l->n_vert, st);
-  }
-  FEMB_REQUIRE(l->pipe_hex_end[nc - 1] == l->n_hex && l->pipe_vert_end[nc - 1] == l->n_vert, "pipeline plan does not cover the level");
-  cudaStream_t side = g_pipe.side;
-  int e0 = 0, v0 = 0;
-  for (int c = 0; c < nc; ++c) {
-    const int e1 = l->pipe_hex_end[c], v1 = l->pipe_vert_end[c];
-    FEMB_REQUIRE(e1 >= e0 && v1 >= v0 && e1 <= l->n_hex && v1 <= l->n_vert, "pipeline plan is not monotone");
-    int rc = launch_element<kMode>(in, e0, e1, elem_f, elem_k, st);
-    if (rc) return rc;
-    if (v1 > v0) {
-      cudaEventRecord(g_pipe.ev_elem, st);                   // chunk c (and everything before it in `st`) is done
-      cudaStreamWaitEvent(side, g_pipe.ev_elem, 0);
-      rc = launch_assemble(as, v0, v1, side);
-      if (rc) return rc;
-    }
-    e0 = e1; v0 = v1;
-  }
-  cudaEventRecord(g_pipe.ev_fold, side);                     // join
-  cudaStreamWaitEvent(st, g_pipe.ev_fold, 0);
-  return check_launch("hessian_pipeline");
+  // (A chunked two-stream software pipeline of the two stages -- the fold of chunk c next to the element kernel of chunk
+  // c+1, element matrices read from L2 -- was built and measured: 1.88-2.10 vs 1.69-1.83 ms back to back, both stages are
+  // bound on the SM side; removed)
+  int rc = launch_element<kMode>(in, 0, l->n_hex, elem_f, elem_k, st);
+  if (rc) return rc;
+  return launch_assemble(as, 0, l->n_vert, st);
 }
 
 }  // namespace femb
@@ -830,12 +777,6 @@ int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm) {
   if (rows_per_warp >= 1 && rows_per_warp <= 64) g_fold_rows_per_warp = rows_per_warp;
   if (min_blocks_per_sm == 4 || min_blocks_per_sm == 5) g_fold_min_blocks = min_blocks_per_sm;
   return FEMB_OK;
-}
-
-int femb_set_pipeline(int enable) {
-  const int old = g_pipe_enabled;
-  g_pipe_enabled = enable != 0;
-  return old;
 }
 
 int femb_prepare_rest(int n_hex, const int* hex, const float* x_rest, float* detJ, float* invJ, void* stream) {

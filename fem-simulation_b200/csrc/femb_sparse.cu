@@ -22,7 +22,7 @@
 
 namespace femb {
 
-constexpr int RP_ROWS = 32;                 // rows per CTA   } of the cooperative kernel and the defaults of the templates;
+constexpr int RP_ROWS = 32;                 // rows per CTA   } defaults of the templates;
 constexpr int RP_SUBS = 4;                  // threads per row } the launchers pick 16 x 8 (FEMB_ROWS_DISPATCH)
 constexpr int RP_THREADS = RP_ROWS * RP_SUBS;
 constexpr int RP_CAP = RP_ROWS * 27;        // staged off-diagonal blocks per CTA (26 neighbours + slack)
@@ -86,8 +86,8 @@ struct RowSmemT {
 };
 using RowSmem = RowSmemT<RP_SUBS>;
 
-// One block of <= RP_ROWS consecutive rows.  kCoherent: x is being updated by other CTAs of the same
-// (cooperative) launch, so it is read through L2 (ld.global.cg) instead of the per-SM L1.
+// One block of <= RP_ROWS consecutive rows.  kCoherent: x is read through L2 (ld.global.cg) instead of the per-SM L1 (for a
+// caller whose other CTAs update x during the same launch; the shipped kernels do not).
 // The values / L_col / U_col arrays must be 16-byte aligned and readable 16 bytes past their end
 // (the bulk copies are rounded out to 16-byte granules).
 template <int kMode, bool kCoherent, bool kPdl = false, int kSubs = RP_SUBS, int kRows = RP_ROWS>
@@ -262,39 +262,6 @@ __global__ void __launch_bounds__(kRows * kSubs) gs_color_kernel(RowArgs a) {
   row_block<RM_GS, false, true, kSubs, kRows>(a, r0, min(kRows, a.row_end - r0), sm, phase);
 }
 
-// Whole femb_gauss_seidel call in ONE cooperative launch (levels whose colour fits the resident grid):
-// iterations x 16 colour phases separated by grid-wide barriers instead of 16 launches per iteration.
-struct GsCoopArgs {
-  RowArgs base;
-  int color_start[9];
-  int iterations;
-};
-}  // namespace femb
-#include <cooperative_groups.h>
-namespace femb {
-__global__ void __launch_bounds__(RP_THREADS) gs_coop_kernel(GsCoopArgs g) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  __shared__ RowSmem sm;
-  if (threadIdx.x == 0) mbar_init(&sm.bar, 1);
-  uint32_t phase = 0;
-  RowArgs a = g.base;
-  for (int it = 0; it < g.iterations; ++it) {
-    for (int half = 0; half < 2; ++half) {
-      for (int ci = 0; ci < 8; ++ci) {
-        const int c = half == 0 ? 7 - ci : ci;                   // backward then forward sweep (object.py:893-908)
-        a.parts = (it == 0 && half == 0) ? FEMB_PART_U : (FEMB_PART_L | FEMB_PART_U);
-        const int rb = g.color_start[c], re = g.color_start[c + 1];
-        for (int r0 = rb + blockIdx.x * RP_ROWS; r0 < re; r0 += gridDim.x * RP_ROWS) {
-          row_block<RM_GS, true>(a, r0, min(RP_ROWS, re - r0), sm, phase);
-          __syncthreads();                                       // smem is reused by the next block
-        }
-        grid.sync();
-      }
-    }
-  }
-}
-
 static RowArgs base_args(const FembLevel* l, const float* values) {
   RowArgs a;
   a.L_ptr = l->L_ptr; a.L_col = l->L_col; a.U_ptr = l->U_ptr; a.U_col = l->U_col;
@@ -306,7 +273,6 @@ static RowArgs base_args(const FembLevel* l, const float* values) {
 
 // rows per CTA x threads per row of the one-block-per-CTA kernels (measured at 1 M hexahedra, per Gauss-Seidel colour
 // launch: 32x4 32.8 us, 32x8 34.7, 16x4 29.3, 16x8 28.8 -- smaller blocks mean more independent chains in flight per SM)
-static int g_coop_max_blocks = 0;    // cooperative single-launch sweep: off (measured slower than PDL colour launches, see below); -1: twice the resident grid
 static int g_gs_rows = 16;
 static int g_gs_subs = 8;
 #define FEMB_ROWS_DISPATCH(KERNEL_EXPR)                                        \
@@ -348,19 +314,6 @@ static int launch_gs_color(const RowArgs& a, bool pdl, cudaStream_t st) {
     return FEMB_E_CUDA;
   }
   return check_launch("gs_color_kernel");
-}
-
-// resident CTAs of gs_coop_kernel on the current device (0 if cooperative launch is unsupported)
-static int coop_capacity() {
-  static int cap = -1;
-  if (cap >= 0) return cap;
-  int dev = 0, coop = 0, sms = 0, per_sm = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_coop_kernel, RP_THREADS, 0);
-  cap = coop ? sms * per_sm : 0;
-  return cap;
 }
 
 // ---- vector kernels -----------------------------------------------------------------------------
@@ -737,12 +690,6 @@ int femb_set_gs_threads_per_row(int subs) {
   return old;
 }
 
-int femb_set_gs_coop_max_blocks(int max_blocks) {
-  const int old = g_coop_max_blocks;
-  g_coop_max_blocks = max_blocks;
-  return old;
-}
-
 int femb_set_gs_rows_per_cta(int rows) {
   const int old = g_gs_rows;
   if (rows == 8 || rows == 16 || rows == 32) g_gs_rows = rows;
@@ -777,28 +724,9 @@ int femb_gauss_seidel(const FembLevel* lvl, const float* values, const float* b,
   if (iterations == 0) return FEMB_OK;
   RowArgs a = base_args(lvl, values);
   a.parts = FEMB_PART_L | FEMB_PART_U; a.x = dx; a.y = dx; a.b = b; a.not_spd = not_spd;
-  int max_blocks = 1;
-  for (int c = 0; c < 8; ++c) max_blocks = max(max_blocks, (int)cdiv(lvl->color_start[c + 1] - lvl->color_start[c], RP_ROWS));
-  // Cooperative variant (one launch, grid.sync between the 16 colour phases).  Measured at 3 iterations: 375 us vs 279 us
-  // for PDL colour launches on 132 651 rows, 189 us vs 133 us on 17 576 rows -- a programmatic dependent launch costs less
-  // than a grid-wide barrier plus the exposed staging latency, so it is off by default (femb_set_gs_coop_max_blocks).
-  const int cap = g_coop_max_blocks != 0 ? coop_capacity() : 0;
-  const int coop_limit = g_coop_max_blocks >= 0 ? g_coop_max_blocks : 2 * cap;
-  if (cap > 0 && max_blocks <= coop_limit) {
-    // small level: one cooperative launch, grid-wide barrier between the 16 colour phases
-    GsCoopArgs g;
-    g.base = a; g.iterations = iterations;
-    for (int c = 0; c < 9; ++c) g.color_start[c] = lvl->color_start[c];
-    void* params[] = {&g};
-    const int grid = min(max_blocks, cap);
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)gs_coop_kernel, dim3(grid), dim3(RP_THREADS), params, 0, st);
-    count_launch();
-    if (e != cudaSuccess) {
-      set_error("gs_coop_kernel: %s", cudaGetErrorString(e));
-      return FEMB_E_CUDA;
-    }
-    return FEMB_OK;
-  }
+  // (A cooperative single-launch variant -- grid-wide barrier between the 16 colour phases -- was measured slower than these
+  // PDL colour launches at every level size, 375 vs 279 us at 132 651 rows and 189 vs 133 us at 17 576 rows for 3 iterations,
+  // and was removed: DESIGN.md 4a.)
   bool first = true;                 // the first colour follows the memset (and whatever wrote the matrix): ordinary launch
   for (int it = 0; it < iterations; ++it) {
     for (int c = 7; c >= 0; --c) {                                                // backward sweep, object.py:893-898
@@ -919,7 +847,10 @@ int femb_galerkin(const FembLevel* fine, const FembLevel* coarse, const float* f
   FEMB_REQUIRE(plan->n_fine == fine->n_vert && us_hat->nrow == fine->n_vert && ut_hat->nrow == plan->n_coarse &&
                    coarse->n_vert == plan->n_coarse, "inconsistent sizes");
   FEMB_REQUIRE(plan->t_slot && plan->c_slot8 && plan->ut_q && plan->t_ptr && plan->c_ptr && plan->c_slot, "plan not initialised");
-  static bool configured = false;
+  static bool configured_dev[64] = {};                         // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 63];
   if (!configured) {
     cudaFuncSetAttribute(galerkin_ap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaSmem));
     cudaFuncSetAttribute(galerkin_ap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaSmem));

@@ -60,7 +60,7 @@ def _dev(a, device):
 class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
                  control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False,
-                 pipe_chunk_hexes=2 * 740 * 16, corrected_hierarchy=False, fused_assembly=False, fused_chunks=0,
+                 corrected_hierarchy=False, fused_assembly=False, fused_chunks=0,
                  lattice_origin=None, use_c_steps=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
@@ -106,7 +106,6 @@ class Object:
             p = H.pattern[l]
             n, nh = H.dims[l], H.hexs[l].shape[0]
             ve = hierarchy.vertex_incidence(H.hexs[l], n)                # e*8+a of the incident hexahedra, -1 padded
-            ap = self._pipe_plan(nh, ve, pipe_chunk_hexes)
             pad = np.zeros(4, np.int32)                                  # bulk copies are rounded out to 16 bytes
             d = dict(L_ptr=_dev(p.L_ptr, dev), L_col=_dev(np.concatenate([p.L_col, pad]), dev)[:p.L_nnz],
                      U_ptr=_dev(p.U_ptr, dev), U_col=_dev(np.concatenate([p.U_col, pad]), dev)[:p.L_nnz],
@@ -127,11 +126,6 @@ class Object:
             d["fold_plan"] = torch.empty(n * 128 + 16, dtype=torch.uint8, device=dev)      # FEMB_FOLD_PLAN_BYTES per vertex
             _lib.check(self.lib.femb_build_fold_plan(C.byref(lv), d["fold_plan"].data_ptr(), self._stream()), "femb_build_fold_plan")
             lv.fold_plan = d["fold_plan"].data_ptr()
-            if ap is not None:                                           # element/fold software pipeline plan (host arrays)
-                d.update(pipe_hex_end=ap[0], pipe_vert_end=ap[1])
-                lv.pipe_chunks = len(ap[0])
-                lv.pipe_hex_end = ap[0].ctypes.data
-                lv.pipe_vert_end = ap[1].ctypes.data
             if fused_assembly:
                 self._attach_lattice_plan(l, lv, d, fused_chunks)
             self.levels.append(lv)
@@ -304,20 +298,6 @@ class Object:
         lv.lat_row_rec = None
         lv.lat_vz = 0
         return lv
-
-    @staticmethod
-    def _pipe_plan(nh, vert_elem, chunk_hexes):
-        """Plan of the element/fold software pipeline (femb200.h, FembLevel.pipe_*): hexahedra in chunks of `chunk_hexes`;
-        after chunk c the rows of all vertices v < vert_end[c] are complete (every hexahedron of every vertex <= v has
-        been processed).  Works for any numbering; it pipelines well when hexahedron and vertex ids grow together."""
-        if nh == 0 or not chunk_hexes or nh <= chunk_hexes:
-            return None
-        hex_end = np.minimum(np.arange(1, (nh + chunk_hexes - 1) // chunk_hexes + 1, dtype=np.int64) * chunk_hexes, nh)
-        last = vert_elem.max(axis=1).astype(np.int64) >> 3               # last hexahedron of every vertex (-1: none)
-        pref = np.maximum.accumulate(last)
-        vert_end = np.searchsorted(pref, hex_end, side="left")           # vertices with pref < hex_end
-        vert_end[-1] = vert_elem.shape[0]
-        return np.ascontiguousarray(hex_end, dtype=np.int32), np.ascontiguousarray(vert_end, dtype=np.int32)
 
     # hooks of the exp3 drivers (exp3/simulation/object.py:258-276, 294-295, 438-441), built on first use
     @property

@@ -19,7 +19,11 @@
  *   - solver vectors are in colour-sorted *index* order, geometry (x, hex, mass, pins) in *vertex*
  *     order, exactly like the reference.
  *   - return value: 0 on success, a negative FEMB_E_* code otherwise (femb_last_error() gives text).
- *   - thread-compatible: no global mutable state except the last-error string.
+ *   - thread-compatible, not thread-safe.  Process-wide state: the last-error string (thread-local), the launch counter
+ *     (atomic), the NCCL function table (written once by the first femb_comm_* call) and the TUNING KNOBS femb_set_pdl /
+ *     femb_set_gs_threads_per_row / femb_set_gs_rows_per_cta / femb_set_fold_config -- plain ints read at launch time, meant to
+ *     be set once before use (benchmark scripts, tests); they change launch shapes, and (threads per row) rounding order,
+ *     never results beyond that.  Kernel attributes are set once per device.
  */
 #ifndef FEMB200_H
 #define FEMB200_H
@@ -33,9 +37,9 @@ extern "C" {
 #define FEMB_E_CUDA (-2)      /* a CUDA runtime call or launch failed                 */
 #define FEMB_E_NODEVICE (-3)  /* no usable sm_100 device                              */
 
-#define FEMB_ABI_VERSION 3
+#define FEMB_ABI_VERSION 4
 
-/* hexahedra per CTA of the element kernel (pipeline chunks should be multiples of it) */
+/* hexahedra per CTA of the element kernel */
 #define FEMB_ASM_CHUNK_HEXES 16
 #define FEMB_FOLD_SLOTS 27
 #define FEMB_FOLD_PLAN_BYTES 128   /* 28*4 contributor bytes + 16 header bytes per vertex: one cache line */
@@ -76,12 +80,6 @@ typedef struct FembLevel {
                                   /* position p; 255 = none) in fold order, a 28th word with contributors 5..8 of the         */
                                   /* diagonal block, then int32 {row, L_ptr[row], U_ptr[row], nL | nU<<8}; filled by          */
                                   /* femb_build_fold_plan from vert_elem + elem2nnz                                          */
-  /* Optional plan of the two-stage software pipeline of femb_hessian / femb_force_hessian (0 / NULL = one chunk).  HOST
-   * arrays: chunk c ends at hexahedron pipe_hex_end[c] (exclusive); every vertex below pipe_vert_end[c] has all its
-   * hexahedra below pipe_hex_end[c].  Both non-decreasing, last entries n_hex and n_vert. */
-  int pipe_chunks;
-  const int* pipe_hex_end;   /* host [pipe_chunks] */
-  const int* pipe_vert_end;  /* host [pipe_chunks] */
   /* Optional lattice plan (0 / NULL = none): the mesh is a subset of a regular lattice (every voxel mesh of the reference,
    * object.py:28-45, and every coarse mesh built from one, object.py:171-241).  With it femb_hessian / femb_force_hessian
    * run as ONE kernel that never writes element matrices to memory (femb_fused.cu); without it they run the element
@@ -190,12 +188,6 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
  *   filled as in femb_force (same optional arguments). */
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add,
                  float* elem_k, float* values, void* stream);
-/* Optional (OFF by default: no gain measured on B200, both stages are bound on the SM side): with femb_set_pipeline(1)
- * and a plan in the level (pipe_*) both calls run the element kernel and the row fold as a software pipeline -- the fold
- * of the rows completed by chunk c runs on a library-owned side stream next to the element kernel of chunk c+1 (event
- * fork/join, graph-capturable) and reads the element matrices from L2.  Results do not depend on the chunking (same
- * fold order).  Returns the old setting. */
-int femb_set_pipeline(int enable);
 /* tuning of the row fold: consecutive rows per warp (default 4) and the occupancy target of the kernel (4 or 5 CTAs per SM) */
 int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm);
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
@@ -230,10 +222,6 @@ int femb_set_pdl(int enable);
 int femb_set_gs_threads_per_row(int subs);
 /* rows per CTA of the colour kernel: 16 (default: more independent row blocks in flight per SM) or 32 */
 int femb_set_gs_rows_per_cta(int rows);
-/* femb_gauss_seidel runs as ONE cooperative launch (grid-wide barrier between colour phases) when the largest colour has
- * at most this many 32-row blocks: 0 = never (default: PDL colour launches were measured faster at every level size),
- * -1 = twice the resident grid */
-int femb_set_gs_coop_max_blocks(int max_blocks);
 /* A run of colour launches of the in-place sweep above: colours first_color..last_color (descending if
  * first > last), dx is NOT zeroed.  femb_gauss_seidel(it=1) == zero dx; colours 7..0 with parts=U; colours 0..7
  * with parts=L|U.  Lets a caller put a halo exchange between colour groups (domain decomposition). */

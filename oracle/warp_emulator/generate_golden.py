@@ -16,7 +16,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF_DIRS = {"quasi": "/root/reference/exp1/quasi_simulation", "dynamic": "/root/reference/exp1/simulation",
-            "cloth": "/root/reference/exp1/cloth_simulation"}
+            "cloth": "/root/reference/exp1/cloth_simulation", "exp2": "/root/reference/exp2/p_hat/quasi_simulation"}
 sys.path.insert(0, ROOT)
 
 _orig_to = torch.Tensor.to
@@ -59,6 +59,9 @@ CASES = {
     "diag_adam": ("quasi", lambda: mesh.jagged_mesh(8, 9, 8, 0.05, seed=11, keep=0.7), 0.05, [40], {"Adam": 100}),
     "dyn5": ("dynamic", lambda: mesh.jagged_mesh(5, 6, 5, 0.05, seed=7, keep=0.8), 0.05, [], {"render": 3}),
     "cloth": ("cloth", None, None, None, {"render": 3}),
+    # exp2 (the canonical p_hat copy): compare() = the two-level forward step with classic and with "trained" position-
+    # restriction weights.  The mesh must have more than 732 vertices (compare perturbs x[732], object.py:1294 there).
+    "exp2": ("exp2", lambda: mesh.jagged_mesh(10, 9, 11, 0.05, seed=1), 0.05, [300], {"compare": 3}),
 }
 
 
@@ -151,7 +154,46 @@ def run_cloth(name):
     print("written", name, flush=True)
 
 
+def run_exp2(name):
+    """exp2/p_hat/quasi_simulation/object.py, unmodified.  Three things its compare() takes from outside are pinned here and
+    recorded in the fixture: the unseeded torch.rand perturbation (torch.manual_seed), and the "trained" weights it loads
+    from assets/p/Ut_noOrder_0.pth (dragon-sized: 26539 entries) -- torch.load is replaced by a stand-in that returns a
+    deterministic perturbation of the classic weights of THIS mesh."""
+    kind, build, dx, pins, methods = CASES[name]
+    use_reference(kind)
+    import object as ref_object
+    pts, hx = build()
+    path = os.path.join(ROOT, "tests", "golden", f"_mesh_{name}.npz")
+    np.savez(path, points=pts, hexagons=hx)
+    out = {"points": pts, "hexagons": hx, "dx": dx, "pinList": np.array(pins, dtype=np.int64)}
+    with contextlib.redirect_stdout(io.StringIO()):
+        obj = ref_object.Object("npz:" + path, dx, list(pins))
+        w0 = obj.Ut_noOrder_value.numpy().copy()
+        out["Ut_noOrder_value_init"] = w0
+        out["x_init"] = obj.dev_x_init.numpy().copy()
+        rng = np.random.default_rng(11)
+        w_tr = (w0 * (1.0 + 0.05 * rng.standard_normal(len(w0)))).astype(np.float32)
+        out["Ut_noOrder_value_trained"] = w_tr
+        torch.load = lambda *a, **k: torch.from_numpy(w_tr.copy())
+        torch.manual_seed(20251018)
+        x_before = obj.x[0].numpy().copy() if hasattr(obj.x[0], "numpy") else np.array(obj.x[0])
+        obj.compare(methods["compare"])
+        x_after = obj.x[0].numpy().copy() if hasattr(obj.x[0], "numpy") else np.array(obj.x[0])
+        out["perturbation"] = (x_after[732].astype(np.float64) - x_before[732].astype(np.float64)).astype(np.float32)
+        out["x_start"] = obj.x_cpu.numpy().copy()
+        out["plot_InfNorm"] = np.array(obj.plot_InfNorm, dtype=np.float64)
+        out["plot_InfNorm_newton"] = np.array(obj.plot_InfNorm_newton, dtype=np.float64)
+        out["x_final"] = obj.x_gpu_layer[0].numpy().copy()
+        out["UtAUs_values0"] = obj.UtAUs_values[0].numpy().copy()
+        out["steps"] = methods["compare"]
+    os.remove(path)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"), **out)
+    print("written", name, flush=True)
+
+
 def run_case(name):
+    if CASES[name][0] == "exp2":
+        return run_exp2(name)
     if CASES[name][0] == "dynamic":
         return run_dynamic(name)
     if CASES[name][0] == "cloth":

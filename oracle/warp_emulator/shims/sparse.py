@@ -107,3 +107,10 @@ def bsr_mm(x, y, z=None, alpha=1.0, beta=0.0, work_arrays=None):
     out = BsrMatrix(x.nrow, y.ncol, x.block_type)
     _from_coo(out, xr[xk], y.columns.data[:y.nnz].astype(np.int64)[ym], vals)
     return out
+
+
+# exp2's sparse.py adds a `*_with_grad` twin (values allocated with requires_grad=True; same triplet semantics,
+# /root/reference/exp2/p_hat/quasi_simulation/sparse.py:293-372)
+def bsr_set_from_triplets_with_grad(dest, rows, columns, values, value_offset=0, row_offset=0, col_offset=0, nnz=0):
+    return bsr_set_from_triplets(dest, rows, columns, values, value_offset=value_offset, row_offset=row_offset,
+                                 col_offset=col_offset, nnz=nnz)

@@ -225,6 +225,22 @@ class _MatMulToCall(ast.NodeTransformer):
         return node
 
 
+class _ValueAssign(ast.NodeTransformer):
+    """Warp vectors / matrices are VALUE types: `r = b` copies.  Python names alias, so a later `r[i] = ...` would also
+    change `b` (exp2's solve3x3 does `Ap = b; r = b; ...; Ap[i] = 0.0`, exp2/p_hat/quasi_simulation/cublas.py:59-77).  Plain
+    name-to-name assignments are routed through a copy."""
+
+    def visit_Assign(self, node):
+        self.generic_visit(node)
+        if len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) and isinstance(node.value, ast.Name):
+            node.value = ast.Call(func=ast.Name(id="__wp_val", ctx=ast.Load()), args=[node.value], keywords=[])
+        return node
+
+
+def _val(v):
+    return v.copy() if isinstance(v, np.ndarray) else v
+
+
 def _recompile(f, fall_through_return=False):
     """Re-compile a kernel/func body with `@` routed through _mm; optionally close an open-ended @wp.func."""
     src = textwrap.dedent(inspect.getsource(f))
@@ -236,8 +252,10 @@ def _recompile(f, fall_through_return=False):
         if not isinstance(fd.body[-1], ast.Return) and len(names) == 1:
             fd.body.append(ast.Return(value=ast.Name(id=names.pop(), ctx=ast.Load())))
     tree = _MatMulToCall().visit(tree)
+    tree = _ValueAssign().visit(tree)
     ast.fix_missing_locations(tree)
     f.__globals__["__wp_mm"] = _mm
+    f.__globals__["__wp_val"] = _val
     ns = {}
     exec(compile(tree, inspect.getsourcefile(f) or "<wp>", "exec"), f.__globals__, ns)
     return ns[fd.name]

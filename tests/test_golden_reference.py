@@ -250,3 +250,57 @@ def test_oracle_diagnostic_drivers_match_reference_class(method):
 def test_cuda_diagnostic_drivers_match_reference_class(method):
     from fem_simulation_b200 import Object
     _run_diag(lambda p, h, dx, pins: Object((p, h), dx, pins), method, lambda x: x.cpu().numpy())
+
+
+# ---- exp2 compare(): the unmodified exp2/p_hat/quasi_simulation/object.py under the emulator (ref_exp2.npz) -------------------
+EXP2 = os.path.join(GOLD, "ref_exp2.npz")
+
+
+def _exp2_gold():
+    g = dict(np.load(EXP2))
+    g["pins"] = [int(v) for v in g["pinList"]]
+    return g
+
+
+@pytest.mark.skipif(not os.path.exists(EXP2), reason="fixture not generated")
+def test_exp2_oracle_matches_reference_class():
+    """oracle/ref_exp2.py vs the reference class: default weights (p_hat_init), both |R|inf curves of compare() -- classic and
+    "trained" weights --, the final state and the last coarse Hessian.  The reference's unseeded perturbation of vertex 732
+    and the weights it loads from assets/p are recorded in the fixture (oracle/warp_emulator/generate_golden.py)."""
+    from oracle.ref_exp2 import RefExp2Object
+    g = _exp2_gold()
+    r = RefExp2Object(g["points"], g["hexagons"], float(g["dx"]), g["pins"])
+    assert np.array_equal(r.w, g["Ut_noOrder_value_init"]) and np.array_equal(r.dev_x_init, g["x_init"])
+    r.x_gpu_layer[0][732] += g["perturbation"]
+    assert np.array_equal(r.x_gpu_layer[0], g["x_start"])
+    x_start = r.x_gpu_layer[0].copy()
+    n = int(g["steps"])
+    r.compare_loop(n, r.w)
+    assert rel(np.array(r.plot_InfNorm), g["plot_InfNorm"]) <= 1e-5
+    r.x_gpu_layer[0][...] = x_start
+    r.plot_InfNorm = []
+    r.compare_loop(n, g["Ut_noOrder_value_trained"])
+    assert rel(np.array(r.plot_InfNorm), g["plot_InfNorm_newton"]) <= 1e-5
+    assert rel(r.x_gpu_layer[0], g["x_final"]) <= 1e-6
+    assert np.abs((r.x_gpu_layer[0] - x_start) - (g["x_final"] - g["x_start"])).max() <= 1e-3 * np.abs(g["x_final"] - g["x_start"]).max()
+    assert rel(r.UtAUs_values[0], g["UtAUs_values0"]) <= 1e-5
+    assert np.abs(g["plot_InfNorm"][1:] - g["plot_InfNorm_newton"][1:]).max() > 0     # the trained weights change the iteration
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(EXP2), reason="fixture not generated")
+def test_exp2_cuda_matches_reference_class():
+    import torch
+    from fem_simulation_b200.object_exp2 import Exp2Object
+    g = _exp2_gold()
+    o = Exp2Object((g["points"], g["hexagons"]), float(g["dx"]), g["pins"])
+    assert np.array_equal(o.Ut_noOrder_value.cpu().numpy(), g["Ut_noOrder_value_init"])
+    n = int(g["steps"])
+    o.compare(n, perturb_vertex=732, perturbation=tuple(float(v) for v in g["perturbation"]),
+              trained=torch.from_numpy(g["Ut_noOrder_value_trained"]))
+    assert rel(np.array(o.plot_InfNorm), g["plot_InfNorm"]) <= 1e-5
+    assert rel(np.array(o.plot_InfNorm_newton), g["plot_InfNorm_newton"]) <= 1e-5
+    x = o.x_gpu_layer[0].cpu().numpy()
+    assert rel(x, g["x_final"]) <= 1e-6
+    assert np.abs((x - g["x_start"]) - (g["x_final"] - g["x_start"])).max() <= 1e-3 * np.abs(g["x_final"] - g["x_start"]).max()
+    assert rel(o.UtAUs_values[0].cpu().numpy(), g["UtAUs_values0"]) <= 2e-5

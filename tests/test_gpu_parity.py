@@ -370,56 +370,6 @@ def test_empty_and_errors():
     assert lib.femb_launch_count() > 0
 
 
-def test_pipelined_assembly_is_bit_identical():
-    """femb_hessian / femb_force_hessian as a chunked two-stream software pipeline (FembLevel.pipe_*) vs the two stages
-    back to back (the default): same fold order => identical bits; eagerly, repeatedly, and replayed from a
-    CUDA graph (event fork/join captured as parallel branches)."""
-    pts, hx = MESHES["jag3"]()
-    obj = Object((pts, hx), 0.05, [], use_graphs=False, pipe_chunk_hexes=160)
-    assert obj.levels[0].pipe_chunks > 4 and obj.levels[1].pipe_chunks >= 2
-    he, ve = obj._pat[0]["pipe_hex_end"], obj._pat[0]["pipe_vert_end"]
-    assert he[-1] == obj.N_hexagons and ve[-1] == obj.N_verts and np.all(np.diff(he) > 0) and np.all(np.diff(ve) >= 0)
-    last = obj._pat[0]["vert_elem"].cpu().numpy().max(axis=1) >> 3
-    for c in range(len(he)):
-        assert last[:ve[c]].max(initial=-1) < he[c]                  # rows below vert_end[c] are complete after chunk c
-    rng = np.random.default_rng(11)
-    x0 = obj.x_gpu_layer[0] + torch.from_numpy(rng.normal(size=(obj.N_verts, 3)).astype(np.float32) * 0.002).to(obj.device)
-    for l in range(2):
-        x = x0 if l == 0 else obj.x_gpu_layer[l] * 1.01
-        diag = obj.diag_fixed if l == 0 else None
-        va, vb = obj.new_values(l), obj.new_values(l)
-        obj._hessian(l, x, va, diag)
-        obj.lib.femb_set_pipeline(1)
-        try:
-            for rep in range(3):
-                vb.fill_(float("nan"))
-                obj._hessian(l, x, vb, diag)
-                torch.cuda.synchronize()
-                assert torch.equal(va, vb), f"level {l} rep {rep}: pipelined assembly differs"
-        finally:
-            obj.lib.femb_set_pipeline(0)
-    f1, f2 = torch.zeros_like(x0), torch.zeros_like(x0)
-    va, vb = obj.new_values(0), obj.new_values(0)
-    obj._force_hessian(x0, f1, va, obj.diag_fixed)
-    obj.lib.femb_set_pipeline(1)
-    try:
-        obj._force_hessian(x0, f2, vb, obj.diag_fixed)
-        torch.cuda.synchronize()
-        assert torch.equal(va, vb) and torch.equal(f1, f2)
-        g = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
-        with torch.cuda.stream(s):
-            with torch.cuda.graph(g, stream=s):
-                obj._force_hessian(x0, f2, vb, obj.diag_fixed)
-        for rep in range(3):
-            vb.fill_(float("nan")); f2.fill_(float("nan"))
-            g.replay()
-            torch.cuda.synchronize()
-            assert torch.equal(va, vb) and torch.equal(f1, f2), f"graph replay {rep} differs"
-    finally:
-        obj.lib.femb_set_pipeline(0)
-
-
 def test_pdl_gauss_seidel_is_bit_identical():
     """The colour launches of femb_gauss_seidel are programmatic dependent launches (matrix staging overlaps the
     previous colour's tail).  Same arithmetic => identical bits with femb_set_pdl(0), eagerly and in a CUDA graph,
@@ -513,17 +463,16 @@ def test_rows_with_more_than_27_blocks():
 @pytest.mark.parametrize("rows,subs", [(8, 4), (8, 8), (16, 4), (16, 8), (32, 4), (32, 8)])
 def test_row_pass_configurations(pair, rows, subs):
     """Every rows-per-CTA x threads-per-row instantiation of the row-pass kernels (Gauss-Seidel colour launches as
-    programmatic dependent launches, and the cooperative single-launch sweep; residual) against the oracle."""
+    programmatic dependent launches; residual) against the oracle."""
     obj, ref, xp = pair
     _load_state(obj, ref, xp)
     ref.PerformGaussSeidel(0, 2)
     old_r, old_s = obj.lib.femb_set_gs_rows_per_cta(rows), obj.lib.femb_set_gs_threads_per_row(subs)
     try:
-        for coop in (0, -1):
-            obj.lib.femb_set_gs_coop_max_blocks(coop)
+        if True:
             obj.dev_delta_x[0].fill_(float("nan"))
             obj.PerformGaussSeidel(0, 2)
-            close(obj.dev_delta_x[0], ref.dev_delta_x[0], what=f"GS x2 rows={rows} subs={subs} coop={coop}")
+            close(obj.dev_delta_x[0], ref.dev_delta_x[0], what=f"GS x2 rows={rows} subs={subs}")
         r = torch.zeros_like(obj.dev_delta_x[0])
         obj._residual(0, obj.dev_B_fixed[0], obj.dev_delta_x[0], r)
         acc = np.zeros_like(ref.dev_delta_x[0])
@@ -531,7 +480,6 @@ def test_row_pass_configurations(pair, rows, subs):
             ref_solvers.bsr_mv(m[0], ref.dev_delta_x[0], acc, alpha=1.0, beta=1.0)
         close(r, ref.grad - acc, what=f"residual rows={rows} subs={subs}")
     finally:
-        obj.lib.femb_set_gs_coop_max_blocks(0)
         obj.lib.femb_set_gs_rows_per_cta(old_r)
         obj.lib.femb_set_gs_threads_per_row(old_s)
 

@@ -159,35 +159,6 @@ def test_galerkin_plan_emulation():
         assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
-def test_pipeline_plan_is_prefix_closed():
-    """Host logic of the optional element/fold software pipeline (FembLevel.pipe_*): chunk ends are increasing and cover
-    the level, and every vertex below vert_end[c] has all its hexahedra below hex_end[c] -- on a ragged mesh and on a
-    first-seen-numbered coarse level."""
-    from fem_simulation_b200.object import Object
-    pts, hx = mesh.jagged_mesh(18, 17, 19, 0.05, seed=2, keep=0.7, origin=(-0.3, 0.1, 0.2))
-    H = hierarchy.build_hierarchy(pts, hx, 0.05, 2)
-    for l in range(2):
-        hexs, n = H.hexs[l], H.dims[l]
-        ve = np.full((n, 8), -1, dtype=np.int32)
-        flat = hexs.reshape(-1).astype(np.int64)
-        o2 = np.argsort(flat, kind="stable")
-        cnt = np.bincount(flat, minlength=n)
-        start = np.cumsum(cnt) - cnt
-        ve[flat[o2], np.arange(len(o2)) - start[flat[o2]]] = o2.astype(np.int32)
-        for chunk in (16, 160, 1000):
-            plan = Object._pipe_plan(hexs.shape[0], ve, chunk)
-            if hexs.shape[0] <= chunk:
-                assert plan is None
-                continue
-            he, vend = plan
-            assert he[-1] == hexs.shape[0] and vend[-1] == n
-            assert np.all(np.diff(he) > 0) and np.all(np.diff(vend) >= 0)
-            last = ve.max(axis=1) >> 3
-            for c in range(len(he)):
-                assert last[:vend[c]].max(initial=-1) < he[c]
-    assert Object._pipe_plan(0, np.zeros((0, 8), np.int32), 16) is None
-
-
 def test_exp3_hooks_edge_index_and_prolongation_chain():
     """exp3/simulation/object.py:258-276 (edge_index, dictionary order) and :294,429,438-441 (A_noOrder chain behind torch_A),
     vectorised vs the literal loops."""
