@@ -107,7 +107,7 @@ class ClockSampler:
 
 
 # DRAM bytes (read + write) per launch measured with `ncu --set full` on the cube n=100 (profiles/README.md), per million hexahedra
-ASM_TRAFFIC_PER_MHEX = 4.55e9      # element_kernel<1> 0.364 + 1.477 GB, assemble_rows_kernel 1.741 + 0.967 GB (profiles/r01b_element_assemble_ncu_raw.txt)
+ASM_TRAFFIC_PER_MHEX = 4.32e9      # element_kernel<1,1> 0.364 + 1.479 GB, fold_lattice_kernel 1.530 + 0.950 GB (profiles/r02_lattice_assembly_ncu_raw.txt)
 GS_TRAFFIC_PER_MHEX = 142e6        # average colour launch of a 3-iteration sweep: 154.8 MB per L|U launch (profiles/r01b_gs_color_ncu_raw.txt), ~80 MB per U-only launch
 
 
@@ -239,7 +239,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_e2e = maxed(ev0.elapsed_time(ev1))
-    # ---- dominant stage of the FAS step: femb_hessian = element_kernel + assemble_rows_kernel (timed through the C ABI) ----
+    # ---- dominant stage of the FAS step: femb_hessian = element_kernel + fold_lattice_kernel (timed through the C ABI) ----
     reps = 5
     vals_tmp = obj.MF_value_gpu
     for _ in range(2):
@@ -324,8 +324,8 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps * world),
         "step_hbm": {"algorithmic_bytes_per_step_per_rank": sb, "achieved_GBps_per_rank": sb / (ms / args.steps * 1e-3) / 1e9,
                      "frac_of_peak": sb / (ms / args.steps * 1e-3) / 1e9 / peak},
-        "roofline": {"bound": "hbm", "kernel": "femb_hessian: element_kernel<1> + assemble_rows_kernel (level 0, the two launches of "
-                     "the assembly stage; the element kernel itself is FP32-issue / shared-memory bound, see DESIGN.md)",
+        "roofline": {"bound": "hbm", "kernel": "femb_hessian: element_kernel<1,1> + fold_lattice_kernel (level 0, the two launches of "
+                     "the assembly stage; the element kernel is bound by the L1 / shared-memory pipe, see DESIGN.md)",
                      "achieved": asm_bytes / (asm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "traffic": ASM_TRAFFIC_PER_MHEX * H.hexs[0].shape[0] / 1e6,
                      "traffic_note": "dram__bytes_read+write of the two kernels, ncu --set full at cube n=100 (profiles/), scaled by hexahedra",

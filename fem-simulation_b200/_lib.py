@@ -12,7 +12,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libfemb200.so")
-SOURCES = ["femb_api.cu", "femb_element.cu", "femb_fused.cu", "femb_comm.cu", "femb_steps.cu", "femb_setup.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
+SOURCES = ["femb_api.cu", "femb_element.cu", "femb_comm.cu", "femb_steps.cu", "femb_setup.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-ldl", "-lgomp"]
 
@@ -31,12 +31,10 @@ class FembLevel(C.Structure):
                 ("elem2nnz", C.c_void_p),
                 ("vert_elem", C.c_void_p), ("invJ", C.c_void_p), ("detJ", C.c_void_p),
                 ("fold_plan", C.c_void_p),
-                ("lat_vx", C.c_int), ("lat_vy", C.c_int), ("lat_vz", C.c_int), ("lat_chunks", C.c_int),
-                ("lat_cell_elem", C.c_void_p), ("lat_row_rec", C.c_void_p)]
+                ("lat_inc8", C.c_void_p), ("lat_row_rec", C.c_void_p)]
 
-ASM_CHUNK_HEXES = 16           # FEMB_ASM_CHUNK_HEXES
+ASM_CHUNK_HEXES = 32           # FEMB_ASM_CHUNK_HEXES
 ELEM_K_FLOATS = 384            # FEMB_ELEM_K_FLOATS
-FUSED_TILE = 7                 # FEMB_FUSED_TILE
 ROW_REC_BYTES = 48             # FEMB_ROW_REC_BYTES
 
 
@@ -113,7 +111,7 @@ PROTOTYPES = {
     "femb_setup_galerkin_fill_host": [I, I] + [P] * 22,
     "femb_prepare_rest": [I, P, P, P, P, P],
     "femb_build_fold_plan": [LV, P, P],
-    "femb_build_lattice_plan": [LV, P, P, P, P],
+    "femb_build_lattice_fold": [LV, P, P, P, P],
     "femb_lumped_mass": [LV, P, P, P],
     "femb_force": [LV, P, F, F, P, F, P, P, F, I, P, P, P],
     "femb_hessian": [LV, P, F, F, P, P, P, P],
@@ -207,7 +205,7 @@ def load(rebuild: bool = False):
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported
         fn.argtypes = args
         fn.restype = _RESTYPE.get(name, C.c_int)
-    if lib.femb_abi_version() != 4:
+    if lib.femb_abi_version() != 5:
         raise FembError("libfemb200 ABI version mismatch")
     _lib = lib
     return lib

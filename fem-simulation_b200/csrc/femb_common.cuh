@@ -20,12 +20,6 @@ int check_launch(const char* what);
     }                                                      \
   } while (0)
 
-// one-kernel assembly of a lattice level (femb_fused.cu); force_out == nullptr: values only
-bool fused_available(const FembLevel* l);
-int launch_fused(const FembLevel* l, const float* x, float mu, float la, const float* diag_add, float* values,
-                 const float* mass, float g, const int* pin, const float* pin_pos, float control_mag, float* force_out,
-                 cudaStream_t st);
-
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 

@@ -8,52 +8,102 @@
 //   compute_partial_elastic_energy_X    quai_hexagon.py:109-133  (N_h*8 threads, 24 float atomics / thread)
 //   gravity / pin-spring forces         quai_hexagon.py:160-186
 //
-// B200 design: 8 lanes per hexahedron (4 hexahedra per warp).  In phase A lane q evaluates everything
-// that depends only on the Gauss point q (F, S, F F^T, g_b = J^-T dN_b, u_b = F g_b, t_b = S g_b) once
-// and parks it in shared memory; in phase B lane a accumulates, over the 8 Gauss points, the 5 blocks
-// K[a][(a+k) & 7], k = 0..4 (the element matrix is symmetric: the cyclic half is enough) with the closed form
+// B200 design.  A thread carries TWO hexahedra, one in each half of 64-bit register pairs, and the whole element
+// arithmetic runs on packed fp32 instructions (fma/mul/add.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2: two FMAs per lane at the
+// issue cost of one FFMA, scalar operands broadcast for free).  8 lanes work on a pair of hexahedra (4 pairs per warp).
+// In phase A lane q evaluates everything that depends only on the Gauss point q
+// (F, S, F F^T, g_b = J^-T dN_b, u_b = F g_b) once and parks it in shared memory; in phase B lane a accumulates, over the
+// 8 Gauss points, the 5 blocks K[a][(a+k) & 7], k = 0..4 (the element matrix is symmetric: the cyclic half is enough)
+// with the closed form
 //     K_ab[j][i] = det * ( (g_a . S g_b) d_ji + mu (g_a . g_b)(F F^T)_ji + mu u_b[j] u_a[i] + la u_a[j] u_b[i] )
-// (== d(P g_a det)_j / d x_b,i of quai_hexagon.py:86-106).  The half rows go to a scratch array (192 bytes per
-// row, written as coalesced 512-byte stores) and are summed into the fixed [L;D;U] value layout by a per-row
-// gather over the fold plan, the precomputed inverse of the element->nnz map (fixed order, no atomics).
+// (== d(P g_a det)_j / d x_b,i of quai_hexagon.py:86-106).  The half rows go to a scratch array and are summed into the
+// fixed [L;D;U] value layout by a gather in a fixed order (no atomics):
+//   * lattice levels (every level of a voxel mesh): the scratch is plane-major, EM[(a*5+k)*9+c][hexahedron], and
+//     fold_lattice_kernel gives every (row, block component) its own thread, which adds its <= 64 contributions through
+//     compile-time offsets (the lattice offset of node b seen from node a) -- coalesced 128-byte lines, no plan decoding;
+//   * any other hexahedral mesh: 192-byte half rows per (hexahedron, node) and the per-row fold plan, the precomputed
+//     inverse of the element->nnz map (assemble_rows_kernel).
 #include <cstdio>
 
 #include "femb_common.cuh"
 
 namespace femb {
 
+constexpr int EPAIRS = FEMB_ASM_CHUNK_HEXES / 2;     // pairs of hexahedra per CTA
 constexpr int EPB = FEMB_ASM_CHUNK_HEXES;            // hexahedra per CTA
-constexpr int ETHREADS = EPB * 8;  // 128 threads
+constexpr int ETHREADS = EPAIRS * 8;                 // 128 threads
 
-// per (hexahedron, Gauss point) record in shared memory, in floats; written and read as float4:
-//   [0..5] det*mu * F F^T (symmetric: 00 01 02 11 12 22)   [6] det*mu   [7] det*la
-//   [8 + 6 b ..] per node b: g_b[3], u_b[3]          (48 floats; broadcast-read by all 8 lanes)
-//   [56 + 3 b ..] per node b: det * S g_b[3]          (24 floats; lane a reads only its own t_a)
+// ---- packed fp32: the two halves of a pair are two hexahedra -----------------------------------------------------
+struct V2 { float2 v; };
+__device__ __forceinline__ unsigned long long pk(const V2& a) { return *reinterpret_cast<const unsigned long long*>(&a.v); }
+__device__ __forceinline__ V2 vfma(V2 a, V2 b, V2 c) {
+  V2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long*>(&d.v)) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
+  return d;
+}
+__device__ __forceinline__ V2 vmul(V2 a, V2 b) {
+  V2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d.v)) : "l"(pk(a)), "l"(pk(b)));
+  return d;
+}
+__device__ __forceinline__ V2 vadd(V2 a, V2 b) {
+  V2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d.v)) : "l"(pk(a)), "l"(pk(b)));
+  return d;
+}
+__device__ __forceinline__ V2 vsub(V2 a, V2 b) {
+  V2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d.v)) : "l"(pk(a)), "l"(pk(b)));
+  return d;
+}
+__device__ __forceinline__ V2 vneg(V2 a) { V2 d; d.v = make_float2(-a.v.x, -a.v.y); return d; }
+// the scalar instantiation rounds exactly like one half of the packed one (no contraction the packed code does not have)
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float vsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+template <class T> __device__ __forceinline__ T bc(float s);
+template <> __device__ __forceinline__ float bc<float>(float s) { return s; }
+template <> __device__ __forceinline__ V2 bc<V2>(float s) { V2 d; d.v = make_float2(s, s); return d; }
+template <class T> __device__ __forceinline__ T dot3(T a0, T b0, T a1, T b1, T a2, T b2) { return vfma(a2, b2, vfma(a1, b1, vmul(a0, b0))); }
+__device__ __forceinline__ V2 vshfl_xor(V2 a, int m) {
+  V2 d;
+  d.v.x = __shfl_xor_sync(0xffffffffu, a.v.x, m);
+  d.v.y = __shfl_xor_sync(0xffffffffu, a.v.y, m);
+  return d;
+}
+__device__ __forceinline__ void store2(float*, float, float) {}   // the scalar instantiation never writes records
+__device__ __forceinline__ void store2(V2* p, V2 a, V2 b) { *reinterpret_cast<float4*>(p) = make_float4(a.v.x, a.v.y, b.v.x, b.v.y); }
+
+// per (pair of hexahedra, Gauss point) record in shared memory, in pairs (T = V2), written and read as float4 = 2 pairs:
+//   [0..5] det*mu * F F^T (symmetric: 00 01 02 11 12 22)   [6] det*mu   [7] det*la   [8..13] det * S (00 01 02 11 12 22)
+//   [14 + 6 b ..] per node b: g_b[3], u_b[3]
 constexpr int QP_FFT = 0;
 constexpr int QP_C = 6;
-constexpr int QP_GU = 8;
-constexpr int QP_T = 56;
-constexpr int QP_SIZE = 84;   // 21 float4: 16-byte accesses of 8 consecutive lanes hit distinct banks (21 is odd)
-// floats between the records of consecutive hexahedra: 8*84 + 16 = 16 (mod 32), so the per-lane 8-byte reads of phase B
-// (two hexahedra per half-warp, 16 banks each) are conflict-free
-constexpr int HEX_STRIDE = 8 * QP_SIZE + 16;
-constexpr int EK_ROW = FEMB_ELEM_K_FLOATS / 8;   // floats per stored row of an element matrix (5 blocks + 3 pad)
+constexpr int QP_S = 8;
+constexpr int QP_GU = 14;
+constexpr int QP_SIZE = 62;   // 31 float4: the 16-byte record writes of 8 consecutive lanes hit distinct banks (31 is odd)
+// pairs between the records of consecutive hexahedron pairs: (8*62 + 4) / 2 = 250 float4 = 2 (mod 8), so the broadcast reads
+// of the 4 pairs of a warp hit distinct banks
+constexpr int PAIR_STRIDE = 8 * QP_SIZE + 4;
+constexpr int XS_STRIDE = 52;                    // floats of staged node positions per pair (24 pairs + 4 pad: 20 mod 32)
+constexpr int EK_ROW = FEMB_ELEM_K_FLOATS / 8;   // floats per stored row of an element matrix, general layout (5 blocks + 3 pad)
+constexpr int EM_PLANES = 360;                   // lattice layout: planes (a*5+k)*9+c of one float per hexahedron
+constexpr int EM_STG = 36;                       // floats per plane in the staging area of a CTA (32 hexahedra + 4: see below)
 
 struct ElemIn {
   const int* hex;
   const float* x;
   const float* invJ;
   const float* detJ;
-  int e_begin, n_hex;    // the launch covers hexahedra [e_begin, n_hex)
+  int e_begin, n_hex;    // the launch covers hexahedra [e_begin, n_hex); e_begin is a multiple of FEMB_ASM_CHUNK_HEXES
   float mu, la;
+  size_t em_stride;      // lattice layout: floats per plane (n_hex rounded up to a multiple of 32)
 };
 
-// Phase A for lane q of hexahedron e.  Writes the Gauss-point record and returns P*det (first
-// Piola-Kirchhoff stress times det J) plus the energy density times det.
-__device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, const float (&X)[8][3], float* rec,
-                                            float (&fq)[8][3], float& energy, bool want_rec) {
-  // shape-function gradients at this Gauss point (q is a runtime value here)
-  float dN[8][3];
+// shape-function gradients at Gauss point q (a runtime value: the lane)
+__device__ __forceinline__ void shape_grads(int q, float (&dN)[8][3]) {
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
 #pragma unroll
@@ -65,89 +115,90 @@ __device__ __forceinline__ void gauss_point(const ElemIn& in, int e, int q, cons
       dN[a][c] = (s * f0) * f1 * 0.125f;
     }
   }
-  float iJ[9];
-  const float* ip = in.invJ + ((size_t)e * 8 + q) * 9;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) iJ[k] = __ldg(ip + k);
-  const float det = __ldg(in.detJ + (size_t)e * 8 + q);
+}
+
+// Phase A at one Gauss point: the record (kRec), the nodal forces -(P g_b) det (kForce), the energy density times det
+// (kEnergy).  T = V2: two hexahedra at once; T = float: one.
+template <class T, bool kRec, bool kForce, bool kEnergy>
+__device__ __forceinline__ void gauss_point(const T (&X)[8][3], const float (&dN)[8][3], const T (&iJ)[9], T det, float mu, float la,
+                                            T* __restrict__ rec, T (&fq)[8][3], T& energy) {
   // F0 = sum_a x_a (x) dN_a ; F = F0 * invJ                                  (quai_hexagon.py:77-84)
-  float F0[9];
+  T F[9];
+  {
+    T F0[9];
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v = 0.f;
+      for (int c = 0; c < 3; ++c) {
+        T v = vmul(X[0][r], bc<T>(dN[0][c]));
 #pragma unroll
-      for (int a = 0; a < 8; ++a) v += X[a][r] * dN[a][c];
-      F0[3 * r + c] = v;
-    }
-  float F[9];
+        for (int a = 1; a < 8; ++a) v = vfma(X[a][r], bc<T>(dN[a][c]), v);
+        F0[3 * r + c] = v;
+      }
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) F[3 * r + c] = F0[3 * r] * iJ[c] + F0[3 * r + 1] * iJ[3 + c] + F0[3 * r + 2] * iJ[6 + c];
+      for (int c = 0; c < 3; ++c) F[3 * r + c] = dot3(F0[3 * r], iJ[c], F0[3 * r + 1], iJ[3 + c], F0[3 * r + 2], iJ[6 + c]);
+  }
   // E = 0.5 (F^T F - I), S = 2 mu E + la tr(E) I   (symmetric: 00 01 02 11 12 22)
-  float E[6];
-  E[0] = 0.5f * (F[0] * F[0] + F[3] * F[3] + F[6] * F[6] - 1.f);
-  E[1] = 0.5f * (F[0] * F[1] + F[3] * F[4] + F[6] * F[7]);
-  E[2] = 0.5f * (F[0] * F[2] + F[3] * F[5] + F[6] * F[8]);
-  E[3] = 0.5f * (F[1] * F[1] + F[4] * F[4] + F[7] * F[7] - 1.f);
-  E[4] = 0.5f * (F[1] * F[2] + F[4] * F[5] + F[7] * F[8]);
-  E[5] = 0.5f * (F[2] * F[2] + F[5] * F[5] + F[8] * F[8] - 1.f);
-  const float trE = E[0] + E[3] + E[5];
-  const float sumE2 = E[0] * E[0] + E[3] * E[3] + E[5] * E[5] + 2.f * (E[1] * E[1] + E[2] * E[2] + E[4] * E[4]);
-  energy = (sumE2 * in.mu + 0.5f * in.la * trE * trE) * det;                 // quai_hexagon.py:47-53
-  float S[6];
-  const float tm = 2.f * in.mu;
-  S[0] = tm * E[0] + in.la * trE; S[1] = tm * E[1]; S[2] = tm * E[2];
-  S[3] = tm * E[3] + in.la * trE; S[4] = tm * E[4]; S[5] = tm * E[5] + in.la * trE;
-  // P = F S
-  float P[9];
+  const T half = bc<T>(0.5f), one = bc<T>(1.f);
+  T E[6];
+  E[0] = vmul(half, vsub(dot3(F[0], F[0], F[3], F[3], F[6], F[6]), one));
+  E[1] = vmul(half, dot3(F[0], F[1], F[3], F[4], F[6], F[7]));
+  E[2] = vmul(half, dot3(F[0], F[2], F[3], F[5], F[6], F[8]));
+  E[3] = vmul(half, vsub(dot3(F[1], F[1], F[4], F[4], F[7], F[7]), one));
+  E[4] = vmul(half, dot3(F[1], F[2], F[4], F[5], F[7], F[8]));
+  E[5] = vmul(half, vsub(dot3(F[2], F[2], F[5], F[5], F[8], F[8]), one));
+  const T trE = vadd(vadd(E[0], E[3]), E[5]);
+  if (kEnergy) {                                                             // quai_hexagon.py:47-53
+    const T off = vfma(E[4], E[4], vfma(E[2], E[2], vmul(E[1], E[1])));
+    const T sumE2 = vfma(bc<T>(2.f), off, dot3(E[0], E[0], E[3], E[3], E[5], E[5]));
+    energy = vmul(vfma(sumE2, bc<T>(mu), vmul(bc<T>(0.5f * la), vmul(trE, trE))), det);
+  }
+  const T tm = bc<T>(2.f * mu), lt = vmul(bc<T>(la), trE);
+  T S[6];
+  S[0] = vfma(tm, E[0], lt); S[1] = vmul(tm, E[1]); S[2] = vmul(tm, E[2]);
+  S[3] = vfma(tm, E[3], lt); S[4] = vmul(tm, E[4]); S[5] = vfma(tm, E[5], lt);
+  T P[9];                                                                    // P = F S
+  if (kForce) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    P[3 * r + 0] = F[3 * r] * S[0] + F[3 * r + 1] * S[1] + F[3 * r + 2] * S[2];
-    P[3 * r + 1] = F[3 * r] * S[1] + F[3 * r + 1] * S[3] + F[3 * r + 2] * S[4];
-    P[3 * r + 2] = F[3 * r] * S[2] + F[3 * r + 1] * S[4] + F[3 * r + 2] * S[5];
+    for (int r = 0; r < 3; ++r) {
+      P[3 * r + 0] = dot3(F[3 * r], S[0], F[3 * r + 1], S[1], F[3 * r + 2], S[2]);
+      P[3 * r + 1] = dot3(F[3 * r], S[1], F[3 * r + 1], S[3], F[3 * r + 2], S[4]);
+      P[3 * r + 2] = dot3(F[3 * r], S[2], F[3 * r + 1], S[4], F[3 * r + 2], S[5]);
+    }
   }
-  float R[QP_SIZE];
-  if (want_rec) {
-    const float cmu = det * in.mu;
-    R[QP_FFT + 0] = cmu * (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
-    R[QP_FFT + 1] = cmu * (F[0] * F[3] + F[1] * F[4] + F[2] * F[5]);
-    R[QP_FFT + 2] = cmu * (F[0] * F[6] + F[1] * F[7] + F[2] * F[8]);
-    R[QP_FFT + 3] = cmu * (F[3] * F[3] + F[4] * F[4] + F[5] * F[5]);
-    R[QP_FFT + 4] = cmu * (F[3] * F[6] + F[4] * F[7] + F[5] * F[8]);
-    R[QP_FFT + 5] = cmu * (F[6] * F[6] + F[7] * F[7] + F[8] * F[8]);
-    R[QP_C + 0] = cmu;
-    R[QP_C + 1] = det * in.la;
+  if (kRec) {
+    const T cmu = vmul(det, bc<T>(mu));
+    store2(rec + QP_FFT + 0, vmul(cmu, dot3(F[0], F[0], F[1], F[1], F[2], F[2])), vmul(cmu, dot3(F[0], F[3], F[1], F[4], F[2], F[5])));
+    store2(rec + QP_FFT + 2, vmul(cmu, dot3(F[0], F[6], F[1], F[7], F[2], F[8])), vmul(cmu, dot3(F[3], F[3], F[4], F[4], F[5], F[5])));
+    store2(rec + QP_FFT + 4, vmul(cmu, dot3(F[3], F[6], F[4], F[7], F[5], F[8])), vmul(cmu, dot3(F[6], F[6], F[7], F[7], F[8], F[8])));
+    store2(rec + QP_C, cmu, vmul(det, bc<T>(la)));
+    store2(rec + QP_S + 0, vmul(det, S[0]), vmul(det, S[1]));
+    store2(rec + QP_S + 2, vmul(det, S[2]), vmul(det, S[3]));
+    store2(rec + QP_S + 4, vmul(det, S[4]), vmul(det, S[5]));
   }
+  const T ndet = vneg(det);
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     // g_b = invJ^T dN_b  (dF row of quai_hexagon.py:95)
-    float g[3];
+    T g[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) g[j] = dN[b][0] * iJ[j] + dN[b][1] * iJ[3 + j] + dN[b][2] * iJ[6 + j];
+    for (int j = 0; j < 3; ++j) g[j] = dot3(bc<T>(dN[b][0]), iJ[j], bc<T>(dN[b][1]), iJ[3 + j], bc<T>(dN[b][2]), iJ[6 + j]);
     // nodal force contribution  -(P g_b) det                                 (quai_hexagon.py:128-133)
+    if (kForce) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) fq[b][r] = -det * (P[3 * r] * g[0] + P[3 * r + 1] * g[1] + P[3 * r + 2] * g[2]);
-    if (want_rec) {
-      float* o = R + QP_GU + 6 * b;
-      o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
+      for (int r = 0; r < 3; ++r) fq[b][r] = vmul(ndet, dot3(P[3 * r], g[0], P[3 * r + 1], g[1], P[3 * r + 2], g[2]));
+    }
+    if (kRec) {
+      T u[3];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) o[3 + r] = F[3 * r] * g[0] + F[3 * r + 1] * g[1] + F[3 * r + 2] * g[2];
-      float* t = R + QP_T + 3 * b;
-      t[0] = det * (S[0] * g[0] + S[1] * g[1] + S[2] * g[2]);
-      t[1] = det * (S[1] * g[0] + S[3] * g[1] + S[4] * g[2]);
-      t[2] = det * (S[2] * g[0] + S[4] * g[1] + S[5] * g[2]);
+      for (int r = 0; r < 3; ++r) u[r] = dot3(F[3 * r], g[0], F[3 * r + 1], g[1], F[3 * r + 2], g[2]);
+      T* o = rec + QP_GU + 6 * b;
+      store2(o, g[0], g[1]); store2(o + 2, g[2], u[0]); store2(o + 4, u[1], u[2]);
     }
   }
-  if (want_rec) {
-    float4* r4 = reinterpret_cast<float4*>(rec);
-#pragma unroll
-    for (int v = 0; v < 20; ++v) r4[v] = make_float4(R[4 * v], R[4 * v + 1], R[4 * v + 2], R[4 * v + 3]);
-  }
 }
-
 // ---- row-centric assembly of one row (vertex v, index-order row r) by one warp -------------------------
 // The row needs row `a` of the element matrices of its <= 8 incident hexahedra: 8 blocks = 288 contiguous,
 // 16-byte aligned bytes each, fetched as 18 float4 by 18 lanes (all 8 fetches in flight before the first is
@@ -366,157 +417,355 @@ __global__ void __launch_bounds__(256) fold_plan_kernel(AsmArgs A, unsigned char
   if (lane == 0) *reinterpret_cast<unsigned*>(out + 27 * 4) = bad ? 0xfefefefeu : hi;
 }
 
-// kMode: 0 = forces only, 1 = Hessian only, 2 = both
-template <int kMode>
-__global__ void __launch_bounds__(ETHREADS, 5) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
+// lattice offset slot of node b seen from node a: 9 (dx+1) + 3 (dy+1) + (dz+1)   (local node = 4 bx + 2 by + bz)
+__host__ __device__ __forceinline__ constexpr int offset_slot(int a, int b) {
+  return 13 + 9 * (((b >> 2) & 1) - ((a >> 2) & 1)) + 3 * (((b >> 1) & 1) - ((a >> 1) & 1)) + ((b & 1) - (a & 1));
+}
+
+// kMode: 0 = forces only, 1 = Hessian only, 2 = both.  kSoA: element matrices in the plane-major lattice layout.
+template <int kMode, bool kSoA>
+__global__ void __launch_bounds__(ETHREADS, 3) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
   extern __shared__ __align__(16) float smem[];
-  float* s_rec = smem;                                                // [EPB][HEX_STRIDE]: 8 records per hexahedron (Hessian only)
+  float* s_x = smem;                                                  // [EPAIRS][XS_STRIDE]: node positions of the pairs
+  V2* s_rec = reinterpret_cast<V2*>(smem + EPAIRS * XS_STRIDE);       // [EPAIRS][PAIR_STRIDE]: 8 records per pair (Hessian only)
   const int sub = threadIdx.x & 7;
-  const int le = threadIdx.x >> 3;
-  const int e = in.e_begin + blockIdx.x * EPB + le;                   // this launch covers hexahedra [e_begin, n_hex)
-  const bool live = e < in.n_hex;
-  const int ee = live ? e : in.n_hex - 1;                             // dead lanes shadow a valid hexahedron
-  // node positions: lane `sub` loads node `sub`, the group shares them with width-8 shuffles
-  const int vtx = __ldg(in.hex + (size_t)ee * 8 + sub);
-  float xn[3] = {__ldg(in.x + 3 * (size_t)vtx), __ldg(in.x + 3 * (size_t)vtx + 1), __ldg(in.x + 3 * (size_t)vtx + 2)};
-  float X[8][3];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) X[a][c] = __shfl_sync(0xffffffffu, xn[c], a, 8);
-
+  const int lp = threadIdx.x >> 3;
+  const int e0 = in.e_begin + (blockIdx.x * EPAIRS + lp) * 2, e1 = e0 + 1;   // this launch covers hexahedra [e_begin, n_hex)
+  const bool live0 = e0 < in.n_hex, live1 = e1 < in.n_hex;
+  const int ee0 = live0 ? e0 : in.n_hex - 1, ee1 = live1 ? e1 : in.n_hex - 1;   // dead halves shadow a valid hexahedron
+  // node positions: lane `sub` loads node `sub` of both hexahedra, the 8 lanes of the pair share them through shared memory
   {
-    float fq[8][3];
-    float energy;
-    float* rec = s_rec + (size_t)le * HEX_STRIDE + sub * QP_SIZE;
-    gauss_point(in, ee, sub, X, rec, fq, energy, kHess);
+    const int v0 = __ldg(in.hex + (size_t)ee0 * 8 + sub), v1 = __ldg(in.hex + (size_t)ee1 * 8 + sub);
+    float2* d = reinterpret_cast<float2*>(s_x + lp * XS_STRIDE) + 3 * sub;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = make_float2(__ldg(in.x + 3 * (size_t)v0 + c), __ldg(in.x + 3 * (size_t)v1 + c));
+  }
+  float dN[8][3];
+  shape_grads(sub, dN);
+  V2 iJ[9], det;
+  {
+    const float* p0 = in.invJ + ((size_t)ee0 * 8 + sub) * 9;
+    const float* p1 = in.invJ + ((size_t)ee1 * 8 + sub) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) iJ[k].v = make_float2(__ldg(p0 + k), __ldg(p1 + k));
+    det.v = make_float2(__ldg(in.detJ + (size_t)ee0 * 8 + sub), __ldg(in.detJ + (size_t)ee1 * 8 + sub));
+  }
+  __syncwarp();
+  {
+    V2 X[8][3];
+    const float4* xs4 = reinterpret_cast<const float4*>(s_x + lp * XS_STRIDE);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const float4 t = xs4[i];
+      X[(2 * i) / 3][(2 * i) % 3].v = make_float2(t.x, t.y);
+      X[(2 * i + 1) / 3][(2 * i + 1) % 3].v = make_float2(t.z, t.w);
+    }
+    V2 fq[8][3], en;
+    gauss_point<V2, kHess, kForce, false>(X, dN, iJ, det, in.mu, in.la, s_rec + (size_t)lp * PAIR_STRIDE + sub * QP_SIZE, fq, en);
     if (kForce) {
       // lane q holds the Gauss-point contributions to all 8 nodes; a reduce-scatter over the 8 lanes of the
-      // hexahedron (xor 4, 2, 1) leaves lane a with the force on node a
-      float h4[4][3], h2[2][3], f[3];
+      // pair (xor 4, 2, 1) leaves lane a with the force on node a
+      V2 h4[4][3], h2[2][3], f[3];
       const bool up4 = (sub & 4) != 0, up2 = (sub & 2) != 0, up1 = (sub & 1) != 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float give = up4 ? fq[i][c] : fq[i + 4][c], keep = up4 ? fq[i + 4][c] : fq[i][c];
-          h4[i][c] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+          const V2 give = up4 ? fq[i][c] : fq[i + 4][c], keep = up4 ? fq[i + 4][c] : fq[i][c];
+          h4[i][c] = vadd(keep, vshfl_xor(give, 4));
         }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float give = up2 ? h4[i][c] : h4[i + 2][c], keep = up2 ? h4[i + 2][c] : h4[i][c];
-          h2[i][c] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+          const V2 give = up2 ? h4[i][c] : h4[i + 2][c], keep = up2 ? h4[i + 2][c] : h4[i][c];
+          h2[i][c] = vadd(keep, vshfl_xor(give, 2));
         }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float give = up1 ? h2[0][c] : h2[1][c], keep = up1 ? h2[1][c] : h2[0][c];
-        f[c] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+        const V2 give = up1 ? h2[0][c] : h2[1][c], keep = up1 ? h2[1][c] : h2[0][c];
+        f[c] = vadd(keep, vshfl_xor(give, 1));
       }
-      if (live) {
-        float* dst = elem_f + ((size_t)e * 8 + sub) * 3;
-        dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2];
+      if (live0) {
+        float* dst = elem_f + ((size_t)e0 * 8 + sub) * 3;
+        dst[0] = f[0].v.x; dst[1] = f[1].v.x; dst[2] = f[2].v.x;
+      }
+      if (live1) {
+        float* dst = elem_f + ((size_t)e1 * 8 + sub) * 3;
+        dst[0] = f[0].v.y; dst[1] = f[1].v.y; dst[2] = f[2].v.y;
       }
     }
   }
   if (!kHess) return;
-  __syncthreads();
+  __syncwarp();                                              // the 8 records of a pair are written by 8 lanes of one warp
 
   // ---- phase B: lane a accumulates the 5 blocks K[a][(a+k) & 7], k = 0..4 ------------------------------
   // K_ab[j][i] = sum_q  d_ji (t_a . g_b) + (det mu FF^T)_ji (g_a . g_b) + det mu u_b[j] u_a[i] + det la u_a[j] u_b[i]
-  // with t_a = det S g_a (S symmetric: g_a . S g_b == S g_a . g_b); every term is one FFMA into an accumulator.
+  // with t_a = det S g_a (S symmetric: g_a . S g_b == S g_a . g_b); every term is one FFMA2 into an accumulator pair.
   // The element matrix is symmetric (K_ba = K_ab^T), so the cyclic half {(a, a+k)} is enough: the blocks
-  // K[a][(a-m) & 7], m = 1..3, are the transposes of block m of lane (a-m) & 7 and arrive by shuffle.
-  float K[5][9], Ks[5];
+  // K[a][(a-m) & 7], m = 1..3, are the transposes of block m of row (a-m) & 7 and are picked up from there by the fold.
+  V2 K[5][9], Ks[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    Ks[k] = 0.f;
+    Ks[k] = bc<V2>(0.f);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) K[k][i] = 0.f;
+    for (int i = 0; i < 9; ++i) K[k][i] = bc<V2>(0.f);
   }
   const bool has_la = in.la != 0.f;
+  const V2* rp = s_rec + (size_t)lp * PAIR_STRIDE;
 #pragma unroll 1
-  for (int q = 0; q < 8; ++q) {
-    const float* r = s_rec + (size_t)le * HEX_STRIDE + q * QP_SIZE;
-    const float4* r4 = reinterpret_cast<const float4*>(r);
-    const float4 h0 = r4[0], h1 = r4[1];                   // broadcast reads (all 8 lanes of a hexahedron, same address)
-    const float FFT[6] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y};
-    const float cmu = h1.z, cla = h1.w;
-    const float2* ga2 = reinterpret_cast<const float2*>(r + QP_GU + 6 * sub);   // own node
-    const float2 o0 = ga2[0], o1 = ga2[1], o2 = ga2[2];
-    const float g_a[3] = {o0.x, o0.y, o1.x};
-    const float ua_mu[3] = {cmu * o1.y, cmu * o2.x, cmu * o2.y};
-    const float ua_la[3] = {cla * o1.y, cla * o2.x, cla * o2.y};
-    const float* tp = r + QP_T + 3 * sub;
-    const float t_a[3] = {tp[0], tp[1], tp[2]};
+  for (int q = 0; q < 8; ++q, rp += QP_SIZE) {
+    const float4* r4 = reinterpret_cast<const float4*>(rp);
+    V2 FFT[6], cmu, cla, Sd[6];
+    {
+      const float4 h0 = r4[0], h1 = r4[1], h2 = r4[2], h3 = r4[3], h4 = r4[4], h5 = r4[5], h6 = r4[6];   // broadcast reads
+      FFT[0].v = make_float2(h0.x, h0.y); FFT[1].v = make_float2(h0.z, h0.w); FFT[2].v = make_float2(h1.x, h1.y);
+      FFT[3].v = make_float2(h1.z, h1.w); FFT[4].v = make_float2(h2.x, h2.y); FFT[5].v = make_float2(h2.z, h2.w);
+      cmu.v = make_float2(h3.x, h3.y); cla.v = make_float2(h3.z, h3.w);
+      Sd[0].v = make_float2(h4.x, h4.y); Sd[1].v = make_float2(h4.z, h4.w); Sd[2].v = make_float2(h5.x, h5.y);
+      Sd[3].v = make_float2(h5.z, h5.w); Sd[4].v = make_float2(h6.x, h6.y); Sd[5].v = make_float2(h6.z, h6.w);
+    }
+    V2 g_a[3], u_a[3];
+    {
+      const float4* na = reinterpret_cast<const float4*>(rp + QP_GU + 6 * sub);   // own node
+      const float4 o0 = na[0], o1 = na[1], o2 = na[2];
+      g_a[0].v = make_float2(o0.x, o0.y); g_a[1].v = make_float2(o0.z, o0.w); g_a[2].v = make_float2(o1.x, o1.y);
+      u_a[0].v = make_float2(o1.z, o1.w); u_a[1].v = make_float2(o2.x, o2.y); u_a[2].v = make_float2(o2.z, o2.w);
+    }
+    V2 t_a[3];
+    t_a[0] = dot3(Sd[0], g_a[0], Sd[1], g_a[1], Sd[2], g_a[2]);
+    t_a[1] = dot3(Sd[1], g_a[0], Sd[3], g_a[1], Sd[4], g_a[2]);
+    t_a[2] = dot3(Sd[2], g_a[0], Sd[4], g_a[1], Sd[5], g_a[2]);
+    const V2 ua_mu[3] = {vmul(cmu, u_a[0]), vmul(cmu, u_a[1]), vmul(cmu, u_a[2])};
+    V2 ua_la[3];
+    if (has_la) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ua_la[i] = vmul(cla, u_a[i]);
+    }
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      const float2* gb2 = reinterpret_cast<const float2*>(r + QP_GU + 6 * ((sub + k) & 7));
-      const float2 p0 = gb2[0], p1 = gb2[1], p2 = gb2[2];
-      const float gb[3] = {p0.x, p0.y, p1.x};
-      const float u_b[3] = {p1.y, p2.x, p2.y};
-      Ks[k] = fmaf(t_a[0], gb[0], fmaf(t_a[1], gb[1], fmaf(t_a[2], gb[2], Ks[k])));
-      const float s2 = fmaf(g_a[0], gb[0], fmaf(g_a[1], gb[1], g_a[2] * gb[2]));
-      K[k][0] = fmaf(FFT[0], s2, fmaf(u_b[0], ua_mu[0], K[k][0]));
-      K[k][1] = fmaf(FFT[1], s2, fmaf(u_b[0], ua_mu[1], K[k][1]));
-      K[k][2] = fmaf(FFT[2], s2, fmaf(u_b[0], ua_mu[2], K[k][2]));
-      K[k][3] = fmaf(FFT[1], s2, fmaf(u_b[1], ua_mu[0], K[k][3]));
-      K[k][4] = fmaf(FFT[3], s2, fmaf(u_b[1], ua_mu[1], K[k][4]));
-      K[k][5] = fmaf(FFT[4], s2, fmaf(u_b[1], ua_mu[2], K[k][5]));
-      K[k][6] = fmaf(FFT[2], s2, fmaf(u_b[2], ua_mu[0], K[k][6]));
-      K[k][7] = fmaf(FFT[4], s2, fmaf(u_b[2], ua_mu[1], K[k][7]));
-      K[k][8] = fmaf(FFT[5], s2, fmaf(u_b[2], ua_mu[2], K[k][8]));
+      V2 gb[3], ub[3];
+      if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { gb[i] = g_a[i]; ub[i] = u_a[i]; }
+      } else {
+        const float4* nb = reinterpret_cast<const float4*>(rp + QP_GU + 6 * ((sub + k) & 7));
+        const float4 p0 = nb[0], p1 = nb[1], p2 = nb[2];
+        gb[0].v = make_float2(p0.x, p0.y); gb[1].v = make_float2(p0.z, p0.w); gb[2].v = make_float2(p1.x, p1.y);
+        ub[0].v = make_float2(p1.z, p1.w); ub[1].v = make_float2(p2.x, p2.y); ub[2].v = make_float2(p2.z, p2.w);
+      }
+      Ks[k] = vfma(t_a[0], gb[0], vfma(t_a[1], gb[1], vfma(t_a[2], gb[2], Ks[k])));
+      const V2 s2 = dot3(g_a[2], gb[2], g_a[1], gb[1], g_a[0], gb[0]);
+      K[k][0] = vfma(FFT[0], s2, vfma(ub[0], ua_mu[0], K[k][0]));
+      K[k][1] = vfma(FFT[1], s2, vfma(ub[0], ua_mu[1], K[k][1]));
+      K[k][2] = vfma(FFT[2], s2, vfma(ub[0], ua_mu[2], K[k][2]));
+      K[k][3] = vfma(FFT[1], s2, vfma(ub[1], ua_mu[0], K[k][3]));
+      K[k][4] = vfma(FFT[3], s2, vfma(ub[1], ua_mu[1], K[k][4]));
+      K[k][5] = vfma(FFT[4], s2, vfma(ub[1], ua_mu[2], K[k][5]));
+      K[k][6] = vfma(FFT[2], s2, vfma(ub[2], ua_mu[0], K[k][6]));
+      K[k][7] = vfma(FFT[4], s2, vfma(ub[2], ua_mu[1], K[k][7]));
+      K[k][8] = vfma(FFT[5], s2, vfma(ub[2], ua_mu[2], K[k][8]));
       if (has_la) {
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
-          for (int i = 0; i < 3; ++i) K[k][3 * j + i] = fmaf(ua_la[j], u_b[i], K[k][3 * j + i]);
+          for (int i = 0; i < 3; ++i) K[k][3 * j + i] = vfma(ua_la[j], ub[i], K[k][3 * j + i]);
       }
     }
   }
-  // Row a of the element matrix is stored ROTATED and HALF: position p = 0..4 holds the block of column (a + p) & 7
-  // (45 floats + 3 pad = 192 bytes).  The blocks of columns (a - m) & 7, m = 1..3, are the transposes of position m of
-  // row (a - m) & 7 and are picked up from there by the assembly.
-  // Layout of the 48 floats: elements 0..7 of position p at [8p, 8p+8), the ninth elements at [40, 45), 3 pad.
-  float row[48];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    K[k][0] += Ks[k]; K[k][4] += Ks[k]; K[k][8] += Ks[k];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) row[8 * k + i] = K[k][i];
-    row[40 + k] = K[k][8];
+    K[k][0] = vadd(K[k][0], Ks[k]); K[k][4] = vadd(K[k][4], Ks[k]); K[k][8] = vadd(K[k][8], Ks[k]);
   }
-  row[45] = 0.f; row[46] = 0.f; row[47] = 0.f;
-  // The warp's 32 half rows are contiguous in elem_k (4 consecutive hexahedra x 8 rows x 192 bytes).  Written straight from
-  // registers every STG.128 would scatter 32 16-byte pieces over 32 sectors (measured: the stores cost as many L1
-  // wavefronts as all shared-memory traffic of the kernel), so the rows are transposed through the warp's own record area
-  // (dead now; read only by this warp) and stored as 12 fully coalesced 512-byte writes.
-  constexpr int WROW = EK_ROW + 4;                                   // padded row: 16-byte stores of 8 lanes hit distinct banks
-  const int lane = threadIdx.x & 31;
-  float* wst = s_rec + (size_t)(threadIdx.x >> 5) * 4 * HEX_STRIDE;  // records of this warp's 4 hexahedra
-  __syncwarp();
-  {
-    float4* my = reinterpret_cast<float4*>(wst + lane * WROW);
+  if (kSoA) {
+    // Lattice layout: plane (a*5+k)*9+c holds one float per hexahedron.  The CTA's 32 hexahedra are transposed through
+    // the record area (dead now, but shared by all warps: two block barriers) and leave as 360 full 128-byte lines.
+    // EM_STG = 36: the 8-byte writes of a half warp (2 pairs x 8 nodes, 45*36 = 20 (mod 32) floats apart) and the 16-byte
+    // reads of a quarter warp (one plane) are conflict-free.
+    __syncthreads();
+    float* stg = reinterpret_cast<float*>(s_rec);
 #pragma unroll
-    for (int v = 0; v < EK_ROW / 4; ++v) my[v] = make_float4(row[4 * v], row[4 * v + 1], row[4 * v + 2], row[4 * v + 3]);
-  }
-  __syncwarp();
-  const int e_w = in.e_begin + blockIdx.x * EPB + (threadIdx.x >> 5) * 4;   // first hexahedron of the warp
-  float4* gdst = reinterpret_cast<float4*>(elem_k + (size_t)e_w * 8 * EK_ROW);
+    for (int k = 0; k < 5; ++k)
 #pragma unroll
-  for (int i = 0; i < EK_ROW / 4; ++i) {
-    const int g = i * 32 + lane;                                     // float4 index inside the warp's 6144 bytes
-    const int rw = g / (EK_ROW / 4), c = g - rw * (EK_ROW / 4);
-    if (e_w + (rw >> 3) < in.n_hex) gdst[g] = *reinterpret_cast<const float4*>(wst + rw * WROW + 4 * c);
+      for (int i = 0; i < 9; ++i) *reinterpret_cast<float2*>(stg + ((sub * 5 + k) * 9 + i) * EM_STG + 2 * lp) = K[k][i].v;
+    __syncthreads();
+    float* gdst = elem_k + (size_t)in.e_begin + (size_t)blockIdx.x * EPB;
+    for (int idx = threadIdx.x; idx < EM_PLANES * 8; idx += ETHREADS) {
+      const int j = idx >> 3, part = idx & 7;
+      *reinterpret_cast<float4*>(gdst + (size_t)j * in.em_stride + 4 * part) = *reinterpret_cast<const float4*>(stg + j * EM_STG + 4 * part);
+    }
+  } else {
+    // General layout: row a of the element matrix is stored ROTATED and HALF: position p = 0..4 holds the block of column
+    // (a + p) & 7 (45 floats + 3 pad = 192 bytes: elements 0..7 of position p at [8p, 8p+8), the ninth elements at [40, 45)).
+    // The blocks of columns (a - m) & 7, m = 1..3, are the transposes of position m of row (a - m) & 7 and are picked up from
+    // there by the assembly.  The warp's 64 half rows are contiguous in elem_k (8 consecutive hexahedra x 8 rows x 192
+    // bytes): they are transposed through the warp's own record area (dead now; read only by this warp) and stored as
+    // fully coalesced 512-byte writes.
+    constexpr int WROW = EK_ROW + 4;                                   // padded row: 16-byte stores of 8 lanes hit distinct banks
+    const int lane = threadIdx.x & 31;
+    float* wst = reinterpret_cast<float*>(s_rec + (size_t)(threadIdx.x >> 5) * 4 * PAIR_STRIDE);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float row[48];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) row[8 * k + i] = h ? K[k][i].v.y : K[k][i].v.x;
+        row[40 + k] = h ? K[k][8].v.y : K[k][8].v.x;
+      }
+      row[45] = 0.f; row[46] = 0.f; row[47] = 0.f;
+      float4* my = reinterpret_cast<float4*>(wst + (((lane >> 3) * 2 + h) * 8 + sub) * WROW);
+#pragma unroll
+      for (int v = 0; v < EK_ROW / 4; ++v) my[v] = make_float4(row[4 * v], row[4 * v + 1], row[4 * v + 2], row[4 * v + 3]);
+    }
+    __syncwarp();
+    const int e_w = in.e_begin + (blockIdx.x * EPAIRS + (threadIdx.x >> 5) * 4) * 2;   // first hexahedron of the warp
+    float4* gdst = reinterpret_cast<float4*>(elem_k + (size_t)e_w * 8 * EK_ROW);
+#pragma unroll 4
+    for (int i = 0; i < 2 * EK_ROW / 4; ++i) {
+      const int g = i * 32 + lane;                                     // float4 index inside the warp's 12288 bytes
+      const int rw = g / (EK_ROW / 4), c = g - rw * (EK_ROW / 4);
+      if (e_w + (rw >> 3) < in.n_hex) gdst[g] = *reinterpret_cast<const float4*>(wst + rw * WROW + 4 * c);
+    }
   }
 }
 
 template <int kMode>
 static size_t element_smem() {
-  return (kMode != 0 ? (size_t)EPB * HEX_STRIDE : 4) * sizeof(float);
+  return ((size_t)EPAIRS * XS_STRIDE + (kMode != 0 ? (size_t)EPAIRS * PAIR_STRIDE * 2 : 0)) * sizeof(float);
+}
+
+// ---- lattice fold: one thread per (row, block component) --------------------------------------------------------
+// On a lattice every row has <= 27 blocks, one per lattice offset of the column vertex, and node b of a hexahedron in
+// which the row vertex is node a always lands in block offset_slot(a, b).  Thread (lane = row, warp = component c) adds
+// the <= 64 contributions of its component with compile-time plane offsets: a warp-wide load reads 32 consecutive
+// hexahedra of one plane.  The sums are parked in shared memory at their sorted position inside the row (row record:
+// lattice offset -> position among the row's L blocks, D, U blocks) and leave as the row's three contiguous segments.
+constexpr int FL_ROWS = 32;
+constexpr int FL_THREADS = 9 * 32;
+constexpr int RR_WORDS = FEMB_ROW_REC_BYTES / 4;
+struct FoldLatArgs {
+  int n_vert;
+  const int* inc8; const unsigned* row_rec;
+  const float* em; unsigned em_stride;
+  const float* diag_add; float* values;
+  int off_l, off_d, off_u;
+};
+template <int kMinBlocks>
+__global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(FoldLatArgs A, int v_begin, int v_end) {
+  __shared__ float st[FL_ROWS * 243];
+  __shared__ unsigned rr[FL_ROWS * RR_WORDS];
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  const int v0 = v_begin + blockIdx.x * FL_ROWS, v = v0 + lane;
+  const bool live = v < v_end;
+  for (int i = threadIdx.x; i < FL_ROWS * RR_WORDS; i += FL_THREADS)
+    if (v0 + i / RR_WORDS < v_end) rr[i] = __ldg(A.row_rec + (size_t)v0 * RR_WORDS + i);
+  int inc[8];
+  {
+    int4 i0 = make_int4(-1, -1, -1, -1), i1 = i0;
+    if (live) {
+      const int4* p = reinterpret_cast<const int4*>(A.inc8 + (size_t)v * 8);
+      i0 = __ldg(p); i1 = __ldg(p + 1);
+    }
+    inc[0] = i0.x; inc[1] = i0.y; inc[2] = i0.z; inc[3] = i0.w; inc[4] = i1.x; inc[5] = i1.y; inc[6] = i1.z; inc[7] = i1.w;
+  }
+  const int cT = (c % 3) * 3 + c / 3;                           // the mirrored blocks are stored transposed
+  // 32-bit element offsets (the launcher checks 360 * em_stride < 2^32): one IMAD + one address per load
+  const unsigned ps = A.em_stride;
+  const unsigned od = (unsigned)c * ps, om = (unsigned)cT * ps;
+  const float* __restrict__ em = A.em;
+  float acc[27];
+#pragma unroll
+  for (int s = 0; s < 27; ++s) acc[s] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int e = inc[a];
+    const bool have = e >= 0;
+    const unsigned ed = od + (have ? (unsigned)e : 0u), emr = om + (have ? (unsigned)e : 0u);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int k = (b - a) & 7;
+      const unsigned idx = k <= 4 ? ed + (unsigned)((a * 5 + k) * 9) * ps : emr + (unsigned)((b * 5 + (8 - k)) * 9) * ps;
+      const float val = have ? __ldg(em + idx) : 0.f;
+      acc[offset_slot(a, b)] += val;
+    }
+  }
+  __syncthreads();
+  if (live) {
+    const unsigned* w = rr + lane * RR_WORDS;
+    unsigned pw[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pw[i] = w[i];
+    float* dst = st + lane * 243 + c;
+#pragma unroll
+    for (int s = 0; s < 27; ++s) {
+      const unsigned pos = (pw[s >> 2] >> (8 * (s & 3))) & 255u;
+      if (pos < 27u) dst[pos * 9] = acc[s];
+    }
+  }
+  __syncthreads();
+  for (int row = c; row < FL_ROWS && v0 + row < v_end; row += FL_THREADS / 32) {
+    const unsigned* w = rr + row * RR_WORDS;
+    const int r = (int)w[8], lp = (int)w[9], up = (int)w[10];
+    const int nl = (int)(w[11] & 255u), nu = (int)((w[11] >> 8) & 255u);
+    const float* src = st + row * 243;
+    float* outL = A.values + ((size_t)A.off_l + lp) * 9;
+    for (int i = lane; i < nl * 9; i += 32) outL[i] = src[i];
+    if (lane < 9) {
+      float d = src[nl * 9 + lane];
+      if (A.diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) d += __ldg(A.diag_add + r);
+      A.values[((size_t)A.off_d + r) * 9 + lane] = d;
+    }
+    float* outU = A.values + ((size_t)A.off_u + up) * 9;
+    for (int i = lane; i < nu * 9; i += 32) outU[i] = src[(nl + 1) * 9 + i];
+  }
+}
+
+// setup of the lattice fold: inc8[v][a] = the hexahedron in which vertex v is local node a (-1: none); row record of v:
+// bytes 0..26 lattice offset slot -> sorted position inside the row (255: no such block), int32 words 7..11
+// {v, index-order row, L_ptr[row], U_ptr[row], nL | nU << 8}
+__global__ void __launch_bounds__(256) lat_init_kernel(int n_vert, const int* __restrict__ v2i, const int* __restrict__ L_ptr,
+                                                      const int* __restrict__ U_ptr, int* __restrict__ inc8,
+                                                      unsigned* __restrict__ rec, int* __restrict__ bad) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vert) return;
+  const int r = __ldg(v2i + v);
+  const int lp = __ldg(L_ptr + r), nl = __ldg(L_ptr + r + 1) - lp, up = __ldg(U_ptr + r), nu = __ldg(U_ptr + r + 1) - up;
+  if (nl + 1 + nu > 27) *bad = 1;
+  unsigned* o = rec + (size_t)v * RR_WORDS;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) o[i] = 0xffffffffu;
+  o[7] = (unsigned)v; o[8] = (unsigned)r; o[9] = (unsigned)lp; o[10] = (unsigned)up;
+  o[11] = (unsigned)((nl & 255) | ((nu & 255) << 8));
+#pragma unroll
+  for (int a = 0; a < 8; ++a) inc8[(size_t)v * 8 + a] = -1;
+}
+// kCheck = false: write; true: verify that every writer agreed (a mesh that is not a lattice subset sets *bad)
+template <bool kCheck>
+__global__ void __launch_bounds__(256) lat_fill_kernel(int n_hex, const int* __restrict__ hex, const int* __restrict__ v2i,
+                                                      const int* __restrict__ L_ptr, const int* __restrict__ U_ptr,
+                                                      const int* __restrict__ elem2nnz, int off_l, int off_d, int off_u,
+                                                      int* __restrict__ inc8, unsigned char* __restrict__ rec, int* __restrict__ bad) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_hex * 8) return;
+  const int a = (int)(t & 7), e = (int)(t >> 3);
+  const int v = __ldg(hex + t);
+  const int r = __ldg(v2i + v);
+  const int lp = __ldg(L_ptr + r), nl = __ldg(L_ptr + r + 1) - lp, up = __ldg(U_ptr + r);
+  if (kCheck) { if (inc8[(size_t)v * 8 + a] != e) *bad = 1; }
+  else inc8[(size_t)v * 8 + a] = e;
+  unsigned char* o = rec + (size_t)v * FEMB_ROW_REC_BYTES;
+  for (int b = 0; b < 8; ++b) {
+    const int s = __ldg(elem2nnz + t * 8 + b);
+    const int loc = s < off_d ? (s - off_l - lp) : (s < off_u ? nl : nl + 1 + (s - off_u - up));
+    if (loc < 0 || loc >= 27) { *bad = 1; continue; }
+    unsigned char* d = o + offset_slot(a, b);
+    if (kCheck) { if (*d != (unsigned char)loc) *bad = 1; }
+    else *d = (unsigned char)loc;
+  }
 }
 
 // two-kernel path: one warp per row
@@ -628,12 +877,15 @@ __global__ void mass_kernel(int n_vert, const int* __restrict__ vert_elem, const
 }
 
 // energy: partial sums per block, then one block adds them in a fixed order
+constexpr int EN_HEX = ETHREADS / 8;                  // hexahedra per group of the energy kernel (8 lanes each, scalar arithmetic)
 __global__ void __launch_bounds__(ETHREADS) elastic_energy_kernel(ElemIn in, int n_groups, float* __restrict__ partial) {
   __shared__ float red[32];
   float acc = 0.f;
   const int sub = threadIdx.x & 7;
+  float dN[8][3];
+  shape_grads(sub, dN);
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int e = grp * EPB + (threadIdx.x >> 3);
+    const int e = grp * EN_HEX + (threadIdx.x >> 3);
     const bool live = e < in.n_hex;
     const int ee = live ? e : in.n_hex - 1;
     const int vtx = __ldg(in.hex + (size_t)ee * 8 + sub);
@@ -643,9 +895,14 @@ __global__ void __launch_bounds__(ETHREADS) elastic_energy_kernel(ElemIn in, int
     for (int a = 0; a < 8; ++a)
 #pragma unroll
       for (int c = 0; c < 3; ++c) X[a][c] = __shfl_sync(0xffffffffu, xn[c], a, 8);
+    float iJ[9];
+    const float* ip = in.invJ + ((size_t)ee * 8 + sub) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) iJ[k] = __ldg(ip + k);
+    const float det = __ldg(in.detJ + (size_t)ee * 8 + sub);
     float fq[8][3];
     float en;
-    gauss_point(in, ee, sub, X, nullptr, fq, en, false);
+    gauss_point<float, false, false, true>(X, dN, iJ, det, in.mu, in.la, nullptr, fq, en);
     if (live) acc += en;
   }
   const float s = block_sum(acc, red);
@@ -700,9 +957,16 @@ __global__ void __launch_bounds__(256) coarse_pin_kernel(int n_coarse, const int
   }
 }
 
+static size_t em_stride_of(int n_hex) { return ((size_t)n_hex + 31) / 32 * 32; }
+// (the lattice fold addresses the plane-major scratch with 32-bit element offsets)
+static bool lattice_available(const FembLevel* l) {
+  return l->lat_inc8 != nullptr && l->lat_row_rec != nullptr && (unsigned long long)EM_PLANES * em_stride_of(l->n_hex) < (1ull << 32);
+}
+
 static ElemIn make_in(const FembLevel* l, const float* x, float mu, float la) {
   ElemIn in;
   in.hex = l->hex; in.x = x; in.invJ = l->invJ; in.detJ = l->detJ; in.e_begin = 0; in.n_hex = l->n_hex; in.mu = mu; in.la = la;
+  in.em_stride = em_stride_of(l->n_hex);
   return in;
 }
 
@@ -714,7 +978,7 @@ static AsmArgs make_asm(const FembLevel* l, const float* diag_add, const float* 
   return A;
 }
 
-template <int kMode>
+template <int kMode, bool kSoA>
 static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
   static bool configured_dev[64] = {};                         // cudaFuncSetAttribute is per device
   int cur_dev = 0;
@@ -722,12 +986,12 @@ static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, floa
   bool& configured = configured_dev[cur_dev & 63];
   const size_t smem = element_smem<kMode>();
   if (!configured) {
-    cudaFuncSetAttribute(element_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(element_kernel<kMode, kSoA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   if (e_end <= e_begin) return FEMB_OK;
   in.e_begin = e_begin; in.n_hex = e_end;
-  element_kernel<kMode><<<cdiv(e_end - e_begin, EPB), ETHREADS, smem, st>>>(in, elem_f, elem_k);
+  element_kernel<kMode, kSoA><<<cdiv(e_end - e_begin, EPB), ETHREADS, smem, st>>>(in, elem_f, elem_k);
   count_launch();
   return check_launch("element_kernel");
 }
@@ -753,16 +1017,38 @@ static int launch_assemble(const AsmArgs& as, int v_begin, int v_end, cudaStream
   return check_launch("assemble_rows_kernel");
 }
 
+static int g_lat_min_blocks = 4;
+static int launch_fold_lattice(const FembLevel* l, const float* diag_add, const float* elem_k, float* values, cudaStream_t st) {
+  FoldLatArgs A;
+  A.n_vert = l->n_vert; A.inc8 = l->lat_inc8; A.row_rec = reinterpret_cast<const unsigned*>(l->lat_row_rec);
+  A.em = elem_k; A.em_stride = (unsigned)em_stride_of(l->n_hex); A.diag_add = diag_add; A.values = values;
+  A.off_l = l->off_l; A.off_d = l->off_d; A.off_u = l->off_u;
+  const unsigned grid = cdiv(l->n_vert, FL_ROWS);
+  if (g_lat_min_blocks == 3) fold_lattice_kernel<3><<<grid, FL_THREADS, 0, st>>>(A, 0, l->n_vert);
+  else if (g_lat_min_blocks == 5) fold_lattice_kernel<5><<<grid, FL_THREADS, 0, st>>>(A, 0, l->n_vert);
+  else fold_lattice_kernel<4><<<grid, FL_THREADS, 0, st>>>(A, 0, l->n_vert);
+  count_launch();
+  return check_launch("fold_lattice_kernel");
+}
+
 // element matrices of all hexahedra + fold of all rows; kMode 1 = Hessian only, 2 = element forces as well
 template <int kMode>
 static int hessian_pipeline(const FembLevel* l, const float* x, float mu, float la, const float* diag_add, float* elem_f,
                             float* elem_k, float* values, cudaStream_t st) {
   const ElemIn in = make_in(l, x, mu, la);
+  // (A chunked two-stream software pipeline of the two stages and a one-kernel variant with the fold inside the SM were
+  // built and measured slower)
+  if (lattice_available(l)) {
+    int rc = launch_element<kMode, true>(in, 0, l->n_hex, elem_f, elem_k, st);
+    if (rc) return rc;
+    return launch_fold_lattice(l, diag_add, elem_k, values, st);
+  }
+  if (!(l->elem2nnz && l->vert_elem && l->i2v && l->fold_plan)) {
+    set_error("assembly: level has neither a lattice fold nor a fold plan");
+    return FEMB_E_INVALID;
+  }
   const AsmArgs as = make_asm(l, diag_add, elem_k, values);
-  // (A chunked two-stream software pipeline of the two stages -- the fold of chunk c next to the element kernel of chunk
-  // c+1, element matrices read from L2 -- was built and measured: 1.88-2.10 vs 1.69-1.83 ms back to back, both stages are
-  // bound on the SM side; removed)
-  int rc = launch_element<kMode>(in, 0, l->n_hex, elem_f, elem_k, st);
+  int rc = launch_element<kMode, false>(in, 0, l->n_hex, elem_f, elem_k, st);
   if (rc) return rc;
   return launch_assemble(as, 0, l->n_vert, st);
 }
@@ -776,6 +1062,7 @@ extern "C" {
 int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm) {
   if (rows_per_warp >= 1 && rows_per_warp <= 64) g_fold_rows_per_warp = rows_per_warp;
   if (min_blocks_per_sm == 4 || min_blocks_per_sm == 5) g_fold_min_blocks = min_blocks_per_sm;
+  if (min_blocks_per_sm >= 3 && min_blocks_per_sm <= 5) g_lat_min_blocks = min_blocks_per_sm;
   return FEMB_OK;
 }
 
@@ -814,7 +1101,7 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
   FEMB_REQUIRE(lvl && x && elem_f && out, "null pointer");
   FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->vert_elem && lvl->v2i, "level not initialised");
   if (lvl->n_hex > 0) {
-    int rc = launch_element<0>(make_in(lvl, x, mu, lambda), 0, lvl->n_hex, elem_f, nullptr, as_stream(stream));
+    int rc = launch_element<0, false>(make_in(lvl, x, mu, lambda), 0, lvl->n_hex, elem_f, nullptr, as_stream(stream));
     if (rc) return rc;
   }
   if (lvl->n_vert == 0) return FEMB_OK;
@@ -823,39 +1110,48 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
 
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add, float* elem_k,
                  float* values, void* stream) {
-  FEMB_REQUIRE(lvl && x && values, "null pointer");
+  FEMB_REQUIRE(lvl && x && values && elem_k, "null pointer");
   if (lvl->n_vert == 0) return FEMB_OK;
-  if (fused_available(lvl)) {
-    FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ, "level not initialised");
-    return launch_fused(lvl, x, mu, lambda, diag_add, values, nullptr, 0.f, nullptr, nullptr, 0.f, nullptr, as_stream(stream));
-  }
-  FEMB_REQUIRE(elem_k, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan, "level not initialised");
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->v2i, "level not initialised");
   return hessian_pipeline<1>(lvl, x, mu, lambda, diag_add, nullptr, elem_k, values, as_stream(stream));
 }
 
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add, float* elem_f,
                        float* elem_k, float* force_out, float* values, void* stream) {
-  FEMB_REQUIRE(lvl && x && force_out && values, "null pointer");
+  FEMB_REQUIRE(lvl && x && force_out && values && elem_f && elem_k, "null pointer");
   if (lvl->n_vert == 0) return FEMB_OK;
-  if (fused_available(lvl)) {
-    FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ, "level not initialised");
-    return launch_fused(lvl, x, mu, lambda, diag_add, values, mass, g, pin, pin_pos, control_mag, force_out, as_stream(stream));
-  }
-  FEMB_REQUIRE(elem_f && elem_k, "null pointer");
-  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->elem2nnz && lvl->vert_elem && lvl->i2v && lvl->fold_plan && lvl->v2i,
-               "level not initialised");
+  FEMB_REQUIRE(lvl->hex && lvl->invJ && lvl->detJ && lvl->vert_elem && lvl->v2i, "level not initialised");
   int rc = hessian_pipeline<2>(lvl, x, mu, lambda, diag_add, elem_f, elem_k, values, as_stream(stream));
   if (rc) return rc;
   return launch_force_gather(lvl, x, mass, g, pin, pin_pos, control_mag, 1, elem_f, force_out, as_stream(stream));
+}
+
+int femb_build_lattice_fold(const FembLevel* lvl, int* inc8, unsigned char* row_rec, int* bad, void* stream) {
+  FEMB_REQUIRE(lvl && inc8 && row_rec && bad, "null pointer");
+  FEMB_REQUIRE(lvl->hex && lvl->v2i && lvl->elem2nnz && lvl->L_ptr && lvl->U_ptr, "level not initialised");
+  cudaStream_t st = as_stream(stream);
+  if (lvl->n_vert > 0) {
+    lat_init_kernel<<<cdiv(lvl->n_vert, 256), 256, 0, st>>>(lvl->n_vert, lvl->v2i, lvl->L_ptr, lvl->U_ptr, inc8,
+                                                           reinterpret_cast<unsigned*>(row_rec), bad);
+    count_launch();
+  }
+  if (lvl->n_hex > 0) {
+    const unsigned grid = cdiv((long long)lvl->n_hex * 8, 256);
+    lat_fill_kernel<false><<<grid, 256, 0, st>>>(lvl->n_hex, lvl->hex, lvl->v2i, lvl->L_ptr, lvl->U_ptr, lvl->elem2nnz, lvl->off_l,
+                                                 lvl->off_d, lvl->off_u, inc8, row_rec, bad);
+    lat_fill_kernel<true><<<grid, 256, 0, st>>>(lvl->n_hex, lvl->hex, lvl->v2i, lvl->L_ptr, lvl->U_ptr, lvl->elem2nnz, lvl->off_l,
+                                                lvl->off_d, lvl->off_u, inc8, row_rec, bad);
+    count_launch(2);
+  }
+  return check_launch("femb_build_lattice_fold");
 }
 
 int femb_energy(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g, const int* pin,
                 const float* pin_pos, float control_mag, float* scratch, float* energy, void* stream) {
   FEMB_REQUIRE(lvl && x && scratch && energy, "null pointer");
   cudaStream_t st = as_stream(stream);
-  const int n_groups = (int)cdiv(lvl->n_hex, EPB);
+  const int n_groups = (int)cdiv(lvl->n_hex, EN_HEX);
   const int gb = n_groups < 512 ? (n_groups > 0 ? n_groups : 1) : 512;
   elastic_energy_kernel<<<gb, ETHREADS, 0, st>>>(make_in(lvl, x, mu, lambda), n_groups, scratch);
   int vb = (int)cdiv(lvl->n_vert, 256);

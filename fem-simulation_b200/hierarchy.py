@@ -408,42 +408,6 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
     return H
 
 
-def lattice_plan(x_lattice: np.ndarray, hexagons: np.ndarray, origin: np.ndarray, spacing: float, tile: int):
-    """Dense lattice view of a level for the one-kernel assembly (femb200.h, FembLevel.lat_*): every vertex sits on the
-    lattice origin + spacing * (i,j,k) and node a of every hexahedron at its node 0 + (bx,by,bz), a = 4bx+2by+bz (what
-    object.py:28-45 and :171-241 produce).  Returns None if the mesh is not of that kind (the caller then keeps the
-    element-kernel + row-fold path), else dict(vx, vy, vz, vert_lat [n_vert] int32, cell_elem int32 [(vz+1),(vy+1),(vx+1)]);
-    vx, vy are rounded up to multiples of `tile`."""
-    x = np.asarray(x_lattice, dtype=np.float64)
-    hx = np.asarray(hexagons, dtype=np.int64)
-    if x.shape[0] == 0 or hx.shape[0] == 0:
-        return None
-    ijk = np.rint((x - np.asarray(origin, dtype=np.float64)) / float(spacing)).astype(np.int64)
-    ijk -= ijk.min(axis=0)
-    dims = ijk.max(axis=0) + 1
-    if np.abs((x - x.min(axis=0)) / float(spacing) - ijk).max() > 0.25:
-        return None
-    node = np.array([[(a >> 2) & 1, (a >> 1) & 1, a & 1] for a in range(8)], dtype=np.int64)
-    c0 = ijk[hx[:, 0]]
-    if not np.array_equal(ijk[hx], c0[:, None, :] + node[None, :, :]):
-        return None
-    vx = int(-(-dims[0] // tile) * tile)
-    vy = int(-(-dims[1] // tile) * tile)
-    vz = int(dims[2])
-    if (vx + 1) * (vy + 1) * (vz + 1) >= 2 ** 31 // 48:
-        return None
-    vert_lat = (ijk[:, 2] * vy + ijk[:, 1]) * vx + ijk[:, 0]
-    if len(np.unique(vert_lat)) != len(vert_lat):
-        return None
-    cell = np.full((vz + 1, vy + 1, vx + 1), -1, dtype=np.int32)
-    if (cell[c0[:, 2] + 1, c0[:, 1] + 1, c0[:, 0] + 1] != -1).any():
-        return None
-    cell[c0[:, 2] + 1, c0[:, 1] + 1, c0[:, 0] + 1] = np.arange(hx.shape[0], dtype=np.int32)
-    if int((cell >= 0).sum()) != hx.shape[0]:
-        return None                                                        # two hexahedra in one lattice cell
-    return dict(vx=vx, vy=vy, vz=vz, vert_lat=vert_lat.astype(np.int32), cell_elem=cell)
-
-
 HEX_EDGES = np.array([[0, 1], [0, 2], [1, 3], [2, 3], [4, 5], [4, 6], [5, 7], [6, 7], [0, 4], [1, 5], [2, 6], [3, 7]], dtype=np.int64)
 
 

@@ -60,7 +60,7 @@ def _dev(a, device):
 class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
                  control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False,
-                 corrected_hierarchy=False, fused_assembly=False, fused_chunks=0,
+                 corrected_hierarchy=False, lattice_fold=True,
                  lattice_origin=None, use_c_steps=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
@@ -126,8 +126,8 @@ class Object:
             d["fold_plan"] = torch.empty(n * 128 + 16, dtype=torch.uint8, device=dev)      # FEMB_FOLD_PLAN_BYTES per vertex
             _lib.check(self.lib.femb_build_fold_plan(C.byref(lv), d["fold_plan"].data_ptr(), self._stream()), "femb_build_fold_plan")
             lv.fold_plan = d["fold_plan"].data_ptr()
-            if fused_assembly:
-                self._attach_lattice_plan(l, lv, d, fused_chunks)
+            if lattice_fold:
+                self._attach_lattice_fold(lv, d)
             self.levels.append(lv)
             self.inverse_pX_peps_gpu.append(d["invJ"])
             self.det_pX_peps_gpu.append(d["detJ"])
@@ -198,7 +198,7 @@ class Object:
         self._cg_state = torch.zeros(16 + 1024, device=dev)
         nh_max = max(h.shape[0] for h in H.hexs)
         self._elem_f = torch.empty(nh_max * 24, device=dev)
-        self._elem_k = torch.empty(nh_max * _lib.ELEM_K_FLOATS, device=dev)
+        self._elem_k = torch.empty((nh_max + 31) // 32 * 32 * _lib.ELEM_K_FLOATS, device=dev)
         self.L = [self._part_view(l, "L") for l in range(L)]
         self.U = [self._part_view(l, "U") for l in range(L)]
         self.D = [self._part_view(l, "D") for l in range(L)]
@@ -229,26 +229,21 @@ class Object:
         from . import voxelize
         return voxelize.voxelize_obj(mesh_path, dx)
 
-    def _attach_lattice_plan(self, l, lv, d, chunks):
-        """FembLevel.lat_*: the dense lattice view that lets femb_hessian / femb_force_hessian run as one kernel
-        (csrc/femb_fused.cu).  Levels that are not lattice subsets keep the element-kernel + row-fold path."""
-        H = self.hierarchy
-        lp = hierarchy.lattice_plan(H.x[l], H.hexs[l], H.box_min, H.spacing[l], _lib.FUSED_TILE)
-        if lp is None:
-            return
+    def _attach_lattice_fold(self, lv, d):
+        """FembLevel.lat_*: per vertex the hexahedron in which it is local node a, and the row record lattice offset ->
+        sorted position (femb_build_lattice_fold).  With it the assembly keeps the element matrices plane-major and folds
+        them with compile-time offsets; levels that are not lattice subsets keep the fold-plan path."""
         dev = self.device
-        d["lat_cell_elem"] = _dev(lp["cell_elem"].reshape(-1), dev)
-        n_lat = lp["vx"] * lp["vy"] * lp["vz"]
-        d["lat_row_rec"] = torch.empty(n_lat * _lib.ROW_REC_BYTES, dtype=torch.uint8, device=dev)
-        vert_lat = _dev(lp["vert_lat"], dev)
+        n = lv.n_vert
+        d["lat_inc8"] = torch.empty(max(n, 1) * 8, dtype=torch.int32, device=dev)
+        d["lat_row_rec"] = torch.empty(max(n, 1) * _lib.ROW_REC_BYTES, dtype=torch.uint8, device=dev)
         bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        lv.lat_vx, lv.lat_vy, lv.lat_vz, lv.lat_chunks = lp["vx"], lp["vy"], lp["vz"], int(chunks)
-        _lib.check(self.lib.femb_build_lattice_plan(C.byref(lv), vert_lat.data_ptr(), d["lat_row_rec"].data_ptr(), bad.data_ptr(),
-                                                    self._stream()), "femb_build_lattice_plan")
-        if int(bad.item()) != 0:                                         # a row with more than 27 blocks
-            lv.lat_vx = lv.lat_vy = lv.lat_vz = 0
+        _lib.check(self.lib.femb_build_lattice_fold(C.byref(lv), d["lat_inc8"].data_ptr(), d["lat_row_rec"].data_ptr(), bad.data_ptr(),
+                                                    self._stream()), "femb_build_lattice_fold")
+        if int(bad.item()) != 0:                                         # not a lattice subset (e.g. a row with more than 27 blocks)
+            del d["lat_inc8"], d["lat_row_rec"]
             return
-        lv.lat_cell_elem = d["lat_cell_elem"].data_ptr()
+        lv.lat_inc8 = d["lat_inc8"].data_ptr()
         lv.lat_row_rec = d["lat_row_rec"].data_ptr()
 
     def _build_context(self):
@@ -291,12 +286,11 @@ class Object:
                 self._ctx_keep["t_values"][i - 1] = t["t_values"].data_ptr()
 
     def level_without_lattice(self, l):
-        """A copy of FembLevel l without the lattice plan: the element-kernel + row-fold assembly path (tests, measurements)."""
+        """A copy of FembLevel l without the lattice fold: the general fold-plan assembly path (tests, measurements)."""
         lv = _lib.FembLevel()
         C.memmove(C.byref(lv), C.byref(self.levels[l]), C.sizeof(_lib.FembLevel))
-        lv.lat_cell_elem = None
+        lv.lat_inc8 = None
         lv.lat_row_rec = None
-        lv.lat_vz = 0
         return lv
 
     # hooks of the exp3 drivers (exp3/simulation/object.py:258-276, 294-295, 438-441), built on first use

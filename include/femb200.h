@@ -37,17 +37,17 @@ extern "C" {
 #define FEMB_E_CUDA (-2)      /* a CUDA runtime call or launch failed                 */
 #define FEMB_E_NODEVICE (-3)  /* no usable sm_100 device                              */
 
-#define FEMB_ABI_VERSION 4
+#define FEMB_ABI_VERSION 5
 
-/* hexahedra per CTA of the element kernel */
-#define FEMB_ASM_CHUNK_HEXES 16
+/* hexahedra per CTA of the element kernel (16 pairs: a thread carries two hexahedra in packed fp32 registers) */
+#define FEMB_ASM_CHUNK_HEXES 32
 #define FEMB_FOLD_SLOTS 27
 #define FEMB_FOLD_PLAN_BYTES 128   /* 28*4 contributor bytes + 16 header bytes per vertex: one cache line */
-/* floats of element-matrix scratch per hexahedron (elem_k of femb_hessian): 8 rows x (5 blocks of 9 + 3 pad) -- the
- * symmetric half in rotated order, see femb_element.cu */
+/* floats of element-matrix scratch per hexahedron (elem_k of femb_hessian; the hexahedron count is rounded up to a multiple
+ * of 32): the symmetric half of the 24x24 element matrix.  General layout: 8 rows x (5 blocks of 9 + 3 pad) per
+ * hexahedron; lattice layout: 360 planes (row a, block k, component c) of one float per hexahedron.  See femb_element.cu */
 #define FEMB_ELEM_K_FLOATS 384
-/* one-kernel assembly on lattice meshes (femb_fused.cu): vertex columns per tile edge, bytes of a row record */
-#define FEMB_FUSED_TILE 7
+/* bytes of a row record of the lattice fold (FembLevel.lat_row_rec) */
 #define FEMB_ROW_REC_BYTES 48
 
 /* matrix part selector for femb_spmv (bsr_mv on self.L / self.D / self.U / self.A) */
@@ -80,19 +80,15 @@ typedef struct FembLevel {
                                   /* position p; 255 = none) in fold order, a 28th word with contributors 5..8 of the         */
                                   /* diagonal block, then int32 {row, L_ptr[row], U_ptr[row], nL | nU<<8}; filled by          */
                                   /* femb_build_fold_plan from vert_elem + elem2nnz                                          */
-  /* Optional lattice plan (0 / NULL = none): the mesh is a subset of a regular lattice (every voxel mesh of the reference,
-   * object.py:28-45, and every coarse mesh built from one, object.py:171-241).  With it femb_hessian / femb_force_hessian
-   * run as ONE kernel that never writes element matrices to memory (femb_fused.cu); without it they run the element
-   * kernel + row fold.  lat_vx, lat_vy: vertex planes along x, y rounded up to multiples of FEMB_FUSED_TILE; lat_vz
-   * along z.  Lattice point (i,j,k) has index (k*lat_vy + j)*lat_vx + i. */
-  int lat_vx, lat_vy, lat_vz;
-  int lat_chunks;                 /* z-chunks per tile column (0 = chosen from the SM count)                          */
-  const int* lat_cell_elem;       /* [(lat_vz+1)*(lat_vy+1)*(lat_vx+1)] hexahedron whose node 0 is lattice point        */
-                                  /* (i-1, j-1, k-1), at index (k*(lat_vy+1) + j)*(lat_vx+1) + i; -1 = empty cell      */
-  const unsigned char* lat_row_rec; /* [lat_vz*lat_vy*lat_vx*FEMB_ROW_REC_BYTES] per lattice point: bytes 0..26 sorted  */
-                                  /* position in the row (L blocks, D, U blocks) -> lattice offset 9(dx+1)+3(dy+1)+dz+1, */
-                                  /* int32 words 7..11 {vertex, row or -1, L_ptr[row], U_ptr[row], nL | nU<<8}; filled  */
-                                  /* by femb_build_lattice_plan                                                        */
+  /* Optional lattice fold (NULL = none): the mesh is a subset of a regular lattice with the reference's local node order
+   * (every voxel mesh of the reference, object.py:28-45, and every coarse mesh built from one, object.py:171-241), so a row
+   * has at most 27 blocks, one per lattice offset of the column vertex.  With it femb_hessian / femb_force_hessian keep
+   * the element matrices plane-major and fold them with compile-time offsets (fold_lattice_kernel); without it they use
+   * fold_plan.  Both filled by femb_build_lattice_fold. */
+  const int* lat_inc8;            /* [n_vert*8] hexahedron in which the vertex is local node a, -1 = none               */
+  const unsigned char* lat_row_rec; /* [n_vert*FEMB_ROW_REC_BYTES] per vertex: bytes 0..26 lattice offset                 */
+                                  /* 9(dx+1)+3(dy+1)+dz+1 -> sorted position in the row (L blocks, D, U blocks; 255 = no */
+                                  /* such block), int32 words 7..11 {vertex, row, L_ptr[row], U_ptr[row], nL | nU<<8}     */
 } FembLevel;
 
 /* CSR matrix with one scalar weight per entry = BSR matrix with blocks w*I3: the interpolation
@@ -166,9 +162,11 @@ int femb_prepare_rest(int n_hex, const int* hex, const float* x_rest, float* det
 /* setup of FembLevel.fold_plan (all other fields of *lvl must be final): the inverse of the element->nnz map per row, so
  * that the assembly is a gather in a fixed order (replaces the atomics of quai_hexagon.py:100-106) */
 int femb_build_fold_plan(const FembLevel* lvl, unsigned char* fold_plan, void* stream);
-/* setup of FembLevel.lat_row_rec (lat_vx/vy/vz and all non-lattice fields of *lvl must be final): vert_lat [n_vert] = lattice
- * index of every vertex; bad (int[1], zeroed by the caller) is set if a row has more than 27 blocks (not a lattice mesh) */
-int femb_build_lattice_plan(const FembLevel* lvl, const int* vert_lat, unsigned char* row_rec, int* bad, void* stream);
+/* setup of FembLevel.lat_inc8 / lat_row_rec (all other fields of *lvl must be final; inc8 [n_vert*8], row_rec
+ * [n_vert*FEMB_ROW_REC_BYTES]); bad (int[1], zeroed by the caller) is set if the mesh is not a lattice subset (a row with
+ * more than 27 blocks, two hexahedra holding a vertex as the same local node, or a lattice offset that names two columns):
+ * leave the level's lat_* fields NULL then */
+int femb_build_lattice_fold(const FembLevel* lvl, int* inc8, unsigned char* row_rec, int* bad, void* stream);
 /* Sum_8 + prepare_mass (cublas.py:215-218, quai_hexagon.py:20-26) as a gather: vol[n_hex], mass[n_vert] */
 int femb_lumped_mass(const FembLevel* lvl, float* vol, float* mass, void* stream);
 
@@ -183,7 +181,8 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
                float* out, void* stream);
 /* compute_elastic_hessian (quai_hexagon.py:69-106) + the `MF_value = MF_value_fixed` copy (object.py:1233):
  * values[slot] = sum of element blocks (+ diag_add[i]*I3 on the diagonal slot of index-order row i).
- *   elem_k scratch [n_hex*FEMB_ELEM_K_FLOATS] (symmetric half of the element matrices); diag_add [n_vert] (index order) or NULL.
+ *   elem_k scratch [roundup32(n_hex)*FEMB_ELEM_K_FLOATS] (symmetric half of the element matrices); diag_add [n_vert] (index
+ *   order) or NULL.
  *   If elem_f != NULL the element forces are produced by the same element pass and `force_out` is
  *   filled as in femb_force (same optional arguments). */
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add,

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(repo_root):
         assert hasattr(lib, n), f"{n} declared in femb200.h but not exported"
         assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
     assert sorted(_lib.PROTOTYPES) == names
-    assert lib.femb_abi_version() == 4
+    assert lib.femb_abi_version() == 5
 
 
 def test_no_device_is_an_error_not_a_fallback():
@@ -53,8 +53,8 @@ def test_ctypes_mirrors_match_header_layout(repo_root, tmp_path):
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
         for f, _ in cls._fields_:
             lines.append(f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
-    lines += ['  printf("consts %d %d %d %d %d %d %d %d %d\\n", FEMB_ABI_VERSION, FEMB_ASM_CHUNK_HEXES, FEMB_ELEM_K_FLOATS, '
-              'FEMB_FOLD_PLAN_BYTES, FEMB_PART_ALL, FEMB_FUSED_TILE, FEMB_ROW_REC_BYTES, FEMB_MAX_NEIGHBOURS, FEMB_COMM_ID_BYTES);',
+    lines += ['  printf("consts %d %d %d %d %d %d %d %d\\n", FEMB_ABI_VERSION, FEMB_ASM_CHUNK_HEXES, FEMB_ELEM_K_FLOATS, '
+              'FEMB_FOLD_PLAN_BYTES, FEMB_PART_ALL, FEMB_ROW_REC_BYTES, FEMB_MAX_NEIGHBOURS, FEMB_COMM_ID_BYTES);',
               '  return 0;', '}']
     src = tmp_path / "layout.c"
     src.write_text("\n".join(lines))
@@ -66,8 +66,8 @@ def test_ctypes_mirrors_match_header_layout(repo_root, tmp_path):
         assert int(got[name]) == C.sizeof(cls), name
         for f, _ in cls._fields_:
             assert int(got[f"{name}.{f}"]) == getattr(cls, f).offset, f"{name}.{f}"
-    assert got["consts"].split() == ["4", str(_lib.ASM_CHUNK_HEXES), str(_lib.ELEM_K_FLOATS), "128", str(_lib.PART_ALL),
-                                     str(_lib.FUSED_TILE), str(_lib.ROW_REC_BYTES), str(_lib.MAX_NEIGHBOURS), str(_lib.COMM_ID_BYTES)]
+    assert got["consts"].split() == ["5", str(_lib.ASM_CHUNK_HEXES), str(_lib.ELEM_K_FLOATS), "128", str(_lib.PART_ALL),
+                                     str(_lib.ROW_REC_BYTES), str(_lib.MAX_NEIGHBOURS), str(_lib.COMM_ID_BYTES)]
 
 
 def test_prototypes_match_header_signatures(repo_root):

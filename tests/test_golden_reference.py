@@ -298,8 +298,20 @@ def test_exp2_cuda_matches_reference_class():
     n = int(g["steps"])
     o.compare(n, perturb_vertex=732, perturbation=tuple(float(v) for v in g["perturbation"]),
               trained=torch.from_numpy(g["Ut_noOrder_value_trained"]))
-    assert rel(np.array(o.plot_InfNorm), g["plot_InfNorm"]) <= 1e-5
-    assert rel(np.array(o.plot_InfNorm_newton), g["plot_InfNorm_newton"]) <= 1e-5
+    # |R|inf at these states is what is left of O(1) stress terms that cancel (strains of a few per cent): the fp32 evaluation
+    # itself is only good to about 1e-5 there, measured as the gap between the oracle's float32 and float64 runs of the same loop
+    from oracle.ref_exp2 import RefExp2Object
+    curves = {}
+    for dt in (np.float32, np.float64):
+        r = RefExp2Object(g["points"], g["hexagons"], float(g["dx"]), g["pins"], dtype=dt)
+        r.x_gpu_layer[0][732] += g["perturbation"].astype(dt)
+        r.compare_loop(n, r.w)
+        curves[dt] = np.array(r.plot_InfNorm, dtype=np.float64)
+    noise = rel(curves[np.float32], curves[np.float64])
+    tol = max(1e-5, 2.0 * noise)
+    assert tol <= 1e-4, noise
+    assert rel(np.array(o.plot_InfNorm), g["plot_InfNorm"]) <= tol
+    assert rel(np.array(o.plot_InfNorm_newton), g["plot_InfNorm_newton"]) <= tol
     x = o.x_gpu_layer[0].cpu().numpy()
     assert rel(x, g["x_final"]) <= 1e-6
     assert np.abs((x - g["x_start"]) - (g["x_final"] - g["x_start"])).max() <= 1e-3 * np.abs(g["x_final"] - g["x_start"]).max()

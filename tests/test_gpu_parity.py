@@ -106,37 +106,38 @@ def test_force_energy_hessian(pair):
         close(v1, r1, what="coarse re-discretised hessian")
 
 
-@pytest.mark.parametrize("name,chunks", [("cube9", 0), ("cube9", 3), ("jag3", 0), ("jag3", 5), ("box", 4)])
-def test_fused_assembly_matches_two_kernel_path(name, chunks):
-    """femb_hessian / femb_force_hessian as ONE kernel on the lattice plan (csrc/femb_fused.cu: 7x7 vertex tiles marching
-    in z, z-chunks, halo cells recomputed) vs the element kernel + row fold on the same level without the plan: same
-    values up to the summation order (the fused kernel adds even and odd Gauss points separately), several tiles,
-    partial tiles, several z-chunks, ragged meshes, both levels."""
-    pts, hx = MESHES[name]() if name in MESHES else mesh.box_mesh(15, 6, 23, 0.05)
-    obj = Object((pts, hx), 0.05, [], use_graphs=False, fused_assembly=True, fused_chunks=chunks)
-    assert obj.levels[0].lat_row_rec and obj.levels[0].lat_vz > 0, "lattice plan missing on a voxel mesh"
+@pytest.mark.parametrize("name", ["cube9", "jag3", "box", "odd"])
+def test_lattice_fold_matches_fold_plan_path(name):
+    """femb_hessian / femb_force_hessian on the lattice fold (plane-major element matrices, one thread per row component,
+    compile-time offsets) vs the general fold-plan path on the same level: same values up to the summation order (incident
+    hexahedra by local node instead of by element number); ragged meshes, odd hexahedron counts, every level."""
+    pts, hx = MESHES[name]() if name in MESHES else (mesh.box_mesh(15, 6, 23, 0.05) if name == "box" else mesh.box_mesh(5, 5, 5, 0.05))
+    obj = Object((pts, hx), 0.05, [], use_graphs=False)
+    assert obj.levels[0].lat_row_rec and obj.levels[0].lat_inc8, "lattice fold missing on a voxel mesh"
+    if name == "odd":
+        assert hx.shape[0] % 2 == 1
     rng = np.random.default_rng(11)
     x = obj.x_gpu_layer[0] + torch.from_numpy(rng.normal(size=pts.shape).astype(np.float32) * 0.003).to(obj.device)
-    for trial in range(2):                                   # twice: the kernel must leave nothing behind
+    for trial in range(2):                                   # twice: the kernels must leave nothing behind
         va, vb = obj.new_values(0), obj.new_values(0)
         fa, fb = torch.zeros_like(x), torch.zeros_like(x)
         va.fill_(7.0); fa.fill_(7.0)                         # every slot must be written, not accumulated
         obj._force_hessian(x, fa, va, obj.diag_fixed)
         obj._force_hessian(x, fb, vb, obj.diag_fixed, level=obj.level_without_lattice(0))
-        close(va, vb.cpu().numpy(), rel=2e-6, what=f"{name}: fused vs two-kernel values")
-        close(fa, fb.cpu().numpy(), rel=2e-6, what=f"{name}: fused vs two-kernel force")
+        close(va, vb.cpu().numpy(), rel=2e-6, what=f"{name}: lattice fold vs fold plan values")
+        assert torch.equal(fa, fb), f"{name}: forces differ between the two layouts"
         vc = obj.new_values(0); vc.fill_(-3.0)
         obj._hessian(0, x, vc)
         vd = obj.new_values(0)
         obj._hessian(0, x, vd, level=obj.level_without_lattice(0))
-        close(vc, vd.cpu().numpy(), rel=2e-6, what=f"{name}: fused vs two-kernel values (Hessian only, no diagonal add)")
+        close(vc, vd.cpu().numpy(), rel=2e-6, what=f"{name}: lattice fold vs fold plan values (Hessian only, no diagonal add)")
     for l in range(1, obj.layer):
-        assert obj.levels[l].lat_row_rec, f"lattice plan missing on level {l}"
+        assert obj.levels[l].lat_row_rec, f"lattice fold missing on level {l}"
         xl = obj.x_gpu_layer[l] * 1.01
         v1, v2 = obj.new_values(l), obj.new_values(l)
         obj._hessian(l, xl, v1)
         obj._hessian(l, xl, v2, level=obj.level_without_lattice(l))
-        close(v1, v2.cpu().numpy(), rel=2e-6, what=f"{name}: level {l} fused vs two-kernel")
+        close(v1, v2.cpu().numpy(), rel=2e-6, what=f"{name}: level {l} lattice fold vs fold plan")
 
 
 def _load_state(obj, ref, xp):
@@ -431,6 +432,7 @@ def test_rows_with_more_than_27_blocks():
     oracle's element matrices through the element->nnz map."""
     pts, hx = _fan_mesh()
     obj = Object((pts, hx), 0.05, [3], layers=1, use_graphs=False, pin_displacement=0.0)
+    assert not obj.levels[0].lat_row_rec, "femb_build_lattice_fold must reject a mesh that is not a lattice subset"
     p = obj.hierarchy.pattern[0]
     assert int(np.diff(p.L_ptr).max() + np.diff(p.U_ptr).max()) >= 56
     rng = np.random.default_rng(5)

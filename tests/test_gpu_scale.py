@@ -77,16 +77,17 @@ def test_cube64_newton_multigrid_steps_match_c_oracle(cube64):
         assert rel(obj.UtAUs_values[l - 1], co.values[l]) <= 2e-5, f"UtAUs_values[{l - 1}]"
 
 
-def test_cube64_fused_assembly(cube64):
-    """The one-kernel lattice assembly (csrc/femb_fused.cu) at a size with 100 tiles x several z-chunks."""
+def test_cube64_lattice_fold(cube64):
+    """The lattice fold (csrc/femb_element.cu) at a size with 8 k element CTAs, against the general fold-plan path."""
     n, pts, obj, H, plans = cube64
-    o2 = Object((pts, mesh.cube_mesh(n)[1]), 1.0 / n, [], use_graphs=False, fused_assembly=True, layers=2)
+    o2 = Object((pts, mesh.cube_mesh(n)[1]), 1.0 / n, [], use_graphs=False, layers=2)
+    assert o2.levels[0].lat_row_rec
     x = o2.x_gpu_layer[0] + torch.randn_like(o2.x_gpu_layer[0]) * 1e-4
     va, vb = o2.new_values(0), o2.new_values(0)
     fa, fb = torch.zeros_like(x), torch.zeros_like(x)
     o2._force_hessian(x, fa, va, o2.diag_fixed)
     o2._force_hessian(x, fb, vb, o2.diag_fixed, level=o2.level_without_lattice(0))
-    assert rel(va, vb.cpu().numpy()) <= 2e-6 and rel(fa, fb.cpu().numpy()) <= 2e-6
+    assert rel(va, vb.cpu().numpy()) <= 2e-6 and torch.equal(fa, fb)
 
 
 def test_c1_cube_obj_compare_1000():
