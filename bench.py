@@ -369,6 +369,7 @@ def cpu_oracle(args, n, H=None):
         H = hierarchy.build_hierarchy(pts, hx, 1.0 / n, args.layers or None, corrected_spacing=args.corrected_hierarchy)
     plans = [hierarchy.build_galerkin_plan(H, l) for l in range(H.layer - 1)] if args.method == "nmg" else []
     co = c_oracle.from_hierarchy(H, plans, pts, 1.0 / n)
+    co._plans_src = plans
     co.set_threads(host_threads())
     return co, H, hx.shape[0]
 
@@ -448,11 +449,25 @@ def parity_check(args, obj, step, H, steps=2):
     xc = co.x.astype(np.float64)
     fc = float(np.abs(co.grad if args.method == "nmg" else co.vec[0]["B_fixed"]).max())
     x0 = obj.x_cpu.numpy().astype(np.float64)
+    # what fp32 itself is worth here: the same oracle in double precision (the per-vertex forces of this mesh sit at the
+    # 1e-10 cut-offs of solve3x3, cublas.py:67-86, so round-off switches rows on and off)
+    from fem_simulation_b200 import mesh
+    from oracle import c_oracle
+    c64 = c_oracle.from_hierarchy(H, co._plans_src, mesh.cube_mesh(args.n)[0], 1.0 / args.n, dtype=np.float64)
+    c64.set_threads(host_threads())
+    f64 = c64.newton_mg_step if args.method == "nmg" else c64.fasv3_step
+    for _ in range(steps):
+        f64()
+    x64 = c64.x.astype(np.float64)
+    disp = max(np.abs(x64 - x0).max(), 1e-30)
     return {"steps": steps, "x_rel_err": float(np.abs(xg - xc).max() / np.abs(xc).max()),
             "displacement_rel_err": float(np.abs(xg - xc).max() / max(np.abs(xc - x0).max(), 1e-30)),
+            "displacement_rel_err_vs_fp64_oracle": float(np.abs(xg - x64).max() / disp),
+            "fp32_oracle_vs_fp64_oracle": float(np.abs(xc - x64).max() / disp),
             "force_inf_norm": fg, "force_inf_norm_ref": fc, "x_checksum": float(np.abs(xg).sum()),
             "x_checksum_ref": float(np.abs(xc).sum()),
-            "ref": "oracle/femb_oracle.c, same mesh, same steps from the rest state (force norm: at the start of the last step)"}, co
+            "ref": "oracle/femb_oracle.c, same mesh, same steps from the rest state (force norm: at the start of the last step); "
+                   "fp32_oracle_vs_fp64_oracle is the round-off level of the algorithm itself on this mesh, in displacement units"}, co
 
 
 def run_reference(args):
