@@ -424,7 +424,7 @@ __host__ __device__ __forceinline__ constexpr int offset_slot(int a, int b) {
 
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both.  kSoA: element matrices in the plane-major lattice layout.
 template <int kMode, bool kSoA>
-__global__ void __launch_bounds__(ETHREADS, 3) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
+__global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
   extern __shared__ __align__(16) float smem[];

@@ -655,6 +655,85 @@ class Object:
             self._run_step("fasv0", self._fas_v0_body)
         self.x[0] = self.dev_x_solved[0].cpu()
 
+    # ---- FAS with the tau correction on more than two levels: FASv0 (object.py:1308-1370) generalised ----
+    def _ml_scratch(self, l):
+        if getattr(self, "_ml_vec", None) is None:
+            self._ml_vec = {}
+        if l not in self._ml_vec:
+            n = self.dims[l]
+            self._ml_vec[l] = (torch.zeros((n, 3), device=self.device), torch.zeros((n, 3), device=self.device))
+        return self._ml_vec[l]
+
+    def _v2i(self, l, src, dst):
+        _lib.check(self.lib.femb_v2i(C.byref(self.levels[l]), src.data_ptr(), dst.data_ptr(), self._stream()), "femb_v2i")
+
+    def _i2v(self, l, src, dst):
+        _lib.check(self.lib.femb_i2v(C.byref(self.levels[l]), src.data_ptr(), dst.data_ptr(), self._stream()), "femb_i2v")
+
+    def _ml_smooth(self, l, nu):
+        """y_l += GS_nu(A_l, b_l - A_l y_l): the reference's symmetric Gauss-Seidel starts from zero (object.py:886-929), so an
+        iterate is smoothed in correction form."""
+        r, d = self._ml_scratch(l)
+        self._residual(l, self.dev_B_fixed[l], self.dev_delta_x[l], r)
+        _lib.check(self.lib.femb_gauss_seidel(C.byref(self.levels[l]), self._values(l).data_ptr(), r.data_ptr(), d.data_ptr(),
+                                              nu, self.not_spd.data_ptr(), self._stream()), "femb_gauss_seidel")
+        self._axpby(1.0, d, 1.0, self.dev_delta_x[l])
+
+    def _ml_level(self, l, last, nu):
+        """Level l of the FAS cycle: A_l = Hessian re-discretised at the restricted state x_l (dev_x_solved[l]), right-hand side
+        b_l = R r_{l-1} + A_l x_l in dev_B_fixed[l], iterate y_l in dev_delta_x[l] (index order, starts at x_l)."""
+        if l == last:
+            self.PerformConjugateGradient_WithInitX(layer=l, iterations=10)              # coarsest: as FASv0, :1356
+            return
+        self._ml_smooth(l, nu)
+        self._i2v(l, self.dev_delta_x[l], self.dev_B[l])                                 # the smoothed state of level l
+        self._transfer(self.Ut_noOrder[l], 1.0, self.dev_B[l], 0.0, self.dev_x_solved[l + 1])
+        self._residual(l, self.dev_B_fixed[l], self.dev_delta_x[l], self.dev_R[l])
+        self._transfer(self.Ut_hat[l], 1.0, self.dev_R[l], 0.0, self.dev_B_fixed[l + 1])
+        self._hessian(l + 1, self.dev_x_solved[l + 1], self.UtAUs_values[l])
+        self._spd(self.UtAUs_values[l])
+        self._v2i(l + 1, self.dev_x_solved[l + 1], self.dev_delta_x[l + 1])
+        self._spmv(l + 1, _lib.PART_ALL, 1.0, self.dev_delta_x[l + 1], 1.0, self.dev_B_fixed[l + 1])   # tau: + A_{l+1} x_{l+1}
+        self._ml_level(l + 1, last, nu)
+        self._i2v(l + 1, self.dev_delta_x[l + 1], self.dev_B[l + 1])
+        self._copy(self.dev_E[l + 1], self.dev_B[l + 1])
+        self._axpby(-1.0, self.dev_x_solved[l + 1], 1.0, self.dev_E[l + 1])               # coarse approximation of the error
+        self._transfer(self.Us_noOrder_hat[l], 1.0, self.dev_E[l + 1], 0.0, self.dev_E[l])
+        _, d = self._ml_scratch(l)
+        self._v2i(l, self.dev_E[l], d)
+        self._axpby(1.0, d, 1.0, self.dev_delta_x[l])
+        self._ml_smooth(l, nu)
+
+    def _fas_ml_body(self, last, nu):
+        x = self.dev_x_solved[0]
+        self._fas_fine(x, True, False, False)
+        self.PerformGaussSeidel(layer=0, iterations=1)
+        self.update_deltaX(x, self.dev_delta_x[0])
+        self._fas_coarse_setup(x, True, False, False)
+        self._v2i(1, self.dev_x_solved[1], self.dev_delta_x[1])
+        self._spmv(1, _lib.PART_ALL, 1.0, self.dev_delta_x[1], 1.0, self.dev_B_fixed[1])
+        self._ml_level(1, last, nu)
+        self._i2v(1, self.dev_delta_x[1], self.dev_B[1])
+        self._copy(self.dev_E[1], self.dev_B[1])
+        self._axpby(-1.0, self.dev_x_solved[1], 1.0, self.dev_E[1])
+        self._transfer(self.Us_noOrder_hat[0], 1.0, self.dev_E[1], 0.0, self.dev_E[0])
+        self._axpby(1.0, self.dev_E[0], 1.0, x)
+
+    def FAS_multilevel(self, iterations=100, levels=None, smoothing=1):
+        """FAS V-cycle with the tau correction over `levels` levels (default: all; meant for `corrected_hierarchy=True`, whose
+        levels really coarsen).  Every coarse level l solves A_l(x_l) y = R r_{l-1} + A_l(x_l) x_l for the full approximation y
+        (A_l = Hessian re-discretised on the level-l mesh at the restricted state x_l = Ut_noOrder y_{l-1}, eigen-clamped),
+        smooths it with `smoothing` symmetric Gauss-Seidel iterations before and after the coarser correction, and hands
+        y - x_l back through Us_noOrder_hat.  With levels=2 this IS the reference's FASv0 (object.py:1308-1370), operation for
+        operation."""
+        L = self.layer if levels is None else int(levels)
+        if not 2 <= L <= self.layer:
+            raise ValueError(f"levels must be in [2, {self.layer}]")
+        self.dev_x_solved[0].copy_(self.x_gpu_layer[0])
+        for _ in range(iterations):
+            self._run_step(f"fasml{L}_{smoothing}", lambda: self._fas_ml_body(L - 1, int(smoothing)))
+        self.x[0] = self.dev_x_solved[0].cpu()
+
     def FASv1(self, iterations=100):
         self.dev_x_solved[0].copy_(self.x_gpu_layer[0])
         for _ in range(iterations):

@@ -430,6 +430,63 @@ class RefObject:
             x[...] = t(1.0) * x + t(1.0) * self.dev_E[0]                                  # axpby, :1364
             self.showError(1)
 
+    # ---- FASv0 generalised to more than two levels (no counterpart in the reference beyond levels=2) ----
+    def _ml_smooth(self, l, nu):
+        """y_l += GS_nu(A_l, b_l - A_l y_l) with the reference's PerformGaussSeidel (which starts from zero)."""
+        b, y = self.dev_B_fixed[l].copy(), self.dev_delta_x[l].copy()
+        r = b.copy()
+        self._A_mv(l, y, r, alpha=-1.0, beta=1.0)
+        self.dev_B_fixed[l][...] = r
+        self.PerformGaussSeidel(layer=l, iterations=nu)
+        self.dev_B_fixed[l][...] = b
+        self.dev_delta_x[l][...] = y + self.dev_delta_x[l]
+
+    def _ml_level(self, l, last, nu):
+        t = self.dtype
+        if l == last:
+            self.PerformConjugateGradient_WithInitX(layer=l, iterations=10)
+            return
+        self._ml_smooth(l, nu)
+        self.dev_B[l][self.i2v[l]] = self.dev_delta_x[l]
+        bsr_mv(self.Ut_noOrder[l], self.dev_B[l], self.dev_x_solved[l + 1], alpha=1.0, beta=0.0)
+        self.dev_R[l][...] = self.dev_B_fixed[l]
+        self._A_mv(l, self.dev_delta_x[l], self.dev_R[l], alpha=-1.0, beta=1.0)
+        bsr_mv(self.Ut_hat[l], self.dev_R[l], self.dev_B_fixed[l + 1], alpha=1.0, beta=0.0)
+        self.UtAUs_values[l][...] = 0
+        self.hessian(l + 1, self.dev_x_solved[l + 1], self.UtAUs_values[l])
+        self.UtAUs_values[l][...] = K.spd_matrix33f(self.UtAUs_values[l], self.spd_value)
+        self.set_LUD(l + 1)
+        self.dev_delta_x[l + 1][self.v2i[l + 1]] = self.dev_x_solved[l + 1]
+        self._A_mv(l + 1, self.dev_delta_x[l + 1], self.dev_B_fixed[l + 1], alpha=1.0, beta=1.0)
+        self._ml_level(l + 1, last, nu)
+        self.dev_B[l + 1][self.i2v[l + 1]] = self.dev_delta_x[l + 1]
+        self.dev_E[l + 1][...] = t(-1.0) * self.dev_x_solved[l + 1] + t(1.0) * self.dev_B[l + 1]
+        bsr_mv(self.Us_noOrder_hat[l], self.dev_E[l + 1], self.dev_E[l], alpha=1.0, beta=0.0)
+        d = np.zeros_like(self.dev_delta_x[l])
+        d[self.v2i[l]] = self.dev_E[l]
+        self.dev_delta_x[l][...] = self.dev_delta_x[l] + d
+        self._ml_smooth(l, nu)
+
+    def FAS_multilevel(self, iterations=100, levels=None, smoothing=1):
+        """Twin of Object.FAS_multilevel (fem-simulation_b200/object.py); levels=2 is FASv0 statement for statement."""
+        L = self.layer if levels is None else int(levels)
+        self.dev_x_solved[0][...] = self.x_gpu_layer[0]
+        x = self.dev_x_solved[0]
+        t = self.dtype
+        for _ in range(iterations):
+            self._fas_fine(x, spd=True, gravity_pins=False, fixed_diag=False)
+            self.set_LUD(0)
+            self.PerformGaussSeidel(layer=0, iterations=1)
+            self.update_deltaX(x, self.dev_delta_x[0])
+            self._fas_coarse_setup(x, spd=True, gravity_pins=False, coarse_pin_penalty=False)
+            self.dev_delta_x[1][self.v2i[1]] = self.dev_x_solved[1]
+            self._A_mv(1, self.dev_delta_x[1], self.dev_B_fixed[1], alpha=1.0, beta=1.0)
+            self._ml_level(1, L - 1, int(smoothing))
+            self.dev_B[1][self.i2v[1]] = self.dev_delta_x[1]
+            self.dev_E[1][...] = t(-1.0) * self.dev_x_solved[1] + t(1.0) * self.dev_B[1]
+            bsr_mv(self.Us_noOrder_hat[0], self.dev_E[1], self.dev_E[0], alpha=1.0, beta=0.0)
+            x[...] = t(1.0) * x + t(1.0) * self.dev_E[0]
+
     def FASv1(self, iterations=100):
         """object.py:1372-1415."""
         self.dev_x_solved[0][...] = self.x_gpu_layer[0]

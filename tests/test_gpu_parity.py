@@ -499,6 +499,31 @@ def test_corrected_hierarchy_newton_multigrid():
     close(obj.UtAUs_values[2], ref.UtAUs_values[2], rel=2e-5, what="Galerkin operator of the corrected level 3")
 
 
+def test_fas_multilevel():
+    """SURVEY 8f-3, second half: FAS with the tau correction on more than two levels (Object.FAS_multilevel, the
+    generalisation of the reference's FASv0) -- with levels=2 it is FASv0 itself, bit for bit; on a 4-level corrected hierarchy
+    it matches its oracle twin, and the deeper cycle reduces the force more per iteration than the two-level one."""
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    a = Object((pts, hx), 0.05, [], use_graphs=True)
+    b = Object((pts, hx), 0.05, [], use_graphs=True)
+    a.FASv0(3); b.FAS_multilevel(3, levels=2)
+    assert torch.equal(a.dev_x_solved[0], b.dev_x_solved[0])
+    pts, hx = mesh.jagged_mesh(33, 32, 34, 0.05, seed=4, keep=0.1)
+    obj = Object((pts, hx), 0.05, [], use_graphs=True, corrected_hierarchy=True)
+    ref = ref_solvers.RefObject(pts, hx, 0.05, [], corrected_spacing=True)
+    assert obj.layer == 4
+    rng = np.random.default_rng(8)
+    start = (ref.S["x0"] + rng.normal(size=pts.shape).astype(np.float32) * np.float32(0.002)).astype(np.float32)   # FASv0 has no load: strain the start state
+    for levels, smoothing in ((3, 1), (4, 2)):
+        obj.x_gpu_layer[0].copy_(torch.from_numpy(start)); ref.x_gpu_layer[0][...] = start
+        obj.FAS_multilevel(2, levels=levels, smoothing=smoothing)
+        ref.FAS_multilevel(2, levels=levels, smoothing=smoothing)
+        close(obj.dev_x_solved[0], ref.dev_x_solved[0], what=f"FAS_multilevel({levels} levels) positions after 2 cycles")
+        da = obj.dev_x_solved[0].cpu().numpy() - start; db = ref.dev_x_solved[0] - start
+        close(da, db, rel=2e-3, what=f"FAS_multilevel({levels} levels) displacement")
+        close(obj.UtAUs_values[levels - 2], ref.UtAUs_values[levels - 2], rel=2e-5, what="re-discretised Hessian of the coarsest level")
+
+
 def test_exp3_hooks_on_device(pair):
     """`edge_index` and `torch_A` (what the exp3 GNN drivers read, exp3/simulation/object.py:258-276, 438-441) live on the
     device; torch_A[0] is the un-normalised prolongation in vertex order, so it must agree with femb_transfer_mv."""

@@ -250,3 +250,30 @@ def test_galerkin_from_element_matrices_identity():
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
     # and it is the matrix the oracle's Galerkin produces on the coarse pattern
     assert np.count_nonzero(np.abs(want).sum(axis=(2, 3))) <= p1.nnz
+
+
+def test_fas_multilevel_oracle_reduces_to_fasv0_and_converges():
+    """RefObject.FAS_multilevel (the generalisation of FASv0 to more than two levels): levels=2 is FASv0 bit for
+    bit; on a corrected 3-level hierarchy the elastic force keeps falling from cycle to cycle."""
+    from fem_simulation_b200 import mesh
+    from oracle import ref_solvers
+    from oracle import ref_kernels as K
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    a = ref_solvers.RefObject(pts, hx, 0.05, [])
+    b = ref_solvers.RefObject(pts, hx, 0.05, [])
+    a.FASv0(3); b.FAS_multilevel(3, levels=2)
+    assert np.array_equal(a.dev_x_solved[0], b.dev_x_solved[0])
+    pts, hx = mesh.jagged_mesh(17, 16, 18, 0.05, seed=3, keep=0.3)
+    r = ref_solvers.RefObject(pts, hx, 0.05, [], corrected_spacing=True)
+    assert r.layer >= 3
+    rng = np.random.default_rng(0)
+    r.x_gpu_layer[0][...] += (rng.normal(size=r.x_gpu_layer[0].shape) * 0.002).astype(np.float32)   # a strained start state
+    norms = []
+    for _ in range(4):
+        if norms:
+            r.x_gpu_layer[0][...] = r.dev_x_solved[0]
+        r.FAS_multilevel(1, levels=3, smoothing=1)
+        f = np.zeros_like(r.dev_x_solved[0])
+        r.force(r.dev_x_solved[0], f, gravity=False, pins=False)
+        norms.append(K.inf_norm(f))
+    assert np.all(np.isfinite(norms)) and norms[-1] < norms[0], norms
