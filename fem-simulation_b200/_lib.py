@@ -167,17 +167,31 @@ class FembError(RuntimeError):
     pass
 
 
-def build(verbose: bool = False) -> str:
+def build(verbose: bool = False, force: bool = True) -> str:
     """Compile libfemb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import fcntl
     src = [os.path.join(_PKG, "csrc", s) for s in SOURCES]
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + src
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise FembError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    # ranks of one job may all find the library stale at once: one builds (file lock), into a temporary file that replaces the
+    # library atomically, the others wait and then find it fresh
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _needs_build():
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", tmp] + src
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise FembError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -199,7 +213,7 @@ def load(rebuild: bool = False):
     if _lib is not None and not rebuild:
         return _lib
     if rebuild or _needs_build():
-        build()
+        build(force=rebuild)
     lib = C.CDLL(LIB_PATH)
     for name, args in PROTOTYPES.items():
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported

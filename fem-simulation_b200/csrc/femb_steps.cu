@@ -3,9 +3,19 @@
 // sequence of operator calls the Python drivers issue (fem-simulation_b200/object.py, object_dynamic.py, cloth.py), on one
 // stream, with no allocation, no synchronisation and no read-back -- graph-capturable, and callable from any host language
 // that can fill the context structs.
+#include <nvtx3/nvToolsExt.h>
+
 #include "femb_common.cuh"
 
 namespace femb {
+
+// NVTX ranges per stage of a step: host-side markers around the enqueue calls -- with ncu / Nsight attached the
+// kernels launched inside a range carry its name (ncu --nvtx --nvtx-include "assembly/"); without a tool they cost nothing
+// (nvtx3 is header-only and resolves to no-ops).
+struct Range {
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+};
 
 #define FEMB_TRY(call)        \
   do {                        \
@@ -27,6 +37,8 @@ static inline size_t vec_bytes(const FembLevel& l) { return sizeof(float) * 3 * 
 // PerformGaussSeidel(layer, 3) -> downSample -> VCycle(layer+1) -> upSample -> PerformGaussSeidel(layer, 3)   (object.py:1216-1226)
 static int vcycle(const FembContext* c, int l, void* st) {
   const FembLevel* lv = &c->levels[l];
+  static const char* const names[] = {"vcycle level 0", "vcycle level 1", "vcycle level 2", "vcycle level 3", "vcycle level 4+"};
+  Range rg(names[l < 4 ? l : 4]);
   FEMB_TRY(femb_gauss_seidel(lv, c->values[l], c->B_fixed[l], c->delta_x[l], 3, c->not_spd, st));
   if (l < c->layers - 1) {
     const FembLevel* lc = &c->levels[l + 1];
@@ -58,6 +70,7 @@ int femb_vcycle(const FembContext* c, int layer, void* stream) {
 
 int femb_galerkin_chain(const FembContext* c, void* stream) {
   FEMB_TRY(check_ctx(c, true));
+  Range rg("galerkin");
   for (int i = 1; i < c->layers; ++i)
     FEMB_TRY(femb_galerkin(&c->levels[i - 1], &c->levels[i], c->values[i - 1], &c->Ut_hat[i - 1], &c->Us_hat[i - 1], &c->plans[i - 1],
                            c->t_values[i - 1], 1, c->spd_value, c->values[i], stream));
@@ -68,9 +81,13 @@ int femb_newton_mg_step(const FembContext* c, void* stream) {
   FEMB_TRY(check_ctx(c, true));
   const FembLevel* l0 = &c->levels[0];
   cudaStream_t st = as_stream(stream);
-  FEMB_TRY(femb_force_hessian(l0, c->x, c->mu, c->la, c->mass0, c->g, c->pin, c->pin_pos, c->control_mag, c->diag_fixed, c->elem_f,
-                              c->elem_k, c->grad, c->values[0], stream));                                   // object.py:1232-1236, 1249
-  if (c->spd_level0) FEMB_TRY(femb_spd_blocks(c->values[0], l0->nnz, c->spd_value, stream));
+  Range step("newton_mg_step");
+  {
+    Range rg("assembly");
+    FEMB_TRY(femb_force_hessian(l0, c->x, c->mu, c->la, c->mass0, c->g, c->pin, c->pin_pos, c->control_mag, c->diag_fixed, c->elem_f,
+                                c->elem_k, c->grad, c->values[0], stream));                                 // object.py:1232-1236, 1249
+    if (c->spd_level0) FEMB_TRY(femb_spd_blocks(c->values[0], l0->nnz, c->spd_value, stream));
+  }
   FEMB_TRY(femb_galerkin_chain(c, stream));                                                                 // :1252-1264
   FEMB_TRY(femb_copy(3 * l0->n_vert, c->grad, c->B_fixed[0], stream));                                      // :1266
   FEMB_TRY(vcycle(c, 0, stream));                                                                           // :1290
@@ -90,14 +107,22 @@ int femb_fas_step(const FembContext* c, int variant, float* x, void* stream) {
   const float* mass = grav_pins ? c->mass0 : nullptr;
   const int* pin = grav_pins ? c->pin : nullptr;
   const float* pin_pos = grav_pins ? c->pin_pos : nullptr;
+  Range step("fas_step");
   // fine level (object.py:1468-1487)
   cudaMemsetAsync(c->B_fixed[1], 0, vec_bytes(*l1), st);
-  FEMB_TRY(femb_force_hessian(l0, x, c->mu, c->la, mass, c->g, pin, pin_pos, c->control_mag, fixed_diag ? c->diag_fixed : nullptr,
-                              c->elem_f, c->elem_k, c->B_fixed[0], c->values[0], stream));
-  if (spd) FEMB_TRY(femb_spd_blocks(c->values[0], l0->nnz, c->spd_value, stream));
-  FEMB_TRY(femb_gauss_seidel(l0, c->values[0], c->B_fixed[0], c->delta_x[0], 1, c->not_spd, stream));
-  FEMB_TRY(femb_update_x(l0, c->delta_x[0], x, stream));
+  {
+    Range rg("assembly");
+    FEMB_TRY(femb_force_hessian(l0, x, c->mu, c->la, mass, c->g, pin, pin_pos, c->control_mag, fixed_diag ? c->diag_fixed : nullptr,
+                                c->elem_f, c->elem_k, c->B_fixed[0], c->values[0], stream));
+    if (spd) FEMB_TRY(femb_spd_blocks(c->values[0], l0->nnz, c->spd_value, stream));
+  }
+  {
+    Range rg("fine smoothing");
+    FEMB_TRY(femb_gauss_seidel(l0, c->values[0], c->B_fixed[0], c->delta_x[0], 1, c->not_spd, stream));
+    FEMB_TRY(femb_update_x(l0, c->delta_x[0], x, stream));
+  }
   // coarse level (object.py:1489-1509)
+  Range rg("coarse correction");
   FEMB_TRY(femb_transfer_mv(&c->Ut_noOrder[0], 1.0f, x, 0.0f, c->x_solved[1], stream));
   FEMB_TRY(femb_force(l0, x, c->mu, c->la, mass, c->g, pin, pin_pos, c->control_mag, 1, c->elem_f, c->R[0], stream));
   FEMB_TRY(femb_transfer_mv(&c->Ut_hat[0], 1.0f, c->R[0], 0.0f, c->B_fixed[1], stream));

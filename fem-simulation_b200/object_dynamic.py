@@ -100,11 +100,14 @@ class DynamicObject(Object):
 
     def step(self):
         """One frame of ``render(pause=False)`` without the GL draw."""
-        d = self._drag_dir()
+        d = tuple(C.c_float(v).value for v in self._drag_dir())          # as the kernel will see it (float32)
         if d != tuple(self._dir):
             self._dir[0], self._dir[1], self._dir[2] = d
             self._graphs.pop("dyn", None)            # the drag direction is a kernel argument
-        self._run_step("dyn", self._frame_body)
+        if any(d):
+            self._frame_body()                       # while a vertex is dragged the direction changes every frame: no re-capture
+        else:
+            self._run_step("dyn", self._frame_body)
 
     def render(self, pause=False):
         if not pause:

@@ -66,10 +66,20 @@ def load(native: bool = True, double: bool = False):
         flags += " -march=native"
     out = os.path.join(_DIR, "_build", f"libfemb_oracle_{tag}{'_f64' if double else ''}.so")
     src = os.path.join(_DIR, "femb_oracle.c")
-    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+    stale = lambda: not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src)
+    if stale():
+        import fcntl
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-        subprocess.run([cc] + flags.split() + ["-shared", "-o", out, src, "-lm"], check=True)
+        with open(out + ".lock", "w") as lock:                  # several ranks may get here at once: one compiles, atomically
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if stale():
+                    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+                    tmp = f"{out}.{os.getpid()}.tmp"
+                    subprocess.run([cc] + flags.split() + ["-shared", "-o", tmp, src, "-lm"], check=True)
+                    os.replace(tmp, out)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     lib = C.CDLL(out)
     lib.orc_num_threads.restype = C.c_int
     lib.orc_energy.restype = C.c_double if double else C.c_float
