@@ -51,8 +51,10 @@ def parse():
                     help="fasv3 (BASELINE configs[4], the mesh-partitioned series) or nmg (Newton-multigrid, the north-star target)")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: partition ONE n^3 cube over the ranks (strong scaling) instead of an n x n x (n N) box (weak)")
-    ap.add_argument("--comm", default="auto", choices=["auto", "torch"],
-                    help="auto: C-ABI NCCL exchanges inside one CUDA graph per rank; torch: torch.distributed exchanges between segment graphs")
+    ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl", "torch"],
+                    help="auto: C-ABI exchanges inside one CUDA graph per rank, through peer memory (NVLink stores + flags) when every "
+                         "rank can map its neighbours, else NCCL send/recv; p2p / nccl: force one; torch: torch.distributed exchanges "
+                         "between segment graphs")
     ap.add_argument("--layers", type=int, default=0, help="0 = the reference's level-count formula")
     ap.add_argument("--cpu-n", type=int, default=0, help="cube edge of the CPU-baseline sample (0 = the benchmark's own n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -314,7 +316,7 @@ def run_ours(args):
                                  "reference coarsening (object.py:175-179: levels >= 3 repeat level 2)"),
                    "parallelism": (f"{world} ranks, z-slab domain decomposition (cuts {so.cuts}, {so.overlap} overlap cell layers below each slab), "
                                    f"{exchanges_per_step} neighbour halo exchanges per step (vector ghosts only, no matrix entries), no all-reduce "
-                                   "on the data path; " + ("C-ABI NCCL send/recv + pack/unpack kernels on the step's stream, ONE CUDA graph per "
+                                   "on the data path; " + ("C-ABI exchanges on the step's stream, transport: " + so.comm.transport + "; ONE CUDA graph per "
                                    "rank per step" if so.comm is not None else "torch.distributed exchanges between CUDA-graph segments")) if world > 1 else
                                   "single GPU, CUDA-graph replay of the step body",
                    "l2": "working set (matrix values %.2f GB per rank) >> 126 MB L2, no flush needed" % (H.pattern[0].nnz * 36 / 1e9),

@@ -149,6 +149,8 @@ PROTOTYPES = {
     "femb_comm_init": [C.POINTER(C.c_void_p), P, I, I],
     "femb_comm_destroy": [P],
     "femb_halo_exchange": [P, HL, P, I, P],
+    "femb_comm_p2p_enable": [P, P, I, C.c_size_t, P],
+    "femb_comm_p2p_error": [P, P],
     "femb_comm_allreduce": [P, P, I, I, P],
     "femb_axpby": [I, F, P, F, P, P],
     "femb_copy": [I, P, P, P],

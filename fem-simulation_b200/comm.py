@@ -29,6 +29,24 @@ class HaloComm:
         self.handle = C.c_void_p()
         _lib.check(self.lib.femb_comm_init(C.byref(self.handle), idb, rank, world), "femb_comm_init")
         self._keep = []
+        self.transport = "nccl"
+
+    def enable_p2p(self, neighbours, slot_bytes):
+        """Peer-memory transport (femb_comm_p2p_enable): collective; False (on every rank) if CUDA IPC / peer access is not
+        available between all neighbours -- the exchanges then stay on NCCL send / recv."""
+        nb = (C.c_int * max(len(neighbours), 1))(*[int(v) for v in neighbours])
+        rc = self.lib.femb_comm_p2p_enable(self.handle, nb, len(neighbours), C.c_size_t(int(slot_bytes)),
+                                           C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc == 0:
+            self.transport = "peer memory (CUDA IPC over NVLink: push kernel + pull kernel per exchange)"
+        return rc == 0
+
+    def check(self):
+        """Raise if a pull kernel ever gave up waiting for a neighbour (synchronises)."""
+        err = C.c_int(0)
+        _lib.check(self.lib.femb_comm_p2p_error(self.handle, C.byref(err)), "femb_comm_p2p_error")
+        if err.value:
+            raise _lib.FembError("halo exchange: a neighbour's data did not arrive (peer-memory transport timed out)")
 
     def plan(self, hp):
         """FembHalo for a distributed.HaloPlan (send / recv row lists per neighbour, already on the device)."""

@@ -3,15 +3,23 @@
 // The reference is single-GPU (zero NCCL / MPI call sites); these entry points are what a partitioned
 // caller of the operator ABI needs (SURVEY.md 8b "femb_comm_init / halo_exchange / allreduce", 8e).
 //
-// A halo exchange is three stream-ordered operations on the caller's stream: a pack kernel gathers the rows every
-// neighbour needs into one staging buffer, one NCCL group of ncclSend / ncclRecv pairs moves the per-neighbour segments
-// over NVLink, an unpack kernel scatters the received segments into the ghost rows.  Nothing synchronises with the host,
-// so a whole step -- ~120 exchanges between its kernels -- is captured into ONE CUDA graph per rank.
+// A halo exchange is stream-ordered work on the caller's stream; nothing synchronises with the host, so a whole step -- ~120
+// exchanges between its kernels -- is captured into ONE CUDA graph per rank.  Two transports:
+//   * peer memory (femb_comm_p2p_enable; the default of the Python drivers on one NVLink box): TWO kernels.  The push kernel
+//     gathers the rows a neighbour needs and stores them straight into that neighbour's receive arena through a CUDA-IPC
+//     mapping (NVLink stores, no staging copy, no NCCL proxy), then the last CTA publishes an epoch flag with a system-scope
+//     release store; the pull kernel spins (acquire, bounded) on the flags of its own arena and scatters the segments into
+//     the ghost rows.  Arena slots are double-buffered by epoch parity: a neighbour can be one exchange ahead, never two
+//     (its push e+2 follows its pull e+1, which waited for my push e+1, which follows my pull e).
+//   * NCCL: a pack kernel, one group of ncclSend / ncclRecv pairs, an unpack kernel (any topology; ~3x the latency).
 //
 // NCCL is loaded with dlopen at femb_comm_init (the library itself has no link-time dependency on it: single-GPU users
 // never need it); in a PyTorch process this resolves to the libnccl.so.2 torch already loaded.
 #include <dlfcn.h>
 #include <nccl.h>
+
+#include <cstring>
+#include <vector>
 
 #include "femb_common.cuh"
 
@@ -28,6 +36,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -62,6 +71,7 @@ static int load_nccl() {
   FEMB_SYM(Send, "ncclSend")
   FEMB_SYM(Recv, "ncclRecv")
   FEMB_SYM(AllReduce, "ncclAllReduce")
+  FEMB_SYM(AllGather, "ncclAllGather")
   FEMB_SYM(GetErrorString, "ncclGetErrorString")
 #undef FEMB_SYM
   g_nccl = a;
@@ -93,6 +103,101 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(int n, int width, cons
   vec[(size_t)__ldg(rows + i) * width + c] = buf[t];
 }
 
+// ---- peer-memory transport --------------------------------------------------------------------------------------------------
+constexpr int NB = FEMB_MAX_NEIGHBOURS;
+// device state words: [0, NB) epochs of my pushes per neighbour slot, [NB, 2 NB) epochs of my pulls, then two "CTAs done"
+// counters and the error word (1 = a pull gave up waiting)
+constexpr int ST_SEND = 0, ST_RECV = NB, ST_DONE_PUSH = 2 * NB, ST_DONE_PULL = 2 * NB + 1, ST_ERR = 2 * NB + 2, ST_WORDS = 2 * NB + 4;
+constexpr long long P2P_SPIN_CYCLES = 60000000000ll;            // ~30 s: a lost peer becomes an error, not a hung GPU
+
+struct P2PArgs {
+  int n_nb, width;
+  int off[NB + 1];                 // prefix sums of the rows per neighbour (send rows for push, recv rows for pull)
+  int slot[NB];                    // push: my slot in the neighbour's arena; pull: the neighbour's slot in mine
+  int ep[NB];                      // index of the neighbour in the communicator's table: where its epochs live in `state`
+  unsigned char* data[NB];         // push: the neighbour's arena; pull: my arena
+  unsigned* flag[NB];              // push: my flag word in the neighbour's arena; pull: the neighbour's flag word in mine
+  size_t slot_bytes;
+  const int* rows;
+  float* vec;
+  unsigned* state;
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int nb_of_row(const P2PArgs& a, int i) {
+  int k = 0;
+#pragma unroll
+  for (int j = 1; j < NB; ++j) k += (j < a.n_nb && i >= a.off[j]) ? 1 : 0;
+  return k;
+}
+
+__global__ void __launch_bounds__(256) halo_push_kernel(P2PArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = a.off[a.n_nb] * a.width;
+  if (t < total) {
+    const int i = t / a.width, c = t - i * a.width;
+    const int k = nb_of_row(a, i);
+    const unsigned e = a.state[ST_SEND + a.ep[k]] + 1u;    // epoch of this push to neighbour k
+    float* dst = reinterpret_cast<float*>(a.data[k] + ((size_t)(e & 1u) * NB + a.slot[k]) * a.slot_bytes);
+    dst[(size_t)(i - a.off[k]) * a.width + c] = a.vec[(size_t)__ldg(a.rows + i) * a.width + c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.state + ST_DONE_PUSH, 1u);
+    if (prev == gridDim.x - 1) {                                  // every CTA has stored and fenced: publish
+      __threadfence_system();
+      for (int k = 0; k < a.n_nb; ++k)
+        if (a.off[k + 1] > a.off[k]) {
+          const unsigned e = a.state[ST_SEND + a.ep[k]] + 1u;
+          st_release_sys(a.flag[k], e);
+          a.state[ST_SEND + a.ep[k]] = e;
+        }
+      a.state[ST_DONE_PUSH] = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_pull_kernel(P2PArgs a) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int k = 0; k < a.n_nb; ++k)
+      if (a.off[k + 1] > a.off[k]) {
+        const unsigned e = a.state[ST_RECV + a.ep[k]] + 1u;
+        while ((int)(ld_acquire_sys(a.flag[k]) - e) < 0) {
+          // a lost peer is reported once; after that nobody waits any more (the results are garbage, the error word says so)
+          if (*reinterpret_cast<volatile unsigned*>(a.state + ST_ERR) != 0u) break;
+          if (clock64() - t0 > P2P_SPIN_CYCLES) { a.state[ST_ERR] = 1u; break; }
+          __nanosleep(64);
+        }
+      }
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = a.off[a.n_nb] * a.width;
+  if (t < total) {
+    const int i = t / a.width, c = t - i * a.width;
+    const int k = nb_of_row(a, i);
+    const unsigned e = a.state[ST_RECV + a.ep[k]] + 1u;
+    const float* src = reinterpret_cast<const float*>(a.data[k] + ((size_t)(e & 1u) * NB + a.slot[k]) * a.slot_bytes);
+    // the arena is written by the peer over NVLink: read through L2 (an L1 line could be two exchanges old)
+    a.vec[(size_t)__ldg(a.rows + i) * a.width + c] = __ldcg(src + (size_t)(i - a.off[k]) * a.width + c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.state + ST_DONE_PULL, 1u);
+    if (prev == gridDim.x - 1) {
+      for (int k = 0; k < a.n_nb; ++k)
+        if (a.off[k + 1] > a.off[k]) a.state[ST_RECV + a.ep[k]] += 1u;
+      a.state[ST_DONE_PULL] = 0u;
+    }
+  }
+}
+
 }  // namespace femb
 
 using namespace femb;
@@ -100,6 +205,15 @@ using namespace femb;
 struct FembComm {
   ncclComm_t comm;
   int rank, nranks, device;
+  // peer-memory transport (femb_comm_p2p_enable)
+  bool p2p = false;
+  size_t slot_bytes = 0, data_bytes = 0;
+  unsigned char* arena = nullptr;                 // [2][NB][slot_bytes] receive slots, then NB flag words
+  unsigned* state = nullptr;                      // ST_WORDS device words
+  int n_nb = 0;
+  int nb[FEMB_MAX_NEIGHBOURS];                    // my neighbour table: slot k of my arena belongs to rank nb[k]
+  int my_slot_at[FEMB_MAX_NEIGHBOURS];            // my slot in the arena of nb[k]
+  unsigned char* peer[FEMB_MAX_NEIGHBOURS];       // IPC mapping of the arena of nb[k]
 };
 
 extern "C" {
@@ -136,9 +250,139 @@ int femb_comm_init(FembComm** out, const unsigned char* id_host, int rank, int n
 
 int femb_comm_destroy(FembComm* c) {
   if (c == nullptr) return FEMB_OK;
+  if (c->p2p) {
+    cudaDeviceSynchronize();
+    for (int k = 0; k < c->n_nb; ++k)
+      if (c->peer[k] != nullptr) cudaIpcCloseMemHandle(c->peer[k]);
+  }
+  if (c->arena != nullptr) cudaFree(c->arena);
+  if (c->state != nullptr) cudaFree(c->state);
   if (g_nccl.handle != nullptr) g_nccl.CommDestroy(c->comm);
   delete c;
   return FEMB_OK;
+}
+
+int femb_comm_p2p_enable(FembComm* c, const int* nb_host, int n_nb, size_t slot_bytes, void* stream) {
+  FEMB_REQUIRE(c && n_nb >= 0 && n_nb <= FEMB_MAX_NEIGHBOURS && (n_nb == 0 || nb_host) && slot_bytes > 0, "bad arguments");
+  FEMB_REQUIRE(!c->p2p, "already enabled");
+  cudaStream_t st = as_stream(stream);
+  slot_bytes = (slot_bytes + 255) / 256 * 256;
+  // one record per rank: IPC handle of its arena, its neighbour table, its slot size
+  struct Rec { cudaIpcMemHandle_t h; int n_nb; int nb[FEMB_MAX_NEIGHBOURS]; unsigned long long slot_bytes; int ok; int pad[3]; };
+  static_assert(sizeof(Rec) % 16 == 0, "record size");
+  Rec mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.n_nb = n_nb; mine.slot_bytes = slot_bytes; mine.ok = 1;
+  for (int k = 0; k < n_nb; ++k) mine.nb[k] = nb_host[k];
+  const size_t data_bytes = (size_t)2 * NB * slot_bytes;
+  unsigned char* arena = nullptr;
+  unsigned* state = nullptr;
+  if (cudaMalloc(&arena, data_bytes + 256) != cudaSuccess || cudaMalloc(&state, ST_WORDS * sizeof(unsigned)) != cudaSuccess ||
+      cudaMemsetAsync(arena, 0, data_bytes + 256, st) != cudaSuccess || cudaMemsetAsync(state, 0, ST_WORDS * sizeof(unsigned), st) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine.h, arena) != cudaSuccess) {
+    cudaGetLastError();
+    mine.ok = 0;                                   // still take part in the collective below: every rank must learn it
+  }
+  Rec* all_dev = nullptr;
+  if (cudaMalloc(&all_dev, sizeof(Rec) * c->nranks) != cudaSuccess) {
+    set_error("femb_comm_p2p_enable: out of memory");
+    return FEMB_E_CUDA;
+  }
+  cudaMemcpyAsync(all_dev + c->rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice, st);
+  FEMB_NCCL(g_nccl.AllGather(all_dev + c->rank, all_dev, sizeof(Rec), ncclInt8, c->comm, st), "femb_comm_p2p_enable");
+  std::vector<Rec> all(c->nranks);
+  cudaMemcpyAsync(all.data(), all_dev, sizeof(Rec) * c->nranks, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(all_dev);
+  bool ok = true;
+  for (int r = 0; r < c->nranks; ++r) ok = ok && all[r].ok && all[r].slot_bytes == slot_bytes;
+  // my slot in every neighbour's table; the relation must be symmetric
+  int my_slot_at[FEMB_MAX_NEIGHBOURS];
+  for (int k = 0; k < n_nb && ok; ++k) {
+    const int q = nb_host[k];
+    my_slot_at[k] = -1;
+    if (q < 0 || q >= c->nranks || q == c->rank) { ok = false; break; }
+    for (int j = 0; j < all[q].n_nb; ++j)
+      if (all[q].nb[j] == c->rank) my_slot_at[k] = j;
+    if (my_slot_at[k] < 0) ok = false;
+  }
+  unsigned char* peer[FEMB_MAX_NEIGHBOURS] = {};
+  int opened = 0;
+  if (ok)
+    for (; opened < n_nb; ++opened) {
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[nb_host[opened]].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); break; }
+      peer[opened] = static_cast<unsigned char*>(ptr);
+    }
+  // second collective: peer memory is used only if EVERY rank could map all its neighbours
+  int* flag_dev = nullptr;
+  cudaMalloc(&flag_dev, sizeof(int));
+  const int good = (ok && opened == n_nb) ? 1 : 0;
+  cudaMemcpyAsync(flag_dev, &good, sizeof(int), cudaMemcpyHostToDevice, st);
+  FEMB_NCCL(g_nccl.AllReduce(flag_dev, flag_dev, 1, ncclInt32, ncclMin, c->comm, st), "femb_comm_p2p_enable");
+  int all_good = 0;
+  cudaMemcpyAsync(&all_good, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(flag_dev);
+  if (!all_good) {
+    for (int k = 0; k < opened; ++k) cudaIpcCloseMemHandle(peer[k]);
+    if (arena) cudaFree(arena);
+    if (state) cudaFree(state);
+    set_error("femb_comm_p2p_enable: peer memory not available between all neighbours (CUDA IPC / NVLink peer access)");
+    return FEMB_E_CUDA;
+  }
+  c->p2p = true; c->slot_bytes = slot_bytes; c->data_bytes = data_bytes; c->arena = arena; c->state = state; c->n_nb = n_nb;
+  for (int k = 0; k < n_nb; ++k) { c->nb[k] = nb_host[k]; c->my_slot_at[k] = my_slot_at[k]; c->peer[k] = peer[k]; }
+  return FEMB_OK;
+}
+
+int femb_comm_p2p_error(FembComm* c, int* err_host) {
+  FEMB_REQUIRE(c && err_host, "bad arguments");
+  *err_host = 0;
+  if (!c->p2p) return FEMB_OK;
+  unsigned e = 0;
+  if (cudaMemcpy(&e, c->state + ST_ERR, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("femb_comm_p2p_error: %s", cudaGetErrorString(cudaGetLastError()));
+    return FEMB_E_CUDA;
+  }
+  *err_host = (int)e;
+  return FEMB_OK;
+}
+
+// vec[recv rows] <- neighbours' vec[send rows] through peer memory; returns false if this plan cannot use it
+static bool halo_exchange_p2p(FembComm* c, const FembHalo* h, float* vec, int width, cudaStream_t st) {
+  P2PArgs push, pull;
+  push.n_nb = pull.n_nb = h->n_nb; push.width = pull.width = width;
+  push.slot_bytes = pull.slot_bytes = c->slot_bytes; push.state = pull.state = c->state;
+  push.rows = h->send_rows; pull.rows = h->recv_rows; push.vec = pull.vec = vec;
+  push.off[0] = pull.off[0] = 0;
+  unsigned* my_flags = reinterpret_cast<unsigned*>(c->arena + c->data_bytes);
+  for (int k = 0; k < h->n_nb; ++k) {
+    int j = -1;
+    for (int q = 0; q < c->n_nb; ++q)
+      if (c->nb[q] == h->nb[k]) j = q;
+    if (j < 0) return false;
+    if ((size_t)h->n_send[k] * width * sizeof(float) > c->slot_bytes || (size_t)h->n_recv[k] * width * sizeof(float) > c->slot_bytes) return false;
+    push.off[k + 1] = push.off[k] + h->n_send[k];
+    pull.off[k + 1] = pull.off[k] + h->n_recv[k];
+    push.slot[k] = c->my_slot_at[j];
+    push.data[k] = c->peer[j];
+    push.flag[k] = reinterpret_cast<unsigned*>(c->peer[j] + c->data_bytes) + c->my_slot_at[j];
+    pull.slot[k] = j;
+    pull.data[k] = c->arena;
+    pull.flag[k] = my_flags + j;
+    push.ep[k] = pull.ep[k] = j;
+  }
+  const int n_send = push.off[h->n_nb], n_recv = pull.off[h->n_nb];
+  if (n_send > 0) {
+    halo_push_kernel<<<cdiv((long long)n_send * width, 256), 256, 0, st>>>(push);
+    count_launch();
+  }
+  if (n_recv > 0) {
+    halo_pull_kernel<<<cdiv((long long)n_recv * width, 256), 256, 0, st>>>(pull);
+    count_launch();
+  }
+  return true;
 }
 
 int femb_halo_exchange(FembComm* c, const FembHalo* h, float* vec, int width, void* stream) {
@@ -147,6 +391,13 @@ int femb_halo_exchange(FembComm* c, const FembHalo* h, float* vec, int width, vo
   cudaStream_t st = as_stream(stream);
   int n_send = 0, n_recv = 0;
   for (int k = 0; k < h->n_nb; ++k) { n_send += h->n_send[k]; n_recv += h->n_recv[k]; }
+  FEMB_REQUIRE((n_send == 0 || h->send_rows) && (n_recv == 0 || h->recv_rows), "row lists");
+  if (c->p2p) {
+    // (both sides of a pair take the same decision: the table and the slot size are communicator-wide, the sizes symmetric)
+    if (halo_exchange_p2p(c, h, vec, width, st)) return check_launch("femb_halo_exchange (peer memory)");
+    set_error("femb_halo_exchange: plan does not fit the peer-memory arena (neighbour not registered or segment > slot)");
+    return FEMB_E_INVALID;
+  }
   if (n_send > 0) {
     FEMB_REQUIRE(h->send_rows && h->send_buf, "send lists");
     halo_pack_kernel<<<cdiv((long long)n_send * width, 256), 256, 0, st>>>(n_send, width, h->send_rows, vec, h->send_buf);

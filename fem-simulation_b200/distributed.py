@@ -31,8 +31,10 @@ floating-point operations as on one GPU except for the order of the <= 8 terms o
 numbering), i.e. results agree to round-off (tests/test_multigpu.py).
 
 `exchange` is the portable (torch.distributed, eager) exchange used by the CPU tests; on CUDA the same plans are handed to
-the C ABI (femb_comm_*, csrc/femb_comm.cu: pack kernel -> NCCL send/recv -> unpack kernel on the step's stream, capturable
-into the step's CUDA graph).
+the C ABI (femb_comm_*, csrc/femb_comm.cu), on the step's stream and capturable into the step's CUDA graph: by default through
+peer memory (`comm="auto"` / `"p2p"`: a push kernel stores the boundary rows straight into the neighbour's arena over NVLink
+and raises an epoch flag, a pull kernel waits for the flags and scatters), else NCCL (`comm="nccl"`: pack kernel -> send/recv
+-> unpack kernel).
 """
 from __future__ import annotations
 
@@ -206,6 +208,15 @@ class SlabObject:
             self.comm = comm_mod.HaloComm(o, self.rank, self.world, group)
             self.hx_v = [self.comm.plan(p) for p in self.plan_v]
             self.hx_i = [self.comm.plan(p) for p in self.plan_i]
+            if comm != "nccl":
+                # peer-memory transport: every neighbour of any plan, slots sized for the largest segment (collective call)
+                nbs = sorted({nb for p in self.plan_v + self.plan_i for nb in p.neighbours()})
+                seg = max([int(t.numel()) for p in self.plan_v + self.plan_i for t in list(p.send.values()) + list(p.recv.values())] + [1])
+                seg_t = torch.tensor([seg], device=o.device)
+                dist.all_reduce(seg_t, op=dist.ReduceOp.MAX, group=group)
+                ok = self.comm.enable_p2p(nbs, int(seg_t.item()) * 3 * 4)
+                if comm == "p2p" and not ok:
+                    raise _lib.FembError("peer-memory transport requested but not available: " + o.lib.femb_last_error().decode())
         # coarse rest state of the re-discretising FAS step: ghost coarse vertices average over children this rank does
         # not have (object.py:730-731)
         if self.layers >= 2:

@@ -374,8 +374,18 @@ typedef struct FembHalo {
 int femb_comm_unique_id(unsigned char* id_host);
 int femb_comm_init(FembComm** comm, const unsigned char* id_host, int rank, int nranks);
 int femb_comm_destroy(FembComm* comm);
-/* vec[recv rows] <- the neighbours' vec[send rows]; vec is float[n * width] (width 3: a level vector, 1: a scalar field):
- * pack kernel, one NCCL group of send / recv pairs, unpack kernel, all on `stream` */
+/* Peer-memory transport for femb_halo_exchange (one NVLink box, one process per GPU).  COLLECTIVE over the communicator:
+ * nb_host[n_nb] = every rank this rank will ever exchange halos with (the relation must be symmetric), slot_bytes >= the
+ * largest per-neighbour segment (rows * width * 4) of any plan.  Allocates the receive arena of this rank (2 * FEMB_MAX_NEIGHBOURS
+ * slots + flags), hands its CUDA-IPC handle to the other ranks and maps theirs.  If any rank cannot map all its neighbours the
+ * call fails on EVERY rank and the communicator keeps using NCCL send / recv. */
+int femb_comm_p2p_enable(FembComm* comm, const int* nb_host, int n_nb, size_t slot_bytes, void* stream);
+/* err_host[0] = 1 if a pull kernel gave up waiting for a neighbour's data (~30 s); synchronises the device */
+int femb_comm_p2p_error(FembComm* comm, int* err_host);
+/* vec[recv rows] <- the neighbours' vec[send rows]; vec is float[n * width] (width 3: a level vector, 1: a scalar field), all on
+ * `stream`.  Peer memory enabled: a push kernel (gather + NVLink stores into the neighbours' arenas + epoch flag) and a pull
+ * kernel (wait for the flags, scatter into the ghost rows); send_buf / recv_buf are not used.  Otherwise: pack kernel, one NCCL
+ * group of send / recv pairs, unpack kernel.  Every rank must issue the same sequence of exchanges. */
 int femb_halo_exchange(FembComm* comm, const FembHalo* halo, float* vec, int width, void* stream);
 /* in-place all-reduce of n floats (batch the scalars of a step into one call): FEMB_REDUCE_SUM or FEMB_REDUCE_MAX */
 int femb_comm_allreduce(FembComm* comm, float* buf, int n, int op, void* stream);

@@ -127,6 +127,10 @@ def _gpu_worker(rank, world, port, steps, out, method, layers, comm, graphs):
         for _ in range(steps):
             so.fasv3_step() if method == "fasv3" else so.nmg_step()
         ids, xs = so.owned_positions()
+        if so.comm is not None:
+            so.comm.check()                                          # no pull kernel timed out
+            if comm == "p2p":
+                assert so.comm.transport.startswith("peer memory")
         out.put((rank, ids.cpu().numpy(), xs.cpu().numpy(), so.force_inf_norm()))
         dist.barrier()
     finally:
@@ -134,11 +138,12 @@ def _gpu_worker(rank, world, port, steps, out, method, layers, comm, graphs):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,layers,comm,graphs", [("fasv3", 2, "auto", True), ("nmg", 3, "auto", True), ("nmg", 4, "torch", False),
-                                                       ("fasv3", 2, "torch", True)])
+@pytest.mark.parametrize("method,layers,comm,graphs", [("fasv3", 2, "p2p", True), ("nmg", 3, "p2p", True), ("nmg", 3, "p2p", False),
+                                                       ("nmg", 3, "nccl", True), ("nmg", 4, "torch", False), ("fasv3", 2, "torch", True)])
 def test_distributed_step_matches_single_gpu(method, layers, comm, graphs):
-    """The mesh-partitioned FASv3 / Newton-multigrid step (C-ABI NCCL exchanges inside one CUDA graph per rank, or the
-    torch.distributed exchange between segment graphs) vs the single-GPU step on the same global mesh."""
+    """The mesh-partitioned FASv3 / Newton-multigrid step (C-ABI exchanges inside one CUDA graph per rank -- peer-memory
+    push / pull kernels or NCCL send / recv --, or the torch.distributed exchange between segment graphs) vs the single-GPU
+    step on the same global mesh."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from fem_simulation_b200 import Object
