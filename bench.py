@@ -153,12 +153,28 @@ def gs_launch_bytes(obj, iterations=3):
     return total / (16 * iterations)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) before anything is allocated, so that the pinned host
+    buffers of the end-to-end loop are first-touched on the GPU's own NUMA node (8 ranks sharing one node was what limited the
+    round-1 e2e scaling).  Returns a short description for the bench line; never fatal."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"process bound to the GPU's NUMA-local CPUs ({len(cpus)} cpus: {cpus[0]}-{cpus[-1]})"
+    except Exception as e:                                   # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -320,7 +336,7 @@ def run_ours(args):
                                    "rank per step" if so.comm is not None else "torch.distributed exchanges between CUDA-graph segments")) if world > 1 else
                                   "single GPU, CUDA-graph replay of the step body",
                    "l2": "working set (matrix values %.2f GB per rank) >> 126 MB L2, no flush needed" % (H.pattern[0].nnz * 36 / 1e9),
-                   "setup_s": round(setup_s, 1), "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
+                   "setup_s": round(setup_s, 1), "host_affinity": numa, "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
         "e2e": {"value": args.steps / (ms_e2e * 1e-3) * mhex, "unit": "Mhex-steps/s", "h2d_bytes_per_step": H.dims[0] * 12 * world,
                 "d2h_bytes_per_step": H.dims[0] * 12 * world},
         "gpu_launches": int(launches_per_step * args.steps * world),
@@ -355,11 +371,21 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+try:
+    _ALL_CPUS = set(os.sched_getaffinity(0))          # before bind_to_gpu_numa_node narrows it
+except Exception:                                     # noqa: BLE001
+    _ALL_CPUS = set()
+
+
 def host_threads():
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except Exception:
-        return max(1, os.cpu_count() or 1)
+    """Threads of the CPU legs: every CPU this process was given at start (the NUMA binding of the GPU arm is lifted for them)."""
+    if _ALL_CPUS:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except Exception:                             # noqa: BLE001
+            pass
+        return len(_ALL_CPUS)
+    return max(1, os.cpu_count() or 1)
 
 
 def cpu_oracle(args, n, H=None):
