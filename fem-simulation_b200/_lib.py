@@ -12,7 +12,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libfemb200.so")
-SOURCES = ["femb_api.cu", "femb_element.cu", "femb_comm.cu", "femb_steps.cu", "femb_setup.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu"]
+SOURCES = ["femb_api.cu", "femb_element.cu", "femb_comm.cu", "femb_steps.cu", "femb_setup.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu", "femb_exp2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-ldl", "-lgomp"]
 
@@ -159,6 +159,11 @@ PROTOTYPES = {
     "femb_update_x": [LV, P, P, P],
     "femb_v2i": [LV, P, P, P],
     "femb_i2v": [LV, P, P, P],
+    "femb_absmax_onehot": [I, P, P, P, P],
+    "femb_solve3x3_vjp": [I, P, P, P, P, P],
+    "femb_coarse_diag_vjp": [LV, P, P, F, F, P, P, P, P, P],
+    "femb_exp2_weight_grad": [TR, P, P, P, P, P, F, P, P, P],
+    "femb_exp2_weight_update": [I, P, P, F, P],
     "femb_inf_norm": [I, P, P, P],
     "femb_dot": [I, P, P, P, P, P],
 }

@@ -390,6 +390,27 @@ int femb_halo_exchange(FembComm* comm, const FembHalo* halo, float* vec, int wid
 /* in-place all-reduce of n floats (batch the scalars of a step into one call): FEMB_REDUCE_SUM or FEMB_REDUCE_MAX */
 int femb_comm_allreduce(FembComm* comm, float* buf, int n, int op, void* stream);
 
+/* ---- exp2 train(): adjoint of the two-level step w.r.t. the interpolation weights (csrc/femb_exp2.cu) --------------------
+ * exp2/p_hat/quasi_simulation/object.py:1202-1287 (wp.Tape) -- the forward pass uses the operators above; these are the
+ * hand-written vector-Jacobian products of the taped kernels (forward mode on dual numbers, one thread per input direction). */
+/* adjoint of `loss` (atomic_max of |component|, cublas.py:274-281 there): onehot[i] = sign(v[i]) where |v[i]| == maxv[0], else 0 */
+int femb_absmax_onehot(int n, const float* v, const float* maxv, float* onehot, void* stream);
+/* adjoint of jacobi_iteration (cublas.py:99-102 there; x = solve3x3(D, b, 0)) w.r.t. the diagonal blocks:
+ * dbar[row*9+k] = lam[row] . d x[row] / d D[row][k]; diag_blocks / dbar [n*9], b / lam [n*3] (any common row order) */
+int femb_solve3x3_vjp(int n, const float* diag_blocks, const float* b, const float* lam, float* dbar, void* stream);
+/* adjoint of prepare_kernal + compute_mat_F + compute_elastic_hessian (diagonal blocks) of level `lvl` w.r.t. the node
+ * positions x and the rest positions x_rest (both [n_vert*3], vertex order): dbar_vertex [n_vert*9] = cotangent of the diagonal
+ * block of every vertex, elem_scratch [n_hex*48]; out: lam_x, lam_rest [n_vert*3] */
+int femb_coarse_diag_vjp(const FembLevel* lvl, const float* x, const float* x_rest, float mu, float lambda, const float* dbar_vertex,
+                         float* elem_scratch, float* lam_x, float* lam_rest, void* stream);
+/* adjoint of Kronecker_product + the two bsr_mv with Ut_noOrder (x1 = Ut X, x_rest1 = Ut x_init) + loss_norm
+ * (cublas.py:284-292 there): grad[p] of entry p = (J, i): lam_x[J].X[i] + lam_rest[J].x_init[i] + 2 alpha (1 - rowsum_J);
+ * reg_rows [nrow] (or NULL) receives (1 - rowsum_J)^2 of the rows that count (|1 - rowsum| >= 1e-6) */
+int femb_exp2_weight_grad(const FembTransfer* ut, const float* w, const float* lam_x, const float* X, const float* lam_rest,
+                          const float* x_init, float alpha, float* grad, float* reg_rows, void* stream);
+/* Valueaxpy (cublas.py:156-166 there): w = clamp(w + lr * grad, 0, 1) */
+int femb_exp2_weight_update(int n, float* w, const float* grad, float lr, void* stream);
+
 /* ---- vectors ------------------------------------------------------------------------------- */
 int femb_axpby(int n, float a, const float* x, float b, float* y, void* stream);          /* y = a x + b y (cublas.py:160-163) */
 int femb_copy(int n, const float* x, float* y, void* stream);

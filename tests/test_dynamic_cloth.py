@@ -111,3 +111,42 @@ def test_exp2_compare_forward():
     assert rel(o.x_gpu_layer[0].cpu().numpy(), r.x_gpu_layer[0]) <= 1e-5
     assert np.abs(x_classic - r.x_gpu_layer[0]).max() > 0          # the trained weights do change the iteration
     assert o.Ut_noOrder_value.numel() == o.Ut_noOrder[0].nnz
+
+
+@pytest.mark.gpu
+def test_exp2_train_step_matches_oracle():
+    """exp2 train(): loss and gradient with respect to the interpolation weights from the hand-written adjoint
+    kernels (csrc/femb_exp2.cu) vs torch.autograd through the oracle's restatement of the taped step (oracle/ref_exp2_train.py,
+    float64; parity of the gradient is unpinned -- no Warp tape here -- but that restatement's forward map is the pinned compare
+    loop and its gradient equals central differences, tests/test_oracle.py).  Tolerance = the float32-vs-float64 gap of the oracle
+    itself on the same inputs."""
+    import torch
+    from fem_simulation_b200.object_exp2 import Exp2Object
+    from oracle.ref_exp2 import RefExp2Object
+    from oracle.ref_exp2_train import Exp2Train
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    obj = Exp2Object((pts, hx), 0.05, [], use_graphs=False)
+    r = RefExp2Object(pts, hx, 0.05, [], dtype=np.float64)
+    rng = np.random.default_rng(3)
+    w = (r.w.astype(np.float64) * (1.0 + 0.05 * rng.standard_normal(r.w.shape))).astype(np.float32)
+    x0 = r.x_gpu_layer[0].astype(np.float32).copy()
+    x0[500] += np.array([7e-4, -4e-4, 9e-4], np.float32)
+    l64, g64, w64, _ = Exp2Train(r, dtype=torch.float64).step(w.astype(np.float64), x0.astype(np.float64))
+    l32, g32, _, _ = Exp2Train(r, dtype=torch.float32).step(w, x0)
+    obj.load_weights(torch.from_numpy(w))
+    loss, grad = obj.train_step(torch.from_numpy(x0).to(obj.device), update=True)
+    g = grad.cpu().numpy().astype(np.float64)
+    scale = np.abs(g64).max()
+    noise = np.abs(g32.astype(np.float64) - g64).max() / scale
+    err = np.abs(g - g64).max() / scale
+    assert abs(loss - l64) <= max(1e-5, 4 * abs(l32 - l64) / abs(l64)) * abs(l64), (loss, l64, l32)
+    assert err <= max(1e-4, 4 * noise), (err, noise)
+    assert noise <= 1e-2
+    # Valueaxpy: w + 1e-3 grad clamped to [0, 1]
+    w_new = obj.Ut_noOrder_value.cpu().numpy()
+    assert np.abs(w_new - np.clip(w + np.float32(1e-3) * grad.cpu().numpy(), 0.0, 1.0)).max() <= 1e-7
+    # and the driver: a few iterations with given perturbations keep the weights in range and return finite losses
+    losses = obj.train(3, perturb_vertex=500, perturbations=[[7e-4, -4e-4, 9e-4]] * 3)
+    assert len(losses) == 3 and np.all(np.isfinite(losses))
+    wv = obj.Ut_noOrder_value
+    assert float(wv.min()) >= 0.0 and float(wv.max()) <= 1.0

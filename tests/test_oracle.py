@@ -277,3 +277,43 @@ def test_fas_multilevel_oracle_reduces_to_fasv0_and_converges():
         r.force(r.dev_x_solved[0], f, gravity=False, pins=False)
         norms.append(K.inf_norm(f))
     assert np.all(np.isfinite(norms)) and norms[-1] < norms[0], norms
+
+
+def test_exp2_train_oracle_forward_and_gradient():
+    """oracle/ref_exp2_train.py (torch restatement of the taped step of exp2 train(), object.py:1202-1287 of exp2/p_hat): its
+    forward map reproduces one step of the numpy oracle's compare loop (pinned by ref_exp2.npz), and its autograd gradient with
+    respect to the interpolation weights equals central differences of that map in float64."""
+    torch = pytest.importorskip("torch")
+    from fem_simulation_b200 import mesh
+    from oracle.ref_exp2 import RefExp2Object
+    from oracle.ref_exp2_train import Exp2Train
+    pts, hx = mesh.cube_mesh(9, 0.05)
+    r = RefExp2Object(pts, hx, 0.05, [], dtype=np.float64)
+    x0 = r.x_gpu_layer[0].copy()
+    x0[500] += np.array([7e-4, -4e-4, 9e-4])
+    rng = np.random.default_rng(3)
+    w = r.w.astype(np.float64) * (1.0 + 0.05 * rng.standard_normal(r.w.shape))      # off the default: every term of the chain is live
+    tr = Exp2Train(r, dtype=torch.float64)
+    loss, g, w_new, aux = tr.step(w, x0)
+    # forward: one step of the pinned compare loop with the same weights
+    r.x_gpu_layer[0][...] = x0
+    r.compare_loop(1, w)
+    assert np.abs(aux["xn"] - r.x_gpu_layer[0]).max() <= 1e-12 * np.abs(x0).max()
+    p = r.pat[1]
+    D_ref = r.UtAUs_values[0][p["off_d"]:p["off_d"] + r.dims[1]]
+    assert np.abs(aux["D"] - D_ref).max() <= 1e-11 * np.abs(D_ref).max()
+    assert np.isfinite(loss) and np.abs(g).max() > 0
+    # gradient: central differences along random directions and on the largest entries
+    f = lambda wv: float(tr.forward(torch.tensor(wv, dtype=torch.float64), torch.tensor(x0, dtype=torch.float64))[0])
+    for k in range(3):
+        d = rng.standard_normal(w.shape)
+        d /= np.linalg.norm(d)
+        h = 1e-6
+        fd = (f(w + h * d) - f(w - h * d)) / (2 * h)
+        assert abs(fd - g @ d) <= 1e-5 * max(abs(fd), np.abs(g).max()), (k, fd, g @ d)
+    for i in np.argsort(-np.abs(g))[:3]:
+        e = np.zeros_like(w); e[i] = 1.0
+        h = 1e-6
+        fd = (f(w + h * e) - f(w - h * e)) / (2 * h)
+        assert abs(fd - g[i]) <= 1e-5 * np.abs(g).max(), (i, fd, g[i])
+    assert np.all(w_new >= 0) and np.all(w_new <= 1)
