@@ -38,7 +38,7 @@ class HaloComm:
         rc = self.lib.femb_comm_p2p_enable(self.handle, nb, len(neighbours), C.c_size_t(int(slot_bytes)),
                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc == 0:
-            self.transport = "peer memory (CUDA IPC over NVLink: push kernel + pull kernel per exchange)"
+            self.transport = "peer memory (CUDA IPC over NVLink: one push-flag-wait-pull kernel per exchange)"
         return rc == 0
 
     def check(self):

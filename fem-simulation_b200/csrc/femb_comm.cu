@@ -5,11 +5,11 @@
 //
 // A halo exchange is stream-ordered work on the caller's stream; nothing synchronises with the host, so a whole step -- ~120
 // exchanges between its kernels -- is captured into ONE CUDA graph per rank.  Two transports:
-//   * peer memory (femb_comm_p2p_enable; the default of the Python drivers on one NVLink box): TWO kernels.  The push kernel
-//     gathers the rows a neighbour needs and stores them straight into that neighbour's receive arena through a CUDA-IPC
-//     mapping (NVLink stores, no staging copy, no NCCL proxy), then the last CTA publishes an epoch flag with a system-scope
-//     release store; the pull kernel spins (acquire, bounded) on the flags of its own arena and scatters the segments into
-//     the ghost rows.  Arena slots are double-buffered by epoch parity: a neighbour can be one exchange ahead, never two
+//   * peer memory (femb_comm_p2p_enable; the default of the Python drivers on one NVLink box): ONE kernel.  Every CTA
+//     gathers its share of the rows a neighbour needs and stores them straight into that neighbour's receive arena through a
+//     CUDA-IPC mapping (NVLink stores, no staging copy, no NCCL proxy), the last CTA to arrive publishes an epoch flag with a
+//     system-scope release store; then the CTAs spin (acquire, bounded) on the flags of their own arena and scatter the
+//     received segments into the ghost rows.  Arena slots are double-buffered by epoch parity: a neighbour can be one exchange ahead, never two
 //     (its push e+2 follows its pull e+1, which waited for my push e+1, which follows my pull e).
 //   * NCCL: a pack kernel, one group of ncclSend / ncclRecv pairs, an unpack kernel (any topology; ~3x the latency).
 //
@@ -135,13 +135,19 @@ __device__ __forceinline__ int nb_of_row(const P2PArgs& a, int i) {
   return k;
 }
 
-__global__ void __launch_bounds__(256) halo_push_kernel(P2PArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = a.off[a.n_nb] * a.width;
-  if (t < total) {
+// ONE kernel per exchange.  Every CTA first stores its share of the boundary rows into the neighbours' arenas and arrives; the
+// last arriver publishes the epoch flags.  Then every CTA waits for the neighbours' flags (they depend on the neighbours' pushes
+// only, never on this kernel's waiting CTAs: no circular wait as long as the grid is co-resident -- the launcher caps it at
+// P2P_MAX_CTAS and the loops stride) and scatters its share of the received rows.
+constexpr int P2P_MAX_CTAS = 296;                               // 2 per SM of the smallest part this is built for: always co-resident
+__global__ void __launch_bounds__(256) halo_exchange_kernel(P2PArgs a, P2PArgs b) {
+  const int stride = gridDim.x * blockDim.x;
+  // ---- push (a: send side) ----------------------------------------------------------------------------------------------
+  const int total_s = a.off[a.n_nb] * a.width;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total_s; t += stride) {
     const int i = t / a.width, c = t - i * a.width;
     const int k = nb_of_row(a, i);
-    const unsigned e = a.state[ST_SEND + a.ep[k]] + 1u;    // epoch of this push to neighbour k
+    const unsigned e = a.state[ST_SEND + a.ep[k]] + 1u;      // epoch of this push to neighbour k
     float* dst = reinterpret_cast<float*>(a.data[k] + ((size_t)(e & 1u) * NB + a.slot[k]) * a.slot_bytes);
     dst[(size_t)(i - a.off[k]) * a.width + c] = a.vec[(size_t)__ldg(a.rows + i) * a.width + c];
   }
@@ -159,41 +165,37 @@ __global__ void __launch_bounds__(256) halo_push_kernel(P2PArgs a) {
         }
       a.state[ST_DONE_PUSH] = 0u;
     }
-  }
-}
-
-__global__ void __launch_bounds__(256) halo_pull_kernel(P2PArgs a) {
-  if (threadIdx.x == 0) {
+    // ---- wait for the neighbours (b: receive side) ----------------------------------------------------------------------
     const long long t0 = clock64();
-    for (int k = 0; k < a.n_nb; ++k)
-      if (a.off[k + 1] > a.off[k]) {
-        const unsigned e = a.state[ST_RECV + a.ep[k]] + 1u;
-        while ((int)(ld_acquire_sys(a.flag[k]) - e) < 0) {
+    for (int k = 0; k < b.n_nb; ++k)
+      if (b.off[k + 1] > b.off[k]) {
+        const unsigned e = b.state[ST_RECV + b.ep[k]] + 1u;
+        while ((int)(ld_acquire_sys(b.flag[k]) - e) < 0) {
           // a lost peer is reported once; after that nobody waits any more (the results are garbage, the error word says so)
-          if (*reinterpret_cast<volatile unsigned*>(a.state + ST_ERR) != 0u) break;
-          if (clock64() - t0 > P2P_SPIN_CYCLES) { a.state[ST_ERR] = 1u; break; }
-          __nanosleep(64);
+          if (*reinterpret_cast<volatile unsigned*>(b.state + ST_ERR) != 0u) break;
+          if (clock64() - t0 > P2P_SPIN_CYCLES) { b.state[ST_ERR] = 1u; break; }
+          __nanosleep(32);
         }
       }
   }
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = a.off[a.n_nb] * a.width;
-  if (t < total) {
-    const int i = t / a.width, c = t - i * a.width;
-    const int k = nb_of_row(a, i);
-    const unsigned e = a.state[ST_RECV + a.ep[k]] + 1u;
-    const float* src = reinterpret_cast<const float*>(a.data[k] + ((size_t)(e & 1u) * NB + a.slot[k]) * a.slot_bytes);
+  // ---- pull ------------------------------------------------------------------------------------------------------------
+  const int total_r = b.off[b.n_nb] * b.width;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total_r; t += stride) {
+    const int i = t / b.width, c = t - i * b.width;
+    const int k = nb_of_row(b, i);
+    const unsigned e = b.state[ST_RECV + b.ep[k]] + 1u;
+    const float* src = reinterpret_cast<const float*>(b.data[k] + ((size_t)(e & 1u) * NB + b.slot[k]) * b.slot_bytes);
     // the arena is written by the peer over NVLink: read through L2 (an L1 line could be two exchanges old)
-    a.vec[(size_t)__ldg(a.rows + i) * a.width + c] = __ldcg(src + (size_t)(i - a.off[k]) * a.width + c);
+    b.vec[(size_t)__ldg(b.rows + i) * b.width + c] = __ldcg(src + (size_t)(i - b.off[k]) * b.width + c);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(a.state + ST_DONE_PULL, 1u);
+    const unsigned prev = atomicAdd(b.state + ST_DONE_PULL, 1u);
     if (prev == gridDim.x - 1) {
-      for (int k = 0; k < a.n_nb; ++k)
-        if (a.off[k + 1] > a.off[k]) a.state[ST_RECV + a.ep[k]] += 1u;
-      a.state[ST_DONE_PULL] = 0u;
+      for (int k = 0; k < b.n_nb; ++k)
+        if (b.off[k + 1] > b.off[k]) b.state[ST_RECV + b.ep[k]] += 1u;
+      b.state[ST_DONE_PULL] = 0u;
     }
   }
 }
@@ -374,12 +376,11 @@ static bool halo_exchange_p2p(FembComm* c, const FembHalo* h, float* vec, int wi
     push.ep[k] = pull.ep[k] = j;
   }
   const int n_send = push.off[h->n_nb], n_recv = pull.off[h->n_nb];
-  if (n_send > 0) {
-    halo_push_kernel<<<cdiv((long long)n_send * width, 256), 256, 0, st>>>(push);
-    count_launch();
-  }
-  if (n_recv > 0) {
-    halo_pull_kernel<<<cdiv((long long)n_recv * width, 256), 256, 0, st>>>(pull);
+  if (n_send + n_recv > 0) {
+    const long long work = (long long)(n_send > n_recv ? n_send : n_recv) * width;
+    unsigned grid = cdiv(work, 256);
+    if (grid > (unsigned)P2P_MAX_CTAS) grid = P2P_MAX_CTAS;
+    halo_exchange_kernel<<<grid, 256, 0, st>>>(push, pull);
     count_launch();
   }
   return true;

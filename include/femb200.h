@@ -383,8 +383,8 @@ int femb_comm_p2p_enable(FembComm* comm, const int* nb_host, int n_nb, size_t sl
 /* err_host[0] = 1 if a pull kernel gave up waiting for a neighbour's data (~30 s); synchronises the device */
 int femb_comm_p2p_error(FembComm* comm, int* err_host);
 /* vec[recv rows] <- the neighbours' vec[send rows]; vec is float[n * width] (width 3: a level vector, 1: a scalar field), all on
- * `stream`.  Peer memory enabled: a push kernel (gather + NVLink stores into the neighbours' arenas + epoch flag) and a pull
- * kernel (wait for the flags, scatter into the ghost rows); send_buf / recv_buf are not used.  Otherwise: pack kernel, one NCCL
+ * `stream`.  Peer memory enabled: ONE kernel (gather + NVLink stores into the neighbours' arenas + epoch flag, then wait for the
+ * neighbours' flags and scatter into the ghost rows); send_buf / recv_buf are not used.  Otherwise: pack kernel, one NCCL
  * group of send / recv pairs, unpack kernel.  Every rank must issue the same sequence of exchanges. */
 int femb_halo_exchange(FembComm* comm, const FembHalo* halo, float* vec, int width, void* stream);
 /* in-place all-reduce of n floats (batch the scalars of a step into one call): FEMB_REDUCE_SUM or FEMB_REDUCE_MAX */
