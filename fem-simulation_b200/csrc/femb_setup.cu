@@ -46,6 +46,35 @@ int femb_setup_incidence_host(int n_vert, int n_hex, const int* hex, int* vert_e
   return FEMB_OK;
 }
 
+int femb_setup_coo_to_csr_host(int nrow, int nnz, const int* rows, const int* cols, const float* w, int* offsets, int* columns,
+                               float* weights) {
+  FEMB_REQUIRE(nrow >= 0 && nnz >= 0 && offsets && (nnz == 0 || (rows && cols && w && columns && weights)), "bad arguments");
+  // counting sort by row (stable), then every row by column: entries are unique, rows are short (<= 27 here)
+  std::vector<int> cur((size_t)nrow + 1, 0);
+  for (int t = 0; t < nnz; ++t) {
+    const int r = rows[t];
+    if (r < 0 || r >= nrow) { set_error("femb_setup_coo_to_csr_host: row %d out of range", r); return FEMB_E_INVALID; }
+    ++cur[(size_t)r + 1];
+  }
+  offsets[0] = 0;
+  for (int r = 0; r < nrow; ++r) offsets[r + 1] = offsets[r] + cur[(size_t)r + 1];
+  for (int r = 0; r < nrow; ++r) cur[r] = offsets[r];
+  for (int t = 0; t < nnz; ++t) {
+    const int p = cur[rows[t]]++;
+    columns[p] = cols[t]; weights[p] = w[t];
+  }
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < nrow; ++r)
+    for (int i = offsets[r] + 1; i < offsets[r + 1]; ++i) {               // insertion sort, stable
+      const int c = columns[i];
+      const float x = weights[i];
+      int j = i - 1;
+      for (; j >= offsets[r] && columns[j] > c; --j) { columns[j + 1] = columns[j]; weights[j + 1] = weights[j]; }
+      columns[j + 1] = c; weights[j + 1] = x;
+    }
+  return FEMB_OK;
+}
+
 int femb_setup_pattern_count_host(int n_vert, const int* hex, const int* v2i, const int* i2v, const int* vert_elem, int* L_ptr,
                                   int* U_ptr) {
   FEMB_REQUIRE(n_vert >= 0 && hex && v2i && i2v && vert_elem && L_ptr && U_ptr, "bad arguments");

@@ -43,8 +43,8 @@ class SparseW:
         return self.weights[:, None, None] * np.eye(3, dtype=F32)
 
 
-def coo_to_csr(nrow, ncol, rows, cols, w) -> SparseW:
-    """sort by (row, col); entries are unique here (sparse.py:173-278 would sum duplicates)."""
+def coo_to_csr_numpy(nrow, ncol, rows, cols, w) -> SparseW:
+    """sort by (row, col); entries are unique here (sparse.py:173-278 would sum duplicates).  numpy restatement (tests)."""
     rows = np.asarray(rows, dtype=np.int64)
     cols = np.asarray(cols, dtype=np.int64)
     order = np.argsort(rows * np.int64(max(ncol, 1)) + cols, kind="stable")
@@ -55,29 +55,66 @@ def coo_to_csr(nrow, ncol, rows, cols, w) -> SparseW:
                    np.asarray(w, dtype=F32)[order])
 
 
-@dataclass
+def coo_to_csr(nrow, ncol, rows, cols, w) -> SparseW:
+    """sort by (row, col) through the host routine of the C ABI (csrc/femb_setup.cu: counting sort by row + per-row sort)."""
+    from . import _lib
+    lib = _lib.load()
+    r = np.ascontiguousarray(rows, dtype=np.int32)
+    c = np.ascontiguousarray(cols, dtype=np.int32)
+    ww = np.ascontiguousarray(w, dtype=F32)
+    nnz = int(r.shape[0])
+    offsets = np.empty(int(nrow) + 1, np.int32)
+    columns, weights = np.empty(nnz, np.int32), np.empty(nnz, F32)
+    hp = lambda a: a.ctypes.data_as(_lib.C.c_void_p)
+    _lib.check(lib.femb_setup_coo_to_csr_host(int(nrow), nnz, hp(r), hp(c), hp(ww), hp(offsets), hp(columns), hp(weights)),
+               "femb_setup_coo_to_csr_host")
+    return SparseW(int(nrow), int(ncol), offsets, columns, weights)
+
+
 class LevelPattern:
-    """Fixed block pattern of one level in the reference's [L;D;U] value layout (object.py:485-697)."""
-    n: int
-    nnz: int
-    L_nnz: int
-    off_l: int
-    off_d: int
-    off_u: int
-    L_row: np.ndarray
-    L_col: np.ndarray
-    U_row: np.ndarray
-    U_col: np.ndarray
-    L_ptr: np.ndarray          # [n+1] row pointers into the L section (ours; rows are contiguous there)
-    U_ptr: np.ndarray          # [n+1] row pointers into the U section
-    GS_L_row: np.ndarray
-    GS_L_col: np.ndarray
-    GS_U_row: np.ndarray
-    GS_U_col: np.ndarray
-    GS_L_Ptr: list
-    GS_U_Ptr: list
-    block_offset: np.ndarray   # UtAUs_block_offset: [L;D;U] slot -> rank in (row,col)-sorted order
-    hex_update_offset: np.ndarray
+    """Fixed block pattern of one level in the reference's [L;D;U] value layout (object.py:485-697).  The per-entry row arrays
+    of the reference (`*_L_row`, `*_U_row`, `*_GS_*_row/col`: what its bsr_set_from_triplets calls consume) are derived from
+    the row pointers on first use -- the product's kernels only read the pointers and the columns."""
+
+    def __init__(self, n, nnz, L_nnz, off_l, off_d, off_u, L_col, U_col, L_ptr, U_ptr, GS_L_Ptr, GS_U_Ptr, block_offset,
+                 hex_update_offset, cvn=None, L_row=None, U_row=None, GS_L_row=None, GS_L_col=None, GS_U_row=None, GS_U_col=None):
+        self.n, self.nnz, self.L_nnz = n, nnz, L_nnz
+        self.off_l, self.off_d, self.off_u = off_l, off_d, off_u
+        self.L_col, self.U_col = L_col, U_col
+        self.L_ptr, self.U_ptr = L_ptr, U_ptr          # [n+1] row pointers into the L / U sections (rows are contiguous there)
+        self.GS_L_Ptr, self.GS_U_Ptr = GS_L_Ptr, GS_U_Ptr
+        self.block_offset = block_offset               # UtAUs_block_offset: [L;D;U] slot -> rank in (row,col)-sorted order
+        self.hex_update_offset = hex_update_offset
+        self._cv = None if cvn is None else np.asarray(cvn, dtype=np.int64)
+        self._lazy = dict(L_row=L_row, U_row=U_row, GS_L_row=GS_L_row, GS_L_col=GS_L_col, GS_U_row=GS_U_row, GS_U_col=GS_U_col)
+
+    def _get(self, name):
+        v = self._lazy[name]
+        if v is None:
+            rows = np.arange(self.n, dtype=np.int32)
+            if name == "L_row":
+                v = np.repeat(rows, np.diff(self.L_ptr))
+            elif name == "U_row":
+                v = np.repeat(rows, np.diff(self.U_ptr))
+            elif name == "GS_L_col":
+                v = self.L_col.copy()
+            else:
+                cv = self._cv
+                row_colour = (np.searchsorted(cv, rows, side="right") - 1).astype(np.int64)
+                if name == "GS_L_row":
+                    v = (self.L_row - cv[np.repeat(row_colour, np.diff(self.L_ptr))]).astype(np.int32)
+                else:
+                    colU = np.repeat(row_colour, np.diff(self.U_ptr))
+                    v = ((self.U_row - cv[colU]) if name == "GS_U_row" else (self.U_col - cv[colU + 1])).astype(np.int32)
+            self._lazy[name] = v
+        return v
+
+    L_row = property(lambda self: self._get("L_row"))
+    U_row = property(lambda self: self._get("U_row"))
+    GS_L_row = property(lambda self: self._get("GS_L_row"))
+    GS_L_col = property(lambda self: self._get("GS_L_col"))
+    GS_U_row = property(lambda self: self._get("GS_U_row"))
+    GS_U_col = property(lambda self: self._get("GS_U_col"))
 
     @property
     def D_row(self):
@@ -241,20 +278,11 @@ def build_pattern(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int, vert
     block_offset = np.empty(nnz, np.int32)
     _lib.check(lib.femb_setup_pattern_fill_host(n, hx.shape[0], _hp(hx), _hp(v2i), _hp(i2v), _hp(ve), _hp(L_ptr), _hp(U_ptr), _hp(L_col),
                                                 _hp(U_col), _hp(e2n), _hp(block_offset)), "femb_setup_pattern_fill_host")
-    rows = np.arange(n, dtype=np.int32)
-    L_row, U_row = np.repeat(rows, np.diff(L_ptr)), np.repeat(rows, np.diff(U_ptr))
     cv = np.asarray(cvn, dtype=np.int64)
-    row_colour = (np.searchsorted(cv, rows, side="right") - 1).astype(np.int64)
-    colU, colL = np.repeat(row_colour, np.diff(U_ptr)), np.repeat(row_colour, np.diff(L_ptr))
-    GS_U_row = (U_row - cv[colU]).astype(np.int32)
-    GS_U_col = (U_col - cv[colU + 1]).astype(np.int32)
-    GS_L_row = (L_row - cv[colL]).astype(np.int32)
     GS_U_Ptr = [int(U_ptr[min(cv[p], n)]) for p in range(8)] + [0]
     GS_L_Ptr = [int(L_ptr[min(cv[p + 1], n)]) for p in range(8)] + [0]
-    return LevelPattern(n=n, nnz=nnz, L_nnz=L_nnz, off_l=0, off_d=L_nnz, off_u=L_nnz + n,
-                        L_row=L_row, L_col=L_col, U_row=U_row, U_col=U_col, L_ptr=L_ptr, U_ptr=U_ptr,
-                        GS_L_row=GS_L_row, GS_L_col=L_col.copy(), GS_U_row=GS_U_row, GS_U_col=GS_U_col,
-                        GS_L_Ptr=GS_L_Ptr, GS_U_Ptr=GS_U_Ptr, block_offset=block_offset, hex_update_offset=e2n)
+    return LevelPattern(n=n, nnz=nnz, L_nnz=L_nnz, off_l=0, off_d=L_nnz, off_u=L_nnz + n, L_col=L_col, U_col=U_col, L_ptr=L_ptr,
+                        U_ptr=U_ptr, GS_L_Ptr=GS_L_Ptr, GS_U_Ptr=GS_U_Ptr, block_offset=block_offset, hex_update_offset=e2n, cvn=cvn)
 
 
 def build_pattern_numpy(hexagons: np.ndarray, v2i: np.ndarray, cvn: list, n: int) -> LevelPattern:

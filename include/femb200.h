@@ -137,6 +137,10 @@ int femb_check_device(int device);
  * the symbolic product every step (sparse.py:1018-1091); here they are built once, with the reference's numbering. */
 /* vert_elem[n_vert*8]: e*8+a of the hexahedra incident to every vertex, ascending, -1 padded (the inverse of `hex`) */
 int femb_setup_incidence_host(int n_vert, int n_hex, const int* hex, int* vert_elem);
+/* CSR (offsets [nrow+1], columns / weights [nnz], sorted by (row, col)) of nnz unique COO entries: the scalar-weight form of
+ * bsr_set_from_triplets (sparse.py:173-278) used for the interpolation operators and their transposes (object.py:247-443) */
+int femb_setup_coo_to_csr_host(int nrow, int nnz, const int* rows, const int* cols, const float* w, int* offsets, int* columns,
+                               float* weights);
 /* pattern of one level = sorted set {(v2i[a], v2i[b]) : a, b in one hexahedron} in the [L;D;U] layout (object.py:485-599):
  * first the row pointers L_ptr / U_ptr [n_vert+1] (L_ptr[n_vert] = L_nnz = U_nnz), then, into arrays the caller sizes from
  * them, the columns, hex_update_offset (elem2nnz [n_hex*64], object.py:563-569) and UtAUs_block_offset (block_offset
