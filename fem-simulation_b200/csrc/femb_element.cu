@@ -423,7 +423,9 @@ __host__ __device__ __forceinline__ constexpr int offset_slot(int a, int b) {
 }
 
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both.  kSoA: element matrices in the plane-major lattice layout.
-template <int kMode, bool kSoA>
+// kLa: the Lame parameter lambda is non-zero (a compile-time switch: a run-time one inside the Gauss-point loop costs a
+// register shuffle per accumulator around the branch)
+template <int kMode, bool kSoA, bool kLa>
 __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
@@ -513,9 +515,10 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
 #pragma unroll
     for (int i = 0; i < 9; ++i) K[k][i] = bc<V2>(0.f);
   }
-  const bool has_la = in.la != 0.f;
+  constexpr bool has_la = kLa;
   const V2* rp = s_rec + (size_t)lp * PAIR_STRIDE;
-#pragma unroll 1
+  // fully unrolled: a rolled loop pays a register copy per accumulator pair per trip (the packed ops are not in place)
+#pragma unroll
   for (int q = 0; q < 8; ++q, rp += QP_SIZE) {
     const float4* r4 = reinterpret_cast<const float4*>(rp);
     V2 FFT[6], cmu, cla, Sd[6];
@@ -978,22 +981,27 @@ static AsmArgs make_asm(const FembLevel* l, const float* diag_add, const float* 
   return A;
 }
 
-template <int kMode, bool kSoA>
-static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
+template <int kMode, bool kSoA, bool kLa>
+static int launch_element_la(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
   static bool configured_dev[64] = {};                         // cudaFuncSetAttribute is per device
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   bool& configured = configured_dev[cur_dev & 63];
   const size_t smem = element_smem<kMode>();
   if (!configured) {
-    cudaFuncSetAttribute(element_kernel<kMode, kSoA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(element_kernel<kMode, kSoA, kLa>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   if (e_end <= e_begin) return FEMB_OK;
   in.e_begin = e_begin; in.n_hex = e_end;
-  element_kernel<kMode, kSoA><<<cdiv(e_end - e_begin, EPB), ETHREADS, smem, st>>>(in, elem_f, elem_k);
+  element_kernel<kMode, kSoA, kLa><<<cdiv(e_end - e_begin, EPB), ETHREADS, smem, st>>>(in, elem_f, elem_k);
   count_launch();
   return check_launch("element_kernel");
+}
+template <int kMode, bool kSoA>
+static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
+  if (kMode != 0 && in.la != 0.f) return launch_element_la<kMode, kSoA, true>(in, e_begin, e_end, elem_f, elem_k, st);
+  return launch_element_la<kMode, kSoA, false>(in, e_begin, e_end, elem_f, elem_k, st);
 }
 
 static int launch_force_gather(const FembLevel* l, const float* x, const float* mass, float g, const int* pin,
