@@ -191,7 +191,8 @@ int femb_force(const FembLevel* lvl, const float* x, float mu, float lambda, con
  *   filled as in femb_force (same optional arguments). */
 int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* diag_add,
                  float* elem_k, float* values, void* stream);
-/* tuning of the row fold: consecutive rows per warp (default 4) and the occupancy target of the kernel (4 or 5 CTAs per SM) */
+/* tuning of the row folds: consecutive rows per warp of the fold-plan kernel (default 4) and the occupancy target of both fold
+ * kernels (CTAs per SM; fold plan: 4 or 5, lattice fold: 3, 4 or 5; default 4) */
 int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm);
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add,
