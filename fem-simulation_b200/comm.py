@@ -94,6 +94,11 @@ class HaloComm:
         return g
 
     def close(self):
+        """Collective: every rank closes its communicator at the same point (a barrier first: with the peer-memory transport
+        no rank may still be storing into another's arena)."""
+        if self.handle and dist.is_available() and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier()
         if self.handle:
             self.lib.femb_comm_destroy(self.handle)
             self.handle = C.c_void_p()

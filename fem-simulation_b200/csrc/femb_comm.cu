@@ -253,6 +253,8 @@ int femb_comm_init(FembComm** out, const unsigned char* id_host, int rank, int n
 int femb_comm_destroy(FembComm* c) {
   if (c == nullptr) return FEMB_OK;
   if (c->p2p) {
+    // the caller destroys the communicators of all ranks together, after a barrier of its own (comm.py): no rank may still be
+    // storing into this arena
     cudaDeviceSynchronize();
     for (int k = 0; k < c->n_nb; ++k)
       if (c->peer[k] != nullptr) cudaIpcCloseMemHandle(c->peer[k]);
@@ -328,6 +330,14 @@ int femb_comm_p2p_enable(FembComm* c, const int* nb_host, int n_nb, size_t slot_
   cudaFree(flag_dev);
   if (!all_good) {
     for (int k = 0; k < opened; ++k) cudaIpcCloseMemHandle(peer[k]);
+    // nobody frees its arena before every rank has closed its mappings of it
+    int* bar_dev = nullptr;
+    if (cudaMalloc(&bar_dev, sizeof(int)) == cudaSuccess) {
+      cudaMemsetAsync(bar_dev, 0, sizeof(int), st);
+      g_nccl.AllReduce(bar_dev, bar_dev, 1, ncclInt32, ncclSum, c->comm, st);
+      cudaStreamSynchronize(st);
+      cudaFree(bar_dev);
+    }
     if (arena) cudaFree(arena);
     if (state) cudaFree(state);
     set_error("femb_comm_p2p_enable: peer memory not available between all neighbours (CUDA IPC / NVLink peer access)");

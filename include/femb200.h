@@ -378,6 +378,8 @@ typedef struct FembHalo {
 /* id_host: FEMB_COMM_ID_BYTES bytes on the host; created on one rank, handed to the others by the caller (any channel) */
 int femb_comm_unique_id(unsigned char* id_host);
 int femb_comm_init(FembComm** comm, const unsigned char* id_host, int rank, int nranks);
+/* with the peer-memory transport: call on every rank at the same point, after a barrier of the caller's (no rank may still
+ * be storing into another's arena) */
 int femb_comm_destroy(FembComm* comm);
 /* Peer-memory transport for femb_halo_exchange (one NVLink box, one process per GPU).  COLLECTIVE over the communicator:
  * nb_host[n_nb] = every rank this rank will ever exchange halos with (the relation must be symmetric), slot_bytes >= the
