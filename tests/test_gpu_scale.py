@@ -158,3 +158,39 @@ def test_c2_dynamic_300_frames():
     err = np.abs(x - r64.dev_x).max()
     assert disp > 1e-3
     assert err <= max(1e-5 * np.abs(r64.dev_x).max(), 4.0 * noise), (err, noise, disp)
+
+
+def test_c0_bundled_horse_mesh_steps_match_c_oracle():
+    """BASELINE config 0: Newton-multigrid and FAS on the reference's bundled `horse.obj` voxelised at dx = 0.05 (a ragged,
+    non-box voxel set of 4 033 hexahedra, 3 levels; fixture tests/golden/horse_0.05.npz made by make_horse_fixture.py), CUDA vs
+    the C oracle in float32 and float64: positions, displacements, fine and coarse operators, and the sampled compare() curve."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "horse_0.05.npz"))
+    pts, hx, dx = g["points"], g["hexagons"], float(g["dx"])
+    obj = Object((pts, hx), dx, [], use_graphs=True)
+    H = obj.hierarchy
+    assert H.layer == 3 and hx.shape[0] == 4033
+    assert all(obj.levels[l].lat_row_rec for l in range(H.layer)), "a voxelised OBJ is a lattice subset on every level"
+    plans = [hierarchy.build_galerkin_plan(H, l) for l in range(H.layer - 1)]
+    x0 = obj.x_cpu.numpy()
+    for method in ("nmg", "fasv3"):
+        co = c_oracle.from_hierarchy(H, plans, pts, dx)
+        co64 = c_oracle.from_hierarchy(H, plans, pts, dx, dtype=np.float64)
+        obj.x_gpu_layer[0].copy_(obj.x_cpu)
+        for _ in range(3):
+            if method == "nmg":
+                obj.NewtonMultigrid(1); co.newton_mg_step(); co64.newton_mg_step()
+            else:
+                obj.step(); co.fasv3_step(); co64.fasv3_step()
+        noise = np.abs(co.x.astype(np.float64) - co64.x).max()
+        err = np.abs(obj.x_gpu_layer[0].cpu().numpy().astype(np.float64) - co64.x).max()
+        assert rel(obj.x_gpu_layer[0], co.x) <= 1e-5, method
+        assert err <= max(1e-5 * np.abs(co64.x - x0).max(), 4.0 * noise), (method, err, noise)
+        assert rel(obj.MF_value_gpu, co.values[0]) <= 2e-5, method
+        assert rel(obj.UtAUs_values[0], co.values[1]) <= 2e-5, method
+    obj.x_gpu_layer[0].copy_(obj.x_cpu)
+    obj.compare(100)
+    c64 = c_oracle.from_hierarchy(H, [], pts, dx, dtype=np.float64)
+    g64 = c64.compare(100)
+    assert obj.plot_x == g64["plot_x"]
+    for mine, key in ((obj.plot_energy_newton, "energy_newton"), (obj.plot_energy_newtonMultigrid, "energy_fas")):
+        assert rel(np.array(mine), np.array(g64[key])) <= 1e-5, key
