@@ -117,6 +117,7 @@ PROTOTYPES = {
     "femb_force": [LV, P, F, F, P, F, P, P, F, I, P, P, P],
     "femb_hessian": [LV, P, F, F, P, P, P, P],
     "femb_set_fold_config": [I, I],
+    "femb_set_assembly_async": [I],
     "femb_force_hessian": [LV, P, F, F, P, F, P, P, F, P, P, P, P, P, P],
     "femb_energy": [LV, P, F, F, P, F, P, P, F, P, P, P],
     "femb_coarse_pin_penalty": [LV, TR, P, F, P, P],

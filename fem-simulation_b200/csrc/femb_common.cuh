@@ -141,6 +141,47 @@ __device__ __forceinline__ void spd_block(float* A, float value) {
       A[3 * i + j] = V[3 * i] * d[0] * V[3 * j] + V[3 * i + 1] * d[1] * V[3 * j + 1] + V[3 * i + 2] * d[2] * V[3 * j + 2];
 }
 
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- TMA tensor store (cp.async.bulk.tensor through a CUtensorMap kernel parameter) ---------------------------------
+// a 3-D box shared -> global as a bulk group (the issuing thread must wait for the group's shared-memory reads before the
+// CTA exits).  (Tensor LOADS need the box to start on a 16-byte boundary of global memory -- a first coordinate that is
+// not a multiple of 4 floats raises an illegal-instruction fault on B200, scripts/tma_probe.cu -- which is why the folds,
+// whose windows start at arbitrary hexahedra, do not use them.)
+__device__ __forceinline__ void tma_store_3d_saddr(const void* tmap, uint32_t src_saddr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(src_saddr), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// generic-proxy writes to shared memory become visible to the async proxy (TMA) after this fence + a barrier
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // block-wide sum; result valid in thread 0.  `red` must hold 32 floats.
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll

@@ -24,6 +24,9 @@
 //   * any other hexahedral mesh: 192-byte half rows per (hexahedron, node) and the per-row fold plan, the precomputed
 //     inverse of the element->nnz map (assemble_rows_kernel).
 #include <cstdio>
+#include <cstring>
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 
 #include "femb_common.cuh"
 
@@ -89,8 +92,10 @@ constexpr int QP_SIZE = 62;   // 31 float4: the 16-byte record writes of 8 conse
 constexpr int PAIR_STRIDE = 8 * QP_SIZE + 4;
 constexpr int XS_STRIDE = 52;                    // floats of staged node positions per pair (24 pairs + 4 pad: 20 mod 32)
 constexpr int EK_ROW = FEMB_ELEM_K_FLOATS / 8;   // floats per stored row of an element matrix, general layout (5 blocks + 3 pad)
-constexpr int EM_PLANES = 360;                   // lattice layout: planes (a*5+k)*9+c of one float per hexahedron
+constexpr int EM_PLANES = 360;                   // lattice layout: planes (a*5+k)*9+c, blocked by 32 hexahedra: EM[e >> 5][plane][e & 31]
+constexpr int EM_BLOCK = EM_PLANES * 32;         // floats per block of 32 hexahedra (46 080 bytes, written by one CTA of the element kernel)
 constexpr int EM_STG = 36;                       // floats per plane in the staging area of a CTA (32 hexahedra + 4: see below)
+constexpr int EM_TMA_BOX_ROWS = 120;             // TMA store variant: planes per tensor store (120 * 128 bytes keeps every box 1024-byte aligned)
 
 struct ElemIn {
   const int* hex;
@@ -98,8 +103,8 @@ struct ElemIn {
   const float* invJ;
   const float* detJ;
   int e_begin, n_hex;    // the launch covers hexahedra [e_begin, n_hex); e_begin is a multiple of FEMB_ASM_CHUNK_HEXES
+  int prefetch_ctas;     // > 0: every CTA pulls the vertex indices of the CTA that far ahead into L2
   float mu, la;
-  size_t em_stride;      // lattice layout: floats per plane (n_hex rounded up to a multiple of 32)
 };
 
 // shape-function gradients at Gauss point q (a runtime value: the lane)
@@ -425,11 +430,14 @@ __host__ __device__ __forceinline__ constexpr int offset_slot(int a, int b) {
 // kMode: 0 = forces only, 1 = Hessian only, 2 = both.  kSoA: element matrices in the plane-major lattice layout.
 // kLa: the Lame parameter lambda is non-zero (a compile-time switch: a run-time one inside the Gauss-point loop costs a
 // register shuffle per accumulator around the branch)
-template <int kMode, bool kSoA, bool kLa>
-__global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k) {
+// kTma (lattice layout only): the CTA's 360 x 32 tile leaves through ONE TMA tensor store instead of a read-back loop.
+constexpr int RD_PITCH = 608;                    // bytes between the staged rest data of consecutive pairs (576 + 32: see element_kernel)
+template <int kMode, bool kSoA, bool kLa, bool kTma, bool kBulk = false>
+__global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(ElemIn in, float* __restrict__ elem_f, float* __restrict__ elem_k,
+                                                                                const __grid_constant__ CUtensorMap em_map) {
   constexpr bool kForce = (kMode != 1);
   constexpr bool kHess = (kMode != 0);
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(1024) float smem[];
   float* s_x = smem;                                                  // [EPAIRS][XS_STRIDE]: node positions of the pairs
   V2* s_rec = reinterpret_cast<V2*>(smem + EPAIRS * XS_STRIDE);       // [EPAIRS][PAIR_STRIDE]: 8 records per pair (Hessian only)
   const int sub = threadIdx.x & 7;
@@ -437,6 +445,12 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
   const int e0 = in.e_begin + (blockIdx.x * EPAIRS + lp) * 2, e1 = e0 + 1;   // this launch covers hexahedra [e_begin, n_hex)
   const bool live0 = e0 < in.n_hex, live1 = e1 < in.n_hex;
   const int ee0 = live0 ? e0 : in.n_hex - 1, ee1 = live1 ? e1 : in.n_hex - 1;   // dead halves shadow a valid hexahedron
+  if (in.prefetch_ctas > 0 && threadIdx.x < 8) {
+    // the CTA's first dependent load chain (hexahedron -> vertex positions) starts with a DRAM miss; a CTA a quarter wave
+    // ahead finds its 1 KB of vertex indices in L2 instead
+    const long long ep = (long long)in.e_begin + ((long long)blockIdx.x + in.prefetch_ctas) * EPB;
+    if (ep + EPB <= in.n_hex) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(in.hex + ep * 8) + threadIdx.x * 128));
+  }
   // node positions: lane `sub` loads node `sub` of both hexahedra, the 8 lanes of the pair share them through shared memory
   {
     const int v0 = __ldg(in.hex + (size_t)ee0 * 8 + sub), v1 = __ldg(in.hex + (size_t)ee1 * 8 + sub);
@@ -447,7 +461,31 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
   float dN[8][3];
   shape_grads(sub, dN);
   V2 iJ[9], det;
-  {
+  if (kBulk && in.e_begin + (int)(blockIdx.x + 1) * EPB <= in.n_hex) {
+    // Rest data through bulk copies (every CTA but a ragged last one): the warp's 8 hexahedra are 2304 + 256 contiguous
+    // bytes of invJ / detJ; they are copied into the head of the warp's own record area (dead until phase A writes it,
+    // after the __syncwarp below), one 576-byte copy per pair at a pitch of 608 bytes so that the per-lane reads (lane
+    // stride 9 words, pair stride 152 words) are conflict-free, instead of 20 strided global loads per lane.  (Hessian
+    // kernels only: the force-only kernel has no record area, and with an area of its own it spilled: 226 vs 199 us.)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_x + (w * 4) * XS_STRIDE + 48);       // the 16 pad bytes of the warp's first position row
+    unsigned char* stg_w = reinterpret_cast<unsigned char*>(s_rec + (size_t)(w * 4) * PAIR_STRIDE);
+    const int e_w = in.e_begin + (blockIdx.x * EPAIRS + w * 4) * 2;                     // first hexahedron of the warp
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    if (lane == 0) {
+      mbar_expect_tx(bar, 4 * 576 + 256);
+      bulk_g2s(stg_w + 4 * RD_PITCH, in.detJ + (size_t)e_w * 8, 256, bar);
+    }
+    __syncwarp();
+    if (sub == 0) bulk_g2s(stg_w + (lane >> 3) * RD_PITCH, in.invJ + (size_t)e0 * 72, 576, bar);
+    mbar_wait(bar, 0);
+    const float* sj = reinterpret_cast<const float*>(stg_w + (lane >> 3) * RD_PITCH) + sub * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) iJ[k].v = make_float2(sj[k], sj[72 + k]);
+    const float* sd = reinterpret_cast<const float*>(stg_w + 4 * RD_PITCH) + (lane >> 3) * 16 + sub;
+    det.v = make_float2(sd[0], sd[8]);
+  } else {
     const float* p0 = in.invJ + ((size_t)ee0 * 8 + sub) * 9;
     const float* p1 = in.invJ + ((size_t)ee1 * 8 + sub) * 9;
 #pragma unroll
@@ -582,7 +620,32 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
   for (int k = 0; k < 5; ++k) {
     K[k][0] = vadd(K[k][0], Ks[k]); K[k][4] = vadd(K[k][4], Ks[k]); K[k][8] = vadd(K[k][8], Ks[k]);
   }
-  if (kSoA) {
+  if (kSoA && kTma) {
+    // Lattice layout through the TMA: the tile is written as 360 rows (plane R = a*45 + k*9 + i) of 32 hexahedra (128
+    // bytes) in the 128-byte swizzle (16-byte chunk ^= R & 7; for a fixed (k, i) the 8 nodes of a pair hit 8 different
+    // chunks because 45 is odd, so the 8-byte writes of a warp -- 4 pairs x 8 nodes -- take 2 wavefronts per 256 bytes),
+    // which is the shared-memory image of boxes {32 hexahedra, 120 planes} of the 2-D view {hexahedron, plane} of the
+    // scratch: three tensor stores per CTA, no read-back, no store loop.
+    __syncthreads();
+    const unsigned stg = (smem_u32(smem) + (unsigned)(EPAIRS * XS_STRIDE * sizeof(float)) + 1023u) & ~1023u;
+    const unsigned rbase = stg + (unsigned)sub * (45u * 128u) + (unsigned)(lp & 1) * 8u;
+    const unsigned r7 = (unsigned)(sub * 45) & 7u, ch = (unsigned)(lp >> 1);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const unsigned addr = rbase + (unsigned)((k * 9 + i) * 128) + ((ch ^ ((r7 + (unsigned)(k * 9 + i)) & 7u)) << 4);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(K[k][i].v.x), "f"(K[k][i].v.y) : "memory");
+      }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int blk = in.e_begin / EPB + (int)blockIdx.x;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tma_store_3d_saddr(&em_map, stg + (unsigned)(j * EM_TMA_BOX_ROWS * 128), 0, j * EM_TMA_BOX_ROWS, blk);
+      tma_store_commit_and_wait_read();
+    }
+  } else if (kSoA) {
     // Lattice layout: plane (a*5+k)*9+c holds one float per hexahedron.  The CTA's 32 hexahedra are transposed through
     // the record area (dead now, but shared by all warps: two block barriers) and leave as 360 full 128-byte lines.
     // EM_STG = 36: the 8-byte writes of a half warp (2 pairs x 8 nodes, 45*36 = 20 (mod 32) floats apart) and the 16-byte
@@ -594,10 +657,10 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
 #pragma unroll
       for (int i = 0; i < 9; ++i) *reinterpret_cast<float2*>(stg + ((sub * 5 + k) * 9 + i) * EM_STG + 2 * lp) = K[k][i].v;
     __syncthreads();
-    float* gdst = elem_k + (size_t)in.e_begin + (size_t)blockIdx.x * EPB;
+    float4* gdst = reinterpret_cast<float4*>(elem_k + ((size_t)(in.e_begin / EPB) + blockIdx.x) * EM_BLOCK);   // the CTA's block: contiguous
     for (int idx = threadIdx.x; idx < EM_PLANES * 8; idx += ETHREADS) {
       const int j = idx >> 3, part = idx & 7;
-      *reinterpret_cast<float4*>(gdst + (size_t)j * in.em_stride + 4 * part) = *reinterpret_cast<const float4*>(stg + j * EM_STG + 4 * part);
+      gdst[idx] = *reinterpret_cast<const float4*>(stg + j * EM_STG + 4 * part);
     }
   } else {
     // General layout: row a of the element matrix is stored ROTATED and HALF: position p = 0..4 holds the block of column
@@ -636,6 +699,8 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
   }
 }
 
+static_assert(EPAIRS * XS_STRIDE * 4 + 1023 + EM_PLANES * 128 <= (EPAIRS * XS_STRIDE + EPAIRS * PAIR_STRIDE * 2) * 4,
+              "the swizzled TMA tile must fit inside the (dead) record area");
 template <int kMode>
 static size_t element_smem() {
   return ((size_t)EPAIRS * XS_STRIDE + (kMode != 0 ? (size_t)EPAIRS * PAIR_STRIDE * 2 : 0)) * sizeof(float);
@@ -653,9 +718,10 @@ constexpr int RR_WORDS = FEMB_ROW_REC_BYTES / 4;
 struct FoldLatArgs {
   int n_vert;
   const int* inc8; const unsigned* row_rec;
-  const float* em; unsigned em_stride;
+  const float* em;
   const float* diag_add; float* values;
   int off_l, off_d, off_u;
+  int prefetch_tiles;   // > 0: every CTA pulls the incidence lists and row records of the tile that far ahead into L2
 };
 template <int kMinBlocks>
 __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(FoldLatArgs A, int v_begin, int v_end) {
@@ -664,6 +730,16 @@ __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(Fo
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
   const int v0 = v_begin + blockIdx.x * FL_ROWS, v = v0 + lane;
   const bool live = v < v_end;
+  if (A.prefetch_tiles > 0 && threadIdx.x < 20) {
+    // the tile's first dependent load chain (incidence list -> element matrices) starts with a DRAM miss; a tile a quarter
+    // wave ahead finds its 1 KB of incidence lists (8 lines) and 1.5 KB of row records (12 lines) in L2 instead
+    const int vp = v0 + A.prefetch_tiles * FL_ROWS;
+    if (vp + FL_ROWS <= v_end) {
+      const char* p = threadIdx.x < 8 ? reinterpret_cast<const char*>(A.inc8 + (size_t)vp * 8) + threadIdx.x * 128
+                                      : reinterpret_cast<const char*>(A.row_rec + (size_t)vp * RR_WORDS) + (threadIdx.x - 8) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
   for (int i = threadIdx.x; i < FL_ROWS * RR_WORDS; i += FL_THREADS)
     if (v0 + i / RR_WORDS < v_end) rr[i] = __ldg(A.row_rec + (size_t)v0 * RR_WORDS + i);
   int inc[8];
@@ -676,9 +752,9 @@ __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(Fo
     inc[0] = i0.x; inc[1] = i0.y; inc[2] = i0.z; inc[3] = i0.w; inc[4] = i1.x; inc[5] = i1.y; inc[6] = i1.z; inc[7] = i1.w;
   }
   const int cT = (c % 3) * 3 + c / 3;                           // the mirrored blocks are stored transposed
-  // 32-bit element offsets (the launcher checks 360 * em_stride < 2^32): one IMAD + one address per load
-  const unsigned ps = A.em_stride;
-  const unsigned od = (unsigned)c * ps, om = (unsigned)cT * ps;
+  // Blocked plane-major scratch: hexahedron e lives in block e >> 5 (360 planes x 32 hexahedra = 46 080 contiguous bytes) at
+  // lane e & 31.  A thread's 8 loads for local node a are one base pointer + compile-time offsets (the launcher checks
+  // 360 * roundup32(n_hex) < 2^32, so the element offset fits 32 bits).
   const float* __restrict__ em = A.em;
   float acc[27];
 #pragma unroll
@@ -687,12 +763,14 @@ __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(Fo
   for (int a = 0; a < 8; ++a) {
     const int e = inc[a];
     const bool have = e >= 0;
-    const unsigned ed = od + (have ? (unsigned)e : 0u), emr = om + (have ? (unsigned)e : 0u);
+    const unsigned eo = have ? ((unsigned)e >> 5) * (unsigned)EM_BLOCK + ((unsigned)e & 31u) : 0u;
+    const float* pd = em + eo + c * 32;
+    const float* pm = em + eo + cT * 32;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       const int k = (b - a) & 7;
-      const unsigned idx = k <= 4 ? ed + (unsigned)((a * 5 + k) * 9) * ps : emr + (unsigned)((b * 5 + (8 - k)) * 9) * ps;
-      const float val = have ? __ldg(em + idx) : 0.f;
+      const float* p = k <= 4 ? pd + ((a * 5 + k) * 9) * 32 : pm + ((b * 5 + (8 - k)) * 9) * 32;
+      const float val = have ? __ldg(p) : 0.f;
       acc[offset_slot(a, b)] += val;
     }
   }
@@ -969,7 +1047,7 @@ static bool lattice_available(const FembLevel* l) {
 static ElemIn make_in(const FembLevel* l, const float* x, float mu, float la) {
   ElemIn in;
   in.hex = l->hex; in.x = x; in.invJ = l->invJ; in.detJ = l->detJ; in.e_begin = 0; in.n_hex = l->n_hex; in.mu = mu; in.la = la;
-  in.em_stride = em_stride_of(l->n_hex);
+  in.prefetch_ctas = 0;
   return in;
 }
 
@@ -981,27 +1059,79 @@ static AsmArgs make_asm(const FembLevel* l, const float* diag_add, const float* 
   return A;
 }
 
-template <int kMode, bool kSoA, bool kLa>
-static int launch_element_la(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
+// ---- tensor maps over the plane-major scratch (host side) ------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is fetched through the runtime so that libcuda is not a link
+// dependency (the library is built on machines without a driver).  No encoder -> the non-TMA kernels run.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+static int g_tma_store = 3;   // 0: store loop, 1: TMA tensor store, 2: + rest data through bulk copies, 3: + L2 prefetch of index data
+struct EmMaps {
+  CUtensorMap store;    // 3-D view {hexahedron in block, plane, block} of the blocked scratch, box {32, 120, 1}, 128-byte swizzle:
+                        // a third of the element kernel's tile
+  bool ok;
+};
+static EmMaps make_em_maps(const float* elem_k, int n_hex) {
+  EmMaps M;
+  memset(&M, 0, sizeof(M));
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr || elem_k == nullptr || (reinterpret_cast<uintptr_t>(elem_k) & 15u) != 0 || n_hex <= 0) return M;
+  void* base = const_cast<float*>(elem_k);
+  const cuuint32_t one3[3] = {1, 1, 1};
+  const cuuint64_t d3[3] = {32, (cuuint64_t)EM_PLANES, (cuuint64_t)(em_stride_of(n_hex) / 32)};
+  const cuuint64_t s3[2] = {32 * sizeof(float), EM_BLOCK * sizeof(float)};
+  const cuuint32_t b3[3] = {32, (cuuint32_t)EM_TMA_BOX_ROWS, 1};
+  M.ok = enc(&M.store, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, d3, s3, b3, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return M;
+}
+
+template <int kMode, bool kSoA, bool kLa, bool kTma, bool kBulk>
+static int launch_element_la(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, const CUtensorMap& map, cudaStream_t st) {
   static bool configured_dev[64] = {};                         // cudaFuncSetAttribute is per device
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   bool& configured = configured_dev[cur_dev & 63];
   const size_t smem = element_smem<kMode>();
   if (!configured) {
-    cudaFuncSetAttribute(element_kernel<kMode, kSoA, kLa>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(element_kernel<kMode, kSoA, kLa, kTma, kBulk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   if (e_end <= e_begin) return FEMB_OK;
   in.e_begin = e_begin; in.n_hex = e_end;
-  element_kernel<kMode, kSoA, kLa><<<cdiv(e_end - e_begin, EPB), ETHREADS, smem, st>>>(in, elem_f, elem_k);
+  element_kernel<kMode, kSoA, kLa, kTma, kBulk><<<cdiv(e_end - e_begin, EPB), ETHREADS, smem, st>>>(in, elem_f, elem_k, map);
   count_launch();
   return check_launch("element_kernel");
 }
+// maps == nullptr (or not usable): the tile leaves through the store loop and the rest data comes through per-lane loads
 template <int kMode, bool kSoA>
-static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st) {
-  if (kMode != 0 && in.la != 0.f) return launch_element_la<kMode, kSoA, true>(in, e_begin, e_end, elem_f, elem_k, st);
-  return launch_element_la<kMode, kSoA, false>(in, e_begin, e_end, elem_f, elem_k, st);
+static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, float* elem_k, cudaStream_t st, const EmMaps* maps = nullptr) {
+  static const CUtensorMap no_map = {};
+  const bool la = kMode != 0 && in.la != 0.f;
+  constexpr bool kCanTma = kSoA && kMode != 0;
+  in.prefetch_ctas = g_tma_store >= 3 ? 111 : 0;
+  if (kCanTma && maps != nullptr && maps->ok && g_tma_store) {
+    const bool bulk = g_tma_store >= 2 && ((reinterpret_cast<uintptr_t>(in.invJ) | reinterpret_cast<uintptr_t>(in.detJ)) & 15u) == 0;
+    if (bulk) {
+      if (la) return launch_element_la<kMode, kSoA, true, kCanTma, kCanTma>(in, e_begin, e_end, elem_f, elem_k, maps->store, st);
+      return launch_element_la<kMode, kSoA, false, kCanTma, kCanTma>(in, e_begin, e_end, elem_f, elem_k, maps->store, st);
+    }
+    if (la) return launch_element_la<kMode, kSoA, true, kCanTma, false>(in, e_begin, e_end, elem_f, elem_k, maps->store, st);
+    return launch_element_la<kMode, kSoA, false, kCanTma, false>(in, e_begin, e_end, elem_f, elem_k, maps->store, st);
+  }
+  if (la) return launch_element_la<kMode, kSoA, true, false, false>(in, e_begin, e_end, elem_f, elem_k, no_map, st);
+  return launch_element_la<kMode, kSoA, false, false, false>(in, e_begin, e_end, elem_f, elem_k, no_map, st);
 }
 
 static int launch_force_gather(const FembLevel* l, const float* x, const float* mass, float g, const int* pin,
@@ -1029,8 +1159,8 @@ static int g_lat_min_blocks = 4;
 static int launch_fold_lattice(const FembLevel* l, const float* diag_add, const float* elem_k, float* values, cudaStream_t st) {
   FoldLatArgs A;
   A.n_vert = l->n_vert; A.inc8 = l->lat_inc8; A.row_rec = reinterpret_cast<const unsigned*>(l->lat_row_rec);
-  A.em = elem_k; A.em_stride = (unsigned)em_stride_of(l->n_hex); A.diag_add = diag_add; A.values = values;
-  A.off_l = l->off_l; A.off_d = l->off_d; A.off_u = l->off_u;
+  A.em = elem_k; A.diag_add = diag_add; A.values = values;
+  A.off_l = l->off_l; A.off_d = l->off_d; A.off_u = l->off_u; A.prefetch_tiles = g_tma_store >= 3 ? 148 : 0;
   const unsigned grid = cdiv(l->n_vert, FL_ROWS);
   if (g_lat_min_blocks == 3) fold_lattice_kernel<3><<<grid, FL_THREADS, 0, st>>>(A, 0, l->n_vert);
   else if (g_lat_min_blocks == 5) fold_lattice_kernel<5><<<grid, FL_THREADS, 0, st>>>(A, 0, l->n_vert);
@@ -1047,7 +1177,8 @@ static int hessian_pipeline(const FembLevel* l, const float* x, float mu, float 
   // (A chunked two-stream software pipeline of the two stages and a one-kernel variant with the fold inside the SM were
   // built and measured slower)
   if (lattice_available(l)) {
-    int rc = launch_element<kMode, true>(in, 0, l->n_hex, elem_f, elem_k, st);
+    const EmMaps maps = g_tma_store ? make_em_maps(elem_k, l->n_hex) : EmMaps{};
+    int rc = launch_element<kMode, true>(in, 0, l->n_hex, elem_f, elem_k, st, &maps);
     if (rc) return rc;
     return launch_fold_lattice(l, diag_add, elem_k, values, st);
   }
@@ -1071,6 +1202,11 @@ int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm) {
   if (rows_per_warp >= 1 && rows_per_warp <= 64) g_fold_rows_per_warp = rows_per_warp;
   if (min_blocks_per_sm == 4 || min_blocks_per_sm == 5) g_fold_min_blocks = min_blocks_per_sm;
   if (min_blocks_per_sm >= 3 && min_blocks_per_sm <= 5) g_lat_min_blocks = min_blocks_per_sm;
+  return FEMB_OK;
+}
+
+int femb_set_assembly_async(int mode) {
+  if (mode >= 0 && mode <= 3) g_tma_store = mode;
   return FEMB_OK;
 }
 

@@ -21,7 +21,7 @@
  *   - return value: 0 on success, a negative FEMB_E_* code otherwise (femb_last_error() gives text).
  *   - thread-compatible, not thread-safe.  Process-wide state: the last-error string (thread-local), the launch counter
  *     (atomic), the NCCL function table (written once by the first femb_comm_* call) and the TUNING KNOBS femb_set_pdl /
- *     femb_set_gs_threads_per_row / femb_set_gs_rows_per_cta / femb_set_fold_config -- plain ints read at launch time, meant to
+ *     femb_set_gs_threads_per_row / femb_set_gs_rows_per_cta / femb_set_fold_config / femb_set_assembly_async -- plain ints read at launch time, meant to
  *     be set once before use (benchmark scripts, tests); they change launch shapes, and (threads per row) rounding order,
  *     never results beyond that.  Kernel attributes are set once per device.
  */
@@ -194,6 +194,13 @@ int femb_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, c
 /* tuning of the row folds: consecutive rows per warp of the fold-plan kernel (default 4) and the occupancy target of both fold
  * kernels (CTAs per SM; fold plan: 4 or 5, lattice fold: 3, 4 or 5; default 4) */
 int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm);
+/* lattice levels, asynchronous data movement of the assembly stage: mode 0 = none (per-lane loads, store loop); 1 = the
+ * element kernel's 360 x 32 tile leaves as three TMA tensor stores (needs the driver's cuTensorMapEncodeTiled, fetched at
+ * run time; without it mode 0 runs); 2 = additionally the rest data (invJ, detJ) of a CTA's hexahedra arrive through bulk
+ * copies into shared memory; 3 (default) = additionally every CTA of the element kernel / the fold prefetches the index
+ * data (vertex indices / incidence lists and row records) of a tile a quarter wave ahead into L2.  Results are
+ * bit-identical in every mode. */
+int femb_set_assembly_async(int mode);
 int femb_force_hessian(const FembLevel* lvl, const float* x, float mu, float lambda, const float* mass, float g,
                        const int* pin, const float* pin_pos, float control_mag, const float* diag_add,
                        float* elem_f, float* elem_k, float* force_out, float* values, void* stream);

@@ -42,6 +42,22 @@ timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed, level=lv), "h
 timed(lambda: obj._force_hessian(x, obj.grad_gpu, obj.MF_value_gpu, obj.diag_fixed, level=lv), "force+hessian level0 fold plan", asm_bytes)
 timed(lambda: obj._hessian(1, obj.x_gpu_layer[1], obj.UtAUs_values[0]), "hessian level1 lattice fold")
 timed(lambda: obj._force(x, obj.grad_gpu), "force level0")
+# femb_set_assembly_async modes (TMA tile store, bulk-copied rest data, L2 prefetch): bit-identical results, per-variant time
+ref = None
+for store_tma in (0, 1, 2, 3):
+    obj.lib.femb_set_assembly_async(store_tma)
+    v = obj.new_values(0)
+    f = torch.zeros_like(x)
+    obj._force_hessian(x, f, v, obj.diag_fixed)
+    torch.cuda.synchronize()
+    if ref is None:
+        ref = (v, f)
+    else:
+        print(f"assembly async mode={store_tma}: values equal {bool(torch.equal(v, ref[0]))} forces equal {bool(torch.equal(f, ref[1]))}", flush=True)
+    timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed), f"hessian level0, assembly async mode={store_tma}", asm_bytes)
+    timed(lambda: obj._force_hessian(x, obj.grad_gpu, obj.MF_value_gpu, obj.diag_fixed), f"force+hessian level0, assembly async mode={store_tma}", asm_bytes)
+    timed(lambda: obj._hessian(1, obj.x_gpu_layer[1], obj.UtAUs_values[0]), f"hessian level1, assembly async mode={store_tma}")
+    timed(lambda: obj._force(x, obj.grad_gpu), f"force level0, assembly async mode={store_tma}")
 for mb in (3, 5, 4):
     obj.lib.femb_set_fold_config(4, mb)
     timed(lambda: obj._hessian(0, x, obj.MF_value_gpu, obj.diag_fixed), f"hessian level0 lattice fold, fold min blocks {mb}", asm_bytes)
