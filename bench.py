@@ -109,7 +109,7 @@ class ClockSampler:
 
 
 # DRAM bytes (read + write) per launch measured with `ncu --set full` on the cube n=100 (profiles/README.md), per million hexahedra
-ASM_TRAFFIC_PER_MHEX = 4.32e9      # element_kernel<1,1> 0.364 + 1.479 GB, fold_lattice_kernel 1.530 + 0.950 GB (profiles/r02_lattice_assembly_ncu_raw.txt)
+ASM_TRAFFIC_PER_MHEX = 4.22e9      # element_kernel<1,1,0,1,1> 0.364 + 1.381 GB, fold_lattice_kernel 1.527 + 0.947 GB (profiles/r02c_assembly_blocked_tma_ncu_raw.txt)
 GS_TRAFFIC_PER_MHEX = 142e6        # average colour launch of a 3-iteration sweep: 154.8 MB per L|U launch (profiles/r01b_gs_color_ncu_raw.txt), ~80 MB per U-only launch
 
 

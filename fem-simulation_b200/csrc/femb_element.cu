@@ -445,6 +445,29 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
   const int e0 = in.e_begin + (blockIdx.x * EPAIRS + lp) * 2, e1 = e0 + 1;   // this launch covers hexahedra [e_begin, n_hex)
   const bool live0 = e0 < in.n_hex, live1 = e1 < in.n_hex;
   const int ee0 = live0 ? e0 : in.n_hex - 1, ee1 = live1 ? e1 : in.n_hex - 1;   // dead halves shadow a valid hexahedron
+  // Rest data through bulk copies (every CTA but a ragged last one), issued before anything else so that their latency
+  // overlaps the chain hexahedron -> vertex positions below: the warp's 8 hexahedra are 2304 + 256 contiguous bytes of
+  // invJ / detJ; they are copied into the head of the warp's own record area (dead until phase A writes it, after the
+  // __syncwarp that follows the reads), one 576-byte copy per pair at a pitch of 608 bytes so that the per-lane reads (lane
+  // stride 9 words, pair stride 152 words) are conflict-free, instead of 20 strided global loads per lane.  (Hessian kernels
+  // only: the force-only kernel has no record area, and with an area of its own it spilled: 226 vs 199 us.)
+  const bool bulk_cta = kBulk && in.e_begin + (int)(blockIdx.x + 1) * EPB <= in.n_hex;
+  uint64_t* bar = nullptr;
+  unsigned char* stg_w = nullptr;
+  if (bulk_cta) {
+    const int w = threadIdx.x >> 5;
+    bar = reinterpret_cast<uint64_t*>(s_x + (w * 4) * XS_STRIDE + 48);                 // the 16 pad bytes of the warp's first position row
+    stg_w = reinterpret_cast<unsigned char*>(s_rec + (size_t)(w * 4) * PAIR_STRIDE);
+    if ((threadIdx.x & 31) == 0) {
+      const int e_w = in.e_begin + (blockIdx.x * EPAIRS + w * 4) * 2;                   // first hexahedron of the warp
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, 4 * 576 + 256);
+      bulk_g2s(stg_w + 4 * RD_PITCH, in.detJ + (size_t)e_w * 8, 256, bar);
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) bulk_g2s(stg_w + pr * RD_PITCH, in.invJ + (size_t)(e_w + 2 * pr) * 72, 576, bar);
+    }
+    __syncwarp();
+  }
   if (in.prefetch_ctas > 0 && threadIdx.x < 8) {
     // the CTA's first dependent load chain (hexahedron -> vertex positions) starts with a DRAM miss; a CTA a quarter wave
     // ahead finds its 1 KB of vertex indices in L2 instead
@@ -461,25 +484,9 @@ __global__ void __launch_bounds__(ETHREADS, kMode == 0 ? 5 : 3) element_kernel(E
   float dN[8][3];
   shape_grads(sub, dN);
   V2 iJ[9], det;
-  if (kBulk && in.e_begin + (int)(blockIdx.x + 1) * EPB <= in.n_hex) {
-    // Rest data through bulk copies (every CTA but a ragged last one): the warp's 8 hexahedra are 2304 + 256 contiguous
-    // bytes of invJ / detJ; they are copied into the head of the warp's own record area (dead until phase A writes it,
-    // after the __syncwarp below), one 576-byte copy per pair at a pitch of 608 bytes so that the per-lane reads (lane
-    // stride 9 words, pair stride 152 words) are conflict-free, instead of 20 strided global loads per lane.  (Hessian
-    // kernels only: the force-only kernel has no record area, and with an area of its own it spilled: 226 vs 199 us.)
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_x + (w * 4) * XS_STRIDE + 48);       // the 16 pad bytes of the warp's first position row
-    unsigned char* stg_w = reinterpret_cast<unsigned char*>(s_rec + (size_t)(w * 4) * PAIR_STRIDE);
-    const int e_w = in.e_begin + (blockIdx.x * EPAIRS + w * 4) * 2;                     // first hexahedron of the warp
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
-    if (lane == 0) {
-      mbar_expect_tx(bar, 4 * 576 + 256);
-      bulk_g2s(stg_w + 4 * RD_PITCH, in.detJ + (size_t)e_w * 8, 256, bar);
-    }
-    __syncwarp();
-    if (sub == 0) bulk_g2s(stg_w + (lane >> 3) * RD_PITCH, in.invJ + (size_t)e0 * 72, 576, bar);
+  if (bulk_cta) {
     mbar_wait(bar, 0);
+    const int lane = threadIdx.x & 31;
     const float* sj = reinterpret_cast<const float*>(stg_w + (lane >> 3) * RD_PITCH) + sub * 9;
 #pragma unroll
     for (int k = 0; k < 9; ++k) iJ[k].v = make_float2(sj[k], sj[72 + k]);
@@ -740,9 +747,7 @@ __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(Fo
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
   }
-  for (int i = threadIdx.x; i < FL_ROWS * RR_WORDS; i += FL_THREADS)
-    if (v0 + i / RR_WORDS < v_end) rr[i] = __ldg(A.row_rec + (size_t)v0 * RR_WORDS + i);
-  int inc[8];
+  int inc[8];                                                   // the head of the dependent chain: issued first
   {
     int4 i0 = make_int4(-1, -1, -1, -1), i1 = i0;
     if (live) {
@@ -751,6 +756,20 @@ __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(Fo
     }
     inc[0] = i0.x; inc[1] = i0.y; inc[2] = i0.z; inc[3] = i0.w; inc[4] = i1.x; inc[5] = i1.y; inc[6] = i1.z; inc[7] = i1.w;
   }
+  // Row records: into registers now, into shared memory after the accumulation -- a warp issues in order, so a shared-memory
+  // store right behind its load would hold back the element loads below for a memory latency.  Same for the diagonal
+  // addend (pin / mass term of row r, components 0, 4, 8): its row index is requested here, the value half way through the
+  // accumulation, and it is added after the last contribution (the order the output loop used to add it in).
+  constexpr int RR_TILE = FL_ROWS * RR_WORDS;
+  static_assert(RR_TILE <= 2 * FL_THREADS, "two row-record words per thread");
+  unsigned rq0 = 0u, rq1 = 0u;
+  if (v0 + (int)threadIdx.x / RR_WORDS < v_end) rq0 = __ldg(A.row_rec + (size_t)v0 * RR_WORDS + threadIdx.x);
+  if (threadIdx.x + FL_THREADS < RR_TILE && v0 + (int)(threadIdx.x + FL_THREADS) / RR_WORDS < v_end)
+    rq1 = __ldg(A.row_rec + (size_t)v0 * RR_WORDS + threadIdx.x + FL_THREADS);
+  const bool diag_warp = A.diag_add != nullptr && (c == 0 || c == 4 || c == 8);
+  int r_mine = 0;
+  if (diag_warp && live) r_mine = (int)__ldg(A.row_rec + (size_t)v * RR_WORDS + 8);
+  float dg = 0.f;
   const int cT = (c % 3) * 3 + c / 3;                           // the mirrored blocks are stored transposed
   // Blocked plane-major scratch: hexahedron e lives in block e >> 5 (360 planes x 32 hexahedra = 46 080 contiguous bytes) at
   // lane e & 31.  A thread's 8 loads for local node a are one base pointer + compile-time offsets (the launcher checks
@@ -773,7 +792,11 @@ __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(Fo
       const float val = have ? __ldg(p) : 0.f;
       acc[offset_slot(a, b)] += val;
     }
+    if (a == 3 && diag_warp && live) dg = __ldg(A.diag_add + r_mine);
   }
+  if (diag_warp) acc[13] += dg;                                 // offset_slot(a, a): the diagonal block
+  rr[threadIdx.x] = rq0;
+  if (threadIdx.x + FL_THREADS < RR_TILE) rr[threadIdx.x + FL_THREADS] = rq1;
   __syncthreads();
   if (live) {
     const unsigned* w = rr + lane * RR_WORDS;
@@ -788,20 +811,18 @@ __global__ void __launch_bounds__(FL_THREADS, kMinBlocks) fold_lattice_kernel(Fo
     }
   }
   __syncthreads();
+  // the row's L blocks, D block and U blocks are contiguous in shared memory (<= 243 floats) and go to three places of the
+  // value array: one unrolled pass with 32-bit value indices (the launcher checks 9 nnz < 2^32)
   for (int row = c; row < FL_ROWS && v0 + row < v_end; row += FL_THREADS / 32) {
     const unsigned* w = rr + row * RR_WORDS;
-    const int r = (int)w[8], lp = (int)w[9], up = (int)w[10];
-    const int nl = (int)(w[11] & 255u), nu = (int)((w[11] >> 8) & 255u);
+    const unsigned nL9 = (w[11] & 255u) * 9u, nD9 = nL9 + 9u, tot = nD9 + ((w[11] >> 8) & 255u) * 9u;
+    const unsigned gL = ((unsigned)A.off_l + w[9]) * 9u, gD = ((unsigned)A.off_d + w[8]) * 9u - nL9, gU = ((unsigned)A.off_u + w[10]) * 9u - nD9;
     const float* src = st + row * 243;
-    float* outL = A.values + ((size_t)A.off_l + lp) * 9;
-    for (int i = lane; i < nl * 9; i += 32) outL[i] = src[i];
-    if (lane < 9) {
-      float d = src[nl * 9 + lane];
-      if (A.diag_add != nullptr && (lane == 0 || lane == 4 || lane == 8)) d += __ldg(A.diag_add + r);
-      A.values[((size_t)A.off_d + r) * 9 + lane] = d;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const unsigned i = (unsigned)lane + 32u * it;
+      if (i < tot) A.values[i < nL9 ? gL + i : (i < nD9 ? gD + i : gU + i)] = src[i];
     }
-    float* outU = A.values + ((size_t)A.off_u + up) * 9;
-    for (int i = lane; i < nu * 9; i += 32) outU[i] = src[(nl + 1) * 9 + i];
   }
 }
 
@@ -1041,7 +1062,9 @@ __global__ void __launch_bounds__(256) coarse_pin_kernel(int n_coarse, const int
 static size_t em_stride_of(int n_hex) { return ((size_t)n_hex + 31) / 32 * 32; }
 // (the lattice fold addresses the plane-major scratch with 32-bit element offsets)
 static bool lattice_available(const FembLevel* l) {
-  return l->lat_inc8 != nullptr && l->lat_row_rec != nullptr && (unsigned long long)EM_PLANES * em_stride_of(l->n_hex) < (1ull << 32);
+  // (32-bit element offsets into the scratch and 32-bit indices into the value array)
+  return l->lat_inc8 != nullptr && l->lat_row_rec != nullptr && (unsigned long long)EM_PLANES * em_stride_of(l->n_hex) < (1ull << 32) &&
+         (unsigned long long)l->nnz * 9ull < (1ull << 32);
 }
 
 static ElemIn make_in(const FembLevel* l, const float* x, float mu, float la) {
