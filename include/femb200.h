@@ -45,7 +45,8 @@ extern "C" {
 #define FEMB_FOLD_PLAN_BYTES 128   /* 28*4 contributor bytes + 16 header bytes per vertex: one cache line */
 /* floats of element-matrix scratch per hexahedron (elem_k of femb_hessian; the hexahedron count is rounded up to a multiple
  * of 32): the symmetric half of the 24x24 element matrix.  General layout: 8 rows x (5 blocks of 9 + 3 pad) per
- * hexahedron; lattice layout: 360 planes (row a, block k, component c) of one float per hexahedron.  See femb_element.cu */
+ * hexahedron; lattice layout: blocks of 32 hexahedra, each 360 planes (row a, block k, component c) x 32 floats = 46 080
+ * contiguous bytes (elem_k must be 16-byte aligned).  See femb_element.cu */
 #define FEMB_ELEM_K_FLOATS 384
 /* bytes of a row record of the lattice fold (FembLevel.lat_row_rec) */
 #define FEMB_ROW_REC_BYTES 48
