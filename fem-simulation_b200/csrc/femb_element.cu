@@ -18,9 +18,11 @@
 //     K_ab[j][i] = det * ( (g_a . S g_b) d_ji + mu (g_a . g_b)(F F^T)_ji + mu u_b[j] u_a[i] + la u_a[j] u_b[i] )
 // (== d(P g_a det)_j / d x_b,i of quai_hexagon.py:86-106).  The half rows go to a scratch array and are summed into the
 // fixed [L;D;U] value layout by a gather in a fixed order (no atomics):
-//   * lattice levels (every level of a voxel mesh): the scratch is plane-major, EM[(a*5+k)*9+c][hexahedron], and
-//     fold_lattice_kernel gives every (row, block component) its own thread, which adds its <= 64 contributions through
-//     compile-time offsets (the lattice offset of node b seen from node a) -- coalesced 128-byte lines, no plan decoding;
+//   * lattice levels (every level of a voxel mesh): the scratch is plane-major and blocked by 32 hexahedra,
+//     EM[e >> 5][(a*5+k)*9+c][e & 31] (a block = the 46 080-byte tile one CTA of the element kernel produces and ships with
+//     three TMA tensor stores), and fold_lattice_kernel gives every (row, block component) its own thread, which adds its
+//     <= 64 contributions through compile-time offsets (the lattice offset of node b seen from node a) from one base
+//     pointer per local node -- coalesced 128-byte lines, no plan decoding;
 //   * any other hexahedral mesh: 192-byte half rows per (hexahedron, node) and the per-row fold plan, the precomputed
 //     inverse of the element->nnz map (assemble_rows_kernel).
 #include <cstdio>
@@ -1099,7 +1101,7 @@ static EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-static int g_tma_store = 3;   // 0: store loop, 1: TMA tensor store, 2: + rest data through bulk copies, 3: + L2 prefetch of index data
+static int g_asm_async = 3;   // 0: store loop, 1: TMA tensor store, 2: + rest data through bulk copies, 3: + L2 prefetch of index data
 struct EmMaps {
   CUtensorMap store;    // 3-D view {hexahedron in block, plane, block} of the blocked scratch, box {32, 120, 1}, 128-byte swizzle:
                         // a third of the element kernel's tile
@@ -1143,9 +1145,9 @@ static int launch_element(ElemIn in, int e_begin, int e_end, float* elem_f, floa
   static const CUtensorMap no_map = {};
   const bool la = kMode != 0 && in.la != 0.f;
   constexpr bool kCanTma = kSoA && kMode != 0;
-  in.prefetch_ctas = g_tma_store >= 3 ? 111 : 0;
-  if (kCanTma && maps != nullptr && maps->ok && g_tma_store) {
-    const bool bulk = g_tma_store >= 2 && ((reinterpret_cast<uintptr_t>(in.invJ) | reinterpret_cast<uintptr_t>(in.detJ)) & 15u) == 0;
+  in.prefetch_ctas = g_asm_async >= 3 ? 111 : 0;            // a quarter of the 148 x 3 resident CTAs
+  if (kCanTma && maps != nullptr && maps->ok && g_asm_async) {
+    const bool bulk = g_asm_async >= 2 && ((reinterpret_cast<uintptr_t>(in.invJ) | reinterpret_cast<uintptr_t>(in.detJ)) & 15u) == 0;
     if (bulk) {
       if (la) return launch_element_la<kMode, kSoA, true, kCanTma, kCanTma>(in, e_begin, e_end, elem_f, elem_k, maps->store, st);
       return launch_element_la<kMode, kSoA, false, kCanTma, kCanTma>(in, e_begin, e_end, elem_f, elem_k, maps->store, st);
@@ -1183,7 +1185,7 @@ static int launch_fold_lattice(const FembLevel* l, const float* diag_add, const 
   FoldLatArgs A;
   A.n_vert = l->n_vert; A.inc8 = l->lat_inc8; A.row_rec = reinterpret_cast<const unsigned*>(l->lat_row_rec);
   A.em = elem_k; A.diag_add = diag_add; A.values = values;
-  A.off_l = l->off_l; A.off_d = l->off_d; A.off_u = l->off_u; A.prefetch_tiles = g_tma_store >= 3 ? 148 : 0;
+  A.off_l = l->off_l; A.off_d = l->off_d; A.off_u = l->off_u; A.prefetch_tiles = g_asm_async >= 3 ? 148 : 0;   // a quarter of the 148 x 4 resident CTAs
   const unsigned grid = cdiv(l->n_vert, FL_ROWS);
   if (g_lat_min_blocks == 3) fold_lattice_kernel<3><<<grid, FL_THREADS, 0, st>>>(A, 0, l->n_vert);
   else if (g_lat_min_blocks == 5) fold_lattice_kernel<5><<<grid, FL_THREADS, 0, st>>>(A, 0, l->n_vert);
@@ -1200,7 +1202,7 @@ static int hessian_pipeline(const FembLevel* l, const float* x, float mu, float 
   // (A chunked two-stream software pipeline of the two stages and a one-kernel variant with the fold inside the SM were
   // built and measured slower)
   if (lattice_available(l)) {
-    const EmMaps maps = g_tma_store ? make_em_maps(elem_k, l->n_hex) : EmMaps{};
+    const EmMaps maps = g_asm_async ? make_em_maps(elem_k, l->n_hex) : EmMaps{};
     int rc = launch_element<kMode, true>(in, 0, l->n_hex, elem_f, elem_k, st, &maps);
     if (rc) return rc;
     return launch_fold_lattice(l, diag_add, elem_k, values, st);
@@ -1229,7 +1231,7 @@ int femb_set_fold_config(int rows_per_warp, int min_blocks_per_sm) {
 }
 
 int femb_set_assembly_async(int mode) {
-  if (mode >= 0 && mode <= 3) g_tma_store = mode;
+  if (mode >= 0 && mode <= 3) g_asm_async = mode;
   return FEMB_OK;
 }
 
