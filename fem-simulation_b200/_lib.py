@@ -106,6 +106,7 @@ PROTOTYPES = {
     "femb_check_device": [I],
     "femb_setup_incidence_host": [I, I, P, P],
     "femb_setup_coo_to_csr_host": [I, I, P, P, P, P, P, P],
+    "femb_setup_coo_to_csr_pair_host": [I, I, P, P, P, P, P, P, P, P],
     "femb_setup_pattern_count_host": [I, P, P, P, P, P, P],
     "femb_setup_pattern_fill_host": [I, I, P, P, P, P, P, P, P, P, P, P],
     "femb_setup_galerkin_count_host": [I, P, P, P, P, P, P, P],

@@ -46,10 +46,13 @@ int femb_setup_incidence_host(int n_vert, int n_hex, const int* hex, int* vert_e
   return FEMB_OK;
 }
 
-int femb_setup_coo_to_csr_host(int nrow, int nnz, const int* rows, const int* cols, const float* w, int* offsets, int* columns,
-                               float* weights) {
+int femb_setup_coo_to_csr_pair_host(int nrow, int nnz, const int* rows, const int* cols, const float* w, const float* w2, int* offsets,
+                                    int* columns, float* weights, float* weights2) {
   FEMB_REQUIRE(nrow >= 0 && nnz >= 0 && offsets && (nnz == 0 || (rows && cols && w && columns && weights)), "bad arguments");
-  // counting sort by row (stable), then every row by column: entries are unique, rows are short (<= 27 here)
+  FEMB_REQUIRE((w2 == nullptr) == (weights2 == nullptr), "w2 and weights2 go together");
+  // counting sort by row (stable), then every row by column: entries are unique, rows are short (<= 27 here); a second weight
+  // array on the same pattern (the normalised and the un-normalised interpolation weights) rides along
+  const bool two = w2 != nullptr;
   std::vector<int> cur((size_t)nrow + 1, 0);
   for (int t = 0; t < nnz; ++t) {
     const int r = rows[t];
@@ -62,17 +65,27 @@ int femb_setup_coo_to_csr_host(int nrow, int nnz, const int* rows, const int* co
   for (int t = 0; t < nnz; ++t) {
     const int p = cur[rows[t]]++;
     columns[p] = cols[t]; weights[p] = w[t];
+    if (two) weights2[p] = w2[t];
   }
 #pragma omp parallel for schedule(static)
   for (int r = 0; r < nrow; ++r)
     for (int i = offsets[r] + 1; i < offsets[r + 1]; ++i) {               // insertion sort, stable
       const int c = columns[i];
-      const float x = weights[i];
+      const float x = weights[i], x2 = two ? weights2[i] : 0.f;
       int j = i - 1;
-      for (; j >= offsets[r] && columns[j] > c; --j) { columns[j + 1] = columns[j]; weights[j + 1] = weights[j]; }
+      for (; j >= offsets[r] && columns[j] > c; --j) {
+        columns[j + 1] = columns[j]; weights[j + 1] = weights[j];
+        if (two) weights2[j + 1] = weights2[j];
+      }
       columns[j + 1] = c; weights[j + 1] = x;
+      if (two) weights2[j + 1] = x2;
     }
   return FEMB_OK;
+}
+
+int femb_setup_coo_to_csr_host(int nrow, int nnz, const int* rows, const int* cols, const float* w, int* offsets, int* columns,
+                               float* weights) {
+  return femb_setup_coo_to_csr_pair_host(nrow, nnz, rows, cols, w, nullptr, offsets, columns, weights, nullptr);
 }
 
 int femb_setup_pattern_count_host(int n_vert, const int* hex, const int* v2i, const int* i2v, const int* vert_elem, int* L_ptr,

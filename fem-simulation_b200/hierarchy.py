@@ -71,6 +71,28 @@ def coo_to_csr(nrow, ncol, rows, cols, w) -> SparseW:
     return SparseW(int(nrow), int(ncol), offsets, columns, weights)
 
 
+def coo_to_csr_pair(nrow, ncol, rows, cols, w_a, w_b):
+    """two matrices on one pattern (same rows / columns, two weight arrays) from one sort; they share the offset and column
+    arrays (nobody writes to them)."""
+    from . import _lib
+    lib = _lib.load()
+    r = np.ascontiguousarray(rows, dtype=np.int32)
+    c = np.ascontiguousarray(cols, dtype=np.int32)
+    wa, wb = np.ascontiguousarray(w_a, dtype=F32), np.ascontiguousarray(w_b, dtype=F32)
+    nnz = int(r.shape[0])
+    offsets = np.empty(int(nrow) + 1, np.int32)
+    columns, wa_out, wb_out = np.empty(nnz, np.int32), np.empty(nnz, F32), np.empty(nnz, F32)
+    hp = lambda a: a.ctypes.data_as(_lib.C.c_void_p)
+    _lib.check(lib.femb_setup_coo_to_csr_pair_host(int(nrow), nnz, hp(r), hp(c), hp(wa), hp(wb), hp(offsets), hp(columns), hp(wa_out),
+                                                   hp(wb_out)), "femb_setup_coo_to_csr_pair_host")
+    return SparseW(int(nrow), int(ncol), offsets, columns, wa_out), SparseW(int(nrow), int(ncol), offsets, columns, wb_out)
+
+
+def transposed_pair(a: SparseW, b: SparseW):
+    """a^T and b^T for two matrices that share their pattern"""
+    return coo_to_csr_pair(a.ncol, a.nrow, a.columns, a.rows(), a.weights, b.weights)
+
+
 class LevelPattern:
     """Fixed block pattern of one level in the reference's [L;D;U] value layout (object.py:485-697).  The per-entry row arrays
     of the reference (`*_L_row`, `*_U_row`, `*_GS_*_row/col`: what its bsr_set_from_triplets calls consume) are derived from
@@ -419,16 +441,16 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
                                  rowInd_noOrder=coarse_id.astype(np.int32), colInd_noOrder=fine_id.astype(np.int32),
                                  value=w, norm=norm))
         nc, nf = H.dims[lay + 1], H.dims[lay]
-        H.Ut.append(coo_to_csr(nc, nf, rowInd, colInd, w_norm))
-        H.Ut_noOrder.append(coo_to_csr(nc, nf, coarse_id, fine_id, w_norm))
-        H.Ut_hat.append(coo_to_csr(nc, nf, rowInd, colInd, w))
-        H.Ut_noOrder_hat.append(coo_to_csr(nc, nf, coarse_id, fine_id, w))
+        ut, ut_hat = coo_to_csr_pair(nc, nf, rowInd, colInd, w_norm, w)                 # same pattern, two weight sets
+        utn, utn_hat = coo_to_csr_pair(nc, nf, coarse_id, fine_id, w_norm, w)
+        H.Ut.append(ut); H.Ut_noOrder.append(utn); H.Ut_hat.append(ut_hat); H.Ut_noOrder_hat.append(utn_hat)
         if lay == 0:
             H.fix_idx[fine_id, ent_k] = coarse_id
             H.fix_values[fine_id, ent_k] = w
     for lay in range(layer - 1):
-        H.Us.append(H.Ut[lay].transposed()); H.Us_noOrder.append(H.Ut_noOrder[lay].transposed())
-        H.Us_hat.append(H.Ut_hat[lay].transposed()); H.Us_noOrder_hat.append(H.Ut_noOrder_hat[lay].transposed())
+        us, us_hat = transposed_pair(H.Ut[lay], H.Ut_hat[lay])
+        usn, usn_hat = transposed_pair(H.Ut_noOrder[lay], H.Ut_noOrder_hat[lay])
+        H.Us.append(us); H.Us_noOrder.append(usn); H.Us_hat.append(us_hat); H.Us_noOrder_hat.append(usn_hat)
 
     for lay in range(layer):                                               # object.py:485-697
         H.pattern.append(build_pattern(H.hexs[lay], H.vertex2index[lay], H.color_vertex_num[lay], H.dims[lay]))

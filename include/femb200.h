@@ -142,6 +142,10 @@ int femb_setup_incidence_host(int n_vert, int n_hex, const int* hex, int* vert_e
  * bsr_set_from_triplets (sparse.py:173-278) used for the interpolation operators and their transposes (object.py:247-443) */
 int femb_setup_coo_to_csr_host(int nrow, int nnz, const int* rows, const int* cols, const float* w, int* offsets, int* columns,
                                float* weights);
+/* the same with a second weight array on the same pattern (w2 / weights2 may both be NULL): the normalised and the
+ * un-normalised interpolation weights of object.py:422-436 share rows and columns, one sort serves both */
+int femb_setup_coo_to_csr_pair_host(int nrow, int nnz, const int* rows, const int* cols, const float* w, const float* w2, int* offsets,
+                                    int* columns, float* weights, float* weights2);
 /* pattern of one level = sorted set {(v2i[a], v2i[b]) : a, b in one hexahedron} in the [L;D;U] layout (object.py:485-599):
  * first the row pointers L_ptr / U_ptr [n_vert+1] (L_ptr[n_vert] = L_nnz = U_nnz), then, into arrays the caller sizes from
  * them, the columns, hex_update_offset (elem2nnz [n_hex*64], object.py:563-569) and UtAUs_block_offset (block_offset
