@@ -238,3 +238,29 @@ def test_host_setup_routines_match_numpy_restatements():
             assert set(g1) == set(g2)
             for k in g2:
                 assert np.array_equal(np.asarray(g1[k]), np.asarray(g2[k])), (l, k)
+
+
+def test_coo_to_csr_pair_matches_numpy_sort():
+    """femb_setup_coo_to_csr_pair_host (counting sort by row + per-row insertion sort, two weight arrays on one pattern) vs the
+    numpy restatement (one global stable sort): offsets, columns and both weight arrays; the two results share their pattern
+    arrays; the transposed pair equals the transposes taken one at a time."""
+    rng = np.random.default_rng(3)
+    nrow, ncol = 57, 301
+    cells = rng.choice(nrow * ncol, size=2000, replace=False)                # unique (row, col) pairs in random order
+    rows, cols = (cells // ncol).astype(np.int32), (cells % ncol).astype(np.int32)
+    wa, wb = rng.normal(size=2000).astype(np.float32), rng.normal(size=2000).astype(np.float32)
+    a, b = hierarchy.coo_to_csr_pair(nrow, ncol, rows, cols, wa, wb)
+    ra, rb = hierarchy.coo_to_csr_numpy(nrow, ncol, rows, cols, wa), hierarchy.coo_to_csr_numpy(nrow, ncol, rows, cols, wb)
+    for got, want in ((a, ra), (b, rb)):
+        assert (got.nrow, got.ncol) == (want.nrow, want.ncol)
+        assert np.array_equal(got.offsets, want.offsets) and np.array_equal(got.columns, want.columns)
+        assert np.array_equal(got.weights, want.weights)
+    assert a.offsets is b.offsets and a.columns is b.columns
+    one = hierarchy.coo_to_csr(nrow, ncol, rows, cols, wa)
+    assert np.array_equal(one.offsets, ra.offsets) and np.array_equal(one.columns, ra.columns) and np.array_equal(one.weights, ra.weights)
+    ta, tb = hierarchy.transposed_pair(a, b)
+    for got, want in ((ta, a.transposed()), (tb, b.transposed())):
+        assert np.array_equal(got.offsets, want.offsets) and np.array_equal(got.columns, want.columns)
+        assert np.array_equal(got.weights, want.weights)
+    empty_a, empty_b = hierarchy.coo_to_csr_pair(4, 5, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.float32))
+    assert empty_a.nnz == 0 and empty_b.offsets.tolist() == [0, 0, 0, 0, 0]
