@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstring>
 #include <vector>
+#include <omp.h>
 
 #include "femb_common.cuh"
 
@@ -53,19 +54,48 @@ int femb_setup_coo_to_csr_pair_host(int nrow, int nnz, const int* rows, const in
   // counting sort by row (stable), then every row by column: entries are unique, rows are short (<= 27 here); a second weight
   // array on the same pattern (the normalised and the un-normalised interpolation weights) rides along
   const bool two = w2 != nullptr;
-  std::vector<int> cur((size_t)nrow + 1, 0);
-  for (int t = 0; t < nnz; ++t) {
-    const int r = rows[t];
-    if (r < 0 || r >= nrow) { set_error("femb_setup_coo_to_csr_host: row %d out of range", r); return FEMB_E_INVALID; }
-    ++cur[(size_t)r + 1];
+  // stable counting sort by row, in parallel: thread t owns the t-th contiguous chunk of the input, counts its rows, and the
+  // starting position of (row r, thread t) is offsets[r] + the counts of row r in the chunks before t -- input order is kept
+  int bad_row = -1;
+  const int T = std::max(1, std::min(omp_get_max_threads(), nnz / 65536 + 1));
+  std::vector<int> cnt((size_t)T * ((size_t)nrow + 1), 0);
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    const long long lo = (long long)nnz * t / T, hi = (long long)nnz * (t + 1) / T;
+    int* c = cnt.data() + (size_t)t * ((size_t)nrow + 1);
+    for (long long i = lo; i < hi; ++i) {
+      const int r = rows[i];
+      if (r < 0 || r >= nrow) {
+#pragma omp atomic write
+        bad_row = r;
+        continue;
+      }
+      ++c[r];
+    }
   }
+  if (bad_row != -1) { set_error("femb_setup_coo_to_csr_host: row %d out of range", bad_row); return FEMB_E_INVALID; }
   offsets[0] = 0;
-  for (int r = 0; r < nrow; ++r) offsets[r + 1] = offsets[r] + cur[(size_t)r + 1];
-  for (int r = 0; r < nrow; ++r) cur[r] = offsets[r];
-  for (int t = 0; t < nnz; ++t) {
-    const int p = cur[rows[t]]++;
-    columns[p] = cols[t]; weights[p] = w[t];
-    if (two) weights2[p] = w2[t];
+  for (int r = 0; r < nrow; ++r) {
+    int n = 0;
+    for (int t = 0; t < T; ++t) {                                         // count -> start of (r, t) relative to the row
+      int& c = cnt[(size_t)t * ((size_t)nrow + 1) + r];
+      const int k = c;
+      c = n; n += k;
+    }
+    offsets[r + 1] = offsets[r] + n;
+  }
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    const long long lo = (long long)nnz * t / T, hi = (long long)nnz * (t + 1) / T;
+    int* c = cnt.data() + (size_t)t * ((size_t)nrow + 1);
+    for (long long i = lo; i < hi; ++i) {
+      const int r = rows[i];
+      const int p = offsets[r] + c[r]++;
+      columns[p] = cols[i]; weights[p] = w[i];
+      if (two) weights2[p] = w2[i];
+    }
   }
 #pragma omp parallel for schedule(static)
   for (int r = 0; r < nrow; ++r)

@@ -402,9 +402,11 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
         coarse_hex = vid.reshape(n_ch, 8).astype(np.int32)
         n_cv = len(uvk)
         vk = np.stack([uvk // (BIG * BIG), (uvk // BIG) % BIG, uvk % BIG], axis=1)
-        ijk_f = _ijk(xl[hx.reshape(-1)], box_min, fine_size, 0.1).astype(np.int64).reshape(-1, 8, 3)
-        rel = ijk_f - 2 * key3[:, None, :]
-        slot = 9 * rel[..., 0] + 3 * rel[..., 1] + rel[..., 2]
+        # slot of node b of hexahedron e inside its coarse cell: 9 di + 3 dj + dk with (di, dj, dk) = ijk(vertex) - 2 key3(e);
+        # the lattice index is a function of the vertex, so it is evaluated once per vertex, folded to 9 i + 3 j + k and gathered
+        ijk_v = _ijk(xl, box_min, fine_size, 0.1).astype(np.int64)
+        code_v = 9 * ijk_v[:, 0] + 3 * ijk_v[:, 1] + ijk_v[:, 2]
+        slot = code_v[hx] - 2 * (9 * key3[:, 0] + 3 * key3[:, 1] + key3[:, 2])[:, None]
         fc = np.full((n_ch, 27), -1, dtype=np.int32)
         fc[np.repeat(hex_id, 8), slot.reshape(-1)] = hx.reshape(-1)
         coarse_vert = (vk.astype(F32) * F32(coarse_size) + box_min).astype(F32)
@@ -423,8 +425,9 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
         chex = H.hexs[lay + 1].astype(np.int64)
         flat = fc.reshape(-1).astype(np.int64)
         pos_valid = np.nonzero(flat != -1)[0]
-        _, first = np.unique(flat[pos_valid], return_index=True)
-        pos = np.sort(pos_valid[first])                                    # (HEX,slot) that handles each fine vertex
+        first_pos = np.full(H.dims[lay], -1, dtype=np.int64)               # first (HEX, slot) that names each fine vertex:
+        first_pos[flat[pos_valid][::-1]] = pos_valid[::-1]                 # assigned back to front, the first one stays
+        pos = np.sort(first_pos[first_pos >= 0])                           # (HEX,slot) that handles each fine vertex
         HEX, s = pos // 27, pos % 27
         cnt = _ST_CNT[s]
         ent_owner = np.repeat(np.arange(len(pos)), cnt)
