@@ -1,8 +1,13 @@
-// Stand-alone probe of the TMA tensor copies the assembly kernels use (plane-major scratch [360][S] of floats):
-//   mode 1: one 2-D load, box {32, 45}, no swizzle, issued by one thread
-//   mode 2: 8 lanes issue 4 loads each against their own mbarrier (the fold's pattern)
-//   mode 3: three 2-D stores, box {32, 120}, 128-byte swizzle, from a tile written with the element kernel's address formula
-// Each mode verifies what arrived.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe scripts/tma_probe.cu
+// Stand-alone probe of the TMA tensor copies around the plane-major element-matrix scratch (a [360][S] array of floats here):
+//   tma_probe 1 [c0 [promo [swizzle]]]  one 2-D load, box {32, 45}, issued by one thread; c0 = first coordinate (hexahedron),
+//                                        promo = L2 promotion enum (0 none, 2 = 128 B), swizzle = enum (0 none, 3 = 128 B)
+//   tma_probe 2                          8 lanes issue 4 loads each (boxes {36, 45} and {36, 9} from 16-byte aligned windows)
+//                                        against their own mbarriers: the pattern of the TMA-staged fold that was not kept
+//   tma_probe 3                          three 2-D stores, box {32, 120}, 128-byte swizzle, from a tile written with the element
+//                                        kernel's address formula (the product uses the same tile through a 3-D view)
+// Each mode verifies what arrived.  Measured on B200 (driver 580, CUDA 12.9): mode 1 with c0 = 36 or 64 passes, with c0 = 37
+// the kernel dies with "an illegal instruction was encountered" whatever the swizzle / promotion -- a tensor load must start
+// on a 16-byte boundary of global memory.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe scripts/tma_probe.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
