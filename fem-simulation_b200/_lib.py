@@ -12,7 +12,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libfemb200.so")
-SOURCES = ["femb_api.cu", "femb_element.cu", "femb_comm.cu", "femb_steps.cu", "femb_setup.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu", "femb_exp2.cu"]
+SOURCES = ["femb_api.cu", "femb_element.cu", "femb_comm.cu", "femb_steps.cu", "femb_setup.cu", "femb_setup_hierarchy.cu", "femb_sparse.cu", "femb_dynamic.cu", "femb_cloth.cu", "femb_exp2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-ldl", "-lgomp"]
 
@@ -111,6 +111,12 @@ PROTOTYPES = {
     "femb_setup_pattern_fill_host": [I, I, P, P, P, P, P, P, P, P, P, P],
     "femb_setup_galerkin_count_host": [I, P, P, P, P, P, P, P],
     "femb_setup_galerkin_fill_host": [I, I] + [P] * 22,
+    "femb_setup_stencil_host": [P, P, P],
+    "femb_setup_color_order_host": [I, P, P, F, P, P, P],
+    "femb_setup_coarsen_count_host": [I, I, P, P, P, F, P, P, P, P],
+    "femb_setup_coarsen_fill_host": [I, I, P, P, P, F, F, P, P, I, I, P, P, P, P, P, P],
+    "femb_setup_interp_count_host": [I, I, P, P, P],
+    "femb_setup_interp_fill_host": [I, I, I, P, P, P, I, P, P, P, P, P, P],
     "femb_prepare_rest": [I, P, P, P, P, P],
     "femb_build_fold_plan": [LV, P, P],
     "femb_build_lattice_fold": [LV, P, P, P, P],

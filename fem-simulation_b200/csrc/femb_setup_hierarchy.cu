@@ -1,0 +1,291 @@
+// Host-side construction of the multigrid hierarchy itself: colour order of a level, one lattice coarsening step (coarse
+// hexahedra, coarse vertices, fine_coarse) and the interpolation triplets between two levels -- what Object.__init__ builds
+// with Python dictionaries (/root/reference/exp1/quasi_simulation/object.py:147-158, 171-241, 265-443).  The reference numbers
+// coarse hexahedra, coarse vertices and interpolation entries in the order its loops first meet them; a dictionary keyed by
+// lattice coordinates is a lookup table over the lattice here (dense when the bounding box is reasonably filled, hashed
+// otherwise), filled by one ordered scan, so the numbering is the reference's by construction.  Every floating-point
+// expression is evaluated in float32 in the reference's order (cpu_function.py:12-20); hierarchy.build_hierarchy_numpy is
+// the numpy restatement the tests compare this file with, bit for bit.
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+#include <omp.h>
+
+#include "femb_common.cuh"
+
+namespace femb {
+
+// cpu_function.py:12-20: ((p - origin) / spacing + shift).int(), float32 throughout, truncation toward zero
+static inline int lattice_index(float p, float origin, float spacing, float shift) {
+  float t = p - origin;
+  t = t / spacing;
+  t = t + shift;
+  return (int)t;
+}
+
+// first-seen numbering over integer lattice keys (i, j, k) in [0, nx) x [0, ny) x [0, nz)
+struct LatticeIds {
+  long long nx, ny, nz;
+  bool dense;
+  std::vector<int> table;
+  std::unordered_map<long long, int> map;
+  int next = 0;
+  LatticeIds(long long nx_, long long ny_, long long nz_, long long expected) : nx(nx_), ny(ny_), nz(nz_) {
+    const long long vol = nx * ny * nz;
+    dense = vol <= std::max<long long>(1ll << 24, 64 * expected);
+    if (dense) table.assign((size_t)vol, -1);
+    else map.reserve((size_t)expected * 2);
+  }
+  inline long long key(long long i, long long j, long long k) const { return (i * ny + j) * nz + k; }
+  inline int find_or_add(long long i, long long j, long long k) {
+    const long long q = key(i, j, k);
+    if (dense) {
+      int& slot = table[(size_t)q];
+      if (slot < 0) slot = next++;
+      return slot;
+    }
+    auto it = map.find(q);
+    if (it != map.end()) return it->second;
+    map.emplace(q, next);
+    return next++;
+  }
+};
+
+// object.py:283-412: slot s = 9 i + 3 j + k of a coarse cell (i, j, k in 0..2) -> its coarse corners (ascending local
+// number 4 bi + 2 bj + bk) and weight: an even coordinate names one side, the middle one both
+struct Stencil {
+  int cnt[27];
+  int corner[27][8];
+  float w[27];
+  Stencil() {
+    for (int s = 0; s < 27; ++s) {
+      const int ax[3] = {s / 9, (s / 3) % 3, s % 3};
+      int n = 0;
+      for (int c = 0; c < 8; ++c) {
+        bool ok = true;
+        for (int d = 0; d < 3; ++d) {
+          const int bit = (c >> (2 - d)) & 1;
+          if (ax[d] != 1 && bit != ax[d] / 2) ok = false;
+        }
+        if (ok) corner[s][n++] = c;
+      }
+      cnt[s] = n;
+      w[s] = 1.0f / (float)n;
+      for (int q = n; q < 8; ++q) corner[s][q] = 0;
+    }
+  }
+};
+static const Stencil g_stencil;
+
+// object.py:151-158: index order = stable sort of the vertices by colour
+static void color_order(int n, const unsigned char* color, int* v2i, int* i2v, int* cvn) {
+  long long count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int v = 0; v < n; ++v) ++count[color[v]];
+  long long start[8];
+  cvn[0] = 0;
+  for (int c = 0; c < 8; ++c) {
+    start[c] = cvn[c];
+    cvn[c + 1] = (int)(cvn[c] + count[c]);
+  }
+  for (int v = 0; v < n; ++v) {
+    const int i = (int)start[color[v]]++;
+    v2i[v] = i;
+    i2v[i] = v;
+  }
+}
+
+static inline int mod2(int v) { return ((v % 2) + 2) % 2; }   // numpy's % (result has the divisor's sign)
+
+}  // namespace femb
+
+using namespace femb;
+
+extern "C" {
+
+int femb_setup_stencil_host(int* cnt, int* corners, float* weight) {
+  FEMB_REQUIRE(cnt && corners && weight, "null pointer");
+  for (int s = 0; s < 27; ++s) {
+    cnt[s] = g_stencil.cnt[s];
+    weight[s] = g_stencil.w[s];
+    for (int q = 0; q < 8; ++q) corners[s * 8 + q] = g_stencil.corner[s][q];
+  }
+  return FEMB_OK;
+}
+
+int femb_setup_color_order_host(int n_vert, const float* x, const float* origin, float spacing, int* v2i, int* i2v,
+                                int* color_vertex_num) {
+  FEMB_REQUIRE(n_vert >= 0 && x && origin && v2i && i2v && color_vertex_num, "bad arguments");
+  std::vector<unsigned char> color((size_t)n_vert);
+#pragma omp parallel for schedule(static)
+  for (int v = 0; v < n_vert; ++v) {
+    const int i = mod2(lattice_index(x[3 * (size_t)v + 0], origin[0], spacing, 0.5f));
+    const int j = mod2(lattice_index(x[3 * (size_t)v + 1], origin[1], spacing, 0.5f));
+    const int k = mod2(lattice_index(x[3 * (size_t)v + 2], origin[2], spacing, 0.5f));
+    color[v] = (unsigned char)(i + 2 * j + 4 * k);
+  }
+  color_order(n_vert, color.data(), v2i, i2v, color_vertex_num);
+  return FEMB_OK;
+}
+
+int femb_setup_coarsen_count_host(int n_vert, int n_hex, const float* x, const int* hex, const float* origin, float coarse_size,
+                                  int* hex_parent, int* coarse_key, int* n_coarse_hex, int* n_coarse_vert) {
+  FEMB_REQUIRE(n_vert > 0 && n_hex > 0 && x && hex && origin && hex_parent && coarse_key && n_coarse_hex && n_coarse_vert,
+               "bad arguments");
+  // coarse cell of every hexahedron: the lattice index of its node 0 at the coarse spacing (object.py:183-188)
+  int kmax[3] = {0, 0, 0};
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(max : kmax[:3]) reduction(| : bad)
+  for (int e = 0; e < n_hex; ++e) {
+    const int v = hex[8 * (size_t)e];
+    if (v < 0 || v >= n_vert) { bad |= 1; continue; }
+    for (int d = 0; d < 3; ++d) {
+      const int q = lattice_index(x[3 * (size_t)v + d], origin[d], coarse_size, 0.1f);
+      coarse_key[3 * (size_t)e + d] = q;
+      if (q < 0 || q >= (1 << 20)) bad |= 2;
+      kmax[d] = std::max(kmax[d], q);
+    }
+  }
+  if (bad & 1) { set_error("femb_setup_coarsen_count_host: vertex id out of range"); return FEMB_E_INVALID; }
+  if (bad & 2) {
+    set_error("femb_setup_coarsen_count_host: coarse cell index outside [0, 2^20): origin above the mesh or spacing too small");
+    return FEMB_E_INVALID;
+  }
+  LatticeIds cells(kmax[0] + 1, kmax[1] + 1, kmax[2] + 1, n_hex);
+  for (int e = 0; e < n_hex; ++e)                                          // ordered scan: ids in first-seen order
+    hex_parent[e] = cells.find_or_add(coarse_key[3 * (size_t)e], coarse_key[3 * (size_t)e + 1], coarse_key[3 * (size_t)e + 2]);
+  const int n_ch = cells.next;
+  // keys of the coarse cells in id order, compacted to the front of coarse_key (cell c first appears at a hexahedron >= c)
+  {
+    std::vector<unsigned char> seen((size_t)n_ch, 0);
+    for (int e = 0; e < n_hex; ++e) {
+      const int c = hex_parent[e];
+      if (seen[c]) continue;
+      seen[c] = 1;
+      for (int d = 0; d < 3; ++d) coarse_key[3 * (size_t)c + d] = coarse_key[3 * (size_t)e + d];
+    }
+  }
+  LatticeIds verts(kmax[0] + 2, kmax[1] + 2, kmax[2] + 2, (long long)n_ch * 2);
+  for (int c = 0; c < n_ch; ++c)
+    for (int a = 0; a < 8; ++a)
+      verts.find_or_add(coarse_key[3 * (size_t)c] + ((a >> 2) & 1), coarse_key[3 * (size_t)c + 1] + ((a >> 1) & 1),
+                        coarse_key[3 * (size_t)c + 2] + (a & 1));
+  *n_coarse_hex = n_ch;
+  *n_coarse_vert = verts.next;
+  return FEMB_OK;
+}
+
+int femb_setup_coarsen_fill_host(int n_vert, int n_hex, const float* x, const int* hex, const float* origin, float fine_size,
+                                 float coarse_size, const int* hex_parent, const int* coarse_key, int n_coarse_hex,
+                                 int n_coarse_vert, int* coarse_hex, float* coarse_x, int* fine_coarse, int* v2i, int* i2v,
+                                 int* color_vertex_num) {
+  FEMB_REQUIRE(n_vert > 0 && n_hex > 0 && n_coarse_hex > 0 && n_coarse_vert > 0, "empty level");
+  FEMB_REQUIRE(x && hex && origin && hex_parent && coarse_key && coarse_hex && coarse_x && fine_coarse && v2i && i2v &&
+                   color_vertex_num, "null pointer");
+  int kmax[3] = {0, 0, 0};
+  for (int c = 0; c < n_coarse_hex; ++c)
+    for (int d = 0; d < 3; ++d) {
+      const int q = coarse_key[3 * (size_t)c + d];
+      FEMB_REQUIRE(q >= 0 && q < (1 << 20), "coarse_key out of range");
+      kmax[d] = std::max(kmax[d], q);
+    }
+  // coarse vertices in the order the corners of the coarse hexahedra first name them (object.py:196-214)
+  LatticeIds verts(kmax[0] + 2, kmax[1] + 2, kmax[2] + 2, (long long)n_coarse_hex * 2);
+  std::vector<unsigned char> color((size_t)n_coarse_vert);
+  for (int c = 0; c < n_coarse_hex; ++c)
+    for (int a = 0; a < 8; ++a) {
+      const int k3[3] = {coarse_key[3 * (size_t)c] + ((a >> 2) & 1), coarse_key[3 * (size_t)c + 1] + ((a >> 1) & 1),
+                         coarse_key[3 * (size_t)c + 2] + (a & 1)};
+      const int before = verts.next;
+      const int id = verts.find_or_add(k3[0], k3[1], k3[2]);
+      if (id >= n_coarse_vert) { set_error("femb_setup_coarsen_fill_host: more coarse vertices than counted"); return FEMB_E_INVALID; }
+      coarse_hex[8 * (size_t)c + a] = id;
+      if (id == before) {                                                  // new vertex: position and colour (object.py:216-230)
+        for (int d = 0; d < 3; ++d) {
+          float p = (float)k3[d] * coarse_size;
+          p = p + origin[d];
+          coarse_x[3 * (size_t)id + d] = p;
+        }
+        color[id] = (unsigned char)(4 * (k3[2] % 2) + 2 * (k3[1] % 2) + (k3[0] % 2));
+      }
+    }
+  if (verts.next != n_coarse_vert) { set_error("femb_setup_coarsen_fill_host: coarse vertex count differs from the counted one"); return FEMB_E_INVALID; }
+  color_order(n_coarse_vert, color.data(), v2i, i2v, color_vertex_num);
+  // fine_coarse[c][9 di + 3 dj + dk] = fine vertex at offset (di, dj, dk) in coarse cell c (object.py:189-194, 231-241)
+  std::memset(fine_coarse, 0xff, sizeof(int) * 27 * (size_t)n_coarse_hex);
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+  for (int e = 0; e < n_hex; ++e) {
+    const int c = hex_parent[e];
+    if (c < 0 || c >= n_coarse_hex) { bad |= 1; continue; }
+    for (int b = 0; b < 8; ++b) {
+      const int v = hex[8 * (size_t)e + b];
+      if (v < 0 || v >= n_vert) { bad |= 1; continue; }
+      int slot = 0;
+      for (int d = 0; d < 3; ++d) {
+        const int q = lattice_index(x[3 * (size_t)v + d], origin[d], fine_size, 0.1f) - 2 * coarse_key[3 * (size_t)c + d];
+        if (q < 0 || q > 2) bad |= 2;
+        slot = 3 * slot + q;
+      }
+      if (bad) continue;
+      fine_coarse[27 * (size_t)c + slot] = v;                              // every writer of a slot writes the same vertex
+    }
+  }
+  if (bad & 1) { set_error("femb_setup_coarsen_fill_host: index out of range"); return FEMB_E_INVALID; }
+  if (bad & 2) { set_error("femb_setup_coarsen_fill_host: a fine vertex lies outside its hexahedron's coarse cell"); return FEMB_E_INVALID; }
+  return FEMB_OK;
+}
+
+int femb_setup_interp_count_host(int n_fine, int n_coarse_hex, const int* fine_coarse, int* first_pos, int* n_entries) {
+  FEMB_REQUIRE(n_fine >= 0 && n_coarse_hex >= 0 && fine_coarse && first_pos && n_entries, "bad arguments");
+  FEMB_REQUIRE((long long)n_coarse_hex * 27 < (1ll << 31), "27 n_coarse_hex must fit in int32");
+  // the (coarse hexahedron, slot) that first names a fine vertex owns its interpolation row (object.py:265-281)
+  for (int v = 0; v < n_fine; ++v) first_pos[v] = -1;
+  const int total = n_coarse_hex * 27;
+  long long n = 0;
+  for (int p = 0; p < total; ++p) {
+    const int v = fine_coarse[p];
+    if (v == -1) continue;
+    if (v < 0 || v >= n_fine) { set_error("femb_setup_interp_count_host: fine vertex %d out of range", v); return FEMB_E_INVALID; }
+    if (first_pos[v] < 0) {
+      first_pos[v] = p;
+      n += g_stencil.cnt[p % 27];
+    }
+  }
+  FEMB_REQUIRE(n < (1ll << 31), "entry count must fit in int32");
+  *n_entries = (int)n;
+  return FEMB_OK;
+}
+
+int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, const int* fine_coarse, const int* coarse_hex,
+                                const int* first_pos, int n_entries, int* coarse_id, int* fine_id, unsigned char* entry_k,
+                                float* weight, float* norm, float* weight_norm) {
+  FEMB_REQUIRE(n_fine >= 0 && n_coarse >= 0 && n_coarse_hex >= 0 && n_entries >= 0, "negative size");
+  FEMB_REQUIRE(fine_coarse && coarse_hex && first_pos && norm && (n_entries == 0 || (coarse_id && fine_id && entry_k && weight && weight_norm)),
+               "null pointer");
+  for (int c = 0; c < n_coarse; ++c) norm[c] = 0.0f;
+  const int total = n_coarse_hex * 27;
+  int n = 0;
+  for (int p = 0; p < total; ++p) {                                        // entries in ascending (hexahedron, slot) order
+    const int v = fine_coarse[p];
+    if (v < 0 || v >= n_fine || first_pos[v] != p) continue;
+    const int s = p % 27;
+    const int* h = coarse_hex + 8 * (size_t)(p / 27);
+    if (n + g_stencil.cnt[s] > n_entries) { set_error("femb_setup_interp_fill_host: more entries than counted"); return FEMB_E_INVALID; }
+    for (int k = 0; k < g_stencil.cnt[s]; ++k, ++n) {
+      const int c = h[g_stencil.corner[s][k]];
+      if (c < 0 || c >= n_coarse) { set_error("femb_setup_interp_fill_host: coarse vertex %d out of range", c); return FEMB_E_INVALID; }
+      coarse_id[n] = c;
+      fine_id[n] = v;
+      entry_k[n] = (unsigned char)k;
+      weight[n] = g_stencil.w[s];
+      norm[c] += g_stencil.w[s];                                           // dyadic weights: exact in any order (object.py:414-420)
+    }
+  }
+  if (n != n_entries) { set_error("femb_setup_interp_fill_host: entry count differs from the counted one"); return FEMB_E_INVALID; }
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_entries; ++i) weight_norm[i] = weight[i] / norm[coarse_id[i]];
+  return FEMB_OK;
+}
+
+}  // extern "C"

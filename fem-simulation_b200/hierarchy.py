@@ -350,8 +350,115 @@ class MeshTooSmallError(ValueError, IndexError):
     its constructor then dies with ``IndexError: list index out of range`` -- same class of error here, with a message."""
 
 
+def _color_order_native(x: np.ndarray, origin: np.ndarray, spacing: float):
+    """object.py:147-158 through femb_setup_color_order_host."""
+    from . import _lib
+    lib = _lib.load()
+    n = x.shape[0]
+    o = np.ascontiguousarray(origin, dtype=F32)
+    v2i, i2v, cvn = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(9, np.int32)
+    _lib.check(lib.femb_setup_color_order_host(n, _hp(x), _hp(o), C.c_float(spacing), _hp(v2i), _hp(i2v), _hp(cvn)),
+               "femb_setup_color_order_host")
+    return v2i, i2v, [int(c) for c in cvn]
+
+
+def _coarsen_numpy(xl, hx, box_min, fine_size, coarse_size):
+    """object.py:171-241 for one level (numpy restatement: dictionary numbering through np.unique + first occurrence)."""
+    BIG = np.int64(1) << 20
+    key3 = _ijk(xl[hx[:, 0]], box_min, coarse_size, 0.1).astype(np.int64)        # [Nh,3]
+    hex_id, ukeys = _first_seen_ids((key3[:, 0] * BIG + key3[:, 1]) * BIG + key3[:, 2])
+    n_ch = len(ukeys)
+    ck = np.stack([ukeys // (BIG * BIG), (ukeys // BIG) % BIG, ukeys % BIG], axis=1)  # coarse hex keys, id order
+    jkl = np.array([[(a >> 2) & 1, (a >> 1) & 1, a & 1] for a in range(8)], dtype=np.int64)
+    vk3 = ck[:, None, :] + jkl[None, :, :]                                        # [n_ch,8,3]
+    vkeys = ((vk3[..., 0] * BIG + vk3[..., 1]) * BIG + vk3[..., 2]).reshape(-1)
+    vid, uvk = _first_seen_ids(vkeys)
+    coarse_hex = vid.reshape(n_ch, 8).astype(np.int32)
+    vk = np.stack([uvk // (BIG * BIG), (uvk // BIG) % BIG, uvk % BIG], axis=1)
+    # slot of node b of hexahedron e inside its coarse cell: 9 di + 3 dj + dk with (di, dj, dk) = ijk(vertex) - 2 key3(e);
+    # the lattice index is a function of the vertex, so it is evaluated once per vertex, folded to 9 i + 3 j + k and gathered
+    ijk_v = _ijk(xl, box_min, fine_size, 0.1).astype(np.int64)
+    code_v = 9 * ijk_v[:, 0] + 3 * ijk_v[:, 1] + ijk_v[:, 2]
+    slot = code_v[hx] - 2 * (9 * key3[:, 0] + 3 * key3[:, 1] + key3[:, 2])[:, None]
+    fc = np.full((n_ch, 27), -1, dtype=np.int32)
+    fc[np.repeat(hex_id, 8), slot.reshape(-1)] = hx.reshape(-1)
+    coarse_vert = (vk.astype(F32) * F32(coarse_size) + box_min).astype(F32)
+    ccolor = 4 * (vk[:, 2] % 2) + 2 * (vk[:, 1] % 2) + (vk[:, 0] % 2)
+    cv2i, ci2v, ccvn = _color_order(ccolor)
+    return hex_id.astype(np.int32), coarse_hex, coarse_vert, fc, cv2i, ci2v, ccvn
+
+
+def _coarsen_native(xl, hx, box_min, fine_size, coarse_size):
+    """object.py:171-241 for one level through femb_setup_coarsen_count_host / _fill_host (csrc/femb_setup_hierarchy.cu)."""
+    from . import _lib
+    lib = _lib.load()
+    nv, nh = xl.shape[0], hx.shape[0]
+    o = np.ascontiguousarray(box_min, dtype=F32)
+    hex_id, key = np.empty(nh, np.int32), np.empty((nh, 3), np.int32)
+    n_ch, n_cv = C.c_int(0), C.c_int(0)
+    ref = lambda v: C.cast(C.byref(v), C.c_void_p)
+    _lib.check(lib.femb_setup_coarsen_count_host(nv, nh, _hp(xl), _hp(hx), _hp(o), C.c_float(coarse_size), _hp(hex_id), _hp(key),
+                                                 ref(n_ch), ref(n_cv)), "femb_setup_coarsen_count_host")
+    n_ch, n_cv = n_ch.value, n_cv.value
+    coarse_hex, coarse_vert = np.empty((n_ch, 8), np.int32), np.empty((n_cv, 3), F32)
+    fc = np.empty((n_ch, 27), np.int32)
+    cv2i, ci2v, ccvn = np.empty(n_cv, np.int32), np.empty(n_cv, np.int32), np.empty(9, np.int32)
+    _lib.check(lib.femb_setup_coarsen_fill_host(nv, nh, _hp(xl), _hp(hx), _hp(o), C.c_float(fine_size), C.c_float(coarse_size),
+                                                _hp(hex_id), _hp(key), n_ch, n_cv, _hp(coarse_hex), _hp(coarse_vert), _hp(fc),
+                                                _hp(cv2i), _hp(ci2v), _hp(ccvn)), "femb_setup_coarsen_fill_host")
+    return hex_id, coarse_hex, coarse_vert, fc, cv2i, ci2v, [int(c) for c in ccvn]
+
+
+def _interp_numpy(fc, chex, n_fine, n_coarse):
+    """object.py:265-420 for one level pair (numpy restatement): the interpolation entries (coarse vertex, fine vertex,
+    position k of the coarse vertex among the fine vertex's parents, weight) in the reference's order, the column sums and
+    the normalised weights."""
+    chex = chex.astype(np.int64)
+    flat = fc.reshape(-1).astype(np.int64)
+    pos_valid = np.nonzero(flat != -1)[0]
+    first_pos = np.full(n_fine, -1, dtype=np.int64)                    # first (HEX, slot) that names each fine vertex:
+    first_pos[flat[pos_valid][::-1]] = pos_valid[::-1]                 # assigned back to front, the first one stays
+    pos = np.sort(first_pos[first_pos >= 0])                           # (HEX,slot) that handles each fine vertex
+    HEX, s = pos // 27, pos % 27
+    cnt = _ST_CNT[s]
+    ent_owner = np.repeat(np.arange(len(pos)), cnt)
+    ent_k = np.arange(len(ent_owner)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    coarse_id = chex[HEX[ent_owner], _ST_CORNERS[s[ent_owner], ent_k]]
+    fine_id = flat[pos][ent_owner]
+    w = _ST_W[s[ent_owner]]
+    norm = np.zeros(n_coarse, dtype=F32)
+    np.add.at(norm, coarse_id, w)                                      # dyadic weights: exact in any order
+    w_norm = (w / norm[coarse_id]).astype(F32)
+    return coarse_id.astype(np.int32), fine_id.astype(np.int32), ent_k, w, norm, w_norm
+
+
+def _interp_native(fc, chex, n_fine, n_coarse):
+    """object.py:265-420 for one level pair through femb_setup_interp_count_host / _fill_host."""
+    from . import _lib
+    lib = _lib.load()
+    fc = np.ascontiguousarray(fc, dtype=np.int32)
+    chex = np.ascontiguousarray(chex, dtype=np.int32)
+    n_ch = fc.shape[0]
+    first_pos = np.empty(n_fine, np.int32)
+    n_ent = C.c_int(0)
+    _lib.check(lib.femb_setup_interp_count_host(n_fine, n_ch, _hp(fc), _hp(first_pos), C.cast(C.byref(n_ent), C.c_void_p)),
+               "femb_setup_interp_count_host")
+    n_ent = n_ent.value
+    coarse_id, fine_id, ent_k = np.empty(n_ent, np.int32), np.empty(n_ent, np.int32), np.empty(n_ent, np.uint8)
+    w, norm, w_norm = np.empty(n_ent, F32), np.empty(n_coarse, F32), np.empty(n_ent, F32)
+    _lib.check(lib.femb_setup_interp_fill_host(n_fine, n_coarse, n_ch, _hp(fc), _hp(chex), _hp(first_pos), n_ent, _hp(coarse_id),
+                                               _hp(fine_id), _hp(ent_k), _hp(w), _hp(norm), _hp(w_norm)), "femb_setup_interp_fill_host")
+    return coarse_id, fine_id, ent_k, w, norm, w_norm
+
+
+def build_hierarchy_numpy(points, hexagons, dx, layers=None, corrected_spacing=False, origin=None) -> Hierarchy:
+    """build_hierarchy with the colour order, the coarsening and the interpolation entries evaluated by the numpy
+    restatements instead of csrc/femb_setup_hierarchy.cu (tests compare the two bit for bit)."""
+    return build_hierarchy(points, hexagons, dx, layers, corrected_spacing, origin, native=False)
+
+
 def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers: int | None = None,
-                    corrected_spacing: bool = False, origin=None) -> Hierarchy:
+                    corrected_spacing: bool = False, origin=None, native: bool = True) -> Hierarchy:
     """object.py:116-697.  ``layers`` overrides the reference's level-count formula (benchmarks only).
     ``corrected_spacing`` (off by default = the reference's behaviour) fixes object.py:175-179, which coarsens every
     level >= 1 with spacing 2 dx so that levels >= 3 are copies of level 2: with it level l has spacing dx 2^l and the
@@ -378,42 +485,26 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
         raise MeshTooSmallError(f"level count {layer} < 1: the smallest bounding-box extent must be at least (about) 4 dx "
                                 f"(extent {float((box_max - box_min).min()):.6g}, dx {dx:.6g}; object.py:143)")
 
-    t = _ijk(x0, box_min, dx, 0.5) % 2                                     # object.py:147-149
-    color = (t[:, 0] + 2 * t[:, 1] + 4 * t[:, 2]).astype(np.int64)
-    v2i, i2v, cvn = _color_order(color)
+    if native:                                                             # object.py:147-158
+        v2i, i2v, cvn = _color_order_native(x0, box_min, dx)
+    else:
+        t = _ijk(x0, box_min, dx, 0.5) % 2
+        color = (t[:, 0] + 2 * t[:, 1] + 4 * t[:, 2]).astype(np.int64)
+        v2i, i2v, cvn = _color_order(color)
+    coarsen = _coarsen_native if native else _coarsen_numpy
+    interp = _interp_native if native else _interp_numpy
     H = Hierarchy(dx=dx, layer=layer, box_min=box_min, box_max=box_max, dims=[x0.shape[0]], hexs=[hex0], x=[x0],
                   fine_coarse=[], color_vertex_num=[cvn], vertex2index=[v2i], index2vertex=[i2v], spacing=[float(dx)])
 
-    BIG = np.int64(1) << 20
     for lay in range(layer - 1):                                           # object.py:171-241
         fine_size = dx if lay == 0 else dx * 2                             # sic (object.py:175-179)
         if corrected_spacing:
             fine_size = dx * (2 ** lay)
         coarse_size = fine_size * 2
-        hx, xl = H.hexs[lay], H.x[lay]
-        key3 = _ijk(xl[hx[:, 0]], box_min, coarse_size, 0.1).astype(np.int64)        # [Nh,3]
-        hex_id, ukeys = _first_seen_ids((key3[:, 0] * BIG + key3[:, 1]) * BIG + key3[:, 2])
-        n_ch = len(ukeys)
-        ck = np.stack([ukeys // (BIG * BIG), (ukeys // BIG) % BIG, ukeys % BIG], axis=1)  # coarse hex keys, id order
-        jkl = np.array([[(a >> 2) & 1, (a >> 1) & 1, a & 1] for a in range(8)], dtype=np.int64)
-        vk3 = ck[:, None, :] + jkl[None, :, :]                                        # [n_ch,8,3]
-        vkeys = ((vk3[..., 0] * BIG + vk3[..., 1]) * BIG + vk3[..., 2]).reshape(-1)
-        vid, uvk = _first_seen_ids(vkeys)
-        coarse_hex = vid.reshape(n_ch, 8).astype(np.int32)
-        n_cv = len(uvk)
-        vk = np.stack([uvk // (BIG * BIG), (uvk // BIG) % BIG, uvk % BIG], axis=1)
-        # slot of node b of hexahedron e inside its coarse cell: 9 di + 3 dj + dk with (di, dj, dk) = ijk(vertex) - 2 key3(e);
-        # the lattice index is a function of the vertex, so it is evaluated once per vertex, folded to 9 i + 3 j + k and gathered
-        ijk_v = _ijk(xl, box_min, fine_size, 0.1).astype(np.int64)
-        code_v = 9 * ijk_v[:, 0] + 3 * ijk_v[:, 1] + ijk_v[:, 2]
-        slot = code_v[hx] - 2 * (9 * key3[:, 0] + 3 * key3[:, 1] + key3[:, 2])[:, None]
-        fc = np.full((n_ch, 27), -1, dtype=np.int32)
-        fc[np.repeat(hex_id, 8), slot.reshape(-1)] = hx.reshape(-1)
-        coarse_vert = (vk.astype(F32) * F32(coarse_size) + box_min).astype(F32)
-        ccolor = 4 * (vk[:, 2] % 2) + 2 * (vk[:, 1] % 2) + (vk[:, 0] % 2)
-        cv2i, ci2v, ccvn = _color_order(ccolor)
+        hex_id, coarse_hex, coarse_vert, fc, cv2i, ci2v, ccvn = coarsen(H.x[lay], H.hexs[lay], box_min, fine_size, coarse_size)
+        n_cv = coarse_vert.shape[0]
         H.dims.append(n_cv); H.hexs.append(coarse_hex); H.x.append(coarse_vert); H.fine_coarse.append(fc)
-        H.fine_hex_parent.append(hex_id.astype(np.int32))
+        H.fine_hex_parent.append(hex_id)
         H.spacing.append(float(coarse_size))
         H.color_vertex_num.append(ccvn); H.vertex2index.append(cv2i); H.index2vertex.append(ci2v)
 
@@ -421,27 +512,11 @@ def build_hierarchy(points: np.ndarray, hexagons: np.ndarray, dx: float, layers:
     H.fix_idx = np.full((n0, 8), -1, dtype=np.int32)
     H.fix_values = np.zeros((n0, 8), dtype=F32)
     for lay in range(layer - 1):                                           # object.py:265-443
-        fc = H.fine_coarse[lay]
-        chex = H.hexs[lay + 1].astype(np.int64)
-        flat = fc.reshape(-1).astype(np.int64)
-        pos_valid = np.nonzero(flat != -1)[0]
-        first_pos = np.full(H.dims[lay], -1, dtype=np.int64)               # first (HEX, slot) that names each fine vertex:
-        first_pos[flat[pos_valid][::-1]] = pos_valid[::-1]                 # assigned back to front, the first one stays
-        pos = np.sort(first_pos[first_pos >= 0])                           # (HEX,slot) that handles each fine vertex
-        HEX, s = pos // 27, pos % 27
-        cnt = _ST_CNT[s]
-        ent_owner = np.repeat(np.arange(len(pos)), cnt)
-        ent_k = np.arange(len(ent_owner)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
-        coarse_id = chex[HEX[ent_owner], _ST_CORNERS[s[ent_owner], ent_k]]
-        fine_id = flat[pos][ent_owner]
-        w = _ST_W[s[ent_owner]]
-        norm = np.zeros(H.dims[lay + 1], dtype=F32)
-        np.add.at(norm, coarse_id, w)                                      # dyadic weights: exact in any order
-        w_norm = (w / norm[coarse_id]).astype(F32)
+        coarse_id, fine_id, ent_k, w, norm, w_norm = interp(H.fine_coarse[lay], H.hexs[lay + 1], H.dims[lay], H.dims[lay + 1])
         v2i_c, v2i_f = H.vertex2index[lay + 1], H.vertex2index[lay]
         rowInd, colInd = v2i_c[coarse_id], v2i_f[fine_id]
         H.U_triplets.append(dict(rowInd=rowInd.astype(np.int32), colInd=colInd.astype(np.int32),
-                                 rowInd_noOrder=coarse_id.astype(np.int32), colInd_noOrder=fine_id.astype(np.int32),
+                                 rowInd_noOrder=coarse_id, colInd_noOrder=fine_id,
                                  value=w, norm=norm))
         nc, nf = H.dims[lay + 1], H.dims[lay]
         ut, ut_hat = coo_to_csr_pair(nc, nf, rowInd, colInd, w_norm, w)                 # same pattern, two weight sets

@@ -23,7 +23,9 @@ def mesh_from_mask(mask: np.ndarray, dx: float, origin=(0.0, 0.0, 0.0), index_of
     for a in range(8):
         bx, by, bz = (a >> 2) & 1, (a >> 1) & 1, a & 1
         corner[:, a] = (ix + bx) + px * ((iy + by) + py * (iz + bz))
-    used = np.unique(corner)
+    mark = np.zeros((nx + 1) * (ny + 1) * (nz + 1), dtype=bool)     # the used lattice points, ascending (= np.unique(corner))
+    mark[corner] = True
+    used = np.nonzero(mark)[0]
     remap = np.full((nx + 1) * (ny + 1) * (nz + 1), -1, dtype=np.int64)
     remap[used] = np.arange(len(used))
     hexagons = remap[corner].astype(np.int32)

@@ -154,6 +154,36 @@ int femb_setup_pattern_count_host(int n_vert, const int* hex, const int* v2i, co
                                   int* U_ptr);
 int femb_setup_pattern_fill_host(int n_vert, int n_hex, const int* hex, const int* v2i, const int* i2v, const int* vert_elem,
                                  const int* L_ptr, const int* U_ptr, int* L_col, int* U_col, int* elem2nnz, int* block_offset);
+/* ---- the hierarchy itself (csrc/femb_setup_hierarchy.cu; host pointers): the dictionaries of Object.__init__ as ordered scans
+ * over lattice lookup tables, numbering identical to the reference's first-seen order.  float arguments are float32 values of
+ * the reference's spacings (dx, 2 dx, ...), `origin` [3] is the lattice origin (the reference: the bounding-box minimum). */
+/* object.py:283-412: slot 9 i + 3 j + k of a coarse cell -> number of coarse corners cnt [27], their local numbers
+ * corners [27*8] (ascending, zero padded) and the un-normalised weight [27] (1, 1/2, 1/4, 1/8) */
+int femb_setup_stencil_host(int* cnt, int* corners, float* weight);
+/* object.py:147-158: colour of vertex v = parity of its lattice index (i + 2 j + 4 k), index order = stable sort by colour:
+ * v2i / i2v [n_vert] (vertex2index / index2vertex), color_vertex_num [9] */
+int femb_setup_color_order_host(int n_vert, const float* x, const float* origin, float spacing, int* v2i, int* i2v,
+                                int* color_vertex_num);
+/* object.py:171-241, one coarsening step, in two calls.  count: hex_parent [n_hex] = coarse hexahedron of every hexahedron,
+ * coarse_key (scratch the caller sizes [n_hex*3]; on return its first n_coarse_hex*3 entries are the lattice cells of the
+ * coarse hexahedra in id order) and the two counts.  fill, into arrays sized from the counts: coarse_hex [n_coarse_hex*8],
+ * coarse_x [n_coarse_vert*3], fine_coarse [n_coarse_hex*27] (-1 = no vertex), and the coarse level's v2i / i2v
+ * [n_coarse_vert] and color_vertex_num [9] */
+int femb_setup_coarsen_count_host(int n_vert, int n_hex, const float* x, const int* hex, const float* origin, float coarse_size,
+                                  int* hex_parent, int* coarse_key, int* n_coarse_hex, int* n_coarse_vert);
+int femb_setup_coarsen_fill_host(int n_vert, int n_hex, const float* x, const int* hex, const float* origin, float fine_size,
+                                 float coarse_size, const int* hex_parent, const int* coarse_key, int n_coarse_hex,
+                                 int n_coarse_vert, int* coarse_hex, float* coarse_x, int* fine_coarse, int* v2i, int* i2v,
+                                 int* color_vertex_num);
+/* object.py:265-420, the interpolation entries between two levels, in two calls.  count: first_pos [n_fine] = the first
+ * (coarse hexahedron * 27 + slot) that names each fine vertex (-1: none) and the number of entries.  fill, entries in
+ * ascending first_pos order: coarse_id / fine_id [n_entries] (vertex numbers: rowInd_noOrder / colInd_noOrder), entry_k
+ * [n_entries] (position of the coarse vertex among the fine vertex's parents), weight (Ut_hat values), norm [n_coarse]
+ * (column sums) and weight_norm = weight / norm[coarse_id] (Ut values) */
+int femb_setup_interp_count_host(int n_fine, int n_coarse_hex, const int* fine_coarse, int* first_pos, int* n_entries);
+int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, const int* fine_coarse, const int* coarse_hex,
+                                const int* first_pos, int n_entries, int* coarse_id, int* fine_id, unsigned char* entry_k,
+                                float* weight, float* norm, float* weight_norm);
 /* symbolic plan of A_c = Ut_hat (A_f Us_hat) (FembGalerkinPlan): t_ptr [n_fine+1] first, then the arrays sized from it:
  * t_col [t_nnz], c_ptr [n_coarse+1], c_col / c_slot [nnz_c], t_slot [nnz_f*8], c_slot8 [t_nnz*8], ut_q [nnz(Ut_hat)];
  * fails if the product pattern is not the coarse hexahedral adjacency (block_values_reorder relies on it, object.py:1261) */

@@ -264,3 +264,76 @@ def test_coo_to_csr_pair_matches_numpy_sort():
         assert np.array_equal(got.weights, want.weights)
     empty_a, empty_b = hierarchy.coo_to_csr_pair(4, 5, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.float32))
     assert empty_a.nnz == 0 and empty_b.offsets.tolist() == [0, 0, 0, 0, 0]
+
+
+def _same_hierarchy(Ha, Hb):
+    assert Ha.layer == Hb.layer and Ha.dims == Hb.dims and Ha.spacing == Hb.spacing
+    for l in range(Ha.layer):
+        for nm in ["hexs", "x", "vertex2index", "index2vertex", "color_vertex_num"]:
+            _eq(getattr(Ha, nm)[l], getattr(Hb, nm)[l], f"{nm}[{l}]")
+    for l in range(Ha.layer - 1):
+        _eq(Ha.fine_coarse[l], Hb.fine_coarse[l], f"fine_coarse[{l}]")
+        _eq(Ha.fine_hex_parent[l], Hb.fine_hex_parent[l], f"fine_hex_parent[{l}]")
+        for nm in ["rowInd", "colInd", "rowInd_noOrder", "colInd_noOrder", "value", "norm"]:
+            _eq(Ha.U_triplets[l][nm], Hb.U_triplets[l][nm], f"U_triplets[{l}].{nm}")
+        for nm in ["Ut", "Ut_hat", "Ut_noOrder", "Us", "Us_hat", "Us_noOrder_hat"]:
+            a, b = getattr(Ha, nm)[l], getattr(Hb, nm)[l]
+            _eq(a.offsets, b.offsets, f"{nm}[{l}].offsets"); _eq(a.columns, b.columns, f"{nm}[{l}].columns")
+            _eq(a.weights, b.weights, f"{nm}[{l}].weights")
+    _eq(Ha.fix_idx, Hb.fix_idx, "fix_idx"); _eq(Ha.fix_values, Hb.fix_values, "fix_values")
+
+
+@pytest.mark.parametrize("case", ["cube40", "jag_sparse", "offset_origin", "corrected"])
+def test_native_hierarchy_matches_numpy_restatement(case):
+    """csrc/femb_setup_hierarchy.cu (colour order, coarsening, interpolation entries: ordered scans over lattice tables)
+    against the numpy restatement (np.unique + first occurrence), which the tests above hold to the literal loops."""
+    kw = {}
+    if case == "cube40":
+        (points, hexs), dx = mesh.cube_mesh(40), 1.0 / 40                        # 5 levels, 64 000 hexahedra
+    elif case == "jag_sparse":
+        (points, hexs), dx = mesh.jagged_mesh(37, 41, 35, 0.05, seed=7, keep=0.3, origin=(-0.7, 0.3, 1.1)), 0.05
+    elif case == "offset_origin":                                                # a slab that counts from the global origin
+        (points, hexs), dx = mesh.box_mesh(12, 10, 9, 0.1, origin=(0.0, 0.0, 0.0), index_offset=(0, 0, 6)), 0.1
+        kw = dict(origin=(0.0, 0.0, 0.0))
+    else:
+        (points, hexs), dx = mesh.jagged_mesh(33, 32, 34, 0.05, seed=4, keep=0.1), 0.05
+        kw = dict(corrected_spacing=True)
+    _same_hierarchy(hierarchy.build_hierarchy(points, hexs, dx, **kw), hierarchy.build_hierarchy_numpy(points, hexs, dx, **kw))
+
+
+def test_native_hierarchy_hashed_lattice_and_stencil_table():
+    """Two small blocks far apart: the coarse lattice of the bounding box (300^3 cells) is far larger than the mesh, the
+    lookup tables switch from dense to hashed; numbering unchanged.  The stencil table equals the Python one."""
+    import ctypes as C
+    from fem_simulation_b200 import _lib
+    lib = _lib.load()
+    cnt, corners, w = np.empty(27, np.int32), np.empty((27, 8), np.int32), np.empty(27, np.float32)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.femb_setup_stencil_host(hp(cnt), hp(corners), hp(w)) == 0
+    _eq(cnt, hierarchy._ST_CNT, "cnt"); _eq(corners, hierarchy._ST_CORNERS, "corners"); _eq(w, hierarchy._ST_W, "weight")
+    pa, ha = mesh.box_mesh(5, 6, 4, 0.05)
+    pb, hb = mesh.box_mesh(4, 5, 6, 0.05, index_offset=(596, 594, 595))
+    points, hexs = np.concatenate([pa, pb]), np.concatenate([ha, hb + len(pa)])
+    _same_hierarchy(hierarchy.build_hierarchy(points, hexs, 0.05, layers=3), hierarchy.build_hierarchy_numpy(points, hexs, 0.05, layers=3))
+
+
+def test_native_hierarchy_rejects_bad_input():
+    import ctypes as C
+    from fem_simulation_b200 import _lib
+    lib = _lib.load()
+    points, hexs = mesh.cube_mesh(4, 0.05)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    parent, key = np.empty(len(hexs), np.int32), np.empty((len(hexs), 3), np.int32)
+    n_ch, n_cv = C.c_int(0), C.c_int(0)
+    ref = lambda v: C.cast(C.byref(v), C.c_void_p)
+    above = np.array([1.0, 0.0, 0.0], np.float32)                                # origin above the mesh: negative cells
+    assert lib.femb_setup_coarsen_count_host(len(points), len(hexs), hp(points), hp(hexs), hp(above), C.c_float(0.1), hp(parent),
+                                             hp(key), ref(n_ch), ref(n_cv)) == -1
+    assert b"origin" in lib.femb_last_error()
+    bad = hexs.copy(); bad[3, 0] = len(points)
+    zero = np.zeros(3, np.float32)
+    assert lib.femb_setup_coarsen_count_host(len(points), len(hexs), hp(points), hp(bad), hp(zero), C.c_float(0.1), hp(parent),
+                                             hp(key), ref(n_ch), ref(n_cv)) == -1
+    fc = np.full((2, 27), -1, np.int32); fc[1, 3] = 99
+    first, n_ent = np.empty(10, np.int32), C.c_int(0)
+    assert lib.femb_setup_interp_count_host(10, 2, hp(fc), hp(first), ref(n_ent)) == -1
