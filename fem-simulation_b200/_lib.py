@@ -54,6 +54,22 @@ MAX_NEIGHBOURS = 8             # FEMB_MAX_NEIGHBOURS
 COMM_ID_BYTES = 128            # FEMB_COMM_ID_BYTES
 
 
+_IP, _FP, _BP = C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_ubyte)
+
+
+class FembHierarchyLevel(C.Structure):
+    _fields_ = [("n_vert", C.c_int), ("n_hex", C.c_int), ("spacing", C.c_float), ("hex", _IP), ("x", _FP), ("v2i", _IP), ("i2v", _IP),
+                ("color_vertex_num", C.c_int * 9), ("L_nnz", C.c_int), ("L_ptr", _IP), ("U_ptr", _IP), ("L_col", _IP), ("U_col", _IP),
+                ("elem2nnz", _IP), ("block_offset", _IP), ("hex_parent", _IP), ("fine_coarse", _IP), ("n_entries", C.c_int),
+                ("coarse_id", _IP), ("fine_id", _IP), ("entry_k", _BP), ("weight", _FP), ("weight_norm", _FP), ("norm", _FP),
+                ("ut_off", _IP), ("ut_col", _IP), ("ut_w", _FP), ("ut_hat_w", _FP), ("us_off", _IP), ("us_col", _IP), ("us_w", _FP),
+                ("us_hat_w", _FP)]
+
+
+class FembHierarchy(C.Structure):
+    _fields_ = [("n_levels", C.c_int), ("origin", C.c_float * 3), ("level", C.POINTER(FembHierarchyLevel))]
+
+
 class FembHalo(C.Structure):
     _fields_ = [("n_nb", C.c_int), ("nb", C.c_int * MAX_NEIGHBOURS), ("n_send", C.c_int * MAX_NEIGHBOURS),
                 ("n_recv", C.c_int * MAX_NEIGHBOURS), ("send_rows", C.c_void_p), ("recv_rows", C.c_void_p),
@@ -117,6 +133,8 @@ PROTOTYPES = {
     "femb_setup_coarsen_fill_host": [I, I, P, P, P, F, F, P, P, I, I, P, P, P, P, P, P],
     "femb_setup_interp_count_host": [I, I, P, P, P],
     "femb_setup_interp_fill_host": [I, I, I, P, P, P, I, P, P, P, P, P, P],
+    "femb_setup_hierarchy_host": [I, I, P, P, F, I, I, P, P],
+    "femb_setup_hierarchy_free": [P],
     "femb_prepare_rest": [I, P, P, P, P, P],
     "femb_build_fold_plan": [LV, P, P],
     "femb_build_lattice_fold": [LV, P, P, P, P],

@@ -7,6 +7,7 @@
 // expression is evaluated in float32 in the reference's order (cpu_function.py:12-20); hierarchy.build_hierarchy_numpy is
 // the numpy restatement the tests compare this file with, bit for bit.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 #include <vector>
@@ -94,6 +95,9 @@ static void color_order(int n, const unsigned char* color, int* v2i, int* i2v, i
     i2v[i] = v;
   }
 }
+
+template <class T>
+static T* grab(size_t n) { return static_cast<T*>(std::malloc(sizeof(T) * std::max<size_t>(n, 1))); }
 
 static inline int mod2(int v) { return ((v % 2) + 2) % 2; }   // numpy's % (result has the divisor's sign)
 
@@ -285,6 +289,112 @@ int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, cons
   if (n != n_entries) { set_error("femb_setup_interp_fill_host: entry count differs from the counted one"); return FEMB_E_INVALID; }
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < n_entries; ++i) weight_norm[i] = weight[i] / norm[coarse_id[i]];
+  return FEMB_OK;
+}
+
+
+// ---- the whole hierarchy in one call (Object.__init__, object.py:116-697) ----------------------------------------------------
+
+int femb_setup_hierarchy_free(FembHierarchy* h) {
+  if (!h) return FEMB_OK;
+  for (int l = 0; l < h->n_levels && h->level; ++l) {
+    FembHierarchyLevel& L = h->level[l];
+    void* owned[] = {L.hex, L.x, L.v2i, L.i2v, L.L_ptr, L.U_ptr, L.L_col, L.U_col, L.elem2nnz, L.block_offset, L.hex_parent,
+                     L.fine_coarse, L.coarse_id, L.fine_id, L.entry_k, L.weight, L.weight_norm, L.norm, L.ut_off, L.ut_col,
+                     L.ut_w, L.ut_hat_w, L.us_off, L.us_col, L.us_w, L.us_hat_w};
+    for (void* q : owned) std::free(q);
+  }
+  std::free(h->level);
+  std::free(h);
+  return FEMB_OK;
+}
+
+int femb_setup_hierarchy_host(int n_vert, int n_hex, const float* x, const int* hex, float dx, int n_levels, int corrected_spacing,
+                              const float* origin, FembHierarchy** out) {
+  FEMB_REQUIRE(out, "null output");
+  *out = nullptr;
+  FEMB_REQUIRE(n_vert > 0 && n_hex > 0 && x && hex && dx > 0.0f && n_levels >= 1 && n_levels <= 32, "bad arguments");
+  float o[3];
+  for (int d = 0; d < 3; ++d) {
+    if (origin) { o[d] = origin[d]; continue; }
+    float m = 1000.0f;                                                     // object.py:131-137: box_min starts at 1000
+    for (int v = 0; v < n_vert; ++v) m = std::min(m, x[3 * (size_t)v + d]);
+    o[d] = m;
+  }
+  FembHierarchy* H = static_cast<FembHierarchy*>(std::calloc(1, sizeof(FembHierarchy)));
+  if (!H) { set_error("femb_setup_hierarchy_host: out of memory"); return FEMB_E_INVALID; }
+  H->level = static_cast<FembHierarchyLevel*>(std::calloc((size_t)n_levels, sizeof(FembHierarchyLevel)));
+  H->n_levels = n_levels;
+  for (int d = 0; d < 3; ++d) H->origin[d] = o[d];
+  int rc = FEMB_OK;
+#define STEP(call) do { rc = (call); if (rc != FEMB_OK) { femb_setup_hierarchy_free(H); return rc; } } while (0)
+#define NEED(ptr) do { if (!(ptr)) { set_error("femb_setup_hierarchy_host: out of memory"); femb_setup_hierarchy_free(H); return FEMB_E_INVALID; } } while (0)
+  if (!H->level) { std::free(H); set_error("femb_setup_hierarchy_host: out of memory"); return FEMB_E_INVALID; }
+  {                                                                        // level 0: the caller's mesh, copied
+    FembHierarchyLevel& L = H->level[0];
+    L.n_vert = n_vert; L.n_hex = n_hex; L.spacing = dx;
+    NEED(L.hex = grab<int>((size_t)n_hex * 8)); NEED(L.x = grab<float>((size_t)n_vert * 3));
+    std::memcpy(L.hex, hex, sizeof(int) * 8 * (size_t)n_hex);
+    std::memcpy(L.x, x, sizeof(float) * 3 * (size_t)n_vert);
+    NEED(L.v2i = grab<int>(n_vert)); NEED(L.i2v = grab<int>(n_vert));
+    STEP(femb_setup_color_order_host(n_vert, L.x, o, dx, L.v2i, L.i2v, L.color_vertex_num));
+  }
+  for (int l = 0; l + 1 < n_levels; ++l) {                                 // object.py:171-241
+    FembHierarchyLevel& F = H->level[l];
+    FembHierarchyLevel& Cc = H->level[l + 1];
+    float fine_size = l == 0 ? dx : dx * 2.0f;                             // sic (object.py:175-179)
+    if (corrected_spacing) fine_size = dx * (float)(1 << l);
+    const float coarse_size = fine_size * 2.0f;
+    NEED(F.hex_parent = grab<int>(F.n_hex));
+    std::vector<int> key((size_t)F.n_hex * 3);
+    STEP(femb_setup_coarsen_count_host(F.n_vert, F.n_hex, F.x, F.hex, o, coarse_size, F.hex_parent, key.data(), &Cc.n_hex, &Cc.n_vert));
+    Cc.spacing = coarse_size;
+    NEED(Cc.hex = grab<int>((size_t)Cc.n_hex * 8)); NEED(Cc.x = grab<float>((size_t)Cc.n_vert * 3));
+    NEED(Cc.v2i = grab<int>(Cc.n_vert)); NEED(Cc.i2v = grab<int>(Cc.n_vert));
+    NEED(F.fine_coarse = grab<int>((size_t)Cc.n_hex * 27));
+    STEP(femb_setup_coarsen_fill_host(F.n_vert, F.n_hex, F.x, F.hex, o, fine_size, coarse_size, F.hex_parent, key.data(), Cc.n_hex,
+                                      Cc.n_vert, Cc.hex, Cc.x, F.fine_coarse, Cc.v2i, Cc.i2v, Cc.color_vertex_num));
+  }
+  for (int l = 0; l + 1 < n_levels; ++l) {                                 // object.py:265-443
+    FembHierarchyLevel& F = H->level[l];
+    const FembHierarchyLevel& Cc = H->level[l + 1];
+    std::vector<int> first_pos((size_t)F.n_vert);
+    STEP(femb_setup_interp_count_host(F.n_vert, Cc.n_hex, F.fine_coarse, first_pos.data(), &F.n_entries));
+    const size_t ne = (size_t)F.n_entries;
+    NEED(F.coarse_id = grab<int>(ne)); NEED(F.fine_id = grab<int>(ne)); NEED(F.entry_k = grab<unsigned char>(ne));
+    NEED(F.weight = grab<float>(ne)); NEED(F.weight_norm = grab<float>(ne)); NEED(F.norm = grab<float>(Cc.n_vert));
+    STEP(femb_setup_interp_fill_host(F.n_vert, Cc.n_vert, Cc.n_hex, F.fine_coarse, Cc.hex, first_pos.data(), F.n_entries, F.coarse_id,
+                                     F.fine_id, F.entry_k, F.weight, F.norm, F.weight_norm));
+    // Ut / Ut_hat in index order (object.py:422-436) and their transposes Us / Us_hat (object.py:438-443)
+    std::vector<int> row(ne), col(ne);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)ne; ++i) { row[i] = Cc.v2i[F.coarse_id[i]]; col[i] = F.v2i[F.fine_id[i]]; }
+    NEED(F.ut_off = grab<int>((size_t)Cc.n_vert + 1)); NEED(F.ut_col = grab<int>(ne));
+    NEED(F.ut_w = grab<float>(ne)); NEED(F.ut_hat_w = grab<float>(ne));
+    STEP(femb_setup_coo_to_csr_pair_host(Cc.n_vert, F.n_entries, row.data(), col.data(), F.weight_norm, F.weight, F.ut_off, F.ut_col,
+                                         F.ut_w, F.ut_hat_w));
+    for (int r = 0; r < Cc.n_vert; ++r)
+      for (int p = F.ut_off[r]; p < F.ut_off[r + 1]; ++p) row[p] = r;      // rows of the sorted Ut = columns of Us
+    NEED(F.us_off = grab<int>((size_t)F.n_vert + 1)); NEED(F.us_col = grab<int>(ne));
+    NEED(F.us_w = grab<float>(ne)); NEED(F.us_hat_w = grab<float>(ne));
+    STEP(femb_setup_coo_to_csr_pair_host(F.n_vert, F.n_entries, F.ut_col, row.data(), F.ut_w, F.ut_hat_w, F.us_off, F.us_col, F.us_w,
+                                         F.us_hat_w));
+  }
+  for (int l = 0; l < n_levels; ++l) {                                     // object.py:485-697
+    FembHierarchyLevel& L = H->level[l];
+    std::vector<int> ve((size_t)L.n_vert * 8);
+    STEP(femb_setup_incidence_host(L.n_vert, L.n_hex, L.hex, ve.data()));
+    NEED(L.L_ptr = grab<int>((size_t)L.n_vert + 1)); NEED(L.U_ptr = grab<int>((size_t)L.n_vert + 1));
+    STEP(femb_setup_pattern_count_host(L.n_vert, L.hex, L.v2i, L.i2v, ve.data(), L.L_ptr, L.U_ptr));
+    L.L_nnz = L.L_ptr[L.n_vert];
+    NEED(L.L_col = grab<int>(L.L_nnz)); NEED(L.U_col = grab<int>(L.L_nnz));
+    NEED(L.elem2nnz = grab<int>((size_t)L.n_hex * 64)); NEED(L.block_offset = grab<int>(2 * (size_t)L.L_nnz + L.n_vert));
+    STEP(femb_setup_pattern_fill_host(L.n_vert, L.n_hex, L.hex, L.v2i, L.i2v, ve.data(), L.L_ptr, L.U_ptr, L.L_col, L.U_col, L.elem2nnz,
+                                      L.block_offset));
+  }
+#undef STEP
+#undef NEED
+  *out = H;
   return FEMB_OK;
 }
 

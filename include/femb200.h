@@ -184,6 +184,56 @@ int femb_setup_interp_count_host(int n_fine, int n_coarse_hex, const int* fine_c
 int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, const int* fine_coarse, const int* coarse_hex,
                                 const int* first_pos, int n_entries, int* coarse_id, int* fine_id, unsigned char* entry_k,
                                 float* weight, float* norm, float* weight_norm);
+/* Object.__init__ (object.py:116-697) in one call: all levels of the hierarchy on the host, in arrays the library owns
+ * (femb_setup_hierarchy_free releases them).  level[l] describes level l and, when a coarser level exists, its link to level
+ * l+1; the names follow the reference (and the functions above, which this call strings together). */
+typedef struct FembHierarchyLevel {
+  int n_vert, n_hex;        /* dims[l], number of hexahedra                                                            */
+  float spacing;            /* lattice spacing the reference assigns to the level (dx, 2 dx, 4 dx, 4 dx, ...)         */
+  int* hex;                 /* [n_hex*8]  hexs[l]                                                                      */
+  float* x;                 /* [n_vert*3] lattice positions (object.py:230)                                            */
+  int* v2i;                 /* [n_vert]   vertex2index[l]                                                              */
+  int* i2v;                 /* [n_vert]   index2vertex[l]                                                              */
+  int color_vertex_num[9];
+  int L_nnz;                /* blocks in the strictly lower (= upper) part; nnz = 2 L_nnz + n_vert                     */
+  int* L_ptr;               /* [n_vert+1] */
+  int* U_ptr;               /* [n_vert+1] */
+  int* L_col;               /* [L_nnz]    */
+  int* U_col;               /* [L_nnz]    */
+  int* elem2nnz;            /* [n_hex*64] hex_update_offset                                                            */
+  int* block_offset;        /* [2 L_nnz + n_vert] UtAUs_block_offset                                                   */
+  /* link to level l+1 (all NULL / 0 on the coarsest level) */
+  int* hex_parent;          /* [n_hex] coarse hexahedron of every hexahedron                                           */
+  int* fine_coarse;         /* [level[l+1].n_hex*27]                                                                   */
+  int n_entries;            /* interpolation entries                                                                   */
+  int* coarse_id;           /* [n_entries] rowInd_noOrder                                                              */
+  int* fine_id;             /* [n_entries] colInd_noOrder                                                              */
+  unsigned char* entry_k;   /* [n_entries]                                                                             */
+  float* weight;            /* [n_entries] un-normalised weights                                                       */
+  float* weight_norm;       /* [n_entries] weight / norm[coarse_id]                                                    */
+  float* norm;              /* [level[l+1].n_vert]                                                                     */
+  int* ut_off;              /* [level[l+1].n_vert+1] CSR of Ut / Ut_hat in index order (coarse x fine)                 */
+  int* ut_col;              /* [n_entries] */
+  float* ut_w;              /* [n_entries] Ut     */
+  float* ut_hat_w;          /* [n_entries] Ut_hat */
+  int* us_off;              /* [n_vert+1] CSR of Us / Us_hat in index order (fine x coarse)                            */
+  int* us_col;              /* [n_entries] */
+  float* us_w;              /* [n_entries] Us     */
+  float* us_hat_w;          /* [n_entries] Us_hat */
+} FembHierarchyLevel;
+
+typedef struct FembHierarchy {
+  int n_levels;
+  float origin[3];          /* lattice origin used (the bounding-box minimum unless the caller gave one)               */
+  FembHierarchyLevel* level;
+} FembHierarchy;
+
+/* n_levels >= 1 is the caller's: the reference derives it from the bounding box in float32 torch arithmetic
+ * (object.py:140-143; hierarchy.level_count restates it).  corrected_spacing != 0 coarsens level l with spacing dx 2^l
+ * instead of the reference's 2 dx for every l >= 1 (object.py:175-179).  origin may be NULL. */
+int femb_setup_hierarchy_host(int n_vert, int n_hex, const float* x, const int* hex, float dx, int n_levels, int corrected_spacing,
+                              const float* origin, FembHierarchy** out);
+int femb_setup_hierarchy_free(FembHierarchy* h);
 /* symbolic plan of A_c = Ut_hat (A_f Us_hat) (FembGalerkinPlan): t_ptr [n_fine+1] first, then the arrays sized from it:
  * t_col [t_nnz], c_ptr [n_coarse+1], c_col / c_slot [nnz_c], t_slot [nnz_f*8], c_slot8 [t_nnz*8], ut_q [nnz(Ut_hat)];
  * fails if the product pattern is not the coarse hexahedral adjacency (block_values_reorder relies on it, object.py:1261) */

@@ -46,7 +46,8 @@ def test_ctypes_mirrors_match_header_layout(repo_root, tmp_path):
     import ctypes as C
     import subprocess
     structs = {"FembLevel": _lib.FembLevel, "FembTransfer": _lib.FembTransfer, "FembGalerkinPlan": _lib.FembGalerkinPlan,
-               "FembHalo": _lib.FembHalo, "FembContext": _lib.FembContext, "FembDynamic": _lib.FembDynamic,
+               "FembHalo": _lib.FembHalo, "FembHierarchyLevel": _lib.FembHierarchyLevel, "FembHierarchy": _lib.FembHierarchy,
+               "FembContext": _lib.FembContext, "FembDynamic": _lib.FembDynamic,
                "FembCloth": _lib.FembCloth}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "femb200.h"', 'int main(void) {']
     for name, cls in structs.items():

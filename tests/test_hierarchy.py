@@ -337,3 +337,69 @@ def test_native_hierarchy_rejects_bad_input():
     fc = np.full((2, 27), -1, np.int32); fc[1, 3] = 99
     first, n_ent = np.empty(10, np.int32), C.c_int(0)
     assert lib.femb_setup_interp_count_host(10, 2, hp(fc), hp(first), ref(n_ent)) == -1
+
+
+@pytest.mark.parametrize("case", ["jag3", "cube12_corrected", "slab_origin"])
+def test_one_call_hierarchy_matches_python_build(case):
+    """femb_setup_hierarchy_host (the whole of Object.__init__'s integer setup behind one C call, library-owned arrays)
+    returns the arrays hierarchy.build_hierarchy assembles from the individual setup calls."""
+    import ctypes as C
+    from fem_simulation_b200 import _lib
+    lib = _lib.load()
+    corrected, origin = False, None
+    if case == "jag3":
+        (points, hexs), dx = CASES["jag3"]()
+    elif case == "cube12_corrected":
+        (points, hexs), dx, corrected = mesh.cube_mesh(12, 0.05), 0.05, True
+    else:
+        (points, hexs), dx = mesh.box_mesh(12, 10, 9, 0.1, index_offset=(0, 0, 6)), 0.1
+        origin = np.zeros(3, np.float32)
+    H = hierarchy.build_hierarchy(points, hexs, dx, corrected_spacing=corrected, origin=origin)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = C.POINTER(_lib.FembHierarchy)()
+    rc = lib.femb_setup_hierarchy_host(len(points), len(hexs), hp(points), hp(hexs), C.c_float(dx), H.layer, int(corrected),
+                                       None if origin is None else hp(origin), C.cast(C.byref(out), C.c_void_p))
+    assert rc == 0, lib.femb_last_error()
+    try:
+        h = out.contents
+        assert h.n_levels == H.layer
+        _eq(np.array(h.origin[:], np.float32), H.box_min, "origin")
+        arr = lambda ptr, n, shape=None: np.ctypeslib.as_array(ptr, shape=(int(n),)).copy().reshape(shape or (int(n),))
+        for l in range(H.layer):
+            L, p = h.level[l], H.pattern[l]
+            assert (L.n_vert, L.n_hex, L.L_nnz) == (H.dims[l], len(H.hexs[l]), p.L_nnz)
+            assert np.float32(L.spacing) == np.float32(H.spacing[l])
+            _eq(arr(L.hex, L.n_hex * 8, (-1, 8)), H.hexs[l], f"hex[{l}]")
+            _eq(arr(L.x, L.n_vert * 3, (-1, 3)), H.x[l], f"x[{l}]")
+            _eq(arr(L.v2i, L.n_vert), H.vertex2index[l], f"v2i[{l}]")
+            _eq(arr(L.i2v, L.n_vert), H.index2vertex[l], f"i2v[{l}]")
+            _eq(list(L.color_vertex_num), H.color_vertex_num[l], f"cvn[{l}]")
+            for nm in ["L_ptr", "U_ptr"]:
+                _eq(arr(getattr(L, nm), L.n_vert + 1), getattr(p, nm), f"{nm}[{l}]")
+            for nm in ["L_col", "U_col"]:
+                _eq(arr(getattr(L, nm), L.L_nnz), getattr(p, nm), f"{nm}[{l}]")
+            _eq(arr(L.elem2nnz, L.n_hex * 64), p.hex_update_offset, f"elem2nnz[{l}]")
+            _eq(arr(L.block_offset, p.nnz), p.block_offset, f"block_offset[{l}]")
+            if l == H.layer - 1:
+                assert not L.hex_parent and not L.fine_coarse and L.n_entries == 0 and not L.ut_off
+                continue
+            t, nc = H.U_triplets[l], H.dims[l + 1]
+            _eq(arr(L.hex_parent, L.n_hex), H.fine_hex_parent[l], f"hex_parent[{l}]")
+            _eq(arr(L.fine_coarse, len(H.hexs[l + 1]) * 27, (-1, 27)), H.fine_coarse[l], f"fine_coarse[{l}]")
+            assert L.n_entries == len(t["value"])
+            _eq(arr(L.coarse_id, L.n_entries), t["rowInd_noOrder"], "coarse_id"); _eq(arr(L.fine_id, L.n_entries), t["colInd_noOrder"], "fine_id")
+            _eq(arr(L.weight, L.n_entries), t["value"], "weight"); _eq(arr(L.norm, nc), t["norm"], "norm")
+            for pre, m, mh, nrow in [("ut", H.Ut[l], H.Ut_hat[l], nc), ("us", H.Us[l], H.Us_hat[l], L.n_vert)]:
+                _eq(arr(getattr(L, pre + "_off"), nrow + 1), m.offsets, pre + "_off")
+                _eq(arr(getattr(L, pre + "_col"), L.n_entries), m.columns, pre + "_col")
+                _eq(arr(getattr(L, pre + "_w"), L.n_entries), m.weights, pre + "_w")
+                _eq(arr(getattr(L, pre + "_hat_w"), L.n_entries), mh.weights, pre + "_hat_w")
+            if l == 0:
+                fix_idx = np.full((L.n_vert, 8), -1, np.int32)
+                fix_idx[arr(L.fine_id, L.n_entries), arr(L.entry_k, L.n_entries)] = arr(L.coarse_id, L.n_entries)
+                _eq(fix_idx, H.fix_idx, "fix_idx from entry_k")
+    finally:
+        assert lib.femb_setup_hierarchy_free(out) == 0
+    bad = C.POINTER(_lib.FembHierarchy)()
+    assert lib.femb_setup_hierarchy_host(len(points), len(hexs), hp(points), hp(hexs), C.c_float(dx), 0, 0, None,
+                                         C.cast(C.byref(bad), C.c_void_p)) == -1 and not bad
