@@ -175,11 +175,94 @@ def build_level_plans(H, dx, z0, z1, cuts, rank, world, overlap):
     return out
 
 
+_KEY_BASE = np.int64(1) << 21
+
+
+def lattice_keys(ijk: np.ndarray) -> np.ndarray:
+    """One int64 per lattice point, ascending in (gz, iy, ix): the order both sides of an exchange list their rows in."""
+    return (ijk[:, 2] * _KEY_BASE + ijk[:, 1]) * _KEY_BASE + ijk[:, 0]
+
+
+def level_recv_keys(H, dx, z0, z1, rank, world, overlap):
+    """Per level: {neighbour rank: ascending lattice keys of the ghost rows this rank reads from it} -- the same planes as
+    `build_level_plans`, restricted to the vertices the local mesh really has (a voxel SET, not a box: `SlabObject(mask=)`)."""
+    out = []
+    for l in range(H.layer):
+        ijk = level_planes(H.x[l], dx)
+        stride = int(round(H.spacing[l] / dx))
+        span = overlap if l == 0 else stride
+        gz, key = ijk[:, 2], lattice_keys(ijk)
+        d = {}
+        if rank > 0:
+            d[rank - 1] = np.sort(key[(gz >= z0 - span) & (gz < z0)])
+        if rank < world - 1:
+            d[rank + 1] = np.sort(key[gz == z1])
+        out.append(d)
+    return out
+
+
+def build_level_plans_matched(H, dx, z0, z1, cuts, rank, world, recv_keys_all):
+    """`build_level_plans` for a voxel set: `recv_keys_all[r]` = `level_recv_keys` of rank r (gathered once at setup); a
+    rank sends exactly the rows its neighbour asks for, in the neighbour's (ascending key) order.  On a box the result is
+    `build_level_plans`' (tests/test_multigpu.py)."""
+    nz_total = cuts[-1]
+    out = []
+    for l in range(H.layer):
+        ijk = level_planes(H.x[l], dx)
+        gz, key = ijk[:, 2], lattice_keys(ijk)
+        order = np.argsort(key, kind="stable")
+        skey = key[order]
+        top = nz_total if rank == world - 1 else -1
+        owned = (gz >= z0) & ((gz < z1) | (gz == top))
+
+        def rows_of(keys, what):
+            pos = np.minimum(np.searchsorted(skey, keys), len(skey) - 1)
+            if len(keys) and not np.array_equal(skey[pos], keys):
+                raise ValueError(f"level {l}: rank {rank} does not hold every lattice point of {what}")
+            return order[pos]
+
+        pv = HaloPlan()
+        for nb in [r for r in (rank - 1, rank + 1) if 0 <= r < world]:
+            recv = rows_of(recv_keys_all[rank][l][nb], f"its own ghost list for rank {nb}")
+            send = rows_of(recv_keys_all[nb][l][rank], f"the ghost list of rank {nb}")
+            if owned[recv].any() or not owned[send].all():
+                raise ValueError(f"level {l}: ghost lists of ranks {rank} and {nb} disagree with the ownership rule")
+            pv.recv[nb], pv.send[nb] = torch.from_numpy(recv).long(), torch.from_numpy(send).long()
+        v2i = torch.from_numpy(np.asarray(H.vertex2index[l])).long()
+        pi = HaloPlan()
+        pi.send = {k: v2i[v] for k, v in pv.send.items()}
+        pi.recv = {k: v2i[v] for k, v in pv.recv.items()}
+        out.append((pv, pi, owned))
+    return out
+
+
+def mask_slab(mask: np.ndarray, dx: float, clo: int, chi: int):
+    """Local mesh of the cells [clo, chi) of a global voxel set, the local ids of the vertices the reference would pin on
+    the GLOBAL mesh (object.py:762-773: y >= y_max - dx - 1e-5, float32) and the global vertex id of every local vertex."""
+    mask = np.asarray(mask, dtype=bool)
+    nx, ny, nz = mask.shape
+    pts, hx = mesh.mesh_from_mask(mask[:, :, clo:chi], dx, index_offset=(0, 0, clo))
+    iy_top = int(np.nonzero(mask.any(axis=(0, 2)))[0].max()) + 1               # highest used vertex row
+    y_max = np.float32(iy_top) * np.float32(dx)
+    thr = np.float32(np.float32(y_max - np.float32(dx)) - np.float32(1e-5))
+    pins = np.nonzero(pts[:, 1] >= thr)[0].astype(np.int32)
+    px, py = nx + 1, ny + 1
+    mark = np.zeros(px * py * (nz + 1), dtype=bool)                            # used lattice points of the global mesh
+    cx, cy, cz = np.nonzero(mask)
+    for a in range(8):
+        mark[(cx + ((a >> 2) & 1)) + px * ((cy + ((a >> 1) & 1)) + py * (cz + (a & 1)))] = True
+    gid_of_lattice = np.cumsum(mark) - 1
+    ijk = level_planes(pts, dx)
+    gid = gid_of_lattice[ijk[:, 0] + px * (ijk[:, 1] + py * ijk[:, 2])]
+    return pts, hx, pins, gid.astype(np.int64)
+
+
 class SlabObject:
-    """One rank of the mesh-partitioned FASv3 / Newton-multigrid step on an nx x ny x nz_total voxel box (dx spacing)."""
+    """One rank of the mesh-partitioned FASv3 / Newton-multigrid step on an nx x ny x nz_total voxel box (dx spacing), or on
+    the voxel set `mask` [nx, ny, nz_total] (bool) inside that box (every slab must keep at least one voxel)."""
 
     def __init__(self, nx, ny, nz_total, dx, *, rank=None, world=None, device=None, group=None, graph_segments=True,
-                 layers=2, comm="auto", **object_kwargs):
+                 layers=2, comm="auto", mask=None, **object_kwargs):
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.group = group
@@ -190,13 +273,32 @@ class SlabObject:
         self.cuts = slab_cuts(nz_total, self.world, self.align)
         z0, z1, clo, chi = slab_planes(nz_total, self.world, self.rank, self.align, self.overlap)
         self.z0, self.z1, self.clo, self.chi = z0, z1, clo, chi
-        pts, hx = mesh.box_mesh(nx, ny, chi - clo, dx, index_offset=(0, 0, clo))
         object_kwargs.setdefault("use_graphs", False)
         object_kwargs.setdefault("lattice_origin", (0.0, 0.0, 0.0))     # colours / coarse cells counted from the GLOBAL corner
-        self.obj = Object((pts, hx), dx, [], device=device, layers=self.layers, **object_kwargs)
+        if mask is None:
+            pts, hx = mesh.box_mesh(nx, ny, chi - clo, dx, index_offset=(0, 0, clo))
+            self.global_ids = None
+            self.obj = Object((pts, hx), dx, [], device=device, layers=self.layers, **object_kwargs)
+        else:
+            if tuple(np.shape(mask)) != (nx, ny, nz_total):
+                raise ValueError(f"mask must have shape {(nx, ny, nz_total)}, got {tuple(np.shape(mask))}")
+            if not np.asarray(mask, dtype=bool)[:, :, clo:chi].any():
+                raise ValueError(f"rank {self.rank}: no voxel in the cell layers [{clo}, {chi})")
+            pts, hx, pins, gid = mask_slab(mask, dx, clo, chi)
+            self.global_ids = gid
+            self.obj = Object((pts, hx), dx, pins.tolist(), device=device, layers=self.layers, pins_exact=True, **object_kwargs)
         o = self.obj
         H = o.hierarchy
-        plans = build_level_plans(H, dx, z0, z1, self.cuts, self.rank, self.world, self.overlap)
+        if mask is None:
+            plans = build_level_plans(H, dx, z0, z1, self.cuts, self.rank, self.world, self.overlap)
+        else:
+            mine = level_recv_keys(H, dx, z0, z1, self.rank, self.world, self.overlap)
+            everyone = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(everyone, mine, group=group)
+            else:
+                everyone[0] = mine
+            plans = build_level_plans_matched(H, dx, z0, z1, self.cuts, self.rank, self.world, everyone)
         self.plan_v = [p[0].to(o.device) for p in plans]
         self.plan_i = [p[1].to(o.device) for p in plans]
         self.owned_level = [torch.from_numpy(p[2]).to(o.device) for p in plans]
@@ -391,6 +493,8 @@ class SlabObject:
     def owned_positions(self):
         """(global vertex ids, positions) of the owned vertices, for gathering / checking."""
         ids = torch.nonzero(self.owned).squeeze(1)
+        if self.global_ids is not None:
+            return torch.from_numpy(self.global_ids).to(ids.device)[ids], self.obj.x_gpu_layer[0][ids]
         return ids + self.global_offset, self.obj.x_gpu_layer[0][ids]
 
     def force_inf_norm(self):

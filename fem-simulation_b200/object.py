@@ -61,7 +61,7 @@ class Object:
     def __init__(self, mesh_path, dx, pinList, *, device="cuda:0", layers=None, use_graphs=True, verbose=False,
                  control_mag=100.0, mu=250.0, la=0.0, g=-9.8 / 2.0, pin_displacement=0.1, spd_level0=False,
                  corrected_hierarchy=False, lattice_fold=True,
-                 lattice_origin=None, use_c_steps=True):
+                 lattice_origin=None, use_c_steps=True, pins_exact=False):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.FembError("femb200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -162,7 +162,9 @@ class Object:
 
         # ---- pins (object.py:761-795) ------------------------------------------------------------
         pinList = list(pinList)
-        if len(pinList) == 0:
+        if pins_exact:
+            pass            # the list as given, possibly empty, nothing displaced (a slab of a partitioned mesh: distributed.py)
+        elif len(pinList) == 0:
             pinList = hierarchy.default_pins(points, dx).tolist()
         else:
             self.x_cpu[pinList[0]][1] += pin_displacement

@@ -31,23 +31,48 @@ def _init(rank, world, port, backend):
     dist.init_process_group(backend, rank=rank, world_size=world)
 
 
-def _cpu_worker(rank, world, port, out, nz, layers):
+def _voxel_set(nz, seed):
+    """a reproducible ragged voxel set in the NX x NY x nz box: every cell layer keeps voxels, the box corners are kept"""
+    rng = np.random.default_rng(seed)
+    mask = rng.random((NX, NY, nz)) < 0.7
+    mask[0, 0, :] = True
+    mask[-1, -1, -1] = mask[0, -1, 0] = mask[-1, 0, 0] = True
+    return mask
+
+
+def _cpu_worker(rank, world, port, out, nz, layers, mask_seed=None):
     _init(rank, world, port, "gloo")
     try:
         align = D.hierarchy_align(layers)
         cuts = D.slab_cuts(nz, world, align)
         z0, z1, clo, chi = D.slab_planes(nz, world, rank, align)
-        pts, hx = mesh.box_mesh(NX, NY, chi - clo, DX, index_offset=(0, 0, clo))
-        H = hierarchy.build_hierarchy(pts, hx, DX, layers=layers, origin=(0.0, 0.0, 0.0))
-        gpts, ghx = mesh.box_mesh(NX, NY, nz, DX)
-        G = hierarchy.build_hierarchy(gpts, ghx, DX, layers=layers)
-        ps = (NX + 1) * (NY + 1)
-        off = ps * clo
-        # local slab == slice of the global mesh: coordinates bit-identical, colours identical
-        assert np.array_equal(pts, gpts[off:off + len(pts)])
         col = lambda Hh, l: np.searchsorted(np.asarray(Hh.color_vertex_num[l]), Hh.vertex2index[l], side="right") - 1
-        assert np.array_equal(col(H, 0), col(G, 0)[off:off + len(pts)])
-        plans = D.build_level_plans(H, DX, z0, z1, cuts, rank, world, align)
+        if mask_seed is None:
+            pts, hx = mesh.box_mesh(NX, NY, chi - clo, DX, index_offset=(0, 0, clo))
+            gpts, ghx = mesh.box_mesh(NX, NY, nz, DX)
+            gid0 = (NX + 1) * (NY + 1) * clo + np.arange(len(pts))
+        else:
+            mask = _voxel_set(nz, mask_seed)
+            pts, hx, pins, gid0 = D.mask_slab(mask, DX, clo, chi)
+            gpts, ghx = mesh.mesh_from_mask(mask, DX)
+            # the slab pins what the reference pins on the whole mesh (object.py:762-773), whatever the slab's own top is
+            gpins = hierarchy.default_pins(gpts, DX)
+            assert np.array_equal(np.sort(gid0[pins]), np.intersect1d(gpins, gid0))
+        H = hierarchy.build_hierarchy(pts, hx, DX, layers=layers, origin=(0.0, 0.0, 0.0))
+        G = hierarchy.build_hierarchy(gpts, ghx, DX, layers=layers, origin=(0.0, 0.0, 0.0))
+        # local slab == part of the global mesh: coordinates bit-identical, colours identical
+        assert np.array_equal(pts, gpts[gid0])
+        assert np.array_equal(col(H, 0), col(G, 0)[gid0])
+        mine = D.level_recv_keys(H, DX, z0, z1, rank, world, align)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        plans = D.build_level_plans_matched(H, DX, z0, z1, cuts, rank, world, everyone)
+        if mask_seed is None:                                                # on a box: the plane rule's lists, entry by entry
+            for (pv, pi, owned), (qv, qi, qowned) in zip(plans, D.build_level_plans(H, DX, z0, z1, cuts, rank, world, align)):
+                assert np.array_equal(owned, qowned)
+                for a, b in [(pv, qv), (pi, qi)]:
+                    assert sorted(a.send) == sorted(b.send) and sorted(a.recv) == sorted(b.recv)
+                    assert all(torch.equal(a.send[k], b.send[k]) for k in a.send) and all(torch.equal(a.recv[k], b.recv[k]) for k in a.recv)
         n_owned_levels = []
         for l in range(H.layer):
             pv, pi, owned = plans[l]
@@ -74,6 +99,17 @@ def _cpu_worker(rank, world, port, out, nz, layers):
             w[v2i[own_t]] = torch.stack([gid, gid, gid], dim=1)[own_t]
             D.exchange(w, pi)
             assert torch.equal(w[v2i[need_t], 0], gid[need_t]), f"level {l} ghosts (index order)"
+            # every owned row has its complete set of blocks locally (assembly and the Galerkin rows need no reduction): the
+            # local pattern restricted to the owned rows is the global pattern's, lattice point by lattice point
+            lp, gp = H.pattern[l], G.pattern[l]
+            li2v, gi2v = np.asarray(H.index2vertex[l]), np.asarray(G.index2vertex[l])
+            lrow, lcol = gid_np[li2v[lp.row]], gid_np[li2v[lp.col]]
+            keep = owned[li2v[lp.row]]
+            local_pairs = np.unique(lrow[keep] * len(gijk) + lcol[keep])
+            grow, gcol = gi2v[gp.row].astype(np.int64), gi2v[gp.col].astype(np.int64)
+            mine_g = np.zeros(len(gijk), bool); mine_g[gid_np[owned]] = True
+            global_pairs = np.unique(grow[mine_g[grow]] * len(gijk) + gcol[mine_g[grow]])
+            assert np.array_equal(local_pairs, global_pairs), f"level {l}: owned rows' blocks"
             # ownership is a partition of the global level
             cnt = torch.zeros(len(gijk))
             cnt[torch.from_numpy(gid_np[owned])] = 1
@@ -88,15 +124,17 @@ def _cpu_worker(rank, world, port, out, nz, layers):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nz,layers", [(2, NZ, 2), (4, NZ, 2), (8, 2 * NZ, 2), (2, 16, 3), (3, 28, 4)])
-def test_halo_plans_gloo(world, nz, layers):
+@pytest.mark.parametrize("world,nz,layers,mask_seed", [(2, NZ, 2, None), (4, NZ, 2, None), (8, 2 * NZ, 2, None), (2, 16, 3, None),
+                                                       (3, 28, 4, None), (2, NZ, 2, 11), (4, 16, 2, 12), (3, 28, 4, 13)])
+def test_halo_plans_gloo(world, nz, layers, mask_seed):
     """world 4 and 8 (2 cell layers per rank) add interior ranks, which talk to both neighbours; 8 is the size of the
     round-end scaling run; layers 3 / 4 are the Newton-multigrid decomposition (cuts on multiples of 4 planes, overlap 4,
-    per-level ghost planes; 28 planes over 3 ranks: uneven slabs 12 / 8 / 8)."""
+    per-level ghost planes; 28 planes over 3 ranks: uneven slabs 12 / 8 / 8).  With a mask seed the mesh is a ragged voxel
+    set instead of the box (`SlabObject(mask=)`): the ghost lists are matched through the gathered lattice keys."""
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, out, nz, layers)) for r in range(world)]
+    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, out, nz, layers, mask_seed)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -119,11 +157,19 @@ def test_slab_planes_validation():
         D.slab_cuts(8, 4, 4)               # fewer aligned groups than ranks
 
 
-def _gpu_worker(rank, world, port, steps, out, method, layers, comm, graphs):
+def _gpu_voxel_set():
+    rng = np.random.default_rng(21)
+    mask = rng.random((12, 10, 32)) < 0.75
+    mask[0, 0, :] = mask[-1, -1, :] = True                           # keeps the bounding box and the top row in every slab
+    return mask
+
+
+def _gpu_worker(rank, world, port, steps, out, method, layers, comm, graphs, masked=False):
     torch.cuda.set_device(rank)
     _init(rank, world, port, "nccl")
     try:
-        so = D.SlabObject(12, 10, 32, DX, device=f"cuda:{rank}", layers=layers, comm=comm, graph_segments=graphs)
+        so = D.SlabObject(12, 10, 32, DX, device=f"cuda:{rank}", layers=layers, comm=comm, graph_segments=graphs,
+                          mask=_gpu_voxel_set() if masked else None)
         for _ in range(steps):
             so.fasv3_step() if method == "fasv3" else so.nmg_step()
         ids, xs = so.owned_positions()
@@ -138,9 +184,11 @@ def _gpu_worker(rank, world, port, steps, out, method, layers, comm, graphs):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,layers,comm,graphs", [("fasv3", 2, "p2p", True), ("nmg", 3, "p2p", True), ("nmg", 3, "p2p", False),
-                                                       ("nmg", 3, "nccl", True), ("nmg", 4, "torch", False), ("fasv3", 2, "torch", True)])
-def test_distributed_step_matches_single_gpu(method, layers, comm, graphs):
+@pytest.mark.parametrize("method,layers,comm,graphs,masked", [
+    ("fasv3", 2, "p2p", True, False), ("nmg", 3, "p2p", True, False), ("nmg", 3, "p2p", False, False), ("nmg", 3, "nccl", True, False),
+    ("nmg", 4, "torch", False, False), ("fasv3", 2, "torch", True, False),
+    ("fasv3", 2, "nccl", True, True), ("nmg", 3, "nccl", True, True)])      # a ragged voxel set instead of the box
+def test_distributed_step_matches_single_gpu(method, layers, comm, graphs, masked):
     """The mesh-partitioned FASv3 / Newton-multigrid step (C-ABI exchanges inside one CUDA graph per rank -- peer-memory
     push / pull kernels or NCCL send / recv --, or the torch.distributed exchange between segment graphs) vs the single-GPU
     step on the same global mesh."""
@@ -148,8 +196,8 @@ def test_distributed_step_matches_single_gpu(method, layers, comm, graphs):
         pytest.skip("needs 2 GPUs")
     from fem_simulation_b200 import Object
     steps = 4
-    pts, hx = mesh.box_mesh(12, 10, 32, DX)
-    ref = Object((pts, hx), DX, [], layers=layers, use_graphs=False)
+    pts, hx = mesh.mesh_from_mask(_gpu_voxel_set(), DX) if masked else mesh.box_mesh(12, 10, 32, DX)
+    ref = Object((pts, hx), DX, [], layers=layers, use_graphs=False, lattice_origin=(0.0, 0.0, 0.0) if masked else None)
     ref.FASv3(steps) if method == "fasv3" else ref.NewtonMultigrid(steps)
     xref = ref.x_gpu_layer[0].cpu().numpy()
     ref._force(ref.x_gpu_layer[0], ref.grad_gpu)
@@ -158,7 +206,7 @@ def test_distributed_step_matches_single_gpu(method, layers, comm, graphs):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, steps, out, method, layers, comm, graphs)) for r in range(world)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, steps, out, method, layers, comm, graphs, masked)) for r in range(world)]
     for p in procs:
         p.start()
     import queue
