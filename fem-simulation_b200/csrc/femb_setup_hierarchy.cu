@@ -34,7 +34,7 @@ struct LatticeIds {
   int next = 0;
   LatticeIds(long long nx_, long long ny_, long long nz_, long long expected) : nx(nx_), ny(ny_), nz(nz_) {
     const long long vol = nx * ny * nz;
-    dense = vol <= std::max<long long>(1ll << 24, 64 * expected);
+    dense = vol <= std::max<long long>(1ll << 24, 8 * expected);   // at most 64 MB, or 32 bytes per expected key
     if (dense) table.assign((size_t)vol, -1);
     else map.reserve((size_t)expected * 2);
   }
