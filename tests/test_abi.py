@@ -92,3 +92,25 @@ def test_prototypes_match_header_signatures(repo_root):
         params = params.strip()
         want = [] if params in ("", "void") else [klass_c(q) for q in params.split(",")]
         assert [klass_ct(t) for t in _lib.PROTOTYPES[name]] == want, name
+
+
+def test_plain_c_consumer_builds_the_hierarchy(repo_root, tmp_path):
+    """examples/setup_from_c.c: a C99 program linked against libfemb200.so (no Python, no torch, no device) calls
+    femb_setup_hierarchy_host and reports the level sizes `hierarchy.build_hierarchy` gives for the same cube."""
+    import subprocess
+    import numpy as np
+    from fem_simulation_b200 import hierarchy, mesh
+    _lib.load()
+    exe = tmp_path / "setup_from_c"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(repo_root, "include"),
+                    os.path.join(repo_root, "examples", "setup_from_c.c"), "-L", libdir, "-lfemb200", f"-Wl,-rpath,{libdir}",
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), "12", "3"], capture_output=True, text=True, check=True).stdout.splitlines()
+    H = hierarchy.build_hierarchy(*mesh.cube_mesh(12), 1.0 / 12, layers=3)
+    assert out[0] == "abi 5 levels 3"
+    for l in range(3):
+        colours = " ".join(str(c) for c in np.diff(H.color_vertex_num[l]))
+        assert out[1 + l].startswith(f"level {l}: {H.dims[l]} vertices, {len(H.hexs[l])} hexahedra, {H.pattern[l].nnz} blocks, "
+                                     f"colours {colours},"), out[1 + l]
+    assert f"interpolation entries {H.Us_hat[0].nnz} " in out[1]
