@@ -6,7 +6,6 @@ from __future__ import annotations
 
 import ctypes as C
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

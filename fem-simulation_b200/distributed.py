@@ -44,7 +44,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _lib, hierarchy, mesh
+from . import _lib, mesh
 from .object import Object
 
 
