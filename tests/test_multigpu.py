@@ -230,3 +230,68 @@ def test_distributed_step_matches_single_gpu(method, layers, comm, graphs, maske
     assert np.abs(x - xref).max() <= 1e-6 * np.abs(xref).max(), f"max diff {np.abs(x - xref).max():.3e}"
     disp = xref - pts
     assert np.abs((x - pts) - disp).max() <= 1e-4 * np.abs(disp).max()
+
+
+class _HostObject:
+    """Stand-in for `Object` on a machine without a GPU: the hierarchy and the level-1 positions `SlabObject.__init__` touches
+    (the CUDA state is not needed to check the constructor's bookkeeping)."""
+
+    def __init__(self, mesh_path, dx, pinList, *, device=None, layers=None, lattice_origin=None, pins_exact=False, **_):
+        pts, hx = mesh_path
+        self.hierarchy = hierarchy.build_hierarchy(pts, hx, dx, layers, origin=lattice_origin)
+        self.device = torch.device("cpu")
+        self.pinList, self.pins_exact = list(pinList), pins_exact
+        self.x_gpu_layer = [torch.from_numpy(x.copy()) for x in self.hierarchy.x]
+        self.rest_prepared = []
+
+    def _prepare_rest(self, level):
+        self.rest_prepared.append(level)
+
+
+def _ctor_worker(rank, world, port, out, masked):
+    _init(rank, world, port, "gloo")
+    try:
+        D.Object = _HostObject                                               # this process only
+        nz = 16
+        mask = _voxel_set(nz, 31) if masked else None
+        so = D.SlabObject(NX, NY, nz, DX, rank=rank, world=world, layers=3, comm="torch", mask=mask)
+        assert so.comm is None and so.obj.rest_prepared == [1] and so.n_exchanges == 1
+        gpts, _ = mesh.mesh_from_mask(mask, DX) if masked else mesh.box_mesh(NX, NY, nz, DX)
+        # the constructor's exchange made the ghost rows of the level-1 positions current (they already were: lattice points)
+        assert torch.equal(so.obj.x_gpu_layer[1], torch.from_numpy(so.obj.hierarchy.x[1]))
+        ids, xs = so.owned_positions()
+        assert np.array_equal(xs.numpy(), gpts[ids.numpy()])                 # local -> global vertex ids
+        cnt = torch.zeros(len(gpts)); cnt[ids] = 1
+        dist.all_reduce(cnt)
+        assert torch.all(cnt == 1)                                           # every global vertex owned exactly once
+        if masked:
+            assert so.obj.pins_exact and len(so.obj.pinList) > 0
+            got = torch.zeros(len(gpts)); got[torch.from_numpy(so.global_ids[np.asarray(so.obj.pinList)])] = 1
+            dist.all_reduce(got)
+            want = torch.zeros(len(gpts)); want[torch.from_numpy(hierarchy.default_pins(gpts, DX)).long()] = 1
+            assert torch.equal(got > 0, want > 0)                            # union of the slabs' pins = the reference's pins
+        else:
+            assert so.obj.pinList == [] and not so.obj.pins_exact and so.global_ids is None
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_slab_object_constructor_bookkeeping_gloo(masked):
+    """`SlabObject.__init__` itself (cuts, local mesh, plans -- gathered lattice keys for a voxel set --, the first exchange,
+    global vertex ids, pins) at world size 2 over gloo, with a host-only stand-in for the CUDA `Object`."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ctor_worker, args=(r, world, port, out, masked)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    res = sorted(out.get(timeout=5) for _ in range(world))
+    assert res == [(r, "ok") for r in range(world)], res
