@@ -187,7 +187,10 @@ def _gpu_worker(rank, world, port, steps, out, method, layers, comm, graphs, mas
 @pytest.mark.parametrize("method,layers,comm,graphs,masked", [
     ("fasv3", 2, "p2p", True, False), ("nmg", 3, "p2p", True, False), ("nmg", 3, "p2p", False, False), ("nmg", 3, "nccl", True, False),
     ("nmg", 4, "torch", False, False), ("fasv3", 2, "torch", True, False),
-    ("fasv3", 2, "nccl", True, True), ("nmg", 3, "nccl", True, True)])      # a ragged voxel set instead of the box
+    # a ragged voxel set instead of the box: written after the round's GPU budget was spent, never run on GPUs yet -- the
+    # outcome is recorded (XPASS / xfail), not asserted, until it has been seen green once
+    pytest.param("fasv3", 2, "nccl", True, True, marks=pytest.mark.xfail(strict=False, reason="voxel-set slabs: not yet run on GPUs")),
+    pytest.param("nmg", 3, "nccl", True, True, marks=pytest.mark.xfail(strict=False, reason="voxel-set slabs: not yet run on GPUs"))])
 def test_distributed_step_matches_single_gpu(method, layers, comm, graphs, masked):
     """The mesh-partitioned FASv3 / Newton-multigrid step (C-ABI exchanges inside one CUDA graph per rank -- peer-memory
     push / pull kernels or NCCL send / recv --, or the torch.distributed exchange between segment graphs) vs the single-GPU
