@@ -42,3 +42,22 @@ def test_reference_arm_sets_its_own_thread_count(repo_root):
 def test_reference_arm_other_ranks_exit_quietly(repo_root):
     r = _run(repo_root, {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_algorithmic_bytes_of_the_stated_workload(repo_root):
+    """The roofline numerators bench.py reports for the cube of 1 M hexahedra (SURVEY.md 8d formulas over the real V, Z, N_h of
+    every level): the values the committed bench lines carry (profiles/r02d_bench_fas_n1.json), so the accounting cannot drift
+    unnoticed."""
+    import importlib.util
+    import types
+    from fem_simulation_b200 import hierarchy, mesh
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(repo_root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    H = hierarchy.build_hierarchy(*mesh.cube_mesh(100), 1.0 / 100)
+    assert H.dims == [1030301, 132651, 17576, 17576, 17576] and H.pattern[0].nnz == 27270901
+    obj = types.SimpleNamespace(hierarchy=H)
+    assert 352 * 1000000 + 36 * H.pattern[0].nnz + 256 * 1000000 == 1589752436          # the assembly stage (roofline.achieved)
+    assert bench.step_bytes(obj, "fasv3") == 4375273208.0
+    assert bench.step_bytes(obj, "nmg") == 20650060952.0
+    assert bench.gs_launch_bytes(obj) == 129713842.5
