@@ -15,17 +15,32 @@
 
 namespace femb {
 
-// sorted unique index-order columns of row v2i[v]; returns the count (<= 64)
-static inline int row_columns(int v, const int* hex, const int* v2i, const int* vert_elem, int* cols) {
+// unique index-order columns of row v2i[v], unsorted; returns the count (<= 64).  The <= 64 candidates (8 nodes of each of <= 8
+// incident hexahedra) hold ~27 distinct ids: a 128-slot open-addressing table on the stack removes the duplicates before
+// anything is sorted
+static inline int row_unique(int v, const int* hex, const int* v2i, const int* vert_elem, int* cols) {
+  int tab[128];
+  std::memset(tab, 0xff, sizeof(tab));
   int n = 0;
   for (int j = 0; j < 8; ++j) {
     const int ea = vert_elem[(size_t)v * 8 + j];
     if (ea < 0) continue;
     const int* h = hex + (size_t)(ea >> 3) * 8;
-    for (int b = 0; b < 8; ++b) cols[n++] = v2i[h[b]];
+    for (int b = 0; b < 8; ++b) {
+      const int c = v2i[h[b]];
+      unsigned s = ((unsigned)c * 2654435761u) >> 25;
+      while (tab[s] != -1 && tab[s] != c) s = (s + 1) & 127;
+      if (tab[s] == -1) { tab[s] = c; cols[n++] = c; }
+    }
   }
+  return n;
+}
+
+// sorted unique index-order columns of row v2i[v]; returns the count (<= 64)
+static inline int row_columns(int v, const int* hex, const int* v2i, const int* vert_elem, int* cols) {
+  const int n = row_unique(v, hex, v2i, vert_elem, cols);
   std::sort(cols, cols + n);
-  return (int)(std::unique(cols, cols + n) - cols);
+  return n;
 }
 
 }  // namespace femb
@@ -125,9 +140,10 @@ int femb_setup_pattern_count_host(int n_vert, const int* hex, const int* v2i, co
 #pragma omp parallel for schedule(static)
   for (int r = 0; r < n_vert; ++r) {
     int cols[64];
-    const int n = row_columns(i2v[r], hex, v2i, vert_elem, cols);
-    const int nl = (int)(std::lower_bound(cols, cols + n, r) - cols);
-    if (n == 0 || nl >= n || cols[nl] != r) bad = 1;                      // a vertex without a hexahedron has no row
+    const int n = row_unique(i2v[r], hex, v2i, vert_elem, cols);         // counting needs no order
+    int nl = 0, self = 0;
+    for (int k = 0; k < n; ++k) { nl += cols[k] < r; self += cols[k] == r; }
+    if (n == 0 || !self) bad = 1;                                         // a vertex without a hexahedron has no row
     L_ptr[r + 1] = nl;
     U_ptr[r + 1] = n - nl - 1;
   }
