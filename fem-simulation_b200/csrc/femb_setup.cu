@@ -36,6 +36,20 @@ static inline int row_unique(int v, const int* hex, const int* v2i, const int* v
   return n;
 }
 
+// removes duplicates from cand[0..n) in place (first occurrences kept, unsorted), n <= 224: 512-slot stack table
+static inline int unique_in_place(int* cand, int n) {
+  int tab[512];
+  std::memset(tab, 0xff, sizeof(tab));
+  int u = 0;
+  for (int k = 0; k < n; ++k) {
+    const int c = cand[k];
+    unsigned s = ((unsigned)c * 2654435761u) >> 23;
+    while (tab[s] != -1 && tab[s] != c) s = (s + 1) & 511;
+    if (tab[s] == -1) { tab[s] = c; cand[u++] = c; }
+  }
+  return u;
+}
+
 // sorted unique index-order columns of row v2i[v]; returns the count (<= 64)
 static inline int row_columns(int v, const int* hex, const int* v2i, const int* vert_elem, int* cols) {
   const int n = row_unique(v, hex, v2i, vert_elem, cols);
@@ -210,8 +224,7 @@ int femb_setup_galerkin_count_host(int n_fine, const int* fL_ptr, const int* fL_
     for (int p = fL_ptr[i]; p < fL_ptr[i + 1]; ++p) add(fL_col[p]);
     add(i);
     for (int p = fU_ptr[i]; p < fU_ptr[i + 1]; ++p) add(fU_col[p]);
-    std::sort(cand, cand + n);
-    const int u = (int)(std::unique(cand, cand + n) - cand);
+    const int u = unique_in_place(cand, n);                                // counting needs no order
     if (u > 27) bad = 1;
     t_ptr[i + 1] = u;
   }
@@ -258,8 +271,8 @@ int femb_setup_galerkin_fill_host(int n_fine, int n_coarse, const int* fL_ptr, c
     for (int p = fL_ptr[i]; p < fL_ptr[i + 1]; ++p) add(fL_col[p]);
     add(i);
     for (int p = fU_ptr[i]; p < fU_ptr[i + 1]; ++p) add(fU_col[p]);
-    std::sort(cand, cand + n);
-    const int u = (int)(std::unique(cand, cand + n) - cand);
+    const int u = unique_in_place(cand, n);                                // ~90 candidates, <= 27 distinct: sort those only
+    std::sort(cand, cand + u);
     int* tc = t_col + t_ptr[i];
     for (int k = 0; k < u; ++k) tc[k] = cand[k];
     auto plan = [&](size_t slot, int j) {
