@@ -12,7 +12,8 @@
  *     are DEVICE pointers owned by the caller unless the name ends in `_host`.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Nothing allocates,
  *     nothing synchronises, nothing reads back: every call only enqueues kernels, so a sequence of
- *     calls can be captured in a CUDA graph.
+ *     calls can be captured in a CUDA graph.  (The femb_setup_*_host entry points are host code on host pointers and
+ *     return when done; femb_setup_hierarchy_host alone allocates -- host arrays it owns until femb_setup_hierarchy_free.)
  *   - vectors are float[n*3] (vec3 per vertex); block values are float[nnz*9], row-major 3x3, in the
  *     reference's [L;D;U] layout (object.py:499-505): L blocks sorted by (row,col) at [off_l, off_d),
  *     the diagonal block of row r at off_d + r, U blocks sorted by (row,col) from off_u.
