@@ -105,6 +105,7 @@ int femb_setup_coo_to_csr_pair_host(int nrow, int nnz, const int* rows, const in
   }
   if (bad_row != -1) { set_error("femb_setup_coo_to_csr_host: row %d out of range", bad_row); return FEMB_E_INVALID; }
   offsets[0] = 0;
+#pragma omp parallel for schedule(static)
   for (int r = 0; r < nrow; ++r) {
     int n = 0;
     for (int t = 0; t < T; ++t) {                                         // count -> start of (r, t) relative to the row
@@ -112,8 +113,9 @@ int femb_setup_coo_to_csr_pair_host(int nrow, int nnz, const int* rows, const in
       const int k = c;
       c = n; n += k;
     }
-    offsets[r + 1] = offsets[r] + n;
+    offsets[r + 1] = n;
   }
+  for (int r = 0; r < nrow; ++r) offsets[r + 1] += offsets[r];
 #pragma omp parallel num_threads(T)
   {
     const int t = omp_get_thread_num();
