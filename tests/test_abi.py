@@ -37,6 +37,12 @@ def test_sass_has_bulk_copy_and_no_legacy_tensor_path():
     import subprocess
     out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in out            # cp.async.bulk staging of the row pass
+    assert "UTMASTG" in out           # TMA tensor store of the element tile (assembly)
+    assert "FFMA2" in out             # packed fp32 in the element kernels
+    # no kernel spills: ptxas assigned zero local (stack) bytes everywhere
+    usage = subprocess.run(["cuobjdump", "--dump-resource-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    local = [int(v) for v in re.findall(r"\bLOCAL:(\d+)", usage)]
+    assert len(local) >= 60 and max(local) == 0
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
 
 
