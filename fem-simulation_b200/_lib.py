@@ -133,6 +133,7 @@ PROTOTYPES = {
     "femb_setup_coarsen_fill_host": [I, I, P, P, P, F, F, P, P, I, I, P, P, P, P, P, P],
     "femb_setup_interp_count_host": [I, I, P, P, P],
     "femb_setup_interp_fill_host": [I, I, I, P, P, P, I, P, P, P, P, P, P],
+    "femb_setup_points_inside_host": [I, P, I, P, I, P, I, P, P],
     "femb_setup_hierarchy_host": [I, I, P, P, F, I, I, P, P],
     "femb_setup_hierarchy_free": [P],
     "femb_prepare_rest": [I, P, P, P, P, P],

@@ -7,6 +7,7 @@
 // expression is evaluated in float32 in the reference's order (cpu_function.py:12-20); hierarchy.build_hierarchy_numpy is
 // the numpy restatement the tests compare this file with, bit for bit.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
@@ -292,6 +293,51 @@ int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, cons
   return FEMB_OK;
 }
 
+
+// ---- surface mesh -> enclosed lattice points (the inside test of the voxeliser; object.py:28-34 calls pv.voxelize) --------------
+
+int femb_setup_points_inside_host(int n_face, const double* tri, int nx, const double* gx, int ny, const double* gy, int nz,
+                                  const double* gz, unsigned char* inside) {
+  FEMB_REQUIRE(n_face >= 0 && nx >= 0 && ny >= 0 && nz >= 0 && inside && (n_face == 0 || tri) && gx && gy && gz, "bad arguments");
+  for (int i = 1; i < nx; ++i) FEMB_REQUIRE(gx[i] > gx[i - 1], "gx must be strictly increasing");
+  for (int i = 1; i < ny; ++i) FEMB_REQUIRE(gy[i] > gy[i - 1], "gy must be strictly increasing");
+  for (int i = 1; i < nz; ++i) FEMB_REQUIRE(gz[i] > gz[i - 1], "gz must be strictly increasing");
+  std::memset(inside, 0, (size_t)nx * ny * nz);
+  // parity of the crossings of the +z ray from every lattice point; a thread owns a range of x indices (a column of the
+  // lattice is touched by one thread only), every thread walks all triangles
+#pragma omp parallel
+  {
+    const int T = omp_get_num_threads(), t = omp_get_thread_num();
+    const int lo = (int)((long long)nx * t / T), hi = (int)((long long)nx * (t + 1) / T);
+    for (int f = 0; f < n_face && lo < hi; ++f) {
+      const double* a = tri + 9 * (size_t)f;
+      const double *b = a + 3, *c = a + 6;
+      const double x0 = std::min(a[0], std::min(b[0], c[0])), x1 = std::max(a[0], std::max(b[0], c[0]));
+      const double y0 = std::min(a[1], std::min(b[1], c[1])), y1 = std::max(a[1], std::max(b[1], c[1]));
+      const int i0 = std::max(lo, (int)(std::lower_bound(gx, gx + nx, x0) - gx));       // gx >= x0
+      const int i1 = std::min(hi, (int)(std::upper_bound(gx, gx + nx, x1) - gx));       // gx <= x1
+      const int j0 = (int)(std::lower_bound(gy, gy + ny, y0) - gy);
+      const int j1 = (int)(std::upper_bound(gy, gy + ny, y1) - gy);
+      if (i0 >= i1 || j0 >= j1) continue;
+      const double d = (b[1] - c[1]) * (a[0] - c[0]) + (c[0] - b[0]) * (a[1] - c[1]);
+      if (std::fabs(d) < 1e-300) continue;                                              // the ray lies in the triangle's plane
+      for (int i = i0; i < i1; ++i)
+        for (int j = j0; j < j1; ++j) {
+          const double px = gx[i], py = gy[j];
+          const double l0 = ((b[1] - c[1]) * (px - c[0]) + (c[0] - b[0]) * (py - c[1])) / d;
+          const double l1 = ((c[1] - a[1]) * (px - c[0]) + (a[0] - c[0]) * (py - c[1])) / d;
+          const double l2 = 1.0 - l0 - l1;
+          // half-open edge rule so that a ray through a shared edge counts once
+          const bool hit = d > 0 ? (l0 >= 0 && l1 >= 0 && l2 > 0) : (l0 > 0 && l1 > 0 && l2 >= 0);
+          if (!hit) continue;
+          const double zc = l0 * a[2] + l1 * b[2] + l2 * c[2];
+          unsigned char* col = inside + ((size_t)i * ny + j) * nz;
+          for (int k = (int)(std::upper_bound(gz, gz + nz, zc) - gz); k < nz; ++k) col[k] ^= 1;   // gz > zc
+        }
+    }
+  }
+  return FEMB_OK;
+}
 
 // ---- the whole hierarchy in one call (Object.__init__, object.py:116-697) ----------------------------------------------------
 

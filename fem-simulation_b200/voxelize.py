@@ -29,7 +29,23 @@ def read_obj(path):
 
 
 def points_inside(verts, faces, gx, gy, gz):
-    """inside[ix,iy,iz] for lattice points (gx[ix], gy[iy], gz[iz]): crossing parity of the +z ray."""
+    """inside[ix,iy,iz] for lattice points (gx[ix], gy[iy], gz[iz]): crossing parity of the +z ray, through the host routine
+    of the C ABI (femb_setup_points_inside_host, csrc/femb_setup_hierarchy.cu: same float64 expressions as
+    `points_inside_numpy`, the restatement tests compare it with)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    tri = np.ascontiguousarray(np.asarray(verts, dtype=np.float64)[np.asarray(faces, dtype=np.int64)].reshape(-1, 9))
+    g = [np.ascontiguousarray(a, dtype=np.float64) for a in (gx, gy, gz)]
+    inside = np.empty((len(g[0]), len(g[1]), len(g[2])), dtype=np.uint8)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.femb_setup_points_inside_host(tri.shape[0], hp(tri), len(g[0]), hp(g[0]), len(g[1]), hp(g[1]), len(g[2]), hp(g[2]),
+                                                 hp(inside)), "femb_setup_points_inside_host")
+    return inside.view(bool)
+
+
+def points_inside_numpy(verts, faces, gx, gy, gz):
+    """inside[ix,iy,iz] for lattice points (gx[ix], gy[iy], gz[iz]): crossing parity of the +z ray (numpy restatement)."""
     inside = np.zeros((len(gx), len(gy), len(gz)), dtype=bool)
     tri = verts[faces]                                       # [F,3,3]
     for t in tri:

@@ -185,6 +185,11 @@ int femb_setup_interp_count_host(int n_fine, int n_coarse_hex, const int* fine_c
 int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, const int* fine_coarse, const int* coarse_hex,
                                 const int* first_pos, int n_entries, int* coarse_id, int* fine_id, unsigned char* entry_k,
                                 float* weight, float* norm, float* weight_norm);
+/* the inside test of the voxeliser (object.py:28-34 calls pv.read + pv.voxelize; voxelize.py): inside [nx*ny*nz] (bytes, 0 / 1,
+ * z fastest) = parity of the crossings of the +z ray from lattice point (gx[i], gy[j], gz[k]) with the n_face triangles
+ * tri [n_face*9] (three xyz corners each, float64); the grids are strictly increasing; half-open edge rule */
+int femb_setup_points_inside_host(int n_face, const double* tri, int nx, const double* gx, int ny, const double* gy, int nz,
+                                  const double* gz, unsigned char* inside);
 /* Object.__init__ (object.py:116-697) in one call: all levels of the hierarchy on the host, in arrays the library owns
  * (femb_setup_hierarchy_free releases them).  level[l] describes level l and, when a coarser level exists, its link to level
  * l+1; the names follow the reference (and the functions above, which this call strings together). */

@@ -101,3 +101,47 @@ def test_reference_rocker_obj_builds_a_hierarchy():
     assert np.allclose(ps, 1.0)                                          # prolongation is a partition of unity
     cv = np.asarray(H.color_vertex_num[0]); p = H.pattern[0]
     assert np.all(np.searchsorted(cv, p.U_row, side="right") != np.searchsorted(cv, p.U_col, side="right"))
+
+
+def _box_triangles(lo, hi):
+    """12 triangles of an axis-aligned box: lattice points land exactly on faces, edges and corners (the tie rules)."""
+    (x0, y0, z0), (x1, y1, z1) = lo, hi
+    v = np.array([[x0, y0, z0], [x1, y0, z0], [x0, y1, z0], [x1, y1, z0], [x0, y0, z1], [x1, y0, z1], [x0, y1, z1], [x1, y1, z1]], float)
+    f = np.array([(0, 2, 1), (1, 2, 3), (4, 5, 6), (5, 7, 6), (0, 1, 4), (1, 5, 4), (2, 6, 3), (3, 6, 7), (0, 4, 2), (2, 4, 6), (1, 3, 5), (3, 7, 5)])
+    return v, f
+
+
+@pytest.mark.parametrize("case", ["tetra", "hull", "box_on_lattice", "empty"])
+def test_native_inside_test_matches_numpy_restatement(case):
+    """femb_setup_points_inside_host (C++/OpenMP) against voxelize.points_inside_numpy: the same booleans, point for point."""
+    from scipy.spatial import ConvexHull
+    if case == "tetra":
+        v, f, _ = _tetra()
+        grids = [[np.arange(v[:, k].min(), v[:, k].max(), dx) for k in range(3)] for dx in (0.05, 0.031, 0.2)]
+    elif case == "hull":
+        rng = np.random.default_rng(3)
+        v = rng.normal(size=(300, 3)) * np.array([1.0, 0.6, 1.7])
+        f = ConvexHull(v).simplices
+        grids = [[np.arange(v[:, k].min(), v[:, k].max(), dx) for k in range(3)] for dx in (0.11, 0.07)]
+    elif case == "box_on_lattice":
+        v, f = _box_triangles((0.0, 0.0, 0.0), (1.0, 0.5, 0.75))
+        grids = [[np.arange(-0.25, 1.5, 0.125)] * 3, [np.arange(0.0, 1.0, 0.25), np.arange(0.0, 0.5, 0.25), np.arange(0.0, 0.75, 0.25)]]
+    else:
+        v, f = np.zeros((3, 3)), np.zeros((0, 3), np.int64)
+        grids = [[np.arange(0.0, 1.0, 0.25)] * 3]
+    for g in grids:
+        got = voxelize.points_inside(v, f, *g)
+        want = voxelize.points_inside_numpy(v, f, *g)
+        assert got.dtype == np.bool_ and got.shape == want.shape and np.array_equal(got, want)
+        if case == "hull":
+            assert want.sum() > 1000
+
+
+@pytest.mark.parametrize("name", ["cube.obj", "rocker.obj", "horse.obj"])
+def test_native_inside_test_on_reference_assets(name):
+    path = os.path.join(ASSETS, name)
+    if not os.path.exists(path):
+        pytest.skip("reference assets not present")
+    v, f = voxelize.read_obj(path)
+    g = [np.arange(v[:, k].min(), v[:, k].max(), 0.05) for k in range(3)]
+    assert np.array_equal(voxelize.points_inside(v, f, *g), voxelize.points_inside_numpy(v, f, *g))
