@@ -29,6 +29,9 @@ T.test_native_hierarchy_rejects_bad_input()
 T.test_host_setup_routines_match_numpy_restatements()
 T.test_coo_to_csr_pair_matches_numpy_sort()
 T.test_galerkin_plan_emulation()
+import test_voxelize as V
+for case in ["tetra", "hull", "box_on_lattice", "empty"]:
+    V.test_native_inside_test_matches_numpy_restatement(case)
 print("host setup under ASan + UBSan: clean")
 PY
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0 python "$OUT/run.py"
