@@ -8,6 +8,7 @@
 // the numpy restatement the tests compare this file with, bit for bit.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
@@ -293,6 +294,75 @@ int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, cons
   return FEMB_OK;
 }
 
+
+// ---- Wavefront OBJ surface meshes (object.py:28 calls pv.read): "v x y z" and "f a b c ..." lines, polygons as fans ------------
+
+namespace femb {
+// one pass over the file; with verts / faces == nullptr it only counts
+static int obj_pass(const char* path, double* verts, long long* faces, long long* n_vert_out, long long* n_tri_out) {
+  FILE* f = std::fopen(path, "r");
+  if (!f) { set_error("femb_setup_obj: cannot open %s", path); return FEMB_E_INVALID; }
+  std::vector<char> line(1 << 16);
+  long long nv = 0, nt = 0;
+  int rc = FEMB_OK;
+  while (std::fgets(line.data(), (int)line.size(), f)) {
+    const char* p = line.data();
+    if (p[0] == 'v' && p[1] == ' ') {
+      double xyz[3] = {0.0, 0.0, 0.0};
+      char* end = nullptr;
+      const char* q = p + 2;
+      for (int d = 0; d < 3; ++d) {
+        xyz[d] = std::strtod(q, &end);
+        if (end == q) { set_error("femb_setup_obj: malformed vertex line %lld", nv + 1); rc = FEMB_E_INVALID; break; }
+        q = end;
+      }
+      if (rc != FEMB_OK) break;
+      if (verts) for (int d = 0; d < 3; ++d) verts[3 * nv + d] = xyz[d];
+      ++nv;
+    } else if (p[0] == 'f' && p[1] == ' ') {
+      long long first = -1, prev = -1;
+      int k = 0;
+      const char* q = p + 2;
+      for (;;) {
+        while (*q == ' ' || *q == '\t' || *q == '\r' || *q == '\n') ++q;
+        if (!*q) break;
+        char* end = nullptr;
+        long long i = std::strtoll(q, &end, 10);
+        if (end == q) { set_error("femb_setup_obj: malformed face line"); rc = FEMB_E_INVALID; break; }
+        i = i > 0 ? i - 1 : nv + i;                                           // 1-based, negative = relative to the vertices so far
+        q = end;
+        while (*q && *q != ' ' && *q != '\t' && *q != '\r' && *q != '\n') ++q;   // skip "/vt/vn"
+        if (k == 0) first = i;
+        else if (k >= 2) {
+          if (faces) { faces[3 * nt] = first; faces[3 * nt + 1] = prev; faces[3 * nt + 2] = i; }
+          ++nt;
+        }
+        prev = i;
+        ++k;
+      }
+      if (rc != FEMB_OK) break;
+    }
+  }
+  std::fclose(f);
+  *n_vert_out = nv;
+  *n_tri_out = nt;
+  return rc;
+}
+}  // namespace femb
+
+int femb_setup_obj_count_host(const char* path, long long* n_vert, long long* n_tri) {
+  FEMB_REQUIRE(path && n_vert && n_tri, "null pointer");
+  return obj_pass(path, nullptr, nullptr, n_vert, n_tri);
+}
+
+int femb_setup_obj_read_host(const char* path, long long n_vert, long long n_tri, double* verts, long long* faces) {
+  FEMB_REQUIRE(path && n_vert >= 0 && n_tri >= 0 && (n_vert == 0 || verts) && (n_tri == 0 || faces), "bad arguments");
+  long long nv = 0, nt = 0;
+  int rc = obj_pass(path, nullptr, nullptr, &nv, &nt);                        // the file may have changed since the count
+  if (rc != FEMB_OK) return rc;
+  if (nv != n_vert || nt != n_tri) { set_error("femb_setup_obj_read_host: the file holds %lld vertices / %lld triangles, not %lld / %lld", nv, nt, n_vert, n_tri); return FEMB_E_INVALID; }
+  return obj_pass(path, verts, faces, &nv, &nt);
+}
 
 // ---- surface mesh -> enclosed lattice points (the inside test of the voxeliser; object.py:28-34 calls pv.voxelize) --------------
 

@@ -15,6 +15,25 @@ from .mesh import mesh_from_mask
 
 
 def read_obj(path):
+    """vertices [N,3] float64 and triangles [F,3] int64 of a Wavefront OBJ file (polygons as fans), through the host routines
+    of the C ABI (femb_setup_obj_count_host / _read_host); `read_obj_python` is the restatement the tests compare it with."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    import os
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)                        # what open() / pv.read raise
+    nv, nt = C.c_longlong(0), C.c_longlong(0)
+    bpath = str(path).encode()
+    _lib.check(lib.femb_setup_obj_count_host(bpath, C.cast(C.byref(nv), C.c_void_p), C.cast(C.byref(nt), C.c_void_p)),
+               "femb_setup_obj_count_host")
+    verts, faces = np.empty((nv.value, 3), dtype=np.float64), np.empty((nt.value, 3), dtype=np.int64)
+    _lib.check(lib.femb_setup_obj_read_host(bpath, nv.value, nt.value, verts.ctypes.data_as(C.c_void_p), faces.ctypes.data_as(C.c_void_p)),
+               "femb_setup_obj_read_host")
+    return verts, faces
+
+
+def read_obj_python(path):
     verts, faces = [], []
     with open(path) as f:
         for line in f:

@@ -185,6 +185,11 @@ int femb_setup_interp_count_host(int n_fine, int n_coarse_hex, const int* fine_c
 int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, const int* fine_coarse, const int* coarse_hex,
                                 const int* first_pos, int n_entries, int* coarse_id, int* fine_id, unsigned char* entry_k,
                                 float* weight, float* norm, float* weight_norm);
+/* Wavefront OBJ surface meshes (object.py:28 calls pv.read): the "v x y z" and "f a b c ..." lines of `path` (indices 1-based or
+ * negative = relative, "a/b/c" forms accepted, polygons split into fans).  count first, then read into verts [n_vert*3] (float64)
+ * and faces [n_tri*3] (int64, 0-based) */
+int femb_setup_obj_count_host(const char* path, long long* n_vert, long long* n_tri);
+int femb_setup_obj_read_host(const char* path, long long n_vert, long long n_tri, double* verts, long long* faces);
 /* the inside test of the voxeliser (object.py:28-34 calls pv.read + pv.voxelize; voxelize.py): inside [nx*ny*nz] (bytes, 0 / 1,
  * z fastest) = parity of the crossings of the +z ray from lattice point (gx[i], gy[j], gz[k]) with the n_face triangles
  * tri [n_face*9] (three xyz corners each, float64); the grids are strictly increasing; half-open edge rule */

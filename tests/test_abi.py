@@ -89,10 +89,10 @@ def test_prototypes_match_header_signatures(repo_root):
         param = " ".join(param.split())
         if "*" in param:
             return "p"
-        return {"int": "i", "float": "f", "size_t": "z"}[param.rsplit(" ", 1)[0].replace("const ", "")]
+        return {"int": "i", "float": "f", "size_t": "z", "long long": "l"}[param.rsplit(" ", 1)[0].replace("const ", "")]
 
     def klass_ct(t):
-        return "i" if t is C.c_int else "f" if t is C.c_float else "z" if t is C.c_size_t else "p"
+        return "i" if t is C.c_int else "f" if t is C.c_float else "z" if t is C.c_size_t else "l" if t is C.c_longlong else "p"
 
     for name, params in decls.items():
         params = params.strip()

@@ -145,3 +145,28 @@ def test_native_inside_test_on_reference_assets(name):
     v, f = voxelize.read_obj(path)
     g = [np.arange(v[:, k].min(), v[:, k].max(), 0.05) for k in range(3)]
     assert np.array_equal(voxelize.points_inside(v, f, *g), voxelize.points_inside_numpy(v, f, *g))
+
+
+def test_native_obj_reader_matches_python_parser(tmp_path):
+    """femb_setup_obj_count_host / _read_host against the line-by-line Python parser: quads and pentagons as fans, a/b/c index
+    forms, negative (relative) indices, comments, other records, exponents; and the reference's own files when present."""
+    p = tmp_path / "mixed.obj"
+    p.write_text("# comment\nmtllib x.mtl\nv 0 0 0\nv 1.5e0 0 0\nv 1 1 -2.5E-1\nvn 0 0 1\nvt 0.5 0.5\nv 0 1 0.125\n"
+                 "f 1 2 3\nf 1/1/1 2/2/1 3//1 4\ng grp\nv 0.3333333333333333 7 1e-3\nf -1 -2 -3 -4 -5\nf 5//2 1//2 3//2\n")
+    v, f = voxelize.read_obj(str(p))
+    pv_, pf = voxelize.read_obj_python(str(p))
+    assert v.dtype == np.float64 and f.dtype == np.int64 and v.shape == (5, 3) and f.shape == (7, 3)
+    assert np.array_equal(v, pv_) and np.array_equal(f, pf)
+    for name in ["cube.obj", "rocker.obj", "horse.obj"]:
+        path = os.path.join(ASSETS, name)
+        if os.path.exists(path):
+            v, f = voxelize.read_obj(path)
+            pv_, pf = voxelize.read_obj_python(path)
+            assert np.array_equal(v, pv_) and np.array_equal(f, pf), name
+    with pytest.raises(FileNotFoundError):
+        voxelize.read_obj(str(tmp_path / "missing.obj"))
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0\n")
+    from fem_simulation_b200 import _lib
+    with pytest.raises(_lib.FembError):
+        voxelize.read_obj(str(bad))
