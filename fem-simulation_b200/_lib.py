@@ -133,6 +133,8 @@ PROTOTYPES = {
     "femb_setup_coarsen_fill_host": [I, I, P, P, P, F, F, P, P, I, I, P, P, P, P, P, P],
     "femb_setup_interp_count_host": [I, I, P, P, P],
     "femb_setup_interp_fill_host": [I, I, I, P, P, P, I, P, P, P, P, P, P],
+    "femb_setup_mask_mesh_count_host": [I, I, I, P, P, P],
+    "femb_setup_mask_mesh_fill_host": [I, I, I, P, F, P, P, I, I, P, P],
     "femb_setup_obj_count_host": [C.c_char_p, P, P],
     "femb_setup_obj_read_host": [C.c_char_p, C.c_longlong, C.c_longlong, P, P],
     "femb_setup_points_inside_host": [I, P, I, P, I, P, I, P, P],

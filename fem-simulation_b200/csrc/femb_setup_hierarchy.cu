@@ -295,6 +295,76 @@ int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, cons
 }
 
 
+// ---- voxel set -> hexahedral mesh in the reference's numbering (object.py:28-45) -----------------------------------
+
+namespace femb {
+// used lattice points of the kept voxels: remap[lattice id] = rank among the used ones (x fastest), -1 if unused
+static long long mark_and_rank(int nx, int ny, int nz, const unsigned char* mask, std::vector<int>& remap, long long* n_hex) {
+  const long long px = nx + 1, py = ny + 1, pz = nz + 1;
+  remap.assign((size_t)(px * py * pz), -1);
+  long long nh = 0;
+  for (int ix = 0; ix < nx; ++ix)                                            // mask is [nx][ny][nz], z fastest
+    for (int iy = 0; iy < ny; ++iy)
+      for (int iz = 0; iz < nz; ++iz) {
+        if (!mask[((size_t)ix * ny + iy) * nz + iz]) continue;
+        ++nh;
+        for (int a = 0; a < 8; ++a)
+          remap[(size_t)((ix + ((a >> 2) & 1)) + px * ((iy + ((a >> 1) & 1)) + py * (iz + (a & 1))))] = 0;
+      }
+  long long n = 0;
+  for (size_t q = 0; q < remap.size(); ++q)
+    if (remap[q] == 0) remap[q] = (int)n++;
+  *n_hex = nh;
+  return n;
+}
+}  // namespace femb
+
+int femb_setup_mask_mesh_count_host(int nx, int ny, int nz, const unsigned char* mask, int* n_vert, int* n_hex) {
+  FEMB_REQUIRE(nx > 0 && ny > 0 && nz > 0 && mask && n_vert && n_hex, "bad arguments");
+  FEMB_REQUIRE((long long)(nx + 1) * (ny + 1) * (nz + 1) < (1ll << 31), "lattice must have fewer than 2^31 points");
+  std::vector<int> remap;
+  long long nh = 0;
+  *n_vert = (int)mark_and_rank(nx, ny, nz, mask, remap, &nh);
+  *n_hex = (int)nh;
+  return FEMB_OK;
+}
+
+int femb_setup_mask_mesh_fill_host(int nx, int ny, int nz, const unsigned char* mask, float dx, const float* origin,
+                                   const int* index_offset, int n_vert, int n_hex, float* points, int* hex) {
+  FEMB_REQUIRE(nx > 0 && ny > 0 && nz > 0 && mask && origin && index_offset && n_vert >= 0 && n_hex >= 0 && points && hex, "bad arguments");
+  FEMB_REQUIRE((long long)(nx + 1) * (ny + 1) * (nz + 1) < (1ll << 31), "lattice must have fewer than 2^31 points");
+  std::vector<int> remap;
+  long long nh = 0;
+  const long long nv = mark_and_rank(nx, ny, nz, mask, remap, &nh);
+  if (nv != n_vert || nh != n_hex) { set_error("femb_setup_mask_mesh_fill_host: the mask has %lld vertices / %lld voxels, not %d / %d", nv, nh, n_vert, n_hex); return FEMB_E_INVALID; }
+  const long long px = nx + 1, py = ny + 1, pz = nz + 1;
+  // points: lattice coordinates (shifted by index_offset) * dx + origin, float32, one multiplication and one addition
+#pragma omp parallel for schedule(static)
+  for (long long gz = 0; gz < pz; ++gz)
+    for (long long gy = 0; gy < py; ++gy)
+      for (long long gx = 0; gx < px; ++gx) {
+        const int v = remap[(size_t)(gx + px * (gy + py * gz))];
+        if (v < 0) continue;
+        const long long g[3] = {gx + index_offset[0], gy + index_offset[1], gz + index_offset[2]};
+        for (int d = 0; d < 3; ++d) {
+          float p = (float)g[d] * dx;
+          p = p + origin[d];
+          points[3 * (size_t)v + d] = p;
+        }
+      }
+  // hexahedra x fastest, local node a = 4 bx + 2 by + bz
+  long long e = 0;
+  for (int iz = 0; iz < nz; ++iz)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nx; ++ix) {
+        if (!mask[((size_t)ix * ny + iy) * nz + iz]) continue;
+        for (int a = 0; a < 8; ++a)
+          hex[8 * (size_t)e + a] = remap[(size_t)((ix + ((a >> 2) & 1)) + px * ((iy + ((a >> 1) & 1)) + py * (iz + (a & 1))))];
+        ++e;
+      }
+  return FEMB_OK;
+}
+
 // ---- Wavefront OBJ surface meshes (object.py:28 calls pv.read): "v x y z" and "f a b c ..." lines, polygons as fans ------------
 
 namespace femb {

@@ -13,7 +13,29 @@ import numpy as np
 def mesh_from_mask(mask: np.ndarray, dx: float, origin=(0.0, 0.0, 0.0), index_offset=(0, 0, 0)):
     """``mask[ix,iy,iz]`` (bool) marks the kept voxels.  Returns (points f32[N,3], hexagons i32[Nh,8]).
     ``index_offset`` shifts the integer lattice coordinates before they are scaled (a slab of a larger lattice gets
-    bit-identical coordinates to the full mesh)."""
+    bit-identical coordinates to the full mesh).  Through the host routines of the C ABI (femb_setup_mask_mesh_count_host /
+    _fill_host); `mesh_from_mask_numpy` is the numpy restatement the tests compare it with."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    m = np.ascontiguousarray(np.asarray(mask, dtype=bool)).view(np.uint8)
+    if m.ndim != 3 or min(m.shape) < 1:
+        raise ValueError(f"mask must be a non-empty [nx, ny, nz] array, got shape {m.shape}")
+    nx, ny, nz = (int(v) for v in m.shape)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    nv, nh = C.c_int(0), C.c_int(0)
+    _lib.check(lib.femb_setup_mask_mesh_count_host(nx, ny, nz, hp(m), C.cast(C.byref(nv), C.c_void_p), C.cast(C.byref(nh), C.c_void_p)),
+               "femb_setup_mask_mesh_count_host")
+    points, hexagons = np.empty((nv.value, 3), np.float32), np.empty((nh.value, 8), np.int32)
+    o = np.ascontiguousarray(origin, dtype=np.float32).reshape(3)
+    off = np.ascontiguousarray(index_offset, dtype=np.int32).reshape(3)
+    _lib.check(lib.femb_setup_mask_mesh_fill_host(nx, ny, nz, hp(m), C.c_float(dx), hp(o), hp(off), nv.value, nh.value, hp(points),
+                                                  hp(hexagons)), "femb_setup_mask_mesh_fill_host")
+    return points, hexagons
+
+
+def mesh_from_mask_numpy(mask: np.ndarray, dx: float, origin=(0.0, 0.0, 0.0), index_offset=(0, 0, 0)):
+    """numpy restatement of `mesh_from_mask`."""
     mask = np.asarray(mask, dtype=bool)
     nx, ny, nz = mask.shape
     iz, iy, ix = np.nonzero(np.transpose(mask, (2, 1, 0)))          # x fastest, then y, then z

@@ -185,6 +185,12 @@ int femb_setup_interp_count_host(int n_fine, int n_coarse_hex, const int* fine_c
 int femb_setup_interp_fill_host(int n_fine, int n_coarse, int n_coarse_hex, const int* fine_coarse, const int* coarse_hex,
                                 const int* first_pos, int n_entries, int* coarse_id, int* fine_id, unsigned char* entry_k,
                                 float* weight, float* norm, float* weight_norm);
+/* voxel set -> hexahedral mesh in the reference's numbering (object.py:28-45: lattice points x fastest restricted to the used
+ * ones, cells x fastest, local node a = 4 bx + 2 by + bz).  mask [nx*ny*nz] bytes (z fastest, as a C-ordered [nx][ny][nz]
+ * array), count first, then points [n_vert*3] = (lattice index + index_offset) * dx + origin (float32) and hex [n_hex*8] */
+int femb_setup_mask_mesh_count_host(int nx, int ny, int nz, const unsigned char* mask, int* n_vert, int* n_hex);
+int femb_setup_mask_mesh_fill_host(int nx, int ny, int nz, const unsigned char* mask, float dx, const float* origin,
+                                   const int* index_offset, int n_vert, int n_hex, float* points, int* hex);
 /* Wavefront OBJ surface meshes (object.py:28 calls pv.read): the "v x y z" and "f a b c ..." lines of `path` (indices 1-based or
  * negative = relative, "a/b/c" forms accepted, polygons split into fans).  count first, then read into verts [n_vert*3] (float64)
  * and faces [n_tri*3] (int64, 0-based) */

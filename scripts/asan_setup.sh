@@ -34,6 +34,7 @@ for case in ["tetra", "hull", "box_on_lattice", "empty"]:
     V.test_native_inside_test_matches_numpy_restatement(case)
 import pathlib, tempfile
 V.test_native_obj_reader_matches_python_parser(pathlib.Path(tempfile.mkdtemp()))
+V.test_native_mask_mesh_matches_numpy_restatement()
 print("host setup under ASan + UBSan: clean")
 PY
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0 python "$OUT/run.py"

@@ -170,3 +170,22 @@ def test_native_obj_reader_matches_python_parser(tmp_path):
     from fem_simulation_b200 import _lib
     with pytest.raises(_lib.FembError):
         voxelize.read_obj(str(bad))
+
+
+def test_native_mask_mesh_matches_numpy_restatement():
+    """femb_setup_mask_mesh_count_host / _fill_host against mesh.mesh_from_mask_numpy: points bit for bit, hexahedra equal --
+    boxes, ragged sets, offsets and origins of a slab, an empty set."""
+    from fem_simulation_b200 import mesh
+    rng = np.random.default_rng(9)
+    cases = [(np.ones((4, 3, 5), bool), 0.05, (0.0, 0.0, 0.0), (0, 0, 0)),
+             (rng.random((9, 11, 7)) < 0.5, 0.1, (-0.3, 1.7, 0.21), (0, 0, 0)),
+             (rng.random((6, 5, 8)) < 0.2, 1.0 / 7, (0.0, 0.0, 0.0), (3, 0, 14)),
+             (rng.random((13, 4, 6)) < 0.9, 0.0125, (5.5, -2.25, 1e-3), (0, 7, 0)),
+             (np.zeros((3, 3, 3), bool), 0.05, (0.0, 0.0, 0.0), (0, 0, 0))]
+    for mask, dx, origin, off in cases:
+        p, h = mesh.mesh_from_mask(mask, dx, origin, off)
+        q, g = mesh.mesh_from_mask_numpy(mask, dx, origin, off)
+        assert p.dtype == np.float32 and h.dtype == np.int32 and p.shape == q.shape and h.shape == g.shape
+        assert np.array_equal(p, q) and np.array_equal(h, g)
+    with pytest.raises(ValueError):
+        mesh.mesh_from_mask(np.ones((3, 3), bool), 0.1)
