@@ -110,7 +110,7 @@ def test_plain_c_consumer_builds_the_hierarchy(repo_root, tmp_path):
     exe = tmp_path / "setup_from_c"
     libdir = os.path.dirname(_lib.LIB_PATH)
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(repo_root, "include"),
-                    os.path.join(repo_root, "examples", "setup_from_c.c"), "-L", libdir, "-lfemb200", f"-Wl,-rpath,{libdir}",
+                    os.path.join(repo_root, "examples", "setup_from_c.c"), "-L", libdir, "-lfemb200", "-lm", f"-Wl,-rpath,{libdir}",
                     "-o", str(exe)], check=True)
     out = subprocess.run([str(exe), "12", "3"], capture_output=True, text=True, check=True).stdout.splitlines()
     H = hierarchy.build_hierarchy(*mesh.cube_mesh(12), 1.0 / 12, layers=3)
@@ -120,3 +120,17 @@ def test_plain_c_consumer_builds_the_hierarchy(repo_root, tmp_path):
         assert out[1 + l].startswith(f"level {l}: {H.dims[l]} vertices, {len(H.hexs[l])} hexahedra, {H.pattern[l].nnz} blocks, "
                                      f"colours {colours},"), out[1 + l]
     assert f"interpolation entries {H.Us_hat[0].nnz} " in out[1]
+    # second mode: a closed surface mesh through the whole native front end (OBJ parser, inside test, kept cells -> mesh,
+    # hierarchy), against voxelize.voxelize_obj + build_hierarchy
+    from fem_simulation_b200 import voxelize
+    obj = tmp_path / "tetra.obj"
+    obj.write_text("v 0.013 0.021 0.037\nv 1.071 0.113 0.091\nv 0.233 0.957 0.171\nv 0.317 0.289 1.043\n"
+                   "f 1 3 2\nf 1 2 4\nf 2 3 4\nf 1 4 3\n")
+    out = subprocess.run([str(exe), str(obj), "0.05", "2"], capture_output=True, text=True, check=True).stdout.splitlines()
+    pts, hx = voxelize.voxelize_obj(str(obj), 0.05)
+    H = hierarchy.build_hierarchy(pts, hx, 0.05, layers=2)
+    assert out[0].startswith("obj: 4 vertices, 4 triangles -> ") and out[0].endswith(f" cells, {len(hx)} kept")
+    for l in range(2):
+        colours = " ".join(str(c) for c in np.diff(H.color_vertex_num[l]))
+        assert out[2 + l].startswith(f"level {l}: {H.dims[l]} vertices, {len(H.hexs[l])} hexahedra, {H.pattern[l].nnz} blocks, "
+                                     f"colours {colours},"), out[2 + l]
