@@ -6,6 +6,10 @@
 // otherwise), filled by one ordered scan, so the numbering is the reference's by construction.  Every floating-point
 // expression is evaluated in float32 in the reference's order (cpu_function.py:12-20); hierarchy.build_hierarchy_numpy is
 // the numpy restatement the tests compare this file with, bit for bit.
+//
+// Also here, the front end the reference leaves to pyvista / VTK (object.py:28-45): the OBJ parser, the inside test of the
+// voxeliser, and voxel set -> points / hexahedra in the reference's numbering (voxelize.py and mesh.py hold the numpy / Python
+// restatements), and femb_setup_hierarchy_host, which strings the setup calls of this file and of femb_setup.cu together.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
